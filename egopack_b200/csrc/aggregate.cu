@@ -1,0 +1,227 @@
+// SAGE mean aggregation (a5): out[i] = s_out(i) * sum_{j in N(i)} s_in(j) * x[j]      -- HBM bound.
+//
+// Replaces the reference's index_select (materialises [E,C]) + atomic scatter_add_ + count + divide inside
+// gnn.SAGEConv (models/graph.py:42).  Algorithmic traffic is one read + one write of the [N,C] activations
+// (2*C*b bytes per node), independent of the window radius, because the adjacency of a temporal graph is a
+// band: consecutive output rows share all but one of their neighbour rows.
+//
+// band kernel: a CTA owns a strip of consecutive rows x a 128-vector (16 B each) column chunk.  Rows stream
+// through a shared-memory ring with cp.async (one commit group per row, P rows in flight); every thread only
+// ever touches its own 16-byte column of the ring, so the pipeline needs no block barrier at all.  Small
+// radii sum the window directly from the ring in ascending neighbour order (bit-identical to a sequential
+// scatter_add); large radii keep a running window sum (add the entering row, subtract the leaving row).
+#include "common.cuh"
+
+namespace egp {
+
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+constexpr int kAggThreads = 128;
+
+template <typename T>
+__device__ __forceinline__ Vec<T> ring_load(const uint4* ring, int slot) {
+  return Vec<T>::load(reinterpret_cast<const T*>(ring + (size_t)slot * kAggThreads + threadIdx.x));
+}
+
+// P = prefetch distance in rows (compile time so cp.async.wait_group gets an immediate)
+template <typename T, int P, bool SLIDING>
+__global__ void __launch_bounds__(kAggThreads)
+sage_mean_band_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n, int64_t channels, int64_t ldx,
+                      int64_t ldo, int rows_per_cta, int ring_rows, const int32_t* __restrict__ win_lo,
+                      const int32_t* __restrict__ win_hi, const float* __restrict__ scale_out,
+                      const float* __restrict__ scale_in) {
+  extern __shared__ uint4 ring[];
+  constexpr int VN = Vec<T>::N;
+  const int64_t col = ((int64_t)blockIdx.y * kAggThreads + threadIdx.x) * VN;
+  if (col >= channels) return;  // no block-level barrier below: safe to drop out
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(r0 + rows_per_cta, n);
+  if (r0 >= r1) return;
+
+  const T* xc = x + col;
+  int64_t issued = (int64_t)win_lo[r0] - 1;  // last row whose copy has been issued
+  auto issue_upto = [&](int64_t last) {
+    for (int64_t j = issued + 1; j <= last; ++j)
+      cp_async_16(ring + (size_t)((int)j % ring_rows) * kAggThreads + threadIdx.x, xc + j * ldx);
+    if (last > issued) issued = last;
+  };
+#pragma unroll 1
+  for (int p = 0; p < P; ++p) {
+    if (r0 + p < r1) issue_upto(win_hi[r0 + p]);
+    cp_async_commit();
+  }
+
+  Vec<T> acc;
+#pragma unroll
+  for (int c = 0; c < VN; ++c) acc.v[c] = 0.f;
+  int64_t cl = win_lo[r0], ch = cl - 1;  // rows currently summed in acc (SLIDING only)
+
+#pragma unroll 1
+  for (int64_t i = r0; i < r1; ++i) {
+    if (i + P < r1) issue_upto(win_hi[i + P]);
+    cp_async_commit();
+    cp_async_wait<P>();  // everything but the newest P groups has landed => rows <= win_hi[i] are in the ring
+    const int64_t lo = win_lo[i], hi = win_hi[i];
+    Vec<T> res;
+    if (!SLIDING) {
+#pragma unroll
+      for (int c = 0; c < VN; ++c) res.v[c] = 0.f;
+      for (int64_t j = lo; j <= hi; ++j) {
+        if (j == i) continue;
+        const Vec<T> v = ring_load<T>(ring, ((int)j % ring_rows));
+        const float s = scale_in ? scale_in[j] : 1.f;
+#pragma unroll
+        for (int c = 0; c < VN; ++c) res.v[c] += s * v.v[c];
+      }
+    } else {
+      if (lo > ch) {  // window left the previous graph entirely: restart (no cancellation residue)
+#pragma unroll
+        for (int c = 0; c < VN; ++c) acc.v[c] = 0.f;
+        cl = lo;
+        ch = lo - 1;
+      }
+      while (ch < hi) {
+        ++ch;
+        const Vec<T> v = ring_load<T>(ring, ((int)ch % ring_rows));
+        const float s = scale_in ? scale_in[ch] : 1.f;
+#pragma unroll
+        for (int c = 0; c < VN; ++c) acc.v[c] += s * v.v[c];
+      }
+      while (cl < lo) {
+        const Vec<T> v = ring_load<T>(ring, ((int)cl % ring_rows));
+        const float s = scale_in ? scale_in[cl] : 1.f;
+#pragma unroll
+        for (int c = 0; c < VN; ++c) acc.v[c] -= s * v.v[c];
+        ++cl;
+      }
+      const Vec<T> self = ring_load<T>(ring, ((int)i % ring_rows));
+      const float s = scale_in ? scale_in[i] : 1.f;
+#pragma unroll
+      for (int c = 0; c < VN; ++c) res.v[c] = acc.v[c] - s * self.v[c];
+    }
+    const float so = scale_out ? scale_out[i] : 1.f;
+#pragma unroll
+    for (int c = 0; c < VN; ++c) res.v[c] *= so;
+    res.store(out + i * ldo + col);
+  }
+  cp_async_wait<0>();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kAggThreads)
+sage_mean_csr_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n, int64_t channels, int64_t ldx,
+                     int64_t ldo, int rows_per_cta, const int32_t* __restrict__ rowptr,
+                     const int32_t* __restrict__ colidx, const float* __restrict__ scale_out,
+                     const float* __restrict__ scale_in) {
+  constexpr int VN = Vec<T>::N;
+  const int64_t col = ((int64_t)blockIdx.y * kAggThreads + threadIdx.x) * VN;
+  if (col >= channels) return;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(r0 + rows_per_cta, n);
+  const T* xc = x + col;
+  for (int64_t i = r0; i < r1; ++i) {
+    const int b = rowptr[i], e = rowptr[i + 1];
+    Vec<T> acc;
+#pragma unroll
+    for (int c = 0; c < VN; ++c) acc.v[c] = 0.f;
+    int p = b;
+    for (; p + 4 <= e; p += 4) {  // 4 independent 16-byte gathers in flight per thread
+      int j[4];
+      Vec<T> v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) j[u] = colidx[p + u];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = Vec<T>::load(xc + (int64_t)j[u] * ldx);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float s = scale_in ? scale_in[j[u]] : 1.f;
+#pragma unroll
+        for (int c = 0; c < VN; ++c) acc.v[c] += s * v[u].v[c];
+      }
+    }
+    for (; p < e; ++p) {
+      const int j = colidx[p];
+      const Vec<T> v = Vec<T>::load(xc + (int64_t)j * ldx);
+      const float s = scale_in ? scale_in[j] : 1.f;
+#pragma unroll
+      for (int c = 0; c < VN; ++c) acc.v[c] += s * v.v[c];
+    }
+    const float so = scale_out ? scale_out[i] : 1.f;
+#pragma unroll
+    for (int c = 0; c < VN; ++c) acc.v[c] *= so;
+    acc.store(out + i * ldo + col);
+  }
+}
+
+template <typename T, int P, bool SLIDING>
+static int launch_band(const void* x, void* out, int64_t n, int64_t channels, int64_t ldx, int64_t ldo, int k,
+                       const int32_t* win_lo, const int32_t* win_hi, const float* scale_out,
+                       const float* scale_in, cudaStream_t stream) {
+  constexpr int VN = Vec<T>::N;
+  const int ring_rows = P + 2 * k + 2;
+  const size_t smem = (size_t)ring_rows * kAggThreads * sizeof(uint4);
+  const unsigned gy = (unsigned)ceil_div(channels, (int64_t)kAggThreads * VN);
+  int64_t rows = (n * gy) / ((int64_t)sm_count() * 8);
+  rows = rows < 4 * P ? 4 * P : rows;
+  rows = rows > 1024 ? 1024 : rows;
+  auto kern = sage_mean_band_kernel<T, P, SLIDING>;
+  if (smem > 48 * 1024) EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div(n, rows), gy);
+  kern<<<grid, kAggThreads, smem, stream>>>((const T*)x, (T*)out, n, channels, ldx, ldo, (int)rows, ring_rows,
+                                            win_lo, win_hi, scale_out, scale_in);
+  EGP_LAUNCH_CHECK();
+  return EGP_OK;
+}
+
+}  // namespace egp
+
+using namespace egp;
+
+extern "C" {
+
+int egp_sage_mean_band(const void* x, void* out, int64_t n, int64_t channels, int64_t ldx, int64_t ldo, int k,
+                       const int32_t* win_lo, const int32_t* win_hi, const float* scale_out,
+                       const float* scale_in, int dtype, void* stream) {
+  EGP_REQUIRE(x && out && win_lo && win_hi, "sage_mean_band: null pointer");
+  EGP_REQUIRE(k >= 0 && k <= 32, "sage_mean_band: radius %d out of range [0,32]", k);
+  const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(channels % vn == 0 && ldx % vn == 0 && ldo % vn == 0 && aligned16(x) && aligned16(out),
+              "sage_mean_band: channels/strides must keep rows 16-byte aligned");
+  if (n == 0 || channels == 0) return EGP_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    if (k <= 4) return launch_band<T, 8, false>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
+    if (k <= 12) return launch_band<T, 16, true>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
+    return launch_band<T, 32, true>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
+  });
+  return EGP_OK;
+}
+
+int egp_sage_mean_csr(const void* x, void* out, int64_t n, int64_t channels, int64_t ldx, int64_t ldo,
+                      const int32_t* rowptr, const int32_t* col, const float* scale_out, const float* scale_in,
+                      int dtype, void* stream) {
+  EGP_REQUIRE(x && out && rowptr, "sage_mean_csr: null pointer");
+  const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(channels % vn == 0 && ldx % vn == 0 && ldo % vn == 0 && aligned16(x) && aligned16(out),
+              "sage_mean_csr: channels/strides must keep rows 16-byte aligned");
+  if (n == 0 || channels == 0) return EGP_OK;
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec<T>::N;
+    const unsigned gy = (unsigned)ceil_div(channels, (int64_t)kAggThreads * VN);
+    int64_t rows = (n * gy) / ((int64_t)sm_count() * 16);
+    rows = rows < 4 ? 4 : (rows > 256 ? 256 : rows);
+    dim3 grid((unsigned)ceil_div(n, rows), gy);
+    sage_mean_csr_kernel<T><<<grid, kAggThreads, 0, (cudaStream_t)stream>>>(
+        (const T*)x, (T*)out, n, channels, ldx, ldo, (int)rows, rowptr, col, scale_out, scale_in);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+// Shared helpers for the egopack_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/egopack_b200.h"
+
+namespace egp {
+
+void set_error(const char* fmt, ...);
+
+#define EGP_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      egp::set_error(__VA_ARGS__);             \
+      return EGP_ERR_INVALID;                  \
+    }                                          \
+  } while (0)
+
+#define EGP_CUDA(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      egp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return EGP_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+// launch-configuration errors only; never synchronises
+#define EGP_LAUNCH_CHECK()                                                                   \
+  do {                                                                                       \
+    cudaError_t _e = cudaPeekAtLastError();                                                  \
+    if (_e != cudaSuccess) {                                                                 \
+      egp::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      (void)cudaGetLastError();                                                              \
+      return EGP_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+int sm_count();
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------------------
+// 16-byte vectors of the storage type, computed on as fp32
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+struct Vec;  // 16 bytes
+
+template <>
+struct Vec<float> {
+  static constexpr int N = 4;
+  float v[4];
+  __device__ __forceinline__ static Vec load(const float* p) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    Vec r;
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    return r;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  float v[8];
+  __device__ __forceinline__ static Vec load(const __nv_bfloat16* p) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    Vec r;
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r.v[2 * i] = __uint_as_float(w[i] << 16);
+      r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+    return r;
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ float to_float(T x);
+template <>
+__device__ __forceinline__ float to_float<float>(float x) { return x; }
+template <>
+__device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+template <typename T>
+__device__ __forceinline__ T from_float(float x);
+template <>
+__device__ __forceinline__ float from_float<float>(float x) { return x; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+__device__ __forceinline__ float apply_act(float x, int act, float slope) {
+  if (act == EGP_ACT_RELU) return x > 0.f ? x : 0.f;
+  if (act == EGP_ACT_LEAKY_RELU) return x > 0.f ? x : x * slope;
+  return x;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// reductions
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum, result valid in every thread; `smem` holds >= 32 T; blockDim.x multiple of 32
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  T r = (lane < nw) ? smem[lane] : T(0);
+  r = warp_sum(r);
+  return r;
+}
+
+// dispatch on the dtype code
+#define EGP_DISPATCH_DTYPE(dtype, T, ...)                         \
+  do {                                                            \
+    if ((dtype) == EGP_F32) {                                     \
+      using T = float;                                            \
+      __VA_ARGS__                                                 \
+    } else if ((dtype) == EGP_BF16) {                             \
+      using T = __nv_bfloat16;                                    \
+      __VA_ARGS__                                                 \
+    } else {                                                      \
+      egp::set_error("unsupported dtype code %d", (int)(dtype));  \
+      return EGP_ERR_INVALID;                                     \
+    }                                                             \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace egp

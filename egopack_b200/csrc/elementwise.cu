@@ -1,0 +1,386 @@
+// Elementwise / small-reduction kernels -- all HBM bound, 128-bit vectorised, grid-stride.
+#include "common.cuh"
+
+namespace egp {
+
+constexpr int kEwThreads = 256;
+
+static int ew_grid(int64_t nvec) {
+  int64_t g = ceil_div(nvec, (int64_t)kEwThreads * 2);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// a4: out = x + [sin(pos*f) | cos(pos*f)]  (gnn.PositionalEncoding, models/graph.py:37,63)
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+posenc_add_kernel(const T* __restrict__ x, const int64_t* __restrict__ pos, const float* __restrict__ freq,
+                  T* __restrict__ out, int64_t nvec, int64_t channels) {
+  constexpr int VN = Vec<T>::N;
+  const int64_t half = channels / 2;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = v * VN;
+    const int64_t row = e0 / channels, c0 = e0 % channels;
+    const float p = (float)pos[row];  // int64 * float32 promotes to float32 in the reference
+    Vec<T> a = Vec<T>::load(x + e0);
+#pragma unroll
+    for (int c = 0; c < VN; ++c) {
+      const int64_t ch = c0 + c;
+      const float pe = ch < half ? sinf(p * freq[ch]) : cosf(p * freq[ch - half]);
+      a.v[c] += pe;
+    }
+    a.store(out + e0);
+  }
+}
+
+template <typename S, typename D>
+__global__ void __launch_bounds__(kEwThreads)
+cast_kernel(const S* __restrict__ src, D* __restrict__ dst, int64_t n) {
+  // 8 elements per thread-iteration: 2x16B loads for fp32 sources, 1x16B for bf16
+  const int64_t n8 = n / 8;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n8; v += (int64_t)gridDim.x * blockDim.x) {
+    float f[8];
+    if constexpr (sizeof(S) == 4) {
+      const Vec<float> a = Vec<float>::load((const float*)src + v * 8);
+      const Vec<float> b = Vec<float>::load((const float*)src + v * 8 + 4);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { f[c] = a.v[c]; f[4 + c] = b.v[c]; }
+    } else {
+      const Vec<__nv_bfloat16> a = Vec<__nv_bfloat16>::load((const __nv_bfloat16*)src + v * 8);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) f[c] = a.v[c];
+    }
+    if constexpr (sizeof(D) == 4) {
+      Vec<float> a, b;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { a.v[c] = f[c]; b.v[c] = f[4 + c]; }
+      a.store((float*)dst + v * 8);
+      b.store((float*)dst + v * 8 + 4);
+    } else {
+      Vec<__nv_bfloat16> a;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a.v[c] = f[c];
+      a.store((__nv_bfloat16*)dst + v * 8);
+    }
+  }
+  // tail
+  const int64_t t = n8 * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] = from_float<D>(to_float<S>(src[t]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t nvec) {
+  constexpr int VN = Vec<T>::N;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    Vec<T> x = Vec<T>::load(a + v * VN);
+    const Vec<T> y = Vec<T>::load(b + v * VN);
+#pragma unroll
+    for (int c = 0; c < VN; ++c) x.v[c] += y.v[c];
+    x.store(out + v * VN);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+axpby_kernel(const T* __restrict__ a, float alpha, const T* __restrict__ b, float beta, T* __restrict__ out,
+             int64_t nvec) {
+  constexpr int VN = Vec<T>::N;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    Vec<T> x = Vec<T>::load(a + v * VN);
+    if (b) {
+      const Vec<T> y = Vec<T>::load(b + v * VN);
+#pragma unroll
+      for (int c = 0; c < VN; ++c) x.v[c] = alpha * x.v[c] + beta * y.v[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < VN; ++c) x.v[c] = alpha * x.v[c];
+    }
+    x.store(out + v * VN);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t nvec, int act,
+               float slope) {
+  constexpr int VN = Vec<T>::N;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    Vec<T> g = Vec<T>::load(dy + v * VN);
+    const Vec<T> o = Vec<T>::load(y + v * VN);
+#pragma unroll
+    for (int c = 0; c < VN; ++c) {
+      if (!(o.v[c] > 0.f)) g.v[c] = (act == EGP_ACT_LEAKY_RELU) ? g.v[c] * slope : 0.f;
+    }
+    g.store(dx + v * VN);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+mask_scale_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mask, T* __restrict__ out, int64_t nvec,
+                  float scale) {
+  constexpr int VN = Vec<T>::N;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    Vec<T> a = Vec<T>::load(x + v * VN);
+    const uint8_t* m = mask + v * VN;
+#pragma unroll
+    for (int c = 0; c < VN; ++c) a.v[c] = m[c] ? a.v[c] * scale : 0.f;
+    a.store(out + v * VN);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+max_combine_fwd_kernel(const T* __restrict__ f, const T* __restrict__ m, T* __restrict__ a, int64_t nvec) {
+  constexpr int VN = Vec<T>::N;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    Vec<T> x = Vec<T>::load(f + v * VN);
+    const Vec<T> y = Vec<T>::load(m + v * VN);
+#pragma unroll
+    for (int c = 0; c < VN; ++c) x.v[c] = fmaxf(x.v[c], y.v[c]);
+    x.store(a + v * VN);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+max_combine_bwd_kernel(const T* __restrict__ da, const T* __restrict__ f, const T* __restrict__ m,
+                       T* __restrict__ df, int64_t nvec) {
+  constexpr int VN = Vec<T>::N;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    Vec<T> g = Vec<T>::load(da + v * VN);
+    const Vec<T> x = Vec<T>::load(f + v * VN);
+    const Vec<T> y = Vec<T>::load(m + v * VN);
+#pragma unroll
+    for (int c = 0; c < VN; ++c) g.v[c] = (x.v[c] >= y.v[c]) ? g.v[c] : 0.f;
+    g.store(df + v * VN);
+  }
+}
+
+// column sums: grid (parts, column chunks); thread owns a 16-byte column, loops over its row strip
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, int64_t ldx, int rows_per_cta,
+                      int vec_ok, float* __restrict__ part) {
+  constexpr int VN = Vec<T>::N;
+  const int64_t col = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * VN;
+  if (col >= cols) return;
+  float acc[VN];
+#pragma unroll
+  for (int c = 0; c < VN; ++c) acc[c] = 0.f;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
+  if (vec_ok && col + VN <= cols) {
+    for (int64_t i = r0; i < r1; ++i) {
+      const Vec<T> a = Vec<T>::load(x + i * ldx + col);
+#pragma unroll
+      for (int c = 0; c < VN; ++c) acc[c] += a.v[c];
+    }
+  } else {  // ragged last chunk / unaligned rows (classifier heads): scalar path
+    for (int64_t i = r0; i < r1; ++i)
+#pragma unroll
+      for (int c = 0; c < VN; ++c)
+        if (col + c < cols) acc[c] += to_float<T>(x[i * ldx + col + c]);
+  }
+#pragma unroll
+  for (int c = 0; c < VN; ++c)
+    if (col + c < cols) part[(size_t)blockIdx.x * cols + col + c] = acc[c];
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+colsum_final_kernel(const float* __restrict__ part, int parts, int64_t cols, float* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float a = 0.f;
+  for (int g = 0; g < parts; ++g) a += part[(size_t)g * cols + c];
+  out[c] = a;
+}
+
+// 1/||x_i||: one warp per row
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+row_inv_norm_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t rows, int64_t cols, int64_t ldx) {
+  constexpr int VN = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + row * ldx;
+  float q = 0.f;
+  for (int64_t v = lane; v < cols / VN; v += 32) {
+    const Vec<T> a = Vec<T>::load(xr + v * VN);
+#pragma unroll
+    for (int c = 0; c < VN; ++c) q += a.v[c] * a.v[c];
+  }
+  q = warp_sum(q);
+  if (lane == 0) out[row] = 1.0f / sqrtf(q);  // no epsilon, as the reference (graphONE.py:148-151)
+}
+
+static int colsum_parts(int64_t rows) {
+  int64_t p = ceil_div(rows, 32);
+  const int64_t cap = (int64_t)sm_count() * 2;
+  return (int)(p < 1 ? 1 : (p > cap ? cap : p));
+}
+
+}  // namespace egp
+
+using namespace egp;
+
+#define EGP_EW_CHECK(name, n, dtype, ...)                                                          \
+  const int64_t _vn = (dtype) == EGP_BF16 ? 8 : 4;                                                 \
+  EGP_REQUIRE((n) % _vn == 0, name ": element count %lld not a multiple of %d", (long long)(n), (int)_vn); \
+  if ((n) == 0) return EGP_OK;
+
+extern "C" {
+
+int egp_posenc_add(const void* x, const int64_t* pos, const float* frequency, void* out, int64_t n,
+                   int64_t channels, int dtype, void* stream) {
+  EGP_REQUIRE(x && pos && frequency && out, "posenc_add: null pointer");
+  const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(channels % 2 == 0 && channels % vn == 0 && aligned16(x) && aligned16(out),
+              "posenc_add: channels must be even and a multiple of %d", (int)vn);
+  if (n == 0) return EGP_OK;
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    const int64_t nvec = n * channels / Vec<T>::N;
+    posenc_add_kernel<T><<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)x, pos, frequency,
+                                                                                 (T*)out, nvec, channels);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+int egp_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream) {
+  EGP_REQUIRE(src && dst, "cast: null pointer");
+  EGP_REQUIRE(aligned16(src) && aligned16(dst), "cast: pointers must be 16-byte aligned");
+  if (n == 0) return EGP_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = ew_grid(ceil_div(n, 8));
+  if (src_dtype == EGP_F32 && dst_dtype == EGP_BF16)
+    cast_kernel<float, __nv_bfloat16><<<grid, kEwThreads, 0, s>>>((const float*)src, (__nv_bfloat16*)dst, n);
+  else if (src_dtype == EGP_BF16 && dst_dtype == EGP_F32)
+    cast_kernel<__nv_bfloat16, float><<<grid, kEwThreads, 0, s>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  else if (src_dtype == dst_dtype && (src_dtype == EGP_F32 || src_dtype == EGP_BF16)) {
+    EGP_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * (src_dtype == EGP_F32 ? 4 : 2), cudaMemcpyDeviceToDevice, s));
+    return EGP_OK;
+  } else {
+    set_error("cast: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
+    return EGP_ERR_INVALID;
+  }
+  EGP_LAUNCH_CHECK();
+  return EGP_OK;
+}
+
+int egp_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream) {
+  EGP_REQUIRE(a && b && out, "add: null pointer");
+  EGP_EW_CHECK("add", n, dtype);
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    const int64_t nvec = n / Vec<T>::N;
+    add_kernel<T><<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, (T*)out, nvec);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+int egp_axpby(const void* a, float alpha, const void* b, float beta, void* out, int64_t n, int dtype, void* stream) {
+  EGP_REQUIRE(a && out, "axpby: null pointer");
+  EGP_EW_CHECK("axpby", n, dtype);
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    const int64_t nvec = n / Vec<T>::N;
+    axpby_kernel<T><<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)a, alpha, (const T*)b, beta, (T*)out, nvec);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+int egp_act_bwd(const void* dy, const void* y, void* dx, int64_t n, int act, float slope, int dtype, void* stream) {
+  EGP_REQUIRE(dy && y && dx, "act_bwd: null pointer");
+  EGP_REQUIRE(act == EGP_ACT_RELU || act == EGP_ACT_LEAKY_RELU, "act_bwd: act must be relu or leaky relu");
+  EGP_EW_CHECK("act_bwd", n, dtype);
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    const int64_t nvec = n / Vec<T>::N;
+    act_bwd_kernel<T><<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)y, (T*)dx,
+                                                                              nvec, act, slope);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+int egp_mask_scale(const void* x, const uint8_t* mask, void* out, int64_t n, float scale, int dtype, void* stream) {
+  EGP_REQUIRE(x && mask && out, "mask_scale: null pointer");
+  EGP_EW_CHECK("mask_scale", n, dtype);
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    const int64_t nvec = n / Vec<T>::N;
+    mask_scale_kernel<T><<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)x, mask, (T*)out, nvec, scale);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+int egp_max_combine_fwd(const void* f, const void* m, void* a, int64_t n, int dtype, void* stream) {
+  EGP_REQUIRE(f && m && a, "max_combine_fwd: null pointer");
+  EGP_EW_CHECK("max_combine_fwd", n, dtype);
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    const int64_t nvec = n / Vec<T>::N;
+    max_combine_fwd_kernel<T><<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)f, (const T*)m, (T*)a, nvec);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+int egp_max_combine_bwd(const void* da, const void* f, const void* m, void* df, int64_t n, int dtype, void* stream) {
+  EGP_REQUIRE(da && f && m && df, "max_combine_bwd: null pointer");
+  EGP_EW_CHECK("max_combine_bwd", n, dtype);
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    const int64_t nvec = n / Vec<T>::N;
+    max_combine_bwd_kernel<T><<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)da, (const T*)f,
+                                                                                      (const T*)m, (T*)df, nvec);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+size_t egp_colsum_workspace(int64_t rows, int64_t cols) {
+  return sizeof(float) * (size_t)colsum_parts(rows) * (size_t)cols + 64;
+}
+
+int egp_colsum(const void* x, float* out, int64_t rows, int64_t cols, int64_t ldx, int dtype, void* workspace,
+               size_t ws_bytes, void* stream) {
+  EGP_REQUIRE(x && out && workspace, "colsum: null pointer");
+  if (ws_bytes < egp_colsum_workspace(rows, cols)) {
+    set_error("colsum: workspace too small");
+    return EGP_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cols == 0) return EGP_OK;
+  if (rows == 0) {
+    EGP_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, s));
+    return EGP_OK;
+  }
+  const int parts = colsum_parts(rows);
+  const int rows_per = (int)ceil_div(rows, parts);
+  float* part = (float*)workspace;
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec<T>::N;
+    const int vec_ok = aligned16(x) && (ldx % VN) == 0;
+    const int gy = (int)ceil_div(cols, (int64_t)kEwThreads * VN);
+    colsum_partial_kernel<T><<<dim3(parts, gy), kEwThreads, 0, s>>>((const T*)x, rows, cols, ldx, rows_per, vec_ok, part);
+    EGP_LAUNCH_CHECK();
+  });
+  colsum_final_kernel<<<(unsigned)ceil_div(cols, kEwThreads), kEwThreads, 0, s>>>(part, parts, cols, out);
+  EGP_LAUNCH_CHECK();
+  return EGP_OK;
+}
+
+int egp_row_inv_norm(const void* x, float* out, int64_t rows, int64_t cols, int64_t ldx, int dtype, void* stream) {
+  EGP_REQUIRE(x && out, "row_inv_norm: null pointer");
+  const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(cols % vn == 0 && ldx % vn == 0 && aligned16(x), "row_inv_norm: cols/ld must be multiples of %d", (int)vn);
+  if (rows == 0) return EGP_OK;
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    row_inv_norm_kernel<T><<<(unsigned)ceil_div(rows, kEwThreads / 32), kEwThreads, 0, (cudaStream_t)stream>>>(
+        (const T*)x, out, rows, cols, ldx);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,559 @@
+// bf16 tensor-core GEMM for sm_100a: tcgen05.mma with fp32 accumulators in TMEM, operands staged by TMA.
+//
+//   C[M,N] = act( sum_k A(m,k) B(n,k) + sum_k A2(m,k) B2(n,k) + bias[n] ) + residual[m,n]
+//
+// Serves every Linear on EgoPack's path (TRNPooling, SAGE lin/lin_l/lin_r, task nets, classifiers, GraphONE
+// stages) in forward (A K-major, B K-major), dgrad (B MN-major) and wgrad (A and B MN-major, split-K), plus the
+// node x prototype similarity.  The second operand pair accumulates into the SAME TMEM tile, which fuses
+// SAGEConv's  lin_l(agg) + lin_r(x)  (and its two dgrads / wgrads) into one pass.
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer   : cp.async.bulk.tensor -> 128B-swizzled smem ring (full/empty mbarriers)
+//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (128 x BN x 16), tcgen05.commit frees slots
+//   warps 2..5  epilogue       : tcgen05.ld TMEM -> registers -> bias/act/residual -> global
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile t overlaps the mainloop
+// of tile t+1.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace egp {
+
+constexpr int TBM = 128;     // tile M (UMMA_M)
+constexpr int TBK = 64;      // k-block: 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;   // bf16
+constexpr int TC_THREADS = 192;
+
+// ------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (~2 s) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xfffu) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("egopack_b200: mbarrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SWIZZLE_128B)
+// K-major  : rows of 128 B (64 bf16 of K); 8-row groups 1024 B apart (SBO); LBO unused.
+// MN-major : 64-element MN atoms; inside an atom K rows are 128 B apart, 8-row groups 1024 B apart (SBO);
+//            atoms are TBK*128 B apart (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kABytes = TBM * TBK * 2;
+  static constexpr int kBBytes = BN * TBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // power of two for BN in {16,...,256}
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TcParams {
+  int64_t M, N;
+  int kb1, kb2;        // k-blocks of the first / second operand pair
+  int splits;          // split-K factor (atomic fp32 accumulation when > 1)
+  int m_tiles, n_tiles;
+  const float* bias;
+  const void* residual;
+  int64_t ldr;
+  void* C;
+  int64_t ldc;
+  int act;
+  float slope;
+  int accumulate;      // C += result (fp32 atomics)
+  uint32_t idesc;
+};
+
+template <int BN, bool A_MN, bool B_MN, typename OutT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2,
+               const TcParams p) {
+  using Cfg = TcCfg<BN>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint64_t* full = bars;            // [S]  TMA -> MMA
+  uint64_t* empty = bars + S;       // [S]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * S;   // [2]  MMA -> epilogue
+  uint64_t* tempty = tfull + 2;     // [2]  epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    if (p.kb2 > 0) { tma_prefetch_desc(&mapA2); tma_prefetch_desc(&mapB2); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int total = tiles_mn * p.splits;
+  const int kb_all = p.kb1 + p.kb2;
+
+  // k-block range of split s: contiguous chunks of the concatenated [pair1 | pair2] k-block list
+  auto split_range = [&](int s, int& b, int& e) {
+    const int per = (kb_all + p.splits - 1) / p.splits;
+    b = s * per;
+    e = min(b + per, kb_all);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int split = t / tiles_mn, mn = t % tiles_mn;
+        const int m0 = (mn / p.n_tiles) * TBM, n0 = (mn % p.n_tiles) * BN;
+        int kb_b, kb_e;
+        split_range(split, kb_b, kb_e);
+        for (int kb = kb_b; kb < kb_e; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          const bool second = kb >= p.kb1;
+          const CUtensorMap* ma = second ? &mapA2 : &mapA;
+          const CUtensorMap* mb = second ? &mapB2 : &mapB;
+          const int k0 = (second ? kb - p.kb1 : kb) * TBK;
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          if (!A_MN) {
+            tma_load_2d(ma, &full[stage], sa, k0, m0);              // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int a = 0; a < TBM / 64; ++a)                       // box {64 m, 64 k} per MN atom
+              tma_load_2d(ma, &full[stage], sa + a * (TBK * 128), m0 + a * 64, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(mb, &full[stage], sb, k0, n0);              // box {64 k, BN rows}
+          } else {
+#pragma unroll
+            for (int a = 0; a < BN / 64; ++a)
+              tma_load_2d(mb, &full[stage], sb + a * (TBK * 128), n0 + a * 64, k0);
+          }
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int split = t / tiles_mn;
+        int kb_b, kb_e;
+        split_range(split, kb_b, kb_e);
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&tempty[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = kb_b; kb < kb_e; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t adesc = A_MN ? make_smem_desc(sa, TBK * 128, 1024) : make_smem_desc(sa, 0, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc(sb, TBK * 128, 1024) : make_smem_desc(sb, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < TBK / UMMA_K; ++k) {
+            // advance the 14-bit start-address field: 32 B per UMMA_K step (K-major) or 16 rows x 128 B (MN-major)
+            const uint64_t ao = (uint64_t)((A_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
+            const uint64_t bo = (uint64_t)((B_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
+            umma_bf16(d_tmem, adesc + ao, bdesc + bo, p.idesc, (kb > kb_b || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tfull[as]);
+      }
+    }
+  } else {
+    // epilogue: TMEM lane quarter is fixed by warp id % 4
+    const int quarter = warp & 3;
+    OutT* C = reinterpret_cast<OutT*>(p.C);
+    const OutT* R = reinterpret_cast<const OutT*>(p.residual);
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int split = t / tiles_mn, mn = t % tiles_mn;
+      const int64_t m0 = (int64_t)(mn / p.n_tiles) * TBM, n0 = (int64_t)(mn % p.n_tiles) * BN;
+      int kb_b, kb_e;
+      split_range(split, kb_b, kb_e);
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const int64_t m = m0 + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      const bool atomic = p.splits > 1 || p.accumulate;
+      const bool has_k = kb_e > kb_b;
+      constexpr int CH = BN >= 32 ? 32 : 16;
+#pragma unroll 1
+      for (int c = 0; c < BN / CH; ++c) {
+        uint32_t r[CH];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c * CH);
+        if (CH == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+        tmem_ld_wait();
+        const int64_t nb = n0 + c * CH;
+        if (row_ok && nb < p.N) {
+          float v[CH];
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = has_k ? __uint_as_float(r[j]) : 0.f;
+          const bool full_chunk = nb + CH <= p.N;
+          if (p.bias && split == 0) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (full_chunk || nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
+          }
+          if (p.act != EGP_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = apply_act(v[j], p.act, p.slope);
+          }
+          OutT* crow = C + m * p.ldc + nb;
+          if (atomic) {
+            if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                if (full_chunk || nb + j < p.N) atomicAdd(reinterpret_cast<float*>(crow) + j, v[j]);
+            }
+          } else {
+            constexpr int VN = 16 / (int)sizeof(OutT);
+            const bool vec = full_chunk && ((reinterpret_cast<uintptr_t>(crow) & 15u) == 0) &&
+                             (!R || ((reinterpret_cast<uintptr_t>(R + m * p.ldr + nb) & 15u) == 0));
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < CH; j += VN) {
+                Vec<OutT> o;
+                if (R) {
+                  const Vec<OutT> rr = Vec<OutT>::load(R + m * p.ldr + nb + j);
+#pragma unroll
+                  for (int q = 0; q < VN; ++q) o.v[q] = v[j + q] + rr.v[q];
+                } else {
+#pragma unroll
+                  for (int q = 0; q < VN; ++q) o.v[q] = v[j + q];
+                }
+                o.store(crow + j);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) {
+                if (full_chunk || nb + j < p.N) {
+                  float o = v[j];
+                  if (R) o += to_float<OutT>(R[m * p.ldr + nb + j]);
+                  crow[j] = from_float<OutT>(o);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side: tensor maps (driver entry point resolved at run time: the library has no link-time libcuda
+// dependency, so it loads on machines without a driver) and launch
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  int64_t inner, outer, ld;
+  int box_outer;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_outer == o.box_outer;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    auto mix = [&](int64_t v) { h ^= std::hash<int64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_outer);
+    return h;
+  }
+};
+
+// 2-D bf16 tensor [outer, inner] (inner contiguous, row stride ld elements), box {64, box_outer}, 128B swizzle
+static int make_map(const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer, CUtensorMap* out) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  const MapKey key{ptr, inner, outer, ld, box_outer};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return EGP_OK; }
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return EGP_ERR_UNSUPPORTED;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%lld outer=%lld ld=%lld box=%d", (int)r, ptr,
+              (long long)inner, (long long)outer, (long long)ld, box_outer);
+    return EGP_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
+  return EGP_OK;
+}
+
+// operand with `rows` (M or N) and `k`: trans=0 -> [rows,k] row-major (K-major); trans=1 -> [k,rows] (MN-major)
+static int operand_map(const void* ptr, int64_t rows, int64_t k, int64_t ld, int trans, int tile_rows, CUtensorMap* out) {
+  if (!trans) return make_map(ptr, k, rows, ld, tile_rows, out);
+  return make_map(ptr, rows, k, ld, 64, out);
+}
+
+bool tc_gemm_supported(const void* A, int64_t lda, const void* B, int64_t ldb, const void* A2, int64_t lda2,
+                       const void* B2, int64_t ldb2) {
+  auto ok = [](const void* p, int64_t ld) { return !p || (aligned16(p) && ld % 8 == 0); };
+  return ok(A, lda) && ok(B, ldb) && ok(A2, lda2) && ok(B2, ldb2);
+}
+
+template <int BN, bool A_MN, bool B_MN, typename OutT>
+static int tc_launch_inst(const CUtensorMap* maps, const TcParams& p, int grid, cudaStream_t stream) {
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, OutT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  kern<<<grid, TC_THREADS, TcCfg<BN>::kSmemBytes, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+  EGP_LAUNCH_CHECK();
+  return EGP_OK;
+}
+
+template <int BN, typename OutT>
+static int tc_launch_major(int a_trans, int b_trans, const CUtensorMap* maps, const TcParams& p, int grid,
+                           cudaStream_t stream) {
+  if (!a_trans && !b_trans) return tc_launch_inst<BN, false, false, OutT>(maps, p, grid, stream);
+  if (!a_trans && b_trans) {
+    if constexpr (BN >= 64) return tc_launch_inst<BN, false, true, OutT>(maps, p, grid, stream);
+  }
+  if (a_trans && !b_trans) return tc_launch_inst<BN, true, false, OutT>(maps, p, grid, stream);
+  if (a_trans && b_trans) {
+    if constexpr (BN >= 64) return tc_launch_inst<BN, true, true, OutT>(maps, p, grid, stream);
+  }
+  set_error("tc_gemm: MN-major B needs a tile N of at least 64");
+  return EGP_ERR_INVALID;
+}
+
+int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, const void* A2,
+                   int64_t lda2, const void* B2, int64_t ldb2, int64_t K2, const float* bias, const void* residual,
+                   int64_t ldr, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int act, float slope,
+                   int out_dtype, int accumulate, cudaStream_t stream) {
+  if (M == 0 || N == 0) return EGP_OK;
+  const int sms = sm_count();
+  const int m_tiles = (int)ceil_div(M, TBM);
+  // tile N: no wider than N needs; then halve (not below 64: narrower tiles are smem-bandwidth bound) while the
+  // tile count leaves SMs idle.  MN-major B needs >= 64 (one swizzle atom).
+  const int bn_min = b_trans ? 64 : 16;
+  int bn = 256;
+  while (bn > bn_min && bn / 2 >= N) bn /= 2;
+  while (bn > 64 && (int64_t)m_tiles * ceil_div(N, bn) < sms) bn /= 2;
+  const int n_tiles = (int)ceil_div(N, bn);
+  const bool has2 = A2 && B2 && K2 > 0;
+  TcParams p;
+  p.M = M; p.N = N;
+  p.kb1 = (int)ceil_div(K, TBK);
+  p.kb2 = has2 ? (int)ceil_div(K2, TBK) : 0;
+  p.m_tiles = m_tiles; p.n_tiles = n_tiles;
+  p.bias = bias; p.residual = residual; p.ldr = ldr; p.C = C; p.ldc = ldc;
+  p.act = act; p.slope = slope; p.accumulate = accumulate;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_trans ? 1 : 0) << 15) |
+            ((uint32_t)(b_trans ? 1 : 0) << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+  // split-K: only for fp32 outputs without a non-linear epilogue (wgrad); keeps >= 4 k-blocks per split
+  int splits = 1;
+  const int tiles = m_tiles * n_tiles, kb_all = p.kb1 + p.kb2;
+  if (out_dtype == EGP_F32 && act == EGP_ACT_NONE && !residual && tiles * 2 <= sms && kb_all >= 8) {
+    splits = sms / tiles;
+    if (splits > kb_all / 4) splits = kb_all / 4;
+    if (splits < 1) splits = 1;
+    const int per = (kb_all + splits - 1) / splits;
+    splits = (kb_all + per - 1) / per;  // no empty split
+  }
+  p.splits = splits;
+  if (accumulate && out_dtype != EGP_F32) {
+    set_error("tc_gemm: accumulate needs an fp32 output");
+    return EGP_ERR_INVALID;
+  }
+  if (splits > 1 && !accumulate) {  // atomics need a zeroed destination
+    if (ldc == N) EGP_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * (size_t)N, stream));
+    else EGP_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, (size_t)M, stream));
+  }
+  CUtensorMap maps[4];
+  int rc;
+  if ((rc = operand_map(A, M, K, lda, a_trans, TBM, &maps[0])) != EGP_OK) return rc;
+  if ((rc = operand_map(B, N, K, ldb, b_trans, bn, &maps[1])) != EGP_OK) return rc;
+  if (has2) {
+    if ((rc = operand_map(A2, M, K2, lda2, a_trans, TBM, &maps[2])) != EGP_OK) return rc;
+    if ((rc = operand_map(B2, N, K2, ldb2, b_trans, bn, &maps[3])) != EGP_OK) return rc;
+  } else {
+    maps[2] = maps[0];
+    maps[3] = maps[1];
+  }
+  const int total = tiles * splits;
+  const int grid = total < sms ? total : sms;
+#define EGP_TC_BN(BNV)                                                                                          \
+  case BNV:                                                                                                     \
+    return out_dtype == EGP_F32 ? tc_launch_major<BNV, float>(a_trans, b_trans, maps, p, grid, stream)          \
+                                : tc_launch_major<BNV, __nv_bfloat16>(a_trans, b_trans, maps, p, grid, stream);
+  switch (bn) {
+    EGP_TC_BN(256)
+    EGP_TC_BN(128)
+    EGP_TC_BN(64)
+    EGP_TC_BN(32)
+    EGP_TC_BN(16)
+  }
+#undef EGP_TC_BN
+  set_error("tc_gemm: no kernel for tile N %d", bn);
+  return EGP_ERR_INVALID;
+}
+
+}  // namespace egp

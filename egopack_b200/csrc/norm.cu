@@ -1,0 +1,603 @@
+// Normalisation kernels -- HBM bound.
+//
+//  graph-mode LayerNorm (+LeakyReLU): gnn.LayerNorm(H) called without `batch` (models/graph.py:43-44), i.e.
+//      mu = mean over ALL N*C elements, sigma = sqrt(mean((x-mu)^2)), y = act((x-mu)/(sigma+eps)*w_c + b_c).
+//      forward : stats pass (read C*b per node) + apply pass (read+write 2*C*b)          = 3*C*b per node
+//      backward: reduce pass (read dy,x) + apply pass (read dy,x, write dx)               = 5*C*b per node
+//  row LayerNorm (+ReLU): nn.LayerNorm in TRNPooling / task heads / GraphONE stages.
+//      forward : one warp per row, row cached in registers                                = 2*C*b per node
+//      backward: dx by one warp per row; dweight/dbias by per-lane column accumulators
+#include "common.cuh"
+
+namespace egp {
+
+constexpr int kNormThreads = 256;
+
+// ---------------------------------------------------------------------------------------------------------
+// graph LayerNorm forward
+// ---------------------------------------------------------------------------------------------------------
+struct GlnWorkspace {            // layout of the caller-provided workspace
+  unsigned int ticket;           // last-block election
+  unsigned int pad[3];
+  double scal[4];                // backward: S1 = sum(g_hat), S2 = sum(g_hat * (x-mu))
+};                               // followed by: double partial[2*G]; float colpart[G][2][C]
+
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+gln_stats_kernel(const T* __restrict__ x, int64_t nvec, double inv_count, double* __restrict__ partial,
+                 unsigned int* __restrict__ ticket, double* __restrict__ stats) {
+  constexpr int VN = Vec<T>::N;
+  __shared__ double red[32];
+  __shared__ bool is_last;
+  double s = 0.0, q = 0.0;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    const Vec<T> a = Vec<T>::load(x + v * VN);
+    float ls = 0.f, lq = 0.f;
+#pragma unroll
+    for (int c = 0; c < VN; ++c) { ls += a.v[c]; lq += a.v[c] * a.v[c]; }
+    s += (double)ls;
+    q += (double)lq;
+  }
+  s = block_sum(s, red);
+  q = block_sum(q, red);
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = s;
+    partial[2 * blockIdx.x + 1] = q;
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {  // deterministic final reduction: fixed order over the per-block partials
+    __threadfence();
+    double ts = 0.0, tq = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+      ts += partial[2 * b];
+      tq += partial[2 * b + 1];
+    }
+    ts = block_sum(ts, red);
+    tq = block_sum(tq, red);
+    if (threadIdx.x == 0) {
+      const double mu = ts * inv_count;
+      double var = tq * inv_count - mu * mu;
+      var = var > 0.0 ? var : 0.0;
+      stats[0] = mu;
+      stats[1] = sqrt(var);
+      *ticket = 0u;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+gln_apply_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                 T* __restrict__ y, const double* __restrict__ stats, int64_t nvec, int64_t channels, float eps,
+                 int act, float slope) {
+  constexpr int VN = Vec<T>::N;
+  const float mu = (float)stats[0];
+  const float rs = (float)(1.0 / (stats[1] + (double)eps));
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c0 = (v * VN) % channels;
+    Vec<T> a = Vec<T>::load(x + v * VN);
+#pragma unroll
+    for (int c = 0; c < VN; ++c) {
+      const float xh = (a.v[c] - mu) * rs;
+      a.v[c] = apply_act(xh * w[c0 + c] + b[c0 + c], act, slope);
+    }
+    a.store(y + v * VN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// graph LayerNorm backward
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_grad(float pre, int act, float slope) {
+  if (act == EGP_ACT_RELU) return pre > 0.f ? 1.f : 0.f;
+  if (act == EGP_ACT_LEAKY_RELU) return pre > 0.f ? 1.f : slope;
+  return 1.f;
+}
+
+// grid (G row strips, column chunks); thread owns one 16-byte column
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+gln_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ w,
+                      const float* __restrict__ b, const double* __restrict__ stats, int64_t n, int64_t channels,
+                      int rows_per_cta, float eps, int act, float slope, float* __restrict__ colpart,
+                      double* __restrict__ scalpart) {
+  constexpr int VN = Vec<T>::N;
+  __shared__ double red[32];
+  const int64_t col = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * VN;
+  const bool live = col < channels;
+  const float mu = (float)stats[0];
+  const float rs = (float)(1.0 / (stats[1] + (double)eps));
+  float wv[VN], bv[VN], dw[VN], db[VN];
+#pragma unroll
+  for (int c = 0; c < VN; ++c) {
+    wv[c] = live ? w[col + c] : 0.f;
+    bv[c] = live ? b[col + c] : 0.f;
+    dw[c] = 0.f;
+    db[c] = 0.f;
+  }
+  double s1 = 0.0, s2 = 0.0;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(r0 + rows_per_cta, n);
+  if (live) {
+    for (int64_t i = r0; i < r1; ++i) {
+      const Vec<T> g = Vec<T>::load(dy + i * channels + col);
+      const Vec<T> a = Vec<T>::load(x + i * channels + col);
+      float l1 = 0.f, l2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < VN; ++c) {
+        const float d = a.v[c] - mu;
+        const float xh = d * rs;
+        const float gp = g.v[c] * act_grad(xh * wv[c] + bv[c], act, slope);
+        dw[c] += gp * xh;
+        db[c] += gp;
+        const float gh = gp * wv[c];
+        l1 += gh;
+        l2 += gh * d;
+      }
+      s1 += (double)l1;
+      s2 += (double)l2;
+    }
+    float* cp = colpart + (size_t)blockIdx.x * 2 * channels;
+#pragma unroll
+    for (int c = 0; c < VN; ++c) {
+      cp[col + c] = dw[c];
+      cp[channels + col + c] = db[c];
+    }
+  }
+  s1 = block_sum(s1, red);
+  s2 = block_sum(s2, red);
+  if (threadIdx.x == 0) {
+    const size_t p = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2;
+    scalpart[p] = s1;
+    scalpart[p + 1] = s2;
+  }
+}
+
+// blocks [0, colblocks): out0[c] = sum_g colpart[g][0][c], out1[c] = sum_g colpart[g][1][c]
+// block colblocks (if scal != null): scal[0..1] = sum of scalpart pairs
+__global__ void __launch_bounds__(kNormThreads)
+col_finalize_kernel(const float* __restrict__ colpart, int parts, int64_t channels, float* __restrict__ out0,
+                    float* __restrict__ out1, const double* __restrict__ scalpart, int scal_parts,
+                    double* __restrict__ scal, int colblocks) {
+  __shared__ double red[32];
+  if ((int)blockIdx.x < colblocks) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels) return;
+    float a0 = 0.f, a1 = 0.f;
+    for (int g = 0; g < parts; ++g) {
+      a0 += colpart[(size_t)g * 2 * channels + c];
+      a1 += colpart[(size_t)g * 2 * channels + channels + c];
+    }
+    if (out0) out0[c] = a0;
+    if (out1) out1[c] = a1;
+  } else {
+    double s1 = 0.0, s2 = 0.0;
+    for (int p = threadIdx.x; p < scal_parts; p += blockDim.x) {
+      s1 += scalpart[2 * p];
+      s2 += scalpart[2 * p + 1];
+    }
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    if (threadIdx.x == 0) { scal[0] = s1; scal[1] = s2; }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+gln_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ w,
+                     const float* __restrict__ b, const double* __restrict__ stats, const double* __restrict__ scal,
+                     T* __restrict__ dx, int64_t nvec, int64_t channels, double inv_count, float eps, int act,
+                     float slope) {
+  constexpr int VN = Vec<T>::N;
+  const double sigma = stats[1];
+  const float mu = (float)stats[0];
+  const float rs = (float)(1.0 / (sigma + (double)eps));
+  const float m1 = (float)(scal[0] * inv_count);  // mean(g_hat)
+  const double den = sigma * (sigma + (double)eps) * (sigma + (double)eps);
+  const float k2 = den > 0.0 ? (float)(scal[1] * inv_count / den) : 0.f;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c0 = (v * VN) % channels;
+    const Vec<T> g = Vec<T>::load(dy + v * VN);
+    Vec<T> a = Vec<T>::load(x + v * VN);
+#pragma unroll
+    for (int c = 0; c < VN; ++c) {
+      const float d = a.v[c] - mu;
+      const float xh = d * rs;
+      const float wc = w[c0 + c];
+      const float gh = g.v[c] * act_grad(xh * wc + b[c0 + c], act, slope) * wc;
+      a.v[c] = (gh - m1) * rs - d * k2;
+    }
+    a.store(dx + v * VN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// row LayerNorm: one warp per row, lane owns vectors lane, lane+32, ...  (NVL of them, cached in registers)
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int NVL>
+__global__ void __launch_bounds__(kNormThreads)
+rln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+               T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t n, int64_t channels,
+               float eps, int act) {
+  constexpr int VN = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int nvec = (int)(channels / VN);
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
+    const T* xr = x + row * channels;
+    Vec<T> a[NVL];
+    float s = 0.f;
+#pragma unroll
+    for (int it = 0; it < NVL; ++it) {
+      const int v = lane + 32 * it;
+      if (v < nvec) {
+        a[it] = Vec<T>::load(xr + (int64_t)v * VN);
+#pragma unroll
+        for (int c = 0; c < VN; ++c) s += a[it].v[c];
+      }
+    }
+    const float mu = warp_sum(s) / (float)channels;
+    float q = 0.f;
+#pragma unroll
+    for (int it = 0; it < NVL; ++it) {
+      const int v = lane + 32 * it;
+      if (v < nvec) {
+#pragma unroll
+        for (int c = 0; c < VN; ++c) { const float d = a[it].v[c] - mu; q += d * d; }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) / (float)channels + eps);
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+    T* yr = y + row * channels;
+#pragma unroll
+    for (int it = 0; it < NVL; ++it) {
+      const int v = lane + 32 * it;
+      if (v < nvec) {
+        Vec<T> o;
+#pragma unroll
+        for (int c = 0; c < VN; ++c)
+          o.v[c] = apply_act((a[it].v[c] - mu) * rs * w[v * VN + c] + b[v * VN + c], act, 0.f);
+        o.store(yr + (int64_t)v * VN);
+      }
+    }
+  }
+}
+
+template <typename T, int NVL>
+__global__ void __launch_bounds__(kNormThreads)
+rln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+               const float* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd,
+               T* __restrict__ dx, int64_t n, int64_t channels, int act, float* __restrict__ colpart) {
+  constexpr int VN = Vec<T>::N;
+  extern __shared__ float cacc[];  // [2][channels] block accumulators for dweight / dbias
+  const int lane = threadIdx.x & 31;
+  const int nvec = (int)(channels / VN);
+  for (int64_t c = threadIdx.x; c < 2 * channels; c += blockDim.x) cacc[c] = 0.f;
+  __syncthreads();
+  float dw[NVL][VN], db[NVL][VN];
+#pragma unroll
+  for (int it = 0; it < NVL; ++it)
+#pragma unroll
+    for (int c = 0; c < VN; ++c) { dw[it][c] = 0.f; db[it][c] = 0.f; }
+
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
+    const float mu = mean[row], rs = rstd[row];
+    Vec<T> gh[NVL], xh[NVL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < NVL; ++it) {
+      const int v = lane + 32 * it;
+      if (v < nvec) {
+        const int64_t o = row * channels + (int64_t)v * VN;
+        const Vec<T> g = Vec<T>::load(dy + o);
+        const Vec<T> a = Vec<T>::load(x + o);
+        Vec<T> yo;
+        if (act == EGP_ACT_RELU) yo = Vec<T>::load(y + o);
+#pragma unroll
+        for (int c = 0; c < VN; ++c) {
+          const float h = (a.v[c] - mu) * rs;
+          float gp = g.v[c];
+          if (act == EGP_ACT_RELU && !(yo.v[c] > 0.f)) gp = 0.f;
+          dw[it][c] += gp * h;
+          db[it][c] += gp;
+          const float t = gp * w[v * VN + c];
+          gh[it].v[c] = t;
+          xh[it].v[c] = h;
+          s1 += t;
+          s2 += t * h;
+        }
+      }
+    }
+    const float c1 = warp_sum(s1) / (float)channels;
+    const float c2 = warp_sum(s2) / (float)channels;
+#pragma unroll
+    for (int it = 0; it < NVL; ++it) {
+      const int v = lane + 32 * it;
+      if (v < nvec) {
+        Vec<T> o;
+#pragma unroll
+        for (int c = 0; c < VN; ++c) o.v[c] = rs * (gh[it].v[c] - c1 - xh[it].v[c] * c2);
+        o.store(dx + row * channels + (int64_t)v * VN);
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < NVL; ++it) {
+    const int v = lane + 32 * it;
+    if (v < nvec) {
+#pragma unroll
+      for (int c = 0; c < VN; ++c) {
+        atomicAdd(&cacc[v * VN + c], dw[it][c]);
+        atomicAdd(&cacc[channels + v * VN + c], db[it][c]);
+      }
+    }
+  }
+  __syncthreads();
+  float* cp = colpart + (size_t)blockIdx.x * 2 * channels;
+  for (int64_t c = threadIdx.x; c < 2 * channels; c += blockDim.x) cp[c] = cacc[c];
+}
+
+// generic fallbacks for very wide rows (no register cache; rows are re-read through L1/L2)
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+rln_fwd_wide_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                    T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t n,
+                    int64_t channels, float eps, int act) {
+  constexpr int VN = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int nvec = (int)(channels / VN);
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
+    const T* xr = x + row * channels;
+    float s = 0.f;
+    for (int v = lane; v < nvec; v += 32) {
+      const Vec<T> a = Vec<T>::load(xr + (int64_t)v * VN);
+#pragma unroll
+      for (int c = 0; c < VN; ++c) s += a.v[c];
+    }
+    const float mu = warp_sum(s) / (float)channels;
+    float q = 0.f;
+    for (int v = lane; v < nvec; v += 32) {
+      const Vec<T> a = Vec<T>::load(xr + (int64_t)v * VN);
+#pragma unroll
+      for (int c = 0; c < VN; ++c) { const float d = a.v[c] - mu; q += d * d; }
+    }
+    const float rs = rsqrtf(warp_sum(q) / (float)channels + eps);
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+    for (int v = lane; v < nvec; v += 32) {
+      Vec<T> a = Vec<T>::load(xr + (int64_t)v * VN);
+#pragma unroll
+      for (int c = 0; c < VN; ++c) a.v[c] = apply_act((a.v[c] - mu) * rs * w[v * VN + c] + b[v * VN + c], act, 0.f);
+      a.store(y + row * channels + (int64_t)v * VN);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+rln_bwd_wide_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+                    const float* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    T* __restrict__ dx, int64_t n, int64_t channels, int act, float* __restrict__ colpart) {
+  constexpr int VN = Vec<T>::N;
+  extern __shared__ float cacc[];
+  const int lane = threadIdx.x & 31;
+  const int nvec = (int)(channels / VN);
+  for (int64_t c = threadIdx.x; c < 2 * channels; c += blockDim.x) cacc[c] = 0.f;
+  __syncthreads();
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+    for (int v = lane; v < nvec; v += 32) {
+      const int64_t o = row * channels + (int64_t)v * VN;
+      const Vec<T> g = Vec<T>::load(dy + o);
+      const Vec<T> a = Vec<T>::load(x + o);
+      Vec<T> yo;
+      if (act == EGP_ACT_RELU) yo = Vec<T>::load(y + o);
+#pragma unroll
+      for (int c = 0; c < VN; ++c) {
+        const float h = (a.v[c] - mu) * rs;
+        float gp = g.v[c];
+        if (act == EGP_ACT_RELU && !(yo.v[c] > 0.f)) gp = 0.f;
+        atomicAdd(&cacc[v * VN + c], gp * h);
+        atomicAdd(&cacc[channels + v * VN + c], gp);
+        const float t = gp * w[v * VN + c];
+        s1 += t;
+        s2 += t * h;
+      }
+    }
+    const float c1 = warp_sum(s1) / (float)channels;
+    const float c2 = warp_sum(s2) / (float)channels;
+    for (int v = lane; v < nvec; v += 32) {
+      const int64_t o = row * channels + (int64_t)v * VN;
+      const Vec<T> g = Vec<T>::load(dy + o);
+      Vec<T> a = Vec<T>::load(x + o);
+      Vec<T> yo;
+      if (act == EGP_ACT_RELU) yo = Vec<T>::load(y + o);
+#pragma unroll
+      for (int c = 0; c < VN; ++c) {
+        const float h = (a.v[c] - mu) * rs;
+        float gp = g.v[c];
+        if (act == EGP_ACT_RELU && !(yo.v[c] > 0.f)) gp = 0.f;
+        a.v[c] = rs * (gp * w[v * VN + c] - c1 - h * c2);
+      }
+      a.store(dx + o);
+    }
+  }
+  __syncthreads();
+  float* cp = colpart + (size_t)blockIdx.x * 2 * channels;
+  for (int64_t c = threadIdx.x; c < 2 * channels; c += blockDim.x) cp[c] = cacc[c];
+}
+
+static int norm_grid(int64_t work_items, int per_block) {
+  int64_t g = ceil_div(work_items, per_block);
+  const int64_t cap = (int64_t)sm_count() * 4;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+static int gln_parts(int64_t n) { return norm_grid(n, 16); }  // row strips of >= 16 rows, <= 4 per SM
+
+}  // namespace egp
+
+using namespace egp;
+
+extern "C" {
+
+size_t egp_graph_layernorm_workspace(int64_t n, int64_t channels) {
+  const int parts = gln_parts(n);
+  const int64_t gy = ceil_div(channels, (int64_t)kNormThreads * 4);
+  const int g_stats = sm_count() * 4;
+  size_t bytes = sizeof(GlnWorkspace);
+  const size_t np = (size_t)(parts * gy > g_stats ? parts * gy : g_stats);
+  bytes += sizeof(double) * 2 * np;
+  bytes += sizeof(float) * 2 * (size_t)parts * (size_t)channels;
+  return bytes + 64;
+}
+
+int egp_graph_layernorm_fwd(const void* x, const float* weight, const float* bias, void* y, double* stats,
+                            int64_t n, int64_t channels, float eps, int act, float slope, int dtype,
+                            void* workspace, size_t ws_bytes, void* stream) {
+  EGP_REQUIRE(x && weight && bias && y && stats && workspace, "graph_layernorm_fwd: null pointer");
+  const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(channels % vn == 0 && aligned16(x) && aligned16(y), "graph_layernorm_fwd: channels %% %d != 0 or unaligned", (int)vn);
+  if (ws_bytes < egp_graph_layernorm_workspace(n, channels)) {
+    set_error("graph_layernorm_fwd: workspace %zu < %zu", ws_bytes, egp_graph_layernorm_workspace(n, channels));
+    return EGP_ERR_WORKSPACE;
+  }
+  if (n == 0) return EGP_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  GlnWorkspace* ws = (GlnWorkspace*)workspace;
+  double* partial = (double*)(ws + 1);
+  EGP_CUDA(cudaMemsetAsync(&ws->ticket, 0, sizeof(unsigned int), s));
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    const int64_t nvec = n * channels / Vec<T>::N;
+    const int g1 = norm_grid(nvec, kNormThreads * 4);
+    gln_stats_kernel<T><<<g1, kNormThreads, 0, s>>>((const T*)x, nvec, 1.0 / ((double)n * (double)channels), partial,
+                                                     &ws->ticket, stats);
+    EGP_LAUNCH_CHECK();
+    const int g2 = norm_grid(nvec, kNormThreads * 2) * 2;
+    gln_apply_kernel<T><<<g2, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, stats, nvec, channels, eps, act, slope);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, const float* bias,
+                            const double* stats, void* dx, float* dweight, float* dbias, int64_t n,
+                            int64_t channels, float eps, int act, float slope, int dtype, void* workspace,
+                            size_t ws_bytes, void* stream) {
+  EGP_REQUIRE(dy && x && weight && bias && stats && dx && workspace, "graph_layernorm_bwd: null pointer");
+  const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(channels % vn == 0 && aligned16(x) && aligned16(dy) && aligned16(dx),
+              "graph_layernorm_bwd: channels %% %d != 0 or unaligned", (int)vn);
+  if (ws_bytes < egp_graph_layernorm_workspace(n, channels)) {
+    set_error("graph_layernorm_bwd: workspace too small");
+    return EGP_ERR_WORKSPACE;
+  }
+  if (n == 0) return EGP_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  GlnWorkspace* ws = (GlnWorkspace*)workspace;
+  const int parts = gln_parts(n);
+  const int rows_per = (int)ceil_div(n, parts);
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec<T>::N;
+    const int gy = (int)ceil_div(channels, (int64_t)kNormThreads * VN);
+    const int g_stats = sm_count() * 4;
+    const size_t np = (size_t)(parts * gy > g_stats ? parts * gy : g_stats);
+    double* scalpart = (double*)(ws + 1);
+    float* colpart = (float*)(scalpart + 2 * np);
+    gln_bwd_reduce_kernel<T><<<dim3(parts, gy), kNormThreads, 0, s>>>(
+        (const T*)dy, (const T*)x, weight, bias, stats, n, channels, rows_per, eps, act, slope, colpart, scalpart);
+    EGP_LAUNCH_CHECK();
+    const int colblocks = (int)ceil_div(channels, kNormThreads);
+    col_finalize_kernel<<<colblocks + 1, kNormThreads, 0, s>>>(colpart, parts, channels, dweight, dbias, scalpart,
+                                                               parts * gy, ws->scal, colblocks);
+    EGP_LAUNCH_CHECK();
+    const int64_t nvec = n * channels / VN;
+    const int g2 = norm_grid(nvec, kNormThreads * 2) * 2;
+    gln_bwd_apply_kernel<T><<<g2, kNormThreads, 0, s>>>((const T*)dy, (const T*)x, weight, bias, stats, ws->scal,
+                                                        (T*)dx, nvec, channels, 1.0 / ((double)n * (double)channels),
+                                                        eps, act, slope);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+size_t egp_row_layernorm_workspace(int64_t n, int64_t channels) {
+  (void)n;
+  return sizeof(float) * 2 * (size_t)(sm_count() * 4) * (size_t)channels + 64;
+}
+
+#define EGP_RLN_DISPATCH_NVL(nvec, ...)                                               \
+  do {                                                                                \
+    const int _per = (int)(((nvec) + 31) / 32);                                       \
+    if (_per <= 1) { constexpr int NVL = 1; __VA_ARGS__ }                             \
+    else if (_per <= 2) { constexpr int NVL = 2; __VA_ARGS__ }                        \
+    else if (_per <= 4) { constexpr int NVL = 4; __VA_ARGS__ }                        \
+    else if (_per <= 8) { constexpr int NVL = 8; __VA_ARGS__ }                        \
+    else { constexpr int NVL = 0; __VA_ARGS__ }                                       \
+  } while (0)
+
+int egp_row_layernorm_fwd(const void* x, const float* weight, const float* bias, void* y, float* mean,
+                          float* rstd, int64_t n, int64_t channels, float eps, int act, int dtype, void* stream) {
+  EGP_REQUIRE(x && weight && bias && y && mean && rstd, "row_layernorm_fwd: null pointer");
+  const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(channels % vn == 0 && aligned16(x) && aligned16(y), "row_layernorm_fwd: channels %% %d != 0 or unaligned", (int)vn);
+  EGP_REQUIRE(act == EGP_ACT_NONE || act == EGP_ACT_RELU, "row_layernorm_fwd: act must be none or relu");
+  if (n == 0) return EGP_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = norm_grid(n, kNormThreads / 32);
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    const int64_t nvec = channels / Vec<T>::N;
+    EGP_RLN_DISPATCH_NVL(nvec, {
+      if constexpr (NVL == 0)
+        rln_fwd_wide_kernel<T><<<grid, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, mean, rstd, n, channels, eps, act);
+      else
+        rln_fwd_kernel<T, NVL><<<grid, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, mean, rstd, n, channels, eps, act);
+    });
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+int egp_row_layernorm_bwd(const void* dy, const void* x, const void* y, const float* weight, const float* mean,
+                          const float* rstd, void* dx, float* dweight, float* dbias, int64_t n, int64_t channels,
+                          int act, int dtype, void* workspace, size_t ws_bytes, void* stream) {
+  EGP_REQUIRE(dy && x && weight && mean && rstd && dx && workspace, "row_layernorm_bwd: null pointer");
+  EGP_REQUIRE(act == EGP_ACT_NONE || (act == EGP_ACT_RELU && y), "row_layernorm_bwd: relu needs the saved output");
+  const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(channels % vn == 0 && aligned16(x) && aligned16(dy) && aligned16(dx), "row_layernorm_bwd: channels/alignment");
+  if (ws_bytes < egp_row_layernorm_workspace(n, channels)) {
+    set_error("row_layernorm_bwd: workspace too small");
+    return EGP_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n == 0) {
+    if (dweight) EGP_CUDA(cudaMemsetAsync(dweight, 0, sizeof(float) * channels, s));
+    if (dbias) EGP_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * channels, s));
+    return EGP_OK;
+  }
+  const int grid = norm_grid(n, kNormThreads / 32);
+  const size_t smem = sizeof(float) * 2 * channels;
+  float* colpart = (float*)workspace;
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    const int64_t nvec = channels / Vec<T>::N;
+    EGP_RLN_DISPATCH_NVL(nvec, {
+      auto kern = rln_bwd_wide_kernel<T>;
+      if constexpr (NVL != 0) kern = rln_bwd_kernel<T, NVL>;
+      if (smem > 48 * 1024) EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, kNormThreads, smem, s>>>((const T*)dy, (const T*)x, (const T*)y, weight, mean, rstd, (T*)dx, n,
+                                            channels, act, colpart);
+    });
+    EGP_LAUNCH_CHECK();
+  });
+  const int colblocks = (int)ceil_div(channels, kNormThreads);
+  col_finalize_kernel<<<colblocks, kNormThreads, 0, s>>>(colpart, grid, channels, dweight, dbias, nullptr, 0, nullptr, colblocks);
+  EGP_LAUNCH_CHECK();
+  return EGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// Per-graph max pooling (a12) and prototype max-gather (a15) -- HBM bound gathers/segment reductions.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace egp {
+
+constexpr int kPoolThreads = 128;
+
+// out[g,c] = max_{i in graph g} x[i,c]; empty graph -> 0 (scatter 'amax' into zeros, include_self=False);
+// ties keep the first row (torch_scatter CUDA arg-max semantics used for the gradient).
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+segment_max_fwd_kernel(const T* __restrict__ x, const int64_t* __restrict__ ptr, T* __restrict__ out,
+                       int32_t* __restrict__ arg, int64_t channels) {
+  constexpr int VN = Vec<T>::N;
+  const int64_t g = blockIdx.x;
+  const int64_t col = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * VN;
+  if (col >= channels) return;
+  const int64_t r0 = ptr[g], r1 = ptr[g + 1];
+  float best[VN];
+  int32_t bi[VN];
+#pragma unroll
+  for (int c = 0; c < VN; ++c) { best[c] = -FLT_MAX; bi[c] = -1; }
+  for (int64_t i = r0; i < r1; ++i) {
+    const Vec<T> a = Vec<T>::load(x + i * channels + col);
+#pragma unroll
+    for (int c = 0; c < VN; ++c)
+      if (a.v[c] > best[c] || bi[c] < 0) { best[c] = a.v[c]; bi[c] = (int32_t)i; }
+  }
+  Vec<T> o;
+#pragma unroll
+  for (int c = 0; c < VN; ++c) {
+    o.v[c] = bi[c] >= 0 ? best[c] : 0.f;
+    arg[g * channels + col + c] = bi[c];
+  }
+  o.store(out + g * channels + col);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+segment_max_bwd_kernel(const T* __restrict__ dout, const int32_t* __restrict__ arg,
+                       const int64_t* __restrict__ batch, T* __restrict__ dx, int64_t nvec, int64_t channels) {
+  constexpr int VN = Vec<T>::N;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = v * VN;
+    const int64_t row = e0 / channels, c0 = e0 % channels;
+    const int64_t g = batch[row];
+    const Vec<T> d = Vec<T>::load(dout + g * channels + c0);
+    Vec<T> o;
+#pragma unroll
+    for (int c = 0; c < VN; ++c) o.v[c] = (arg[g * channels + c0 + c] == (int32_t)row) ? d.v[c] : 0.f;
+    o.store(dx + e0);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+proto_max_gather_kernel(const T* __restrict__ protos, const int64_t* __restrict__ idx, T* __restrict__ m,
+                        int64_t nvec, int64_t k, int64_t channels) {
+  constexpr int VN = Vec<T>::N;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = v * VN;
+    const int64_t row = e0 / channels, c0 = e0 % channels;
+    Vec<T> best = Vec<T>::load(protos + idx[row * k] * channels + c0);
+    for (int64_t j = 1; j < k; ++j) {
+      const Vec<T> a = Vec<T>::load(protos + idx[row * k + j] * channels + c0);
+#pragma unroll
+      for (int c = 0; c < VN; ++c) best.v[c] = fmaxf(best.v[c], a.v[c]);
+    }
+    best.store(m + e0);
+  }
+}
+
+static int pool_grid(int64_t nvec) {
+  int64_t g = ceil_div(nvec, (int64_t)kPoolThreads * 2);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace egp
+
+using namespace egp;
+
+extern "C" {
+
+int egp_segment_max_pool_fwd(const void* x, const int64_t* ptr, void* out, int32_t* arg, int64_t num_graphs,
+                             int64_t channels, int dtype, void* stream) {
+  EGP_REQUIRE(x && ptr && out && arg, "segment_max_pool_fwd: null pointer");
+  const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(channels % vn == 0 && aligned16(x) && aligned16(out), "segment_max_pool_fwd: channels %% %d", (int)vn);
+  if (num_graphs == 0 || channels == 0) return EGP_OK;
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    const unsigned gy = (unsigned)ceil_div(channels, (int64_t)kPoolThreads * Vec<T>::N);
+    segment_max_fwd_kernel<T><<<dim3((unsigned)num_graphs, gy), kPoolThreads, 0, (cudaStream_t)stream>>>(
+        (const T*)x, ptr, (T*)out, arg, channels);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+int egp_segment_max_pool_bwd(const void* dout, const int32_t* arg, const int64_t* batch, void* dx,
+                             int64_t num_nodes, int64_t channels, int dtype, void* stream) {
+  EGP_REQUIRE(dout && arg && batch && dx, "segment_max_pool_bwd: null pointer");
+  const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(channels % vn == 0 && aligned16(dout) && aligned16(dx), "segment_max_pool_bwd: channels %% %d", (int)vn);
+  if (num_nodes == 0 || channels == 0) return EGP_OK;
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    const int64_t nvec = num_nodes * channels / Vec<T>::N;
+    segment_max_bwd_kernel<T><<<pool_grid(nvec), kPoolThreads, 0, (cudaStream_t)stream>>>(
+        (const T*)dout, arg, batch, (T*)dx, nvec, channels);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+int egp_proto_max_gather(const void* protos, const int64_t* idx, void* m, int64_t num_nodes, int64_t k,
+                         int64_t channels, int proto_dtype, int out_dtype, void* stream) {
+  EGP_REQUIRE(protos && idx && m, "proto_max_gather: null pointer");
+  EGP_REQUIRE(proto_dtype == out_dtype, "proto_max_gather: bank and output dtypes must match");
+  EGP_REQUIRE(k >= 1, "proto_max_gather: k must be >= 1");
+  const int64_t vn = out_dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(channels % vn == 0 && aligned16(protos) && aligned16(m), "proto_max_gather: channels %% %d", (int)vn);
+  if (num_nodes == 0 || channels == 0) return EGP_OK;
+  EGP_DISPATCH_DTYPE(out_dtype, T, {
+    const int64_t nvec = num_nodes * channels / Vec<T>::N;
+    proto_max_gather_kernel<T><<<pool_grid(nvec), kPoolThreads, 0, (cudaStream_t)stream>>>(
+        (const T*)protos, idx, (T*)m, nvec, k, channels);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+"""Minimal stand-ins for ``torch_geometric.data.Data`` / ``Batch`` (PyG is not a dependency of this package).
+
+The models only duck-type their input (``.x .pos .batch .ptr .edge_index .y``), so real PyG batches work too.
+``Batch.from_data_list`` follows PyG's collate for the attributes the reference uses: tensors are concatenated
+along dim 0 (0-dim tensors are stacked), ``edge_index`` along dim -1 with cumulative node offsets, and
+``batch`` / ``ptr`` are added (data/ego4d_fho.py:242, data/ego4d_oscc.py:223 build the per-sample ``Data``).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Iterable, List, Sequence
+
+import torch
+
+
+class Data:
+    def __init__(self, x=None, edge_index=None, edge_attr=None, y=None, pos=None, **kwargs):
+        object.__setattr__(self, "_fields", {})
+        for k, v in dict(x=x, edge_index=edge_index, edge_attr=edge_attr, y=y, pos=pos, **kwargs).items():
+            if v is not None:
+                self._fields[k] = v
+
+    # attribute protocol: missing attributes read as None (PyG behaviour the reference relies on:
+    # lta_temp_connectivity.py:31 tests ``data.batch is not None``)
+    def __getattr__(self, key: str) -> Any:
+        if key.startswith("__"):
+            raise AttributeError(key)
+        return object.__getattribute__(self, "_fields").get(key)
+
+    def __setattr__(self, key: str, value: Any) -> None:
+        if value is None:
+            self._fields.pop(key, None)
+        else:
+            self._fields[key] = value
+
+    def __contains__(self, key: str) -> bool:
+        return key in self._fields
+
+    def keys(self) -> List[str]:
+        return list(self._fields)
+
+    @property
+    def num_nodes(self) -> int:
+        f = self._fields
+        for k in ("x", "pos", "batch"):
+            if k in f:
+                return int(f[k].shape[0])
+        return 0
+
+    def to(self, device, non_blocking: bool = False) -> "Data":
+        for k, v in list(self._fields.items()):
+            if torch.is_tensor(v):
+                self._fields[k] = v.to(device, non_blocking=non_blocking)
+        self._fields.pop("_egp_structure", None)            # device-specific cache
+        return self
+
+    def pin_memory(self) -> "Data":
+        for k, v in list(self._fields.items()):
+            if torch.is_tensor(v):
+                self._fields[k] = v.pin_memory()
+        return self
+
+    def __repr__(self) -> str:
+        body = ", ".join(f"{k}={list(v.shape) if torch.is_tensor(v) else type(v).__name__}"
+                         for k, v in self._fields.items() if not k.startswith("_"))
+        return f"{type(self).__name__}({body})"
+
+
+class Batch(Data):
+    @classmethod
+    def from_data_list(cls, graphs: Sequence[Data]) -> "Batch":
+        out = cls()
+        keys = [k for k in graphs[0].keys() if not k.startswith("_")]
+        columns: Dict[str, list] = {k: [] for k in keys}
+        sizes = []
+        offset = 0
+        band = None
+        for d in graphs:
+            n = d.num_nodes
+            sizes.append(n)
+            for k in keys:
+                v = getattr(d, k)
+                if k == "edge_index":
+                    v = v + offset
+                elif torch.is_tensor(v) and v.dim() == 0:
+                    v = v.unsqueeze(0)
+                columns[k].append(v)
+            offset += n
+        for k in keys:
+            if k == "band_k":                                # structural hint from our transforms
+                ks = set(int(v) for v in columns[k])
+                band = ks.pop() if len(ks) == 1 else None
+            elif k == "edge_index":
+                out.edge_index = torch.cat(columns[k], dim=-1)
+            elif torch.is_tensor(columns[k][0]):
+                setattr(out, k, torch.cat(columns[k], dim=0))
+            else:
+                setattr(out, k, columns[k])
+        if band is not None:
+            out.band_k = band
+        sz = torch.tensor(sizes, dtype=torch.long)
+        out.batch = torch.repeat_interleave(torch.arange(len(sizes), dtype=torch.long), sz)
+        out.ptr = torch.cat([torch.zeros(1, dtype=torch.long), sz.cumsum(0)])
+        return out
+
+    @property
+    def num_graphs(self) -> int:
+        return int(self.ptr.numel() - 1) if self.ptr is not None else int(self.batch.max()) + 1

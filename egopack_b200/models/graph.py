@@ -1,0 +1,98 @@
+"""Drop-in for the reference's ``models/graph.py:15-65`` (``Graph``): TRN pooling MLP, positional encoding,
+``depth`` x [SAGEConv(project, mean) -> graph-mode LayerNorm -> LeakyReLU(0.2)], final Linear, outer residual.
+
+Same constructor and ``forward(data)`` signature, same attributes, same ``state_dict`` keys
+(``temporal_pooling.proj.*``, ``positional_encoding.frequency``, ``net.module_{i}.*``) -- but the forward is a
+fixed sequence of sm_100a kernels:
+
+    x = TRNPooling(x)                                  3 GEMMs (tcgen05) + 2 row-LN/ReLU kernels
+    z = x + PE(pos)                                    1 elementwise kernel
+    per layer:  xs = relu(z Wp^T + bp)                 GEMM, ReLU in the epilogue
+                agg = band/CSR mean(xs)                sliding-window aggregation kernel
+                u = agg Wl^T + bl + z Wr^T             ONE dual-operand GEMM
+                z = leaky_relu(graph_LN(u))            stats kernel + apply kernel
+    out = x + z Wf^T + bf                              GEMM, residual in the epilogue
+"""
+from __future__ import annotations
+
+import importlib
+from typing import Any, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import config, ops
+from ..ops import ACT_LEAKY
+from .layers import GraphLayerNorm, PositionalEncoding, SAGEConv, structure_for
+
+
+def _instantiate(spec: Any, *args):
+    """hydra.utils.instantiate stand-in for ``temporal_pooling`` (models/graph.py:32-33 passes
+    ``(input_size, hidden_size, num_segments)`` positionally): accepts a module, a callable, or a dict /
+    DictConfig with ``_target_`` -- reference target paths are mapped onto this package."""
+    if isinstance(spec, nn.Module):
+        return spec
+    if callable(spec):
+        return spec(*args)
+    cfg = dict(spec)
+    target = cfg.pop("_target_", "models.temporal_pooling.trn_pooling.TRNPooling")
+    cfg.pop("_recursive_", None)
+    mod_name, cls_name = target.rsplit(".", 1)
+    if mod_name.startswith("models."):
+        mod_name = "egopack_b200." + mod_name
+    return getattr(importlib.import_module(mod_name), cls_name)(*args, **cfg)
+
+
+class TemporalNet(nn.Module):
+    """Stand-in for the ``gnn.Sequential`` at models/graph.py:48: children are named ``module_{i}`` exactly
+    as PyG registers them (SAGEConv, LayerNorm, LeakyReLU) x depth, then the final Linear."""
+
+    def __init__(self, hidden_size: int, depth: int):
+        super().__init__()
+        self.depth = depth
+        for d in range(depth):
+            setattr(self, f"module_{3 * d}", SAGEConv(hidden_size, hidden_size, project=True))
+            setattr(self, f"module_{3 * d + 1}", GraphLayerNorm(hidden_size))
+            setattr(self, f"module_{3 * d + 2}", nn.LeakyReLU(negative_slope=0.2))
+        setattr(self, f"module_{3 * depth}", nn.Linear(hidden_size, hidden_size))
+
+    def forward(self, z, gs, residual=None):
+        for d in range(self.depth):
+            conv = getattr(self, f"module_{3 * d}")
+            norm = getattr(self, f"module_{3 * d + 1}")
+            slope = getattr(self, f"module_{3 * d + 2}").negative_slope
+            z = norm(conv(z, gs), act=ACT_LEAKY, slope=slope)
+        last = getattr(self, f"module_{3 * self.depth}")
+        return ops.linear(z, last.weight, last.bias, residual=residual)
+
+
+class Graph(nn.Module):
+    def __init__(self, input_size: int, hidden_size: int = 1024, depth: int = 3, pre_dropout: float = 0,
+                 temporal_pooling=None, num_segments: int = 8, *args, **kwargs):
+        super().__init__()
+        self.num_segments = num_segments
+        self.pre_dropout = nn.Dropout(pre_dropout)
+        self.temporal_pooling = _instantiate(temporal_pooling, input_size, hidden_size, num_segments) \
+            if temporal_pooling else None
+        self.positional_encoding = PositionalEncoding(hidden_size)
+        if depth > 0:
+            self.net = TemporalNet(hidden_size, depth)
+
+    def configure_optimizers(self, _):
+        return self.parameters()
+
+    def forward(self, data, *args, **kwargs):
+        x = data.x
+        if not x.is_cuda:
+            raise RuntimeError("egopack_b200.Graph runs on CUDA only (no CPU fallback); move the batch to the GPU")
+        x = ops.Cast.apply(x, config.compute_dtype())
+        x = ops.dropout(x, self.pre_dropout.p, self.training)
+        if self.temporal_pooling is not None:
+            x = self.temporal_pooling(x, data.batch, data.pos)
+        elif x.dim() != 2:
+            raise ValueError("without temporal pooling the node features must be [N, hidden]")
+        if hasattr(self, "net"):
+            gs = structure_for(data, x.shape[0])
+            z = self.positional_encoding.add_to(x, data.pos)
+            x = self.net(z, gs, residual=x)
+        return x

@@ -1,0 +1,113 @@
+"""Drop-in for ``models/graphONE/graphONE.py:13-141`` (``GraphONE``): the EgoPack "backpack" interaction.
+
+Same constructor, ``interact`` signature, attributes (``embeddings``, ``conv_stages``, ``task_labels``) and
+``state_dict`` keys (``embeddings.{task}.weight``, ``conv_stages.{task}.{d}.module_{0,1,3}.*``).
+
+The reference builds, per stage and per task, a (K+B)-node graph ``cat([bank, feats])`` with k prototype->node
+edges plus self loops, re-sorting the full B x K distance matrix twice each time, and runs a max-SAGE layer over
+all K+B rows.  This module computes the algebraically identical reduced form (the oracle's
+``interact_reduced`` is proven equal to the literal form in tests/test_oracle_golden.py):
+
+    idx  = cos-kNN(F0, bank)            once per task: tensor-core similarity + fused top-k + exact fp32 re-rank
+    M    = max_j bank[idx[:, j]]        once per task
+    per stage:  A = max(F, M);  U = A Wl^T + F Wr^T (one dual GEMM);  G = relu(LN_row(U));  F = G Wp^T + bp (+F)
+"""
+from __future__ import annotations
+
+import logging
+from typing import Dict, List, Literal, Tuple
+
+import torch
+import torch.nn as nn
+
+from ... import config, ops
+from ...ops import ACT_RELU
+from ..layers import SAGEConv, row_layernorm
+
+logger = logging.getLogger(__name__)
+
+
+class _Stage(nn.Module):
+    """Stand-in for the per-stage ``gnn.Sequential`` (graphONE.py:66-71): children ``module_0`` (SAGEConv, no
+    biases), ``module_1`` (nn.LayerNorm), ``module_2`` (ReLU), ``module_3`` (Linear)."""
+
+    def __init__(self, features_size: int, hidden_size: int):
+        super().__init__()
+        self.module_0 = SAGEConv(features_size, hidden_size, aggr="max", project=False, bias=False)
+        self.module_1 = nn.LayerNorm(hidden_size)
+        self.module_2 = nn.ReLU()
+        self.module_3 = nn.Linear(hidden_size, features_size)
+
+    def forward(self, f: torch.Tensor, m: torch.Tensor, residual: bool) -> torch.Tensor:
+        a = ops.MaxCombine.apply(f, m)                       # max over {self} U {k nearest prototypes}
+        u = ops.linear(a, self.module_0.lin_l.weight, None, x2=f, w2=self.module_0.lin_r.weight)
+        g = row_layernorm(self.module_1, u, act=ACT_RELU)
+        return ops.linear(g, self.module_3.weight, self.module_3.bias, residual=f if residual else None)
+
+
+class GraphONE(nn.Module):
+    def __init__(self, graphone: Dict[str, torch.Tensor], features_size: int = 1024, hidden_size: int = 1024,
+                 freeze: bool = True, k: int = 8, depth: int = 3,
+                 distance_func: Literal["l2", "cosine"] = "cosine", residual: bool = False,
+                 mix_strategy: Literal["mean", "max", "transformer"] = "max", update_edges_interval: int = 1,
+                 share_params: bool = False, *args, **kwargs) -> None:
+        super().__init__()
+        self.feature_size = features_size
+        self.k, self.distance_func, self.residual, self.mix_strategy = k, distance_func, residual, mix_strategy
+        self.update_edges_interval, self.share_cnn_params = update_edges_interval, share_params
+        logger.info("GraphONE initialized with %d tasks using depth=%d and K=%d.", len(graphone), depth, k)
+        if not freeze:
+            logger.warning("GraphONE initialized with trainable prototypes.")
+        if distance_func != "cosine":
+            raise NotImplementedError("only the default cosine distance is on the reference's configured path")
+        self.freeze = freeze
+        self.task_labels = sorted(graphone.keys())
+        self.embeddings = nn.ModuleDict({
+            task: nn.Embedding.from_pretrained(graphone[task], freeze=freeze) for task in self.task_labels})
+        self.depth = depth
+        self.conv_stages = nn.ModuleDict({
+            task: nn.ModuleList([_Stage(features_size, hidden_size) for _ in range(depth)])
+            for task in self.task_labels})
+        self._bank_cache: Dict[str, tuple] = {}
+
+    # normalised fp32 / bf16 copies of a bank, recomputed only when the embedding changes
+    def _bank(self, task: str):
+        w = self.embeddings[task].weight
+        cd = config.compute_dtype()
+        key = (w.data_ptr(), w._version, cd)
+        hit = self._bank_cache.get(task)
+        if hit is None or hit[0] != key:
+            wd = w.detach()
+            pn = ops.row_normalize(wd, torch.float32)
+            pn16 = ops.row_normalize(wd, torch.bfloat16) if cd == torch.bfloat16 else None
+            hit = (key, pn, pn16, ops.cast(wd, cd))
+            self._bank_cache[task] = hit
+        return hit[1], hit[2], hit[3]
+
+    @torch.no_grad()
+    def nearest_prototypes(self, task: str, features: torch.Tensor) -> torch.Tensor:
+        """[B, k] indices of the k nearest prototypes (cosine), nearest first -- graphONE.py:119-141."""
+        pn, pn16, _ = self._bank(task)
+        fn = ops.row_normalize(features.detach(), torch.float32)
+        fn16 = ops.row_normalize(features.detach(), torch.bfloat16) if pn16 is not None else None
+        return ops.cos_topk(fn, pn, self.k, fn16, pn16)
+
+    def interact(self, features: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch.Tensor], Dict[str, List[torch.Tensor]]]:
+        output: Dict[str, torch.Tensor] = {}
+        closest_nodes: Dict[str, List[torch.Tensor]] = {}
+        for task in features.keys():
+            output[task], closest_nodes[task] = self._task_interaction(task, features[task])
+        return output, closest_nodes
+
+    def _task_interaction(self, task: str, features: torch.Tensor):
+        if not features.is_cuda:
+            raise RuntimeError("egopack_b200.GraphONE runs on CUDA only (no CPU fallback)")
+        if not self.freeze and self.embeddings[task].weight.requires_grad:
+            raise NotImplementedError("trainable prototype banks (freeze=False) are not built yet")
+        f = ops.Cast.apply(features, config.compute_dtype())
+        idx = self.nearest_prototypes(task, f)                # constant across stages: matched on the inputs
+        _, _, bank = self._bank(task)
+        m = ops.proto_max_gather(bank, idx)
+        for stage in self.conv_stages[task]:
+            f = stage(f, m, self.residual)
+        return f, [idx[:, 0]] * self.depth

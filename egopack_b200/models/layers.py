@@ -1,0 +1,96 @@
+"""Parameter containers that reproduce the reference's ``state_dict`` layout for the third-party layers it uses
+(torch_geometric 2.3.0 ``SAGEConv`` / ``LayerNorm`` / ``PositionalEncoding`` / ``Sequential`` / ``Linear``), plus
+their kernel-backed forwards.  Nothing here depends on torch_geometric.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .. import ops
+from ..ops import ACT_LEAKY, ACT_NONE, ACT_RELU, GraphStructure
+
+
+def structure_for(data, n: int) -> GraphStructure:
+    """Aggregation structure of a batch, cached on the batch object.
+
+    ``band_k`` (set by our RadiusGraph when positions are unit spaced) selects the sliding-window kernel;
+    any other ``edge_index`` -- LTA star edges, graphs built by real PyG -- goes through a deterministic CSR.
+    """
+    cached = getattr(data, "_egp_structure", None)
+    dev = data.pos.device if getattr(data, "pos", None) is not None else data.x.device
+    if cached is not None and cached.n == n and cached.inv_deg.device == dev:
+        return cached
+    band_k = getattr(data, "band_k", None)
+    if band_k is not None:
+        batch = data.batch if getattr(data, "batch", None) is not None else torch.zeros(n, dtype=torch.long, device=dev)
+        ptr = getattr(data, "ptr", None)
+        if ptr is None:
+            counts = torch.bincount(batch)
+            ptr = torch.cat([counts.new_zeros(1), counts.cumsum(0)])
+        gs = ops.band_structure(batch, ptr, int(band_k))
+    else:
+        gs = ops.csr_structure(data.edge_index, n)
+    try:
+        data._egp_structure = gs
+    except Exception:  # foreign batch types may refuse new attributes; rebuilding per call is still correct
+        pass
+    return gs
+
+
+class PositionalEncoding(nn.Module):
+    """gnn.PositionalEncoding(out_channels): buffer ``frequency = logspace(0, 1, C/2, base=1e-4)``."""
+
+    def __init__(self, out_channels: int, base_freq: float = 1e-4, granularity: float = 1.0):
+        super().__init__()
+        if out_channels % 2:
+            raise ValueError(f"Cannot use sinusoidal positional encoding with odd 'out_channels' (got {out_channels}).")
+        self.out_channels, self.base_freq, self.granularity = out_channels, base_freq, granularity
+        self.register_buffer("frequency", torch.logspace(0, 1, out_channels // 2, base_freq))
+
+    def add_to(self, x: Tensor, pos: Tensor) -> Tensor:
+        if self.granularity != 1.0:
+            raise NotImplementedError("the reference uses the default granularity of 1.0")
+        return ops.PosEncAdd.apply(x, pos, self.frequency)
+
+
+class SAGEConv(nn.Module):
+    """Parameters of gnn.SAGEConv: ``lin`` (only if project, with bias), ``lin_l`` (bias = ctor bias), ``lin_r``
+    (no bias).  Forward (mean aggregation): ``lin_l(mean_j relu(lin(x_j))) + lin_r(x)`` -- the projection ReLU
+    is the GEMM epilogue, and ``lin_l``/``lin_r`` accumulate into one TMEM tile."""
+
+    def __init__(self, in_channels: int, out_channels: int, aggr: str = "mean", project: bool = False, bias: bool = True):
+        super().__init__()
+        self.in_channels, self.out_channels, self.aggr, self.project = in_channels, out_channels, aggr, project
+        if project:
+            self.lin = nn.Linear(in_channels, in_channels, bias=True)
+        self.lin_l = nn.Linear(in_channels, out_channels, bias=bias)
+        self.lin_r = nn.Linear(in_channels, out_channels, bias=False)
+
+    def forward(self, x: Tensor, gs: GraphStructure) -> Tensor:
+        if self.aggr != "mean":
+            raise NotImplementedError("max aggregation is implemented by GraphONE's reduced stage")
+        xs = ops.linear(x, self.lin.weight, self.lin.bias, act=ACT_RELU) if self.project else x
+        agg = ops.SageMean.apply(xs, gs)
+        return ops.linear(agg, self.lin_l.weight, self.lin_l.bias, x2=x, w2=self.lin_r.weight)
+
+
+class GraphLayerNorm(nn.Module):
+    """Parameters of gnn.LayerNorm(C) (``weight``, ``bias``); graph-mode statistics over the whole call."""
+
+    def __init__(self, in_channels: int, eps: float = 1e-5):
+        super().__init__()
+        self.in_channels, self.eps = in_channels, eps
+        self.weight = nn.Parameter(torch.ones(in_channels))
+        self.bias = nn.Parameter(torch.zeros(in_channels))
+
+    def forward(self, x: Tensor, act: int = ACT_NONE, slope: float = 0.0) -> Tensor:
+        return ops.GraphLayerNorm.apply(x, self.weight, self.bias, self.eps, act, slope)
+
+
+def row_layernorm(ln: nn.LayerNorm, x: Tensor, act: int = ACT_NONE) -> Tensor:
+    return ops.RowLayerNorm.apply(x, ln.weight, ln.bias, ln.eps, act)

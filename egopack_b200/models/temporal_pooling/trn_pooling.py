@@ -1,0 +1,47 @@
+"""Drop-in for ``models/temporal_pooling/trn_pooling.py:10-45`` (``TRNPooling``).
+
+``(N, S, D) -> (N, S*D)`` is a free view of the contiguous features; then
+Linear(S*D, HT) -> LayerNorm -> ReLU -> Dropout -> Linear(HT, HT) -> LayerNorm -> ReLU -> Dropout -> Linear(HT, H).
+``self.proj`` keeps the reference's nn.Sequential layout (indices 0,1,4,5,8 hold parameters) so checkpoints
+load unchanged; the forward issues 3 tcgen05 GEMMs and 2 fused row-LayerNorm+ReLU kernels.
+"""
+from __future__ import annotations
+
+import logging
+
+import torch.nn as nn
+
+from ... import ops
+from ...ops import ACT_RELU
+from ..layers import row_layernorm
+from .pooling import TemporalPooling
+
+logger = logging.getLogger(__name__)
+
+
+class TRNPooling(TemporalPooling):
+    def __init__(self, input_size: int = 1024, output_size: int = 1024, num_segments: int = 8,
+                 hidden_size: int = 1024, dropout: float = 0.0) -> None:
+        super().__init__(input_size, output_size, num_segments)
+        self.input_size, self.num_segments = input_size, num_segments
+        logger.info("TRNPooling(input=%d, hidden=%d, output=%d, segments=%d, dropout=%s)", input_size, hidden_size,
+                    output_size, num_segments, dropout)
+        self.proj = nn.Sequential(
+            nn.Linear(num_segments * input_size, hidden_size), nn.LayerNorm(hidden_size), nn.ReLU(inplace=True),
+            nn.Dropout(dropout),
+            nn.Linear(hidden_size, hidden_size), nn.LayerNorm(hidden_size), nn.ReLU(inplace=True),
+            nn.Dropout(dropout),
+            nn.Linear(hidden_size, output_size),
+        )
+
+    def forward(self, x, *_):
+        n = x.shape[0]
+        if x.dim() == 3 and (x.shape[1] != self.num_segments or x.shape[2] != self.input_size):
+            raise ValueError(f"expected [N, {self.num_segments}, {self.input_size}] features, got {tuple(x.shape)}")
+        h = x.reshape(n, self.num_segments * self.input_size)
+        p = self.proj
+        for lin, ln, drop in ((p[0], p[1], p[3]), (p[4], p[5], p[7])):
+            h = ops.linear(h, lin.weight, lin.bias)
+            h = row_layernorm(ln, h, act=ACT_RELU)
+            h = ops.dropout(h, drop.p, self.training)
+        return ops.linear(h, p[8].weight, p[8].bias)

@@ -1,0 +1,536 @@
+"""Host-side operators: thin wrappers over the C ABI plus the ``torch.autograd.Function``s the modules use.
+
+PyTorch supplies device memory, streams and autograd bookkeeping; every arithmetic step is a kernel of
+``libegopack_b200.so``.  Nothing here runs on the CPU and nothing falls back to aten math.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+F32, BF16 = 0, 1
+
+
+def _code(t: Tensor) -> int:
+    try:
+        return L.DTYPE_CODE[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}; egopack_b200 computes in float32 or bfloat16") from None
+
+
+def _c(t: Optional[Tensor]) -> Optional[Tensor]:
+    return None if t is None else (t if t.is_contiguous() else t.contiguous())
+
+
+# =====================================================================================================
+# graph structure
+# =====================================================================================================
+def band_edge_index(pos: Tensor, batch: Tensor, ptr: Tensor, r: float, max_num_neighbors: int = 32,
+                    monotone: Optional[bool] = None) -> Tensor:
+    """``RadiusGraph(r, loop=False)`` over a batch of graphs: int64 [2,E], dst-major, src ascending."""
+    pos, batch, ptr = _c(pos.view(-1)), _c(batch), _c(ptr)
+    n = pos.numel()
+    if monotone is None:
+        monotone = True if n < 2 else bool(((pos[1:] >= pos[:-1]) | (batch[1:] != batch[:-1])).all().item())
+    deg = torch.empty(n, dtype=torch.int32, device=pos.device)
+    L.call("egp_band_edge_count", L.ptr(pos), L.ptr(batch), L.ptr(ptr), n, float(r), int(max_num_neighbors),
+           int(monotone), L.ptr(deg), L.stream())
+    rowptr = torch.empty(n + 1, dtype=torch.int64, device=pos.device)
+    L.call("egp_exclusive_scan_i32", L.ptr(deg), n, L.ptr(rowptr), L.stream())
+    e = int(rowptr[-1].item())
+    edge_index = torch.empty((2, e), dtype=torch.int64, device=pos.device)
+    L.call("egp_band_edge_fill", L.ptr(pos), L.ptr(batch), L.ptr(ptr), n, float(r), int(max_num_neighbors),
+           int(monotone), L.ptr(rowptr), e, L.ptr(edge_index), L.stream())
+    return edge_index
+
+
+def lta_edge_index(pos: Tensor, y: Tensor, batch: Tensor, ptr: Tensor, r: float, max_num_neighbors: int = 32) -> Tensor:
+    """``LTATemporalConnectivity(r)`` applied per graph of a batch: int64 [2,E] sorted by (src,dst)."""
+    pos, y, batch, ptr = _c(pos.view(-1)), _c(y), _c(batch), _c(ptr)
+    n = pos.numel()
+    ycols = y.shape[1] if y.dim() > 1 else 1
+    deg = torch.empty(n, dtype=torch.int32, device=pos.device)
+    L.call("egp_lta_edge_count", L.ptr(pos), L.ptr(y), ycols, L.ptr(batch), L.ptr(ptr), n, float(r),
+           int(max_num_neighbors), L.ptr(deg), L.stream())
+    rowptr = torch.empty(n + 1, dtype=torch.int64, device=pos.device)
+    L.call("egp_exclusive_scan_i32", L.ptr(deg), n, L.ptr(rowptr), L.stream())
+    e = int(rowptr[-1].item())
+    edge_index = torch.empty((2, e), dtype=torch.int64, device=pos.device)
+    L.call("egp_lta_edge_fill", L.ptr(pos), L.ptr(y), ycols, L.ptr(batch), L.ptr(ptr), n, float(r),
+           int(max_num_neighbors), L.ptr(rowptr), e, L.ptr(edge_index), L.stream())
+    return edge_index
+
+
+@dataclass
+class GraphStructure:
+    """What the aggregation kernels need; built once per batch and cached on the batch object."""
+    n: int
+    band_k: Optional[int] = None
+    win_lo: Optional[Tensor] = None
+    win_hi: Optional[Tensor] = None
+    inv_deg: Optional[Tensor] = None          # 1/max(in-degree,1)
+    rowptr_in: Optional[Tensor] = None        # CSR grouped by dst (forward)
+    col_in: Optional[Tensor] = None
+    rowptr_out: Optional[Tensor] = None       # CSR grouped by src (backward)
+    col_out: Optional[Tensor] = None
+
+
+def band_structure(batch: Tensor, ptr: Tensor, k: int) -> GraphStructure:
+    n = batch.numel()
+    dev = batch.device
+    lo = torch.empty(n, dtype=torch.int32, device=dev)
+    hi = torch.empty(n, dtype=torch.int32, device=dev)
+    inv = torch.empty(n, dtype=torch.float32, device=dev)
+    L.call("egp_band_windows", L.ptr(_c(batch)), L.ptr(_c(ptr)), n, int(k), L.ptr(lo), L.ptr(hi), L.ptr(inv), L.stream())
+    return GraphStructure(n=n, band_k=int(k), win_lo=lo, win_hi=hi, inv_deg=inv)
+
+
+def csr_structure(edge_index: Tensor, n: int) -> GraphStructure:
+    edge_index = _c(edge_index)
+    e = edge_index.shape[1]
+    dev = edge_index.device
+    out = GraphStructure(n=n)
+    cursor = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    for by_dst in (1, 0):
+        rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(max(e, 1), dtype=torch.int32, device=dev)
+        L.call("egp_csr_build", L.ptr(edge_index), e, n, by_dst, L.ptr(rowptr), L.ptr(col), L.ptr(cursor), L.stream())
+        if by_dst:
+            out.rowptr_in, out.col_in = rowptr, col
+        else:
+            out.rowptr_out, out.col_out = rowptr, col
+    out.inv_deg = torch.empty(n, dtype=torch.float32, device=dev)
+    L.call("egp_csr_inv_degree", L.ptr(out.rowptr_in), n, L.ptr(out.inv_deg), L.stream())
+    return out
+
+
+def _aggregate(x: Tensor, gs: GraphStructure, backward: bool) -> Tensor:
+    x = _c(x)
+    n, c = x.shape
+    out = torch.empty_like(x)
+    so, si = (None, gs.inv_deg) if backward else (gs.inv_deg, None)
+    if gs.band_k is not None:
+        L.call("egp_sage_mean_band", L.ptr(x), L.ptr(out), n, c, c, c, gs.band_k, L.ptr(gs.win_lo), L.ptr(gs.win_hi),
+               L.ptr(so), L.ptr(si), _code(x), L.stream())
+    else:
+        rp, col = (gs.rowptr_out, gs.col_out) if backward else (gs.rowptr_in, gs.col_in)
+        L.call("egp_sage_mean_csr", L.ptr(x), L.ptr(out), n, c, c, c, L.ptr(rp), L.ptr(col), L.ptr(so), L.ptr(si),
+               _code(x), L.stream())
+    return out
+
+
+class SageMean(torch.autograd.Function):
+    """agg_i = mean_{j -> i} x_j (0 for isolated nodes) -- the aggregation inside gnn.SAGEConv (models/graph.py:42)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, gs: GraphStructure) -> Tensor:
+        ctx.gs = gs
+        return _aggregate(x, gs, backward=False)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        return _aggregate(g, ctx.gs, backward=True), None
+
+
+# =====================================================================================================
+# GEMM
+# =====================================================================================================
+def gemm(a: Tensor, a_trans: bool, b: Tensor, b_trans: bool, m: int, n: int, k: int, *, a2: Optional[Tensor] = None,
+         b2: Optional[Tensor] = None, k2: int = 0, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None,
+         act: int = ACT_NONE, slope: float = 0.0, out_dtype: Optional[torch.dtype] = None,
+         out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+    """C[m,n] = act(A B^T + A2 B2^T + bias) + residual, see ``egp_gemm``.  Operands must be 2-D contiguous."""
+    assert a.dtype == b.dtype, (a.dtype, b.dtype)
+    out_dtype = out_dtype or a.dtype
+    if out is None:
+        out = torch.empty((m, n), dtype=out_dtype, device=a.device)
+    a, b, a2, b2, residual = _c(a), _c(b), _c(a2), _c(b2), _c(residual)
+    if bias is not None:
+        assert bias.dtype == torch.float32
+    if residual is not None:
+        assert residual.dtype == out.dtype and residual.shape == out.shape
+    L.call("egp_gemm", L.ptr(a), a.stride(0), int(a_trans), L.ptr(b), b.stride(0), int(b_trans),
+           L.ptr(a2), a2.stride(0) if a2 is not None else 0, L.ptr(b2), b2.stride(0) if b2 is not None else 0, int(k2),
+           L.ptr(_c(bias)), L.ptr(residual), residual.stride(0) if residual is not None else 0,
+           L.ptr(out), out.stride(0), m, n, k, int(act), float(slope), _code(a), L.DTYPE_CODE[out.dtype],
+           int(accumulate), None, 0, L.stream())
+    return out
+
+
+def colsum(x: Tensor) -> Tensor:
+    x = _c(x)
+    rows, cols = x.shape
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    nb = L.size("egp_colsum_workspace", rows, cols)
+    ws = L.workspace(nb, x.device)
+    L.call("egp_colsum", L.ptr(x), L.ptr(out), rows, cols, x.stride(0), _code(x), L.ptr(ws), nb, L.stream())
+    return out
+
+
+def cast(x: Tensor, dtype: torch.dtype) -> Tensor:
+    if x.dtype == dtype:
+        return x
+    x = _c(x)
+    out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    L.call("egp_cast", L.ptr(x), L.ptr(out), x.numel(), _code(x), L.DTYPE_CODE[dtype], L.stream())
+    return out
+
+
+def act_bwd(dy: Tensor, y: Tensor, act: int, slope: float) -> Tensor:
+    dy, y = _c(dy), _c(y)
+    dx = torch.empty_like(dy)
+    L.call("egp_act_bwd", L.ptr(dy), L.ptr(y), L.ptr(dx), dy.numel(), act, float(slope), _code(dy), L.stream())
+    return dx
+
+
+def add(a: Tensor, b: Tensor) -> Tensor:
+    a, b = _c(a), _c(b)
+    out = torch.empty_like(a)
+    L.call("egp_add", L.ptr(a), L.ptr(b), L.ptr(out), a.numel(), _code(a), L.stream())
+    return out
+
+
+def axpby(a: Tensor, alpha: float, b: Optional[Tensor] = None, beta: float = 0.0) -> Tensor:
+    a, b = _c(a), _c(b)
+    out = torch.empty_like(a)
+    n = a.numel()
+    vn = 8 if a.dtype == torch.bfloat16 else 4
+    if n % vn:                                           # ragged tail (tiny logits tensors): pad to a vector multiple
+        pad = vn - n % vn
+        af = torch.cat([a.reshape(-1), a.new_zeros(pad)])
+        bf = torch.cat([b.reshape(-1), b.new_zeros(pad)]) if b is not None else None
+        of = torch.empty_like(af)
+        L.call("egp_axpby", L.ptr(af), float(alpha), L.ptr(bf), float(beta), L.ptr(of), af.numel(), _code(a), L.stream())
+        return of[:n].reshape(a.shape)
+    L.call("egp_axpby", L.ptr(a), float(alpha), L.ptr(b), float(beta), L.ptr(out), n, _code(a), L.stream())
+    return out
+
+
+class Scale(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, alpha: float):
+        ctx.alpha = alpha
+        return axpby(x, alpha)
+
+    @staticmethod
+    def backward(ctx, g):
+        return axpby(g, ctx.alpha), None
+
+
+class _WeightCache:
+    """bf16 copies of fp32 parameters, refreshed when the parameter is updated in place (optimizer step)."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, w: Tensor, dtype: torch.dtype) -> Tensor:
+        if w.dtype == dtype:
+            return w
+        key = (w.data_ptr(), tuple(w.shape), dtype)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == w._version:
+            return hit[1]
+        c = cast(w.detach(), dtype)
+        self._store[key] = (w._version, c)
+        return c
+
+
+weight_cache = _WeightCache()
+
+
+def _pad_cols(x: Tensor, mult: int) -> Tensor:
+    """Zero-pad the last dim up to a multiple of `mult` (bf16 operands must have 16-byte row strides for TMA)."""
+    c = x.shape[1]
+    if c % mult == 0:
+        return x
+    cp = (c + mult - 1) // mult * mult
+    out = torch.zeros((x.shape[0], cp), dtype=x.dtype, device=x.device)
+    out[:, :c].copy_(x)
+    return out
+
+
+class Linear(torch.autograd.Function):
+    """y = act(x W^T [+ x2 W2^T] + b) [+ residual].
+
+    Forward / dgrad / wgrad are all ``egp_gemm`` calls (tcgen05 for bf16 activations, FFMA for fp32); the
+    two-operand form is SAGEConv's ``lin_l(agg) + lin_r(x)`` accumulated in one TMEM tile.
+    Weights stay fp32 parameters; bf16 copies come from ``weight_cache``.  ``out_dtype`` lets classifier heads
+    emit fp32 logits from bf16 features.
+    """
+
+    @staticmethod
+    def forward(ctx, x, w, b, x2, w2, residual, act: int, slope: float, out_dtype):
+        cd = x.dtype                                     # compute dtype follows the activations
+        m, k = x.shape
+        n = w.shape[0]
+        wc = weight_cache.get(w, cd)
+        w2c = weight_cache.get(w2, cd) if w2 is not None else None
+        out_dtype = out_dtype or cd
+        y = gemm(x, False, wc, False, m, n, k, a2=x2, b2=w2c, k2=(x2.shape[1] if x2 is not None else 0), bias=b,
+                 residual=residual, act=act, slope=slope, out_dtype=out_dtype)
+        ctx.save_for_backward(x, w, x2, w2, y if act != ACT_NONE else None)
+        ctx.act, ctx.slope, ctx.has_bias, ctx.has_res = act, slope, b is not None, residual is not None
+        ctx.res_dtype = residual.dtype if residual is not None else None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, x2, w2, y = ctx.saved_tensors
+        cd = x.dtype
+        m, k = x.shape
+        n = w.shape[0]
+        dy = _c(dy)
+        dres = dy if ctx.has_res else None
+        g = dy
+        if ctx.act != ACT_NONE:
+            if ctx.has_res:
+                raise RuntimeError("Linear: activation together with a residual is not differentiable here")
+            g = act_bwd(dy, y, ctx.act, ctx.slope)
+        gc = cast(g, cd)                                 # fp32 logits gradients -> bf16 operand
+        db = colsum(g) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        if cd == torch.bfloat16 and n % 8 != 0:          # TMA needs 16-byte row strides: pad the class dim
+            gc = _pad_cols(gc, 8)
+        npad = gc.shape[1]
+        dx = dx2 = dw = dw2 = None
+        wc = weight_cache.get(w, cd)
+        if npad != n:
+            wc = torch.cat([wc, wc.new_zeros((npad - n, k))], 0)
+        if ctx.needs_input_grad[0]:
+            dx = gemm(gc, False, wc, True, m, k, npad)                           # dx = g W
+        if ctx.needs_input_grad[1]:
+            dw = gemm(gc, True, x, True, n, k, m, out_dtype=torch.float32)       # dW = g^T x
+        if x2 is not None:
+            k2 = x2.shape[1]
+            w2c = weight_cache.get(w2, cd)
+            if npad != n:
+                w2c = torch.cat([w2c, w2c.new_zeros((npad - n, k2))], 0)
+            if ctx.needs_input_grad[3]:
+                dx2 = gemm(gc, False, w2c, True, m, k2, npad)
+            if ctx.needs_input_grad[4]:
+                dw2 = gemm(gc, True, x2, True, n, k2, m, out_dtype=torch.float32)
+        if dres is not None and dres.dtype != ctx.res_dtype:
+            dres = cast(dres, ctx.res_dtype)
+        return dx, dw, db, dx2, dw2, dres, None, None, None
+
+
+def linear(x, w, b=None, *, x2=None, w2=None, residual=None, act=ACT_NONE, slope=0.0, out_dtype=None):
+    return Linear.apply(x, w, b, x2, w2, residual, act, slope, out_dtype)
+
+
+# =====================================================================================================
+# normalisation / elementwise
+# =====================================================================================================
+class RowLayerNorm(torch.autograd.Function):
+    """nn.LayerNorm over the last dim, optionally fused with ReLU (TRNPooling / task nets / GraphONE stages)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps: float, act: int):
+        x = _c(x)
+        n, c = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(n, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(n, dtype=torch.float32, device=x.device)
+        L.call("egp_row_layernorm_fwd", L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(mean), L.ptr(rstd), n, c,
+               float(eps), act, _code(x), L.stream())
+        ctx.save_for_backward(x, y if act == ACT_RELU else None, w, mean, rstd)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, w, mean, rstd = ctx.saved_tensors
+        dy = _c(dy)
+        n, c = x.shape
+        dx = torch.empty_like(x)
+        dw = torch.empty(c, dtype=torch.float32, device=x.device)
+        db = torch.empty(c, dtype=torch.float32, device=x.device)
+        nb = L.size("egp_row_layernorm_workspace", n, c)
+        ws = L.workspace(nb, x.device)
+        L.call("egp_row_layernorm_bwd", L.ptr(dy), L.ptr(x), L.ptr(y), L.ptr(w), L.ptr(mean), L.ptr(rstd), L.ptr(dx),
+               L.ptr(dw), L.ptr(db), n, c, ctx.act, _code(x), L.ptr(ws), nb, L.stream())
+        return dx, dw, db, None, None
+
+
+class GraphLayerNorm(torch.autograd.Function):
+    """gnn.LayerNorm in graph mode WITHOUT a batch vector (models/graph.py:43): statistics over the whole
+    [N,C] tensor, ``x / (std + eps)``, per-channel affine; fused with LeakyReLU (models/graph.py:44)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps: float, act: int, slope: float):
+        x = _c(x)
+        n, c = x.shape
+        y = torch.empty_like(x)
+        stats = torch.empty(2, dtype=torch.float64, device=x.device)
+        nb = L.size("egp_graph_layernorm_workspace", n, c)
+        ws = L.workspace(nb, x.device)
+        L.call("egp_graph_layernorm_fwd", L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(stats), n, c, float(eps), act,
+               float(slope), _code(x), L.ptr(ws), nb, L.stream())
+        ctx.save_for_backward(x, w, b, stats)
+        ctx.cfg = (float(eps), act, float(slope))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, b, stats = ctx.saved_tensors
+        eps, act, slope = ctx.cfg
+        dy = _c(dy)
+        n, c = x.shape
+        dx = torch.empty_like(x)
+        dw = torch.empty(c, dtype=torch.float32, device=x.device)
+        db = torch.empty(c, dtype=torch.float32, device=x.device)
+        nb = L.size("egp_graph_layernorm_workspace", n, c)
+        ws = L.workspace(nb, x.device)
+        L.call("egp_graph_layernorm_bwd", L.ptr(dy), L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(stats), L.ptr(dx), L.ptr(dw),
+               L.ptr(db), n, c, eps, act, slope, _code(x), L.ptr(ws), nb, L.stream())
+        return dx, dw, db, None, None, None
+
+
+class PosEncAdd(torch.autograd.Function):
+    """x + gnn.PositionalEncoding(pos) (models/graph.py:63); the encoding has no parameters."""
+
+    @staticmethod
+    def forward(ctx, x, pos, freq):
+        x = _c(x)
+        n, c = x.shape
+        out = torch.empty_like(x)
+        L.call("egp_posenc_add", L.ptr(x), L.ptr(_c(pos.view(-1))), L.ptr(_c(freq)), L.ptr(out), n, c, _code(x), L.stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None, None
+
+
+class Cast(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src = x.dtype
+        return cast(x, dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return cast(g, ctx.src), None
+
+
+class Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return add(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+class Dropout(torch.autograd.Function):
+    """Inverted dropout.  The keep mask is drawn by torch's generator (plumbing); apply/backward are kernels."""
+
+    @staticmethod
+    def forward(ctx, x, p: float):
+        x = _c(x)
+        mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device).bernoulli_(1.0 - p)
+        ctx.save_for_backward(mask)
+        ctx.scale = 1.0 / (1.0 - p)
+        out = torch.empty_like(x)
+        L.call("egp_mask_scale", L.ptr(x), L.ptr(mask), L.ptr(out), x.numel(), ctx.scale, _code(x), L.stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        g = _c(g)
+        out = torch.empty_like(g)
+        L.call("egp_mask_scale", L.ptr(g), L.ptr(mask), L.ptr(out), g.numel(), ctx.scale, _code(g), L.stream())
+        return out, None
+
+
+def dropout(x: Tensor, p: float, training: bool) -> Tensor:
+    if not training or p <= 0.0:
+        return x
+    if p >= 1.0:
+        return x * 0
+    return Dropout.apply(x, float(p))
+
+
+# =====================================================================================================
+# pooling / GraphONE pieces
+# =====================================================================================================
+class SegmentMaxPool(torch.autograd.Function):
+    """gnn.pool.global_max_pool (models/tasks/oscc.py:68,85): per-graph channel-wise max."""
+
+    @staticmethod
+    def forward(ctx, x, ptr, batch):
+        x = _c(x)
+        g, c = ptr.numel() - 1, x.shape[1]
+        out = torch.empty((g, c), dtype=x.dtype, device=x.device)
+        arg = torch.empty((g, c), dtype=torch.int32, device=x.device)
+        L.call("egp_segment_max_pool_fwd", L.ptr(x), L.ptr(_c(ptr)), L.ptr(out), L.ptr(arg), g, c, _code(x), L.stream())
+        ctx.save_for_backward(arg, _c(batch))
+        ctx.n = x.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        arg, batch = ctx.saved_tensors
+        dout = _c(dout)
+        c = dout.shape[1]
+        dx = torch.empty((ctx.n, c), dtype=dout.dtype, device=dout.device)
+        L.call("egp_segment_max_pool_bwd", L.ptr(dout), L.ptr(arg), L.ptr(batch), L.ptr(dx), ctx.n, c, _code(dout),
+               L.stream())
+        return dx, None, None
+
+
+class MaxCombine(torch.autograd.Function):
+    """a = max(f, m) with m constant: the max-aggregation over {self} U {k nearest prototypes}."""
+
+    @staticmethod
+    def forward(ctx, f, m):
+        f, m = _c(f), _c(m)
+        a = torch.empty_like(f)
+        L.call("egp_max_combine_fwd", L.ptr(f), L.ptr(m), L.ptr(a), f.numel(), _code(f), L.stream())
+        ctx.save_for_backward(f, m)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        f, m = ctx.saved_tensors
+        da = _c(da)
+        df = torch.empty_like(f)
+        L.call("egp_max_combine_bwd", L.ptr(da), L.ptr(f), L.ptr(m), L.ptr(df), f.numel(), _code(f), L.stream())
+        return df, None
+
+
+def row_normalize(x: Tensor, out_dtype: torch.dtype = torch.float32) -> Tensor:
+    x = _c(x)
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    L.call("egp_row_normalize", L.ptr(x), L.ptr(out), x.shape[0], x.shape[1], _code(x), L.DTYPE_CODE[out_dtype], L.stream())
+    return out
+
+
+def cos_topk(fn: Tensor, pn: Tensor, k: int, fn16: Optional[Tensor] = None, pn16: Optional[Tensor] = None) -> Tensor:
+    """k nearest prototypes by cosine dissimilarity for every row of the NORMALISED fp32 features ``fn``."""
+    fn, pn = _c(fn), _c(pn)
+    assert fn.dtype == torch.float32 and pn.dtype == torch.float32
+    b, c = fn.shape
+    kp = pn.shape[0]
+    idx = torch.empty((b, k), dtype=torch.int64, device=fn.device)
+    nb = L.size("egp_cos_topk_workspace", b, kp, k)
+    ws = L.workspace(nb, fn.device, "topk")
+    L.call("egp_cos_topk", L.ptr(fn), L.ptr(pn), L.ptr(_c(fn16)), L.ptr(_c(pn16)), b, kp, c, int(k), L.ptr(idx),
+           L.ptr(ws), nb, L.stream())
+    return idx
+
+
+def proto_max_gather(bank: Tensor, idx: Tensor) -> Tensor:
+    bank, idx = _c(bank), _c(idx)
+    b, k = idx.shape
+    c = bank.shape[1]
+    m = torch.empty((b, c), dtype=bank.dtype, device=bank.device)
+    L.call("egp_proto_max_gather", L.ptr(bank), L.ptr(idx), L.ptr(m), b, k, c, _code(bank), _code(bank), L.stream())
+    return m

@@ -1,0 +1,189 @@
+/* egopack_b200 -- C ABI of the B200 (sm_100a) kernels behind EgoPack's temporal-graph hot path.
+ *
+ * This is the drop-in boundary.  The reference (sapeirone/EgoPack) is pure Python and has
+ * no FFI of its own: its hot path dispatches into torch / torch_geometric 2.3.0 / torch_cluster 1.6.1 /
+ * torch_scatter 2.1.1 kernels.  Each entry point below replaces one of those dispatches; the reference call
+ * site it serves is cited as (file:line, relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is DEVICE memory owned by the caller (the library never
+ *     allocates, frees or retains device memory; `workspace` is caller-provided scratch).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no device synchronisation.
+ *   - return value: EGP_OK (0) or a negative egp_status; the message is kept per thread (egp_last_error).
+ *   - dtype codes: EGP_F32 = 0 (float), EGP_BF16 = 1 (__nv_bfloat16).  Index tensors are int64 where the
+ *     reference hands int64 around (pos, batch, ptr, edge_index, knn indices); library-internal graph
+ *     structure (window bounds, CSR) is int32.
+ *   - row-major everywhere; `ld*` arguments are row strides in ELEMENTS.
+ */
+#ifndef EGOPACK_B200_H
+#define EGOPACK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  EGP_OK = 0,
+  EGP_ERR_INVALID = -1,     /* bad argument (null pointer, unsupported size/alignment) */
+  EGP_ERR_CUDA = -2,        /* a CUDA runtime/driver call or a kernel launch failed */
+  EGP_ERR_UNSUPPORTED = -3, /* valid request this build cannot serve (e.g. no sm_100 device) */
+  EGP_ERR_WORKSPACE = -4    /* workspace too small */
+} egp_status;
+
+enum { EGP_F32 = 0, EGP_BF16 = 1 };
+enum { EGP_ACT_NONE = 0, EGP_ACT_RELU = 1, EGP_ACT_LEAKY_RELU = 2 };
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+int egp_version(void);                               /* ABI version, bumped on any signature change */
+int egp_last_error(char* buf, size_t len);           /* copies the calling thread's last error message */
+int egp_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- a1: band edge_index (replaces torch_cluster.radius_graph behind RadiusGraph(r=k+0.5, loop=False);
+ *      main_temporal.py:168-169,189-190,225-226; main_egopack.py:196-197,213-214,248-249) -------------------
+ * Graph g owns nodes [ptr[g], ptr[g+1]).  For node i the matches are the nodes j of the same graph with
+ * (pos_i-pos_j)^2 < r^2, visited in ascending j, truncated to the first `max_num_neighbors + 1` (self
+ * included), self then removed.  `monotone` != 0 promises pos is non-decreasing inside every graph
+ * (window scan); 0 scans the whole graph.
+ *   count: deg[i]   = number of edges into i                              (int32 [N])
+ *   fill : edge_index[0][e] = src j, edge_index[1][e] = dst i, dst-major, src ascending, e = rowptr[i]..
+ *          (rowptr = exclusive scan of deg, int64 [N+1], see egp_exclusive_scan_i32)                       */
+int egp_band_edge_count(const int64_t* pos, const int64_t* batch, const int64_t* ptr, int64_t num_nodes,
+                        float r, int max_num_neighbors, int monotone, int32_t* deg, void* stream);
+int egp_band_edge_fill(const int64_t* pos, const int64_t* batch, const int64_t* ptr, int64_t num_nodes,
+                       float r, int max_num_neighbors, int monotone, const int64_t* rowptr,
+                       int64_t num_edges, int64_t* edge_index, void* stream);
+/* out[0]=0, out[i+1]=sum_{j<=i} in[j]; one block, workspace-free; n <= 2^31 */
+int egp_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* out, void* stream);
+
+/* ---- a2: LTA connectivity (models/transforms/lta_temp_connectivity.py:30-56), batched over graphs --------
+ * Per graph: n_in = #(y[:,0]==-1), n_fc = #(y[:,0]>0); edges = band(r) U {s->t : s in [max(ceil(n_in-r),0), n_in),
+ * t in [n_in, n_in+n_fc)}, de-duplicated, sorted by (src,dst) (RemoveDuplicatedEdges == coalesce).
+ *   count: deg_out[s]; fill: edge_index sorted by (src,dst) using rowptr = scan(deg_out).
+ * `y` is int64 [N, y_cols], column 0 = verb label.                                                         */
+int egp_lta_edge_count(const int64_t* pos, const int64_t* y, int64_t y_cols, const int64_t* batch,
+                       const int64_t* ptr, int64_t num_nodes, float r, int max_num_neighbors,
+                       int32_t* deg_out, void* stream);
+int egp_lta_edge_fill(const int64_t* pos, const int64_t* y, int64_t y_cols, const int64_t* batch,
+                      const int64_t* ptr, int64_t num_nodes, float r, int max_num_neighbors,
+                      const int64_t* rowptr, int64_t num_edges, int64_t* edge_index, void* stream);
+
+/* ---- graph structure used by the aggregation kernels ------------------------------------------------------
+ * band windows: win_lo[i], win_hi[i] (inclusive, self included) for unit-spaced pos and radius k, and
+ * inv_deg[i] = 1/max(win_hi-win_lo, 1).                                                                      */
+int egp_band_windows(const int64_t* batch, const int64_t* ptr, int64_t num_nodes, int k,
+                     int32_t* win_lo, int32_t* win_hi, float* inv_deg, void* stream);
+/* CSR from an arbitrary int64 edge_index [2,E]: group_by = 1 groups by dst (rows = dst, cols = src; forward),
+ * 0 groups by src (rows = src, cols = dst; backward).  Columns inside a row are sorted ascending
+ * (deterministic).  rowptr int32 [N+1], col int32 [E]; `cursor` is int32 [N] scratch.                       */
+int egp_csr_build(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, int group_by_dst,
+                  int32_t* rowptr, int32_t* col, int32_t* cursor, void* stream);
+/* inv_deg[i] = 1 / max(rowptr[i+1]-rowptr[i], 1) */
+int egp_csr_inv_degree(const int32_t* rowptr, int64_t num_nodes, float* inv_deg, void* stream);
+
+/* ---- a5: SAGE mean aggregation (replaces index_select + scatter_add_/count/div inside gnn.SAGEConv,
+ *      models/graph.py:42) --------------------------------------------------------------------------------
+ * band:  out[i] = s_out(i) * sum_{j in [win_lo[i],win_hi[i]], j != i} s_in(j) * x[j]
+ *        forward : scale_out = inv_deg, scale_in = NULL      (mean over in-neighbours)
+ *        backward: scale_out = NULL,    scale_in = inv_deg   (band is symmetric)
+ * csr :  out[i] = s_out(i) * sum_{e in row i} s_in(col[e]) * x[col[e]]                                     */
+int egp_sage_mean_band(const void* x, void* out, int64_t num_nodes, int64_t channels, int64_t ldx,
+                       int64_t ldo, int k, const int32_t* win_lo, const int32_t* win_hi,
+                       const float* scale_out, const float* scale_in, int dtype, void* stream);
+int egp_sage_mean_csr(const void* x, void* out, int64_t num_nodes, int64_t channels, int64_t ldx,
+                      int64_t ldo, const int32_t* rowptr, const int32_t* col, const float* scale_out,
+                      const float* scale_in, int dtype, void* stream);
+
+/* ---- a6+a7: graph-mode LayerNorm over the WHOLE [N,C] tensor + LeakyReLU (gnn.LayerNorm batch=None,
+ *      models/graph.py:43-44): mu = mean(x), sigma = sqrt(mean((x-mu)^2)), y = act((x-mu)/(sigma+eps)*w+b) ---
+ * stats: double[2] = {mu, sigma};  workspace: see egp_graph_layernorm_workspace.                           */
+size_t egp_graph_layernorm_workspace(int64_t num_nodes, int64_t channels);
+int egp_graph_layernorm_fwd(const void* x, const float* weight, const float* bias, void* y, double* stats,
+                            int64_t num_nodes, int64_t channels, float eps, int act, float slope, int dtype,
+                            void* workspace, size_t ws_bytes, void* stream);
+/* dx, dweight[C], dbias[C] from dy (gradient w.r.t. the activated output), the saved input x and stats. */
+int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, const float* bias,
+                            const double* stats, void* dx, float* dweight, float* dbias, int64_t num_nodes,
+                            int64_t channels, float eps, int act, float slope, int dtype, void* workspace,
+                            size_t ws_bytes, void* stream);
+
+/* ---- row LayerNorm (+ReLU) (nn.LayerNorm in TRNPooling trn_pooling.py:30,35; tasks task.py:20; GraphONE
+ *      graphONE.py:61) ; mean/rstd float [N] are saved for the backward ------------------------------------ */
+size_t egp_row_layernorm_workspace(int64_t num_nodes, int64_t channels);
+int egp_row_layernorm_fwd(const void* x, const float* weight, const float* bias, void* y, float* mean,
+                          float* rstd, int64_t num_nodes, int64_t channels, float eps, int act, int dtype,
+                          void* stream);
+int egp_row_layernorm_bwd(const void* dy, const void* x, const void* y, const float* weight, const float* mean,
+                          const float* rstd, void* dx, float* dweight, float* dbias, int64_t num_nodes,
+                          int64_t channels, int act, int dtype, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a4: out = x + [sin(pos*f) | cos(pos*f)]  (gnn.PositionalEncoding, models/graph.py:37,63) ---------- */
+int egp_posenc_add(const void* x, const int64_t* pos, const float* frequency, void* out, int64_t num_nodes,
+                   int64_t channels, int dtype, void* stream);
+
+/* ---- elementwise helpers ------------------------------------------------------------------------------- */
+int egp_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
+/* out = a + b (same dtype) */
+int egp_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
+/* out = alpha*a + beta*b (b may be NULL: out = alpha*a) */
+int egp_axpby(const void* a, float alpha, const void* b, float beta, void* out, int64_t n, int dtype, void* stream);
+/* dx = dy * act'(y) with y the activated output (ReLU / LeakyReLU) */
+int egp_act_bwd(const void* dy, const void* y, void* dx, int64_t n, int act, float slope, int dtype, void* stream);
+/* out[c] = sum_i x[i,c] (bias gradients); workspace float [blocks*C], see egp_colsum_workspace */
+size_t egp_colsum_workspace(int64_t rows, int64_t cols);
+int egp_colsum(const void* x, float* out, int64_t rows, int64_t cols, int64_t ldx, int dtype, void* workspace,
+               size_t ws_bytes, void* stream);
+/* dropout apply with a caller-generated keep mask (uint8): out = x * mask * scale */
+int egp_mask_scale(const void* x, const uint8_t* mask, void* out, int64_t n, float scale, int dtype, void* stream);
+
+/* ---- Linear layers (nn.Linear / gnn.Linear everywhere on the path) ---------------------------------------
+ * C[M,N] = act( A[M,K] * B^T + A2[M,K2] * B2^T + bias[N] ) + residual[M,N]
+ *   a_trans = 0: A is [M,K] row-major (lda);   a_trans = 1: A is [K,M] row-major (lda)      (same for A2)
+ *   b_trans = 0: B is [N,K] row-major (ldb);   b_trans = 1: B is [K,N] row-major (ldb)      (same for B2)
+ *   forward  y = x W^T      : A=x  (a_trans 0), B=W  (b_trans 0)
+ *   dgrad    dx = dy W      : A=dy (a_trans 0), B=W  (b_trans 1)
+ *   wgrad    dW = dy^T x    : A=dy (a_trans 1), B=x  (b_trans 1)
+ * in_dtype EGP_BF16 -> tcgen05/TMEM tensor-core kernel fed by TMA (fp32 accumulate);
+ * in_dtype EGP_F32  -> fp32 FFMA kernel (parity mode).  out_dtype may differ from in_dtype.
+ * accumulate != 0: C += (fp32 C only; used by split-K wgrad).  bias/residual/A2/B2 may be NULL.            */
+size_t egp_gemm_workspace(int64_t M, int64_t N, int64_t K);
+int egp_gemm(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans,
+             const void* A2, int64_t lda2, const void* B2, int64_t ldb2, int64_t K2,
+             const float* bias, const void* residual, int64_t ldr, void* C, int64_t ldc,
+             int64_t M, int64_t N, int64_t K, int act, float slope, int in_dtype, int out_dtype,
+             int accumulate, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a14: cosine k-NN of nodes against a prototype bank (GraphONE.__compute_edges, graphONE.py:119-141) ---
+ * d = 1 - (F/|F|)(P/|P|)^T ; idx[i,:] = the k smallest d, ascending, ties -> lower prototype index.
+ *   egp_row_normalize: out = x / ||x||_2 per row (fp32 math, no epsilon -- cos_dissimilarity, graphONE.py:148-151)
+ *   egp_cos_topk     : fn/pn = fp32 NORMALISED rows [B,C] / [Kp,C].  With fn16/pn16 == NULL the similarity is an
+ *                      fp32 GEMM.  With bf16 normalised copies the similarity runs on the tensor cores, the top
+ *                      candidates (k+8 rounded up to 16/32) are re-scored exactly in fp32 from fn/pn.
+ *   workspace        : egp_cos_topk_workspace(B, Kp, k) bytes (row-chunked [<=32768, Kp] fp32 similarities).    */
+int egp_row_normalize(const void* x, void* out, int64_t rows, int64_t cols, int in_dtype, int out_dtype, void* stream);
+int egp_row_inv_norm(const void* x, float* out, int64_t rows, int64_t cols, int64_t ldx, int dtype, void* stream);
+size_t egp_cos_topk_workspace(int64_t num_nodes, int64_t num_protos, int64_t k);
+int egp_cos_topk(const float* fn, const float* pn, const void* fn16, const void* pn16, int64_t num_nodes,
+                 int64_t num_protos, int64_t channels, int k, int64_t* idx, void* workspace, size_t ws_bytes,
+                 void* stream);
+
+/* ---- a15: prototype max-gather and max-combine (reduced GraphONE stage) ------------
+ * m[i,c] = max_j P[idx[i,j], c];  a = max(f, m);  backward of the combine: df = da * (f >= m).              */
+int egp_proto_max_gather(const void* protos, const int64_t* idx, void* m, int64_t num_nodes, int64_t k,
+                         int64_t channels, int proto_dtype, int out_dtype, void* stream);
+int egp_max_combine_fwd(const void* f, const void* m, void* a, int64_t n, int dtype, void* stream);
+int egp_max_combine_bwd(const void* da, const void* f, const void* m, void* df, int64_t n, int dtype, void* stream);
+
+/* ---- a12: per-graph channel-wise max pooling (gnn.pool.global_max_pool, models/tasks/oscc.py:68,85) ------
+ * out[g,c] = max_{i in [ptr[g],ptr[g+1])} x[i,c] (0 for an empty graph); arg int32 [G,C] (-1 if empty).     */
+int egp_segment_max_pool_fwd(const void* x, const int64_t* ptr, void* out, int32_t* arg, int64_t num_graphs,
+                             int64_t channels, int dtype, void* stream);
+int egp_segment_max_pool_bwd(const void* dout, const int32_t* arg, const int64_t* batch, void* dx,
+                             int64_t num_nodes, int64_t channels, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGOPACK_B200_H */
