@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Benchmark of EgoPack's temporal-graph hot path on B200 (BASELINE.json metric: graph-nodes/s, forward+backward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--videos V] [--nodes n]
+
+Workload (BASELINE.json configs[1], "c2"): multi-task AR+LTA+PNR training step over ONE shared temporal GNN
+(experiments/mtl.yaml: k=1, hidden 1024, depth 3, TRN hidden 1024, dropout 0.5), synthetic Ego4D-shaped features
+``[N, 3, 1536]`` fp32.  A step = zero_grad + 3 Graph forwards + 3 task heads + losses + ONE backward + gradient
+all-reduce (N>1) + Adam step -- i.e. the body of main_temporal.py:76-130; nothing is skipped.  Per GPU every
+task batch holds ``--videos`` graphs of ``--nodes`` segments (weak scaling: per-GPU work is fixed as N grows).
+
+One JSON line on rank 0.  ``value`` = nodes/s with inputs resident in HBM; ``e2e`` = the same step fed from pinned
+HOST memory every step (H2D of features/labels/structure inside the timed region, D2H of the loss);
+``roofline`` = the dominant kernel family (tcgen05 GEMMs) traced per launch with CUDA events on the launching
+stream; ``cpu_baseline`` = the oracle (CPU restatement of the reference) on a bounded sample of the same workload.
+``--impl reference`` times that CPU oracle alone (the reference's own torch_geometric stack is not installable).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "temporal_graph_nodes_per_sec_fwd_bwd"
+UNIT = "nodes/s"
+TASKS = ("ar", "lta", "pnr")
+HIDDEN, DEPTH, TRN_HIDDEN, DROPOUT, K_RADIUS = 1024, 3, 1024, 0.5, 1
+SEED = 1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--videos", type=int, default=256, help="graphs per task batch per GPU")
+    ap.add_argument("--nodes", type=int, default=128, help="segments (nodes) per graph")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-videos", type=int, default=16, help="graphs per task batch of the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident timing only (for profiler runs)")
+    ap.add_argument("--trace-out", default=None, help="write the per-launch trace summary to this JSON file")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm": p["hbm_gbs"], "tensor_burst": p["bf16_tflops"],
+                "tensor_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (reference restatement) -- used for cpu_baseline and for --impl reference
+# ------------------------------------------------------------------------------------------------------------
+def cpu_oracle_run(videos: int, nodes: int, steps: int, warmup: int):
+    from oracle import egopack_oracle as eo
+    from oracle import pyg_restated as pyg
+    from egopack_b200 import synthetic as syn
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(SEED)
+    model = eo.GraphOracle(syn.FEATURE_DIM, HIDDEN, DEPTH, temporal_pooling={"hidden_size": TRN_HIDDEN, "dropout": DROPOUT},
+                           num_segments=syn.NUM_SEGMENTS)
+    heads = (syn.N_VERBS, syn.N_NOUNS)
+    tasks = {"ar": eo.RecognitionTaskOracle(HIDDEN, HIDDEN, heads), "lta": eo.LTATaskOracle(HIDDEN, HIDDEN, heads),
+             "pnr": eo.PNRTaskOracle(HIDDEN, HIDDEN)}
+    params = list(model.parameters()) + [p for t in tasks.values() for p in t.parameters()]
+    opt = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5)
+    model.train()
+    for t in tasks.values():
+        t.train()
+    gen = syn.generator(SEED, 2, 0)
+    batches = {}
+    for t in TASKS:
+        b = syn.make_batch(t, videos, nodes, gen)
+        d = pyg.Data(x=b.x, pos=b.pos, y=b.y)
+        d.batch, d.ptr = b.batch, b.ptr
+        if t == "lta":                                       # per-sample transform, then collate offsets
+            eis = []
+            for g in range(videos):
+                s = pyg.Data(x=b.x[g * nodes:(g + 1) * nodes], pos=b.pos[g * nodes:(g + 1) * nodes], y=b.y[g * nodes:(g + 1) * nodes])
+                eis.append(eo.lta_temporal_connectivity(s, K_RADIUS + 0.5).edge_index + g * nodes)
+            d.edge_index = torch.cat(eis, 1)
+        else:
+            d.edge_index = pyg.radius_graph(b.pos, K_RADIUS + 0.5, b.batch)
+        batches[t] = d
+    n_nodes = videos * nodes * len(TASKS)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss, _ = eo.mtl_step(model, tasks, batches)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    med = statistics.median(times)
+    return {"value": n_nodes / med, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{len(TASKS)} task batches x {videos} graphs x {nodes} nodes ({n_nodes} nodes/step), fp32, "
+                      f"{steps} timed steps (median {med:.3f} s/step), torch {torch.__version__} CPU, "
+                      f"oracle = CPU restatement of the reference (torch_geometric is not installable here)",
+            "ms_per_step": med * 1e3}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------------------
+def native_run(args, rank: int, world: int, local_rank: int):
+    import egopack_b200
+    from egopack_b200 import _lib, ops, steps
+    from egopack_b200 import synthetic as syn
+    from egopack_b200.dp import GradientAllReduce
+    from egopack_b200.models.graph import Graph
+    from egopack_b200.models.tasks import LTATask, PNRTask, RecognitionTask
+    from egopack_b200.models.transforms import LTATemporalConnectivity
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    egopack_b200.set_precision(args.precision)
+    torch.manual_seed(SEED)                                   # identical replicas on every rank
+    model = Graph(syn.FEATURE_DIM, HIDDEN, DEPTH, temporal_pooling={"hidden_size": TRN_HIDDEN, "dropout": DROPOUT},
+                  num_segments=syn.NUM_SEGMENTS).to(dev)
+    heads = (syn.N_VERBS, syn.N_NOUNS)
+    tasks = {"ar": RecognitionTask(HIDDEN, HIDDEN, heads).to(dev), "lta": LTATask(HIDDEN, HIDDEN, heads).to(dev),
+             "pnr": PNRTask(HIDDEN, HIDDEN).to(dev)}
+    model.train()
+    for t in tasks.values():
+        t.train()
+    params = list(model.parameters()) + [p for t in tasks.values() for p in t.parameters()]
+    opt = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5, fused=True)
+    sync = GradientAllReduce(params) if world > 1 else None
+    lta_edges = LTATemporalConnectivity(r=K_RADIUS + 0.5)
+
+    gen = syn.generator(SEED, 2, rank)                        # every rank draws its own shard of graphs
+    host = {t: syn.make_batch(t, args.videos, args.nodes, gen, band_k=K_RADIUS, pin=True) for t in TASKS}
+    n_nodes = args.videos * args.nodes * len(TASKS)
+    h2d_bytes = sum(v.numel() * v.element_size() for b in host.values() for v in (b.x, b.pos, b.y, b.batch, b.ptr))
+
+    def upload(stream=None):
+        """H2D of one step's inputs + device-side edge/structure construction (what a DataLoader hands over)."""
+        out = {}
+        with torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
+            for t, hb in host.items():
+                d = egopack_b200.Batch()
+                for k in ("x", "pos", "y", "batch", "ptr"):
+                    setattr(d, k, getattr(hb, k).to(dev, non_blocking=True))
+                if t == "lta":
+                    lta_edges(d)                               # band + star edges, on the device
+                else:
+                    d.band_k = K_RADIUS                        # unit-spaced pos: the band needs no edge_index
+                out[t] = d
+        return out
+
+    def step(batches):
+        opt.zero_grad(set_to_none=True)
+        loss, _ = steps.mtl_losses(model, tasks, batches)
+        loss.backward()
+        if sync is not None:
+            sync.finish()
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing ------------------------------------------------------------------------
+    resident = upload()
+    for _ in range(args.warmup):
+        step(resident)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    _lib.CALL_COUNTS.clear()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(resident)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clock_info = clocks.stop()
+    launches = _lib.kernel_launches()
+    ms_per_step = ms_total / args.steps
+    value = world * n_nodes / (ms_per_step / 1e3)
+
+    if args.quick:
+        return {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "gpu_launches": int(launches), "quick": True}
+
+    # ---- end-to-end timing: pinned host -> device every step, loss read back every step -------------------
+    copy_stream = torch.cuda.Stream()
+    for _ in range(2):
+        b = upload(copy_stream)
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        float(step(b).item())
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    nxt = upload(copy_stream)
+    for i in range(args.steps):
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        cur = nxt
+        for d in cur.values():                                 # keep the allocator honest across streams
+            for k in ("x", "pos", "y", "batch", "ptr"):
+                getattr(d, k).record_stream(torch.cuda.current_stream())
+        loss = step(cur)                                       # enqueue this step's kernels first ...
+        if i + 1 < args.steps:
+            nxt = upload(copy_stream)                          # ... so the next step's copy overlaps them
+        last = float(loss.item())                              # D2H of the loss every step
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e_value = world * n_nodes / (e2e_ms / 1e3)
+
+    # ---- per-launch trace for the roofline (separate, untimed steps) ---------------------------------------
+    pk = peaks()
+    ops.TRACE = []
+    for _ in range(2):
+        step(resident)
+    torch.cuda.synchronize()
+    trace, ops.TRACE = ops.TRACE, None
+    agg = {}
+    for name, work, unit, a, b in trace:
+        r = agg.setdefault(name, {"work": 0.0, "ms": 0.0, "n": 0, "unit": unit})
+        r["work"] += work
+        r["ms"] += a.elapsed_time(b)
+        r["n"] += 1
+    roof, roof_hbm = None, None
+    if "gemm_tcgen05" in agg or "gemm_ffma" in agg:
+        g = agg.get("gemm_tcgen05") or agg["gemm_ffma"]
+        ach = g["work"] / (g["ms"] / 1e3) / 1e12
+        peak = pk["tensor_sustained"]
+        roof = {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05/TMEM/TMA)" if "gemm_tcgen05" in agg else "sgemm_kernel",
+                "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None,
+                "launches_per_step": g["n"] // 2, "ms_per_step": round(g["ms"] / 2, 3),
+                "share_of_step": round(g["ms"] / 2 / ms_per_step, 3), "peak_source": f"{pk['source']} (sustained bf16 GEMM)"}
+    for nme in ("sage_mean_band", "sage_mean_csr"):
+        if nme in agg:
+            a = agg[nme]
+            ach = a["work"] / (a["ms"] / 1e3) / 1e9
+            r = {"bound": "hbm", "kernel": nme, "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
+                 "frac": round(ach / pk["hbm"], 4), "traffic": None, "launches_per_step": a["n"] // 2,
+                 "ms_per_step": round(a["ms"] / 2, 3), "peak_source": pk["source"]}
+            roof_hbm = roof_hbm or []
+            roof_hbm.append(r)
+    if args.trace_out and rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(args.trace_out)), exist_ok=True)
+        json.dump({k: {**v, "ms_per_step": v["ms"] / 2} for k, v in agg.items()}, open(args.trace_out, "w"), indent=1)
+
+    out = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": "c2: MTL AR+LTA+PNR shared temporal GNN (experiments/mtl.yaml: k=1, hidden 1024, depth 3, "
+                               "TRN hidden 1024, dropout 0.5), full train step = zero_grad+fwd+loss+bwd+grad-allreduce+Adam",
+                   "graphs_per_task_per_gpu": args.videos, "nodes_per_graph": args.nodes,
+                   "nodes_per_step_per_gpu": n_nodes, "features": "[N,3,1536] fp32 N(0,1)", "parallelism": f"dp{world}",
+                   "l2": f"inputs larger than L2 ({h2d_bytes / 2**20:.0f} MiB of features per step)",
+                   "final_loss": round(last, 4)},
+        "clocks": clock_info,
+        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
+                "ms_per_step": round(e2e_ms, 3), "note": "pinned host -> device copy of every step's inputs on a copy stream "
+                                                          "(overlapping the previous step), device-side edge construction, loss.item() per step"},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+    }
+    if roof_hbm:
+        out["roofline_hbm"] = roof_hbm
+    return out
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_oracle_run(args.cpu_videos, args.nodes, max(args.steps, 1), min(args.warmup, 2))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": round(r["value"], 1), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": round(r["ms_per_step"], 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "c2: MTL AR+LTA+PNR shared temporal GNN, full train step (CPU oracle, bounded sample)",
+                       "graphs_per_task": args.cpu_videos, "nodes_per_graph": args.nodes},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": round(r["value"], 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device; there is no CPU fallback. Use --impl reference for the CPU arm.")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    out = native_run(args, rank, world, local_rank)
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1 and not args.quick:
+            r = cpu_oracle_run(args.cpu_videos, args.nodes, 3, 1)
+            out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        elif not args.no_cpu_baseline:
+            out["cpu_baseline"] = None
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -108,9 +108,28 @@ def check(rc: int, name: str):
         raise RuntimeError(f"{name} failed (status {rc}): {last_error()}")
 
 
+CALL_COUNTS: Dict[str, int] = {}
+
+# kernels launched per entry-point call (memsets excluded) -- used by bench.py's `gpu_launches` claim
+KERNELS_PER_CALL = {
+    "egp_band_edge_count": 1, "egp_band_edge_fill": 1, "egp_exclusive_scan_i32": 1, "egp_lta_edge_count": 1,
+    "egp_lta_edge_fill": 1, "egp_band_windows": 1, "egp_csr_build": 4, "egp_csr_inv_degree": 1,
+    "egp_sage_mean_band": 1, "egp_sage_mean_csr": 1, "egp_graph_layernorm_fwd": 2, "egp_graph_layernorm_bwd": 3,
+    "egp_row_layernorm_fwd": 1, "egp_row_layernorm_bwd": 2, "egp_posenc_add": 1, "egp_cast": 1, "egp_add": 1,
+    "egp_axpby": 1, "egp_act_bwd": 1, "egp_colsum": 2, "egp_mask_scale": 1, "egp_gemm": 1, "egp_row_normalize": 1,
+    "egp_row_inv_norm": 1, "egp_cos_topk": 3, "egp_proto_max_gather": 1, "egp_max_combine_fwd": 1,
+    "egp_max_combine_bwd": 1, "egp_segment_max_pool_fwd": 1, "egp_segment_max_pool_bwd": 1,
+}
+
+
 def call(name: str, *args):
     rc = getattr(load(), name)(*args)
+    CALL_COUNTS[name] = CALL_COUNTS.get(name, 0) + 1
     check(rc, name)
+
+
+def kernel_launches() -> int:
+    return sum(n * KERNELS_PER_CALL.get(k, 1) for k, n in CALL_COUNTS.items())
 
 
 def size(name: str, *args) -> int:

@@ -5,6 +5,7 @@ PyTorch supplies device memory, streams and autograd bookkeeping; every arithmet
 """
 from __future__ import annotations
 
+import weakref
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -15,6 +16,30 @@ from . import _lib as L
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 F32, BF16 = 0, 1
+
+
+# Optional per-launch tracing for bench.py's roofline numbers: when TRACE is a list, traced ops append
+# (name, work, unit, start_event, end_event) with CUDA events recorded on the launching (current) stream.
+TRACE = None
+
+
+class _Traced:
+    def __init__(self, name: str, work: float, unit: str):
+        self.on = TRACE is not None
+        if self.on:
+            self.name, self.work, self.unit = name, work, unit
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def __enter__(self):
+        if self.on:
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.e1.record()
+            TRACE.append((self.name, self.work, self.unit, self.e0, self.e1))
+        return False
 
 
 def _code(t: Tensor) -> int:
@@ -36,6 +61,8 @@ def band_edge_index(pos: Tensor, batch: Tensor, ptr: Tensor, r: float, max_num_n
     """``RadiusGraph(r, loop=False)`` over a batch of graphs: int64 [2,E], dst-major, src ascending."""
     pos, batch, ptr = _c(pos.view(-1)), _c(batch), _c(ptr)
     n = pos.numel()
+    if n == 0:
+        return torch.empty((2, 0), dtype=torch.int64, device=pos.device)
     if monotone is None:
         monotone = True if n < 2 else bool(((pos[1:] >= pos[:-1]) | (batch[1:] != batch[:-1])).all().item())
     deg = torch.empty(n, dtype=torch.int32, device=pos.device)
@@ -54,6 +81,8 @@ def lta_edge_index(pos: Tensor, y: Tensor, batch: Tensor, ptr: Tensor, r: float,
     """``LTATemporalConnectivity(r)`` applied per graph of a batch: int64 [2,E] sorted by (src,dst)."""
     pos, y, batch, ptr = _c(pos.view(-1)), _c(y), _c(batch), _c(ptr)
     n = pos.numel()
+    if n == 0:
+        return torch.empty((2, 0), dtype=torch.int64, device=pos.device)
     ycols = y.shape[1] if y.dim() > 1 else 1
     deg = torch.empty(n, dtype=torch.int32, device=pos.device)
     L.call("egp_lta_edge_count", L.ptr(pos), L.ptr(y), ycols, L.ptr(batch), L.ptr(ptr), n, float(r),
@@ -115,6 +144,12 @@ def _aggregate(x: Tensor, gs: GraphStructure, backward: bool) -> Tensor:
     n, c = x.shape
     out = torch.empty_like(x)
     so, si = (None, gs.inv_deg) if backward else (gs.inv_deg, None)
+    with _Traced("sage_mean_band" if gs.band_k is not None else "sage_mean_csr", 2.0 * n * c * x.element_size(), "B"):
+        _aggregate_launch(x, out, gs, backward, so, si, n, c)
+    return out
+
+
+def _aggregate_launch(x, out, gs, backward, so, si, n, c):
     if gs.band_k is not None:
         L.call("egp_sage_mean_band", L.ptr(x), L.ptr(out), n, c, c, c, gs.band_k, L.ptr(gs.win_lo), L.ptr(gs.win_hi),
                L.ptr(so), L.ptr(si), _code(x), L.stream())
@@ -122,7 +157,6 @@ def _aggregate(x: Tensor, gs: GraphStructure, backward: bool) -> Tensor:
         rp, col = (gs.rowptr_out, gs.col_out) if backward else (gs.rowptr_in, gs.col_in)
         L.call("egp_sage_mean_csr", L.ptr(x), L.ptr(out), n, c, c, c, L.ptr(rp), L.ptr(col), L.ptr(so), L.ptr(si),
                _code(x), L.stream())
-    return out
 
 
 class SageMean(torch.autograd.Function):
@@ -155,12 +189,18 @@ def gemm(a: Tensor, a_trans: bool, b: Tensor, b_trans: bool, m: int, n: int, k: 
         assert bias.dtype == torch.float32
     if residual is not None:
         assert residual.dtype == out.dtype and residual.shape == out.shape
+    name = "gemm_tcgen05" if a.dtype == torch.bfloat16 else "gemm_ffma"
+    with _Traced(name, 2.0 * m * n * (k + k2), "FLOP"):
+        _gemm_launch(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate)
+    return out
+
+
+def _gemm_launch(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate):
     L.call("egp_gemm", L.ptr(a), a.stride(0), int(a_trans), L.ptr(b), b.stride(0), int(b_trans),
            L.ptr(a2), a2.stride(0) if a2 is not None else 0, L.ptr(b2), b2.stride(0) if b2 is not None else 0, int(k2),
            L.ptr(_c(bias)), L.ptr(residual), residual.stride(0) if residual is not None else 0,
            L.ptr(out), out.stride(0), m, n, k, int(act), float(slope), _code(a), L.DTYPE_CODE[out.dtype],
            int(accumulate), None, 0, L.stream())
-    return out
 
 
 def colsum(x: Tensor) -> Tensor:
@@ -224,7 +264,10 @@ class Scale(torch.autograd.Function):
 
 
 class _WeightCache:
-    """bf16 copies of fp32 parameters, refreshed when the parameter is updated in place (optimizer step)."""
+    """bf16 copies of fp32 parameters, refreshed when the parameter is updated in place (optimizer step).
+
+    Entries are keyed by storage address but validated through a weak reference to the source tensor, so a new
+    parameter that happens to reuse a freed address can never pick up a stale copy."""
 
     def __init__(self):
         self._store = {}
@@ -234,10 +277,14 @@ class _WeightCache:
             return w
         key = (w.data_ptr(), tuple(w.shape), dtype)
         hit = self._store.get(key)
-        if hit is not None and hit[0] == w._version:
-            return hit[1]
+        if hit is not None:
+            src = hit[0]()
+            if src is not None and src.data_ptr() == w.data_ptr() and hit[1] == w._version:
+                return hit[2]
         c = cast(w.detach(), dtype)
-        self._store[key] = (w._version, c)
+        if len(self._store) > 4096:
+            self._store = {k: v for k, v in self._store.items() if v[0]() is not None}
+        self._store[key] = (weakref.ref(w), w._version, c)
         return c
 
 

@@ -1,0 +1,110 @@
+"""GPU parity: integer work (edge_index construction, CSR) must be bit-exact against the oracle."""
+import pytest
+import torch
+
+from egopack_b200 import Batch, Data, ops
+from egopack_b200.models.transforms import LTATemporalConnectivity, RadiusGraph
+from oracle import egopack_oracle as eo
+from oracle import pyg_restated as pyg
+from tests.gpu_util import DEV, canon_edges, graph_sizes_to_index
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("r", [0.5, 1.5, 2.5, 8.5, 16.5, 20.5])
+def test_band_edges_match_radius_graph(r):
+    sizes = [1, 2, 7, 40, 3, 100, 33, 34]
+    batch, ptr = graph_sizes_to_index(sizes)
+    pos = torch.cat([torch.arange(s) - 4 for s in sizes])           # AR-style shifted positions (ego4d_fho.py:224)
+    want = pyg.radius_graph(pos, r, batch)
+    got = ops.band_edge_index(pos.to(DEV), batch.to(DEV), ptr.to(DEV), r)
+    assert got.dtype == torch.int64 and got.shape == want.shape
+    assert canon_edges(got) == canon_edges(want)
+    dst = got[1].cpu()
+    assert bool((dst[1:] >= dst[:-1]).all()), "canonical order is dst-major"
+
+
+def test_band_edges_unsorted_and_repeated_positions():
+    g = torch.Generator().manual_seed(1)
+    sizes = [9, 1, 30, 17]
+    batch, ptr = graph_sizes_to_index(sizes)
+    pos = torch.cat([torch.randint(0, 12, (s,), generator=g) for s in sizes])
+    for r in (1.5, 3.5):
+        want = pyg.radius_graph(pos, r, batch)
+        got = ops.band_edge_index(pos.to(DEV), batch.to(DEV), ptr.to(DEV), r)
+        assert canon_edges(got) == canon_edges(want)
+
+
+def test_band_edges_empty_and_single():
+    z = torch.zeros(0, dtype=torch.long, device=DEV)
+    got = ops.band_edge_index(z, z, torch.zeros(1, dtype=torch.long, device=DEV), 1.5)
+    assert got.shape == (2, 0)
+    one = ops.band_edge_index(torch.zeros(1, dtype=torch.long, device=DEV), torch.zeros(1, dtype=torch.long, device=DEV),
+                              torch.tensor([0, 1], device=DEV), 1.5)
+    assert one.shape == (2, 0)
+
+
+def test_band_edges_long_video_count_and_order():
+    """config 4 shape: 2048-node graphs, k=16 -- closed-form edge count, sortedness, symmetry."""
+    v, n, k = 64, 2048, 16
+    pos = torch.arange(n).repeat(v).to(DEV)
+    batch = torch.arange(v).repeat_interleave(n).to(DEV)
+    ptr = (torch.arange(v + 1) * n).to(DEV)
+    e = ops.band_edge_index(pos, batch, ptr, k + 0.5)
+    assert e.shape[1] == v * (2 * k * n - k * (k + 1))
+    src, dst = e[0], e[1]
+    assert bool((dst[1:] >= dst[:-1]).all())
+    same = dst[1:] == dst[:-1]
+    assert bool((src[1:][same] > src[:-1][same]).all())
+    assert bool(((src - dst).abs() <= k).all()) and bool((src != dst).all())
+    assert bool((batch[src] == batch[dst]).all())
+    key = lambda a, b: a * (v * n) + b
+    assert torch.equal(key(src, dst).sort().values, key(dst, src).sort().values)     # symmetric
+
+
+def test_radius_graph_transform_sets_band_hint():
+    d = Batch.from_data_list([Data(x=torch.zeros(5, 1), pos=torch.arange(5) - 2), Data(x=torch.zeros(3, 1), pos=torch.arange(3))])
+    d = RadiusGraph(r=1.5)(d)
+    assert d.band_k == 1 and d.edge_index.device.type == "cpu"
+    want = pyg.radius_graph(d.pos, 1.5, d.batch)
+    assert canon_edges(d.edge_index) == canon_edges(want)
+    d2 = Data(x=torch.zeros(4, 1), pos=torch.tensor([0, 2, 4, 6]))
+    assert RadiusGraph(r=2.5)(d2).band_k is None                     # not unit spaced -> generic CSR path
+
+
+def test_lta_connectivity_golden_and_random(golden):
+    for case in golden("lta_edges.pt"):
+        n = case["y"].shape[0]
+        d = LTATemporalConnectivity(r=case["r"])(Data(x=torch.zeros(n, 1), y=case["y"], pos=torch.arange(n)))
+        assert torch.equal(d.edge_index, case["edge_index"])
+    g = torch.Generator().manual_seed(2)
+    graphs, want, off = [], [], 0
+    for _ in range(12):
+        n_in, n_fc = int(torch.randint(1, 5, (1,), generator=g)), int(torch.randint(1, 21, (1,), generator=g))
+        y = torch.full((n_in + n_fc, 2), -1, dtype=torch.long)
+        y[n_in:, 0] = torch.randint(0, 5, (n_fc,), generator=g)      # verb 0 appears: the `> 0` quirk is exercised
+        y[n_in:, 1] = torch.randint(0, 5, (n_fc,), generator=g)
+        n = n_in + n_fc
+        graphs.append(Data(x=torch.zeros(n, 1), y=y, pos=torch.arange(n)))
+        ref = eo.lta_temporal_connectivity(pyg.Data(x=torch.zeros(n, 1), y=y, pos=torch.arange(n)), 2.5)
+        want.append(ref.edge_index + off)
+        off += n
+    b = LTATemporalConnectivity(r=2.5)(Batch.from_data_list(graphs))
+    assert torch.equal(b.edge_index, torch.cat(want, 1))
+    with pytest.raises(ValueError):
+        LTATemporalConnectivity(r=2.5, strict=True)(b)
+
+
+def test_csr_structure_is_deterministic_and_complete():
+    g = torch.Generator().manual_seed(3)
+    n, e = 200, 1500
+    ei = torch.randint(0, n, (2, e), generator=g)
+    gs = ops.csr_structure(ei.to(DEV), n)
+    for rowptr, col, key, val in ((gs.rowptr_in, gs.col_in, ei[1], ei[0]), (gs.rowptr_out, gs.col_out, ei[0], ei[1])):
+        rowptr, col = rowptr.cpu().long(), col.cpu().long()
+        assert rowptr[0] == 0 and rowptr[-1] == e
+        for i in range(n):
+            want = sorted(val[key == i].tolist())
+            assert col[rowptr[i]:rowptr[i + 1]].tolist() == want
+    deg = torch.bincount(ei[1], minlength=n).clamp(min=1).float()
+    assert torch.allclose(gs.inv_deg.cpu(), 1.0 / deg)

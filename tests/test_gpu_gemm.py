@@ -1,0 +1,102 @@
+"""GPU parity of ``egp_gemm``: the tcgen05/TMEM/TMA bf16 kernel and the fp32 FFMA kernel, every operand layout the
+path uses (forward, dgrad, wgrad + split-K, dual-operand SAGE form), epilogues, ragged sizes."""
+import pytest
+import torch
+
+from egopack_b200 import ops
+from tests.gpu_util import DEV, rel_max
+
+pytestmark = pytest.mark.gpu
+BF, F32 = torch.bfloat16, torch.float32
+
+
+def run_case(dtype, m, n, k, a_trans=False, b_trans=False, k2=0, bias=False, act=0, residual=False, out_dtype=None, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    q = lambda t: None if t is None else t.to(dtype)
+    A = q(torch.randn((k, m) if a_trans else (m, k), generator=g))
+    B = q(torch.randn((k, n) if b_trans else (n, k), generator=g))
+    A2 = q(torch.randn((k2, m) if a_trans else (m, k2), generator=g)) if k2 else None
+    B2 = q(torch.randn((k2, n) if b_trans else (n, k2), generator=g)) if k2 else None
+    bi = torch.randn(n, generator=g) if bias else None
+    out_dtype = out_dtype or dtype
+    R = torch.randn(m, n, generator=g).to(out_dtype) if residual else None
+    mm = lambda a, b: (a.double().t() if a_trans else a.double()) @ (b.double() if b_trans else b.double().t())
+    ref = mm(A, B) + (mm(A2, B2) if k2 else 0)
+    if bias:
+        ref = ref + bi.double()
+    ref = ref.relu() if act == 1 else (torch.where(ref > 0, ref, 0.2 * ref) if act == 2 else ref)
+    if residual:
+        ref = ref + R.double()
+    d = lambda t: None if t is None else t.to(DEV)
+    out = ops.gemm(d(A), a_trans, d(B), b_trans, m, n, k, a2=d(A2), b2=d(B2), k2=k2, bias=d(bi), residual=d(R), act=act,
+                   slope=0.2, out_dtype=out_dtype)
+    assert out.dtype == out_dtype and out.shape == (m, n)
+    # products of bf16 inputs are exact in fp32; only accumulation order and the output rounding differ
+    tol = 1e-2 if out_dtype == BF else (2e-5 if k + k2 <= 8192 else 2e-4)   # fp32 accumulation grows ~sqrt(K)
+    assert rel_max(out, ref) < tol, (m, n, k, a_trans, b_trans)
+
+
+FWD = [dict(m=128, n=256, k=64), dict(m=128, n=128, k=128), dict(m=128, n=64, k=128), dict(m=128, n=32, k=128),
+       dict(m=128, n=16, k=128), dict(m=1024, n=1024, k=512), dict(m=300, n=520, k=200), dict(m=19, n=32, k=72),
+       dict(m=19, n=32, k=40), dict(m=2048, n=1024, k=4608), dict(m=200, n=115, k=1024), dict(m=200, n=478, k=1024),
+       dict(m=130, n=2, k=1024), dict(m=130, n=1, k=1024)]
+
+
+@pytest.mark.parametrize("kw", FWD)
+def test_tc_forward_layout(kw):
+    run_case(BF, out_dtype=F32, **kw)
+    run_case(BF, bias=True, act=1, **kw)
+
+
+@pytest.mark.parametrize("kw", [dict(m=128, n=256, k=64), dict(m=1024, n=1024, k=512), dict(m=300, n=200, k=120),
+                                dict(m=19, n=72, k=40), dict(m=2048, n=4608, k=1024), dict(m=333, n=1024, k=120)])
+def test_tc_dgrad_layout(kw):
+    run_case(BF, b_trans=True, out_dtype=F32, **kw)
+    run_case(BF, b_trans=True, k2=kw["k"], **kw)
+
+
+@pytest.mark.parametrize("kw", [dict(m=128, n=256, k=64), dict(m=256, n=512, k=8192), dict(m=120, n=1000, k=2048),
+                                dict(m=40, n=72, k=19), dict(m=1024, n=4608, k=2048), dict(m=1024, n=1024, k=32768)])
+def test_tc_wgrad_layout_split_k(kw):
+    run_case(BF, a_trans=True, b_trans=True, out_dtype=F32, **kw)
+
+
+def test_tc_dual_and_epilogues():
+    run_case(BF, 512, 256, 256, k2=320, bias=True)
+    run_case(BF, 384, 512, 192, bias=True, residual=True)
+    run_case(BF, 384, 512, 192, bias=True, residual=True, out_dtype=F32)
+    run_case(BF, 200, 115, 1024, bias=True, act=2, out_dtype=F32)
+    run_case(BF, 128, 128, 512, k2=512, a_trans=True, b_trans=True, out_dtype=F32)
+    run_case(BF, 128, 128, 256, a_trans=True, out_dtype=F32)
+
+
+@pytest.mark.parametrize("kw", [dict(m=100, n=70, k=50), dict(m=300, n=130, k=77, b_trans=True, bias=True, act=1),
+                                dict(m=64, n=200, k=300, a_trans=True, b_trans=True),
+                                dict(m=256, n=128, k=96, k2=64, bias=True, residual=True), dict(m=1024, n=1024, k=1024)])
+def test_ffma_fp32(kw):
+    run_case(F32, **kw)
+
+
+def test_ffma_serves_bf16_operands_tma_cannot_address():
+    run_case(BF, 100, 7, 36, out_dtype=F32)              # K=36: row stride 72 B, not a multiple of 16 B
+
+
+def test_linear_autograd_matches_torch():
+    g = torch.Generator().manual_seed(0)
+    for dtype, tol in ((F32, 1e-4), (BF, 2e-2)):
+        m, k, n = 257, 192, 115                            # n=115: padded class dim in the bf16 backward
+        x = torch.randn(m, k, generator=g)
+        w = (torch.randn(n, k, generator=g) / k ** 0.5).requires_grad_(True)
+        b = torch.randn(n, generator=g).requires_grad_(True)
+        dy = torch.randn(m, n, generator=g)
+        xr = x.to(dtype).float().clone().requires_grad_(True)
+        want = torch.nn.functional.linear(xr, w.to(dtype).float() if dtype == BF else w, b)
+        want.backward(dy)
+        gw_ref, gb_ref = w.grad.clone(), b.grad.clone()
+        xd = x.to(dtype).to(DEV).requires_grad_(True)
+        wd, bd = w.detach().to(DEV).requires_grad_(True), b.detach().to(DEV).requires_grad_(True)
+        y = ops.linear(xd, wd, bd, out_dtype=F32)
+        y.backward(dy.to(DEV))
+        assert rel_max(y, want) < tol and rel_max(xd.grad, xr.grad) < tol
+        assert rel_max(wd.grad, gw_ref) < tol and rel_max(bd.grad, gb_ref) < tol
+        assert wd.grad.dtype == F32

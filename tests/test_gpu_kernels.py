@@ -1,0 +1,176 @@
+"""GPU parity of the memory-bound kernels against the oracle's third-party restatement (same seeded inputs)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from egopack_b200 import ops
+from egopack_b200.ops import ACT_LEAKY, ACT_NONE, ACT_RELU
+from oracle import pyg_restated as pyg
+from tests.gpu_util import DEV, TOL_BF16, TOL_F32, graph_sizes_to_index, rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+DTYPES = [(torch.float32, TOL_F32), (torch.bfloat16, TOL_BF16)]
+
+
+def band_edges(batch, k):
+    n = batch.numel()
+    idx = torch.arange(n)
+    a = ((idx[:, None] - idx[None, :]).abs() <= k) & (batch[:, None] == batch[None, :]) & (idx[:, None] != idx[None, :])
+    dst, src = a.nonzero(as_tuple=True)
+    return torch.stack([src, dst])
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+@pytest.mark.parametrize("k", [1, 2, 5, 16])
+def test_sage_mean_band_and_csr_forward_backward(dtype, tol, k):
+    g = torch.Generator().manual_seed(k)
+    sizes = [5, 1, 300, 64, 2, 407]
+    batch, ptr = graph_sizes_to_index(sizes)
+    n, c = batch.numel(), 264
+    x = torch.randn(n, c, generator=g).to(dtype)
+    w = torch.randn(n, c, generator=g).to(dtype)
+    ei = band_edges(batch, k)
+    xr = x.float().clone().requires_grad_(True)
+    want = pyg.scatter(xr.index_select(0, ei[0]), ei[1], 0, n, "mean")      # what SAGEConv's propagate does
+    want.backward(w.float())
+    for gs in (ops.band_structure(batch.to(DEV), ptr.to(DEV), k), ops.csr_structure(ei.to(DEV), n)):
+        xd = x.detach().to(DEV).requires_grad_(True)
+        y = ops.SageMean.apply(xd, gs)
+        y.backward(w.to(DEV))
+        assert y.dtype == dtype
+        assert rel_max(y, want) < tol and rel_max(xd.grad, xr.grad) < tol
+    if dtype == torch.float32 and k <= 4:                                   # direct window sum is order-exact
+        gs = ops.band_structure(batch.to(DEV), ptr.to(DEV), k)
+        y = ops.SageMean.apply(x.to(DEV), gs)
+        assert rel_max(y, want) < 2e-7
+
+
+def test_sage_mean_isolated_nodes_and_directed_star():
+    # node 3 has no in-edges (mean of nothing = 0); star edges are directed (LTA connectivity)
+    ei = torch.tensor([[0, 1, 0, 1, 2], [1, 0, 4, 4, 4]])
+    x = torch.arange(5 * 8, dtype=torch.float32).view(5, 8)
+    xr = x.clone().requires_grad_(True)
+    want = pyg.scatter(xr.index_select(0, ei[0]), ei[1], 0, 5, "mean")
+    want.sum().backward()
+    xd = x.detach().to(DEV).requires_grad_(True)
+    y = ops.SageMean.apply(xd, ops.csr_structure(ei.to(DEV), 5))
+    y.sum().backward()
+    assert torch.equal(y.cpu(), want.detach()) and torch.allclose(xd.grad.cpu(), xr.grad)
+    assert float(y[3].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+@pytest.mark.parametrize("n,c", [(19, 32), (777, 256), (2048, 1024)])
+def test_graph_layernorm_leaky_relu(dtype, tol, n, c):
+    g = torch.Generator().manual_seed(n)
+    x = (torch.randn(n, c, generator=g) * 1.7 + 0.3).to(dtype)
+    dy = torch.randn(n, c, generator=g).to(dtype)
+    ln = pyg.LayerNorm(c)
+    with torch.no_grad():
+        ln.weight.copy_(torch.randn(c, generator=g) * 0.5 + 1)
+        ln.bias.copy_(torch.randn(c, generator=g) * 0.1)
+    xr = x.float().clone().requires_grad_(True)
+    want = F.leaky_relu(ln(xr), 0.2)                                         # models/graph.py:43-44
+    want.backward(dy.float())
+    xd = x.detach().to(DEV).requires_grad_(True)
+    wd, bd = ln.weight.detach().to(DEV).requires_grad_(True), ln.bias.detach().to(DEV).requires_grad_(True)
+    y = ops.GraphLayerNorm.apply(xd, wd, bd, 1e-5, ACT_LEAKY, 0.2)
+    y.backward(dy.to(DEV))
+    assert rel_max(y, want) < tol and rel_max(xd.grad, xr.grad) < tol
+    gtol = tol if dtype == torch.float32 else 5 * tol
+    assert rel_max(wd.grad, ln.weight.grad) < gtol and rel_max(bd.grad, ln.bias.grad) < gtol
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+@pytest.mark.parametrize("c,act", [(32, ACT_RELU), (40, ACT_RELU), (1024, ACT_RELU), (256, ACT_NONE), (4096, ACT_RELU)])
+def test_row_layernorm(dtype, tol, c, act):
+    g = torch.Generator().manual_seed(c)
+    n = 333
+    x = (torch.randn(n, c, generator=g) * 2 - 0.5).to(dtype)
+    dy = torch.randn(n, c, generator=g).to(dtype)
+    w = (torch.randn(c, generator=g) * 0.5 + 1).requires_grad_(True)
+    b = (torch.randn(c, generator=g) * 0.1).requires_grad_(True)
+    xr = x.float().clone().requires_grad_(True)
+    want = F.layer_norm(xr, (c,), w, b, 1e-5)
+    want = want.relu() if act == ACT_RELU else want
+    want.backward(dy.float())
+    xd = x.detach().to(DEV).requires_grad_(True)
+    wd, bd = w.detach().to(DEV).requires_grad_(True), b.detach().to(DEV).requires_grad_(True)
+    y = ops.RowLayerNorm.apply(xd, wd, bd, 1e-5, act)
+    y.backward(dy.to(DEV))
+    assert rel_max(y, want) < tol and rel_max(xd.grad, xr.grad) < tol
+    gtol = tol if dtype == torch.float32 else 5 * tol
+    assert rel_max(wd.grad, w.grad) < gtol and rel_max(bd.grad, b.grad) < gtol
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_positional_encoding_add(dtype, tol):
+    g = torch.Generator().manual_seed(0)
+    n, c = 300, 128
+    x = torch.randn(n, c, generator=g).to(dtype)
+    pos = torch.randint(-4, 2048, (n,), generator=g)
+    pe = pyg.PositionalEncoding(c)
+    want = x.float() + pe(pos)
+    y = ops.PosEncAdd.apply(x.to(DEV), pos.to(DEV), pe.frequency.to(DEV))
+    assert rel_max(y, want) < (1e-6 if dtype == torch.float32 else tol)
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_segment_max_pool(dtype, tol):
+    g = torch.Generator().manual_seed(0)
+    sizes = [4, 1, 16, 128, 7]
+    batch, ptr = graph_sizes_to_index(sizes)
+    n, c = batch.numel(), 96
+    # distinct small integers per column: exact in bf16 and tie-free (with ties the reference's CPU scatter splits
+    # the gradient while its CUDA torch_scatter path -- and this kernel -- credit the first arg-max)
+    x = torch.stack([torch.randperm(n, generator=g) for _ in range(c)], 1).float().sub(70).to(dtype)
+    dy = torch.randn(len(sizes), c, generator=g).to(dtype)
+    xr = x.float().clone().requires_grad_(True)
+    want = pyg.global_max_pool(xr, batch)
+    want.backward(dy.float())
+    xd = x.detach().to(DEV).requires_grad_(True)
+    y = ops.SegmentMaxPool.apply(xd, ptr.to(DEV), batch.to(DEV))
+    y.backward(dy.to(DEV))
+    assert torch.equal(y.float().cpu(), want.detach()) and rel_max(xd.grad, xr.grad) < 1e-6
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_prototype_max_gather_and_combine(dtype, tol):
+    g = torch.Generator().manual_seed(0)
+    b, kp, c, k = 200, 57, 64, 4
+    # odd/even multiples of 1/32: exact in bf16, f never ties with a prototype value
+    bank = (torch.randint(-60, 60, (kp, c), generator=g) * 2 / 32.0).to(dtype)
+    idx = torch.randint(0, kp, (b, k), generator=g)
+    f = ((torch.randint(-60, 60, (b, c), generator=g) * 2 + 1) / 32.0).to(dtype)
+    da = torch.randn(b, c, generator=g).to(dtype)
+    m = ops.proto_max_gather(bank.to(DEV), idx.to(DEV))
+    want_m = bank.float()[idx].max(1).values
+    assert torch.equal(m.float().cpu(), want_m)
+    fr = f.float().clone().requires_grad_(True)
+    want = torch.maximum(fr, want_m)
+    want.backward(da.float())
+    fd = f.detach().to(DEV).requires_grad_(True)
+    a = ops.MaxCombine.apply(fd, m)
+    a.backward(da.to(DEV))
+    assert torch.equal(a.float().cpu(), want.detach()) and torch.equal(fd.grad.float().cpu(), fr.grad)
+
+
+def test_colsum_cast_axpby_dropout():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1001, 520, generator=g)
+    assert rel_max(ops.colsum(x.to(DEV)), x.double().sum(0)) < 1e-5
+    x7 = torch.randn(501, 7, generator=g)                                     # ragged classifier-width columns
+    assert rel_max(ops.colsum(x7.to(DEV)), x7.double().sum(0)) < 1e-5
+    xb = ops.cast(x.to(DEV), torch.bfloat16)
+    assert torch.equal(xb.cpu(), x.to(torch.bfloat16))
+    assert torch.equal(ops.cast(xb, torch.float32).cpu(), x.to(torch.bfloat16).float())
+    y = torch.randn(1001, 520, generator=g)
+    assert rel_max(ops.axpby(x.to(DEV), 0.5, y.to(DEV), -2.0), 0.5 * x - 2.0 * y) < 1e-6
+    assert rel_max(ops.axpby(x7.to(DEV), 0.25), 0.25 * x7) < 1e-6
+    xd = torch.ones(4096, 256, device=DEV, requires_grad=True)
+    out = ops.dropout(xd, 0.5, True)
+    out.sum().backward()
+    keep = out > 0
+    assert 0.45 < float(keep.float().mean()) < 0.55
+    assert torch.equal(out, keep.float() * 2.0) and torch.equal(xd.grad, keep.float() * 2.0)
+    assert ops.dropout(xd, 0.5, False) is xd

@@ -1,0 +1,269 @@
+"""GPU parity of the drop-in modules against the golden fixtures (produced by the reference's own model code) and
+against the oracle on seeded synthetic batches: fp32 mode within 1e-4, bf16 tensor-core mode within 2e-2."""
+import pytest
+import torch
+
+import egopack_b200
+from egopack_b200 import Batch, Data, steps
+from egopack_b200 import synthetic as syn
+from egopack_b200.models.graph import Graph
+from egopack_b200.models.graphONE.graphONE import GraphONE
+from egopack_b200.models.tasks import LTATask, OSCCTask, PNRTask, RecognitionTask
+from egopack_b200.models.transforms import LTATemporalConnectivity, RadiusGraph
+from oracle import egopack_oracle as eo
+from oracle import pyg_restated as pyg
+from tests.gpu_util import DEV, TOL_BF16, TOL_F32, rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+TP = {"_target_": "models.temporal_pooling.trn_pooling.TRNPooling", "dropout": 0.0}
+
+
+@pytest.fixture(autouse=True)
+def _restore_precision():
+    yield
+    egopack_b200.set_precision("bf16")
+
+
+def golden_graph(golden, struct):
+    g = golden("graph_band.pt")
+    c = g["cfg"]
+    m = Graph(c["input_size"], c["hidden_size"], c["depth"], temporal_pooling=dict(TP, hidden_size=c["trn_hidden"]),
+              num_segments=c["num_segments"]).to(DEV)
+    m.load_state_dict(g["state"])
+    d = Data(x=g["x"].clone().to(DEV).requires_grad_(True), pos=g["pos"].to(DEV), edge_index=g["edge_index"].to(DEV))
+    d.batch, d.ptr = g["batch"].to(DEV), g["ptr"].to(DEV)
+    if struct == "band":
+        d.band_k = c["k"]
+    return g, m, d
+
+
+@pytest.mark.parametrize("struct", ["band", "csr"])
+def test_graph_fp32_matches_reference_golden(golden, struct):
+    egopack_b200.set_precision("fp32")
+    g, m, d = golden_graph(golden, struct)
+    y = m(d)
+    assert y.dtype == torch.float32
+    (y * g["w"].to(DEV)).sum().backward()
+    assert rel_max(y, g["out"]) < TOL_F32 and rel_max(d.x.grad, g["grad_x"]) < TOL_F32
+    for k, p in m.named_parameters():
+        assert rel_max(p.grad, g["grads"][k]) < TOL_F32, k
+
+
+def test_graph_bf16_matches_reference_golden(golden):
+    """bf16 activations: forward within 2e-2.  The 19-node fixture is too small for a gradient bound (one ReLU flip
+    moves a whole gradient row); gradients are bounded on a realistic batch in test_graph_bf16_realistic_batch."""
+    egopack_b200.set_precision("bf16")
+    g, m, d = golden_graph(golden, "band")
+    y = m(d)
+    assert y.dtype == torch.bfloat16 and rel_max(y, g["out"]) < TOL_BF16
+
+
+def test_graph_bf16_realistic_batch():
+    gen = torch.Generator().manual_seed(7)
+    D, S, H, HT = 128, 3, 256, 256
+    b = syn.make_batch("ar", 6, 50, gen, feature_dim=D, num_segments=S, band_k=2, n_verbs=9, n_nouns=11)
+    ref = eo.GraphOracle(D, H, 2, temporal_pooling={"hidden_size": HT}, num_segments=S)
+    rb = pyg.Data(x=b.x.clone().requires_grad_(True), pos=b.pos)
+    rb.batch, rb.ptr, rb.edge_index = b.batch, b.ptr, pyg.radius_graph(b.pos, 2.5, b.batch)
+    w = torch.randn(300, H, generator=gen)
+    ry = ref(rb)
+    (ry * w).sum().backward()
+    ref_grads = dict(ref.named_parameters())
+    egopack_b200.set_precision("bf16")
+    m = Graph(D, H, 2, temporal_pooling=dict(TP, hidden_size=HT), num_segments=S).to(DEV)
+    m.load_state_dict(ref.state_dict())
+    nb = syn.make_batch("ar", 6, 50, torch.Generator().manual_seed(7), feature_dim=D, num_segments=S, band_k=2,
+                        n_verbs=9, n_nouns=11).to(DEV)               # same seed -> same batch, on the device
+    nb.x.requires_grad_(True)
+    y = m(nb)
+    (y.float() * w.to(DEV)).sum().backward()
+    assert rel_max(y, ry) < TOL_BF16
+    # Gradients: bf16 rounding flips individual ReLU / LeakyReLU decisions, and the random-sign test loss makes
+    # every gradient a heavily cancelling sum, so even PyTorch's own bf16 autocast of the ORACLE is ~7e-2 (L2) away
+    # from fp32 on this model.  The bound is therefore relative to that: no worse than 1.5x the autocast error.
+    rg = {k: p.grad.clone() for k, p in ref_grads.items()}
+    ref.zero_grad()
+    ab = pyg.Data(x=b.x.detach().cpu().clone().requires_grad_(True), pos=b.pos.cpu())
+    ab.batch, ab.ptr, ab.edge_index = rb.batch, rb.ptr, rb.edge_index
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        ay = ref(ab)
+    (ay.float() * w).sum().backward()
+    bound = lambda got_err, auto_err: got_err < max(TOL_BF16, 1.5 * auto_err)
+    assert bound(rel_l2(nb.x.grad, rb.x.grad), rel_l2(ab.x.grad, rb.x.grad))
+    for k, p in m.named_parameters():
+        auto = rel_l2(dict(ref.named_parameters())[k].grad, rg[k])
+        assert bound(rel_l2(p.grad, rg[k]), auto), (k, rel_l2(p.grad, rg[k]), auto)
+
+
+def _native_task(name, g, aux):
+    H, C, heads = g["H"], g["C"], g["heads"]
+    return {"ar": lambda: RecognitionTask(H, C, heads, aux_tasks=aux), "lta": lambda: LTATask(H, C, heads, aux_tasks=aux),
+            "oscc": lambda: OSCCTask(H, C, aux_tasks=aux, average_logits=True), "pnr": lambda: PNRTask(H, C, aux_tasks=aux)}[name]()
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", TOL_F32), ("bf16", TOL_BF16)])
+def test_task_heads_match_reference_golden(golden, mode, tol):
+    egopack_b200.set_precision(mode)
+    g = golden("task_heads.pt")
+    for name, ref in g["tasks"].items():
+        aux_names = tuple(t for t in ("ar", "lta", "oscc", "pnr") if t != name)
+        task = _native_task(name, g, aux_names).to(DEV)
+        task.load_state_dict(ref["state"])
+        f = g["feat"].clone().to(DEV).requires_grad_(True)
+        aux = {t: v.clone().to(DEV).requires_grad_(True) for t, v in g["aux"].items() if t != name}
+        kw = {"batch": g["batch"].to(DEV)} if name == "oscc" else {}
+        y = {"ar": g["y_ar"], "lta": g["y_ar"], "oscc": g["y_oscc"], "pnr": g["y_pnr"]}[name].to(DEV)
+        ff = task.forward_features(f)
+        assert rel_max(ff, ref["features"]) < tol
+        plain = task.forward_logits(ff, **kw)
+        fused = task.forward_logits(features=ff, aux_features=aux, **kw)
+        pl, fu = (plain, fused) if isinstance(plain, tuple) else ((plain,), (fused,))
+        rp, rf = (ref["plain"], ref["fused"]) if isinstance(ref["plain"], list) else ([ref["plain"]], [ref["fused"]])
+        for a, b_ in zip(pl, rp):
+            assert a.dtype == torch.float32 and a.shape == b_.shape and rel_max(a, b_) < tol
+        for a, b_ in zip(fu, rf):
+            assert rel_max(a, b_) < tol
+        loss = task.compute_loss(fused, y)
+        assert rel_max(loss, ref["loss"]) < tol
+        if mode == "fp32":
+            loss.mean().backward()
+            assert rel_max(f.grad, ref["grad_feat"]) < tol
+            for t, v in aux.items():
+                assert rel_max(v.grad, ref["grad_aux"][t]) < tol, (name, t)
+            for k, p in task.named_parameters():
+                if k in ref["grads"]:
+                    assert rel_max(p.grad, ref["grads"][k]) < tol, (name, k)
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", TOL_F32), ("bf16", TOL_BF16)])
+def test_graphone_matches_reference_golden(golden, mode, tol):
+    egopack_b200.set_precision(mode)
+    for case in golden("graphone.pt"):
+        go = GraphONE({t: b.clone() for t, b in case["banks"].items()}, **case["cfg"]).to(DEV)
+        go.load_state_dict(case["state"])
+        feats = {t: f.clone().to(DEV).requires_grad_(True) for t, f in case["feats"].items()}
+        out, closest = go.interact(feats)
+        assert list(out) == list(case["out"])                     # dict order of the INPUT (graphONE.py:80)
+        for t in out:
+            assert rel_max(out[t], case["out"][t]) < tol
+            if mode == "fp32":
+                assert len(closest[t]) == case["cfg"]["depth"]
+                for a, b_ in zip(closest[t], case["closest"][t]):
+                    assert torch.equal(a.cpu(), b_)                  # nearest prototype: bit-exact
+        if mode == "fp32":
+            sum((out[t] * case["w"][t].to(DEV)).sum() for t in out).backward()
+            for t in feats:
+                assert rel_max(feats[t].grad, case["grad_feats"][t]) < tol
+            for k, p in go.named_parameters():
+                if k in case["grads"]:
+                    assert rel_max(p.grad, case["grads"][k]) < tol, k
+
+
+def _mtl_pair(gen, D, S, H, HT, heads, V, n):
+    ref_model = eo.GraphOracle(D, H, 2, temporal_pooling={"hidden_size": HT}, num_segments=S)
+    ref_tasks = {"ar": eo.RecognitionTaskOracle(H, H, heads), "lta": eo.LTATaskOracle(H, H, heads),
+                 "oscc": eo.OSCCTaskOracle(H, H), "pnr": eo.PNRTaskOracle(H, H)}
+    host = {t: syn.make_batch(t, V, n, gen, feature_dim=D, num_segments=S, band_k=1, n_verbs=heads[0], n_nouns=heads[1],
+                              unlabeled=0.3) for t in ("ar", "lta", "oscc", "pnr")}
+    ref_batches = {}
+    for t, b in host.items():
+        d = pyg.Data(x=b.x, pos=b.pos, y=b.y)
+        d.batch, d.ptr = b.batch, b.ptr
+        if t == "lta":
+            eis = [eo.lta_temporal_connectivity(pyg.Data(x=b.x[g * n:(g + 1) * n], pos=b.pos[g * n:(g + 1) * n],
+                                                         y=b.y[g * n:(g + 1) * n]), 1.5).edge_index + g * n for g in range(V)]
+            d.edge_index = torch.cat(eis, 1)
+        else:
+            d.edge_index = pyg.radius_graph(b.pos, 1.5, b.batch)
+        ref_batches[t] = d
+    return ref_model, ref_tasks, host, ref_batches
+
+
+def test_mtl_step_fp32_losses_gradients_and_metrics_match_oracle():
+    """main_temporal.py:76-128 on all four tasks: losses, every gradient, and the AR/OSCC/PNR metrics."""
+    egopack_b200.set_precision("fp32")
+    gen = torch.Generator().manual_seed(11)
+    D, S, H, HT, heads, V, n = 48, 3, 64, 72, (7, 11), 5, 12
+    ref_model, ref_tasks, host, ref_batches = _mtl_pair(gen, D, S, H, HT, heads, V, n)
+    weights = {"ar": 1.0, "lta": 0.5, "oscc": 2.0, "pnr": 1.5}
+    ref_loss, ref_per = eo.mtl_step(ref_model, ref_tasks, ref_batches, weights)
+    ref_loss.backward()
+    model = Graph(D, H, 2, temporal_pooling=dict(TP, hidden_size=HT), num_segments=S).to(DEV)
+    model.load_state_dict(ref_model.state_dict())
+    tasks = {"ar": RecognitionTask(H, H, heads), "lta": LTATask(H, H, heads), "oscc": OSCCTask(H, H), "pnr": PNRTask(H, H)}
+    for t in tasks:
+        tasks[t].load_state_dict(ref_tasks[t].state_dict())
+        tasks[t].to(DEV)
+    batches = {}
+    for t, b in host.items():
+        nb = Batch()
+        for key in ("x", "pos", "y", "batch", "ptr"):
+            setattr(nb, key, getattr(b, key).to(DEV))
+        batches[t] = LTATemporalConnectivity(1.5)(nb) if t == "lta" else RadiusGraph(1.5)(nb)
+        assert sorted(zip(*batches[t].edge_index.cpu().tolist())) == sorted(zip(*ref_batches[t].edge_index.tolist()))
+    loss, per = steps.mtl_losses(model, tasks, batches, weights)
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) / abs(float(ref_loss)) < TOL_F32
+    for t in per:
+        assert rel_max(per[t], ref_per[t]) < TOL_F32, t
+    for (k, p), (_, rp) in zip(model.named_parameters(), ref_model.named_parameters()):
+        assert rel_max(p.grad, rp.grad) < TOL_F32, k
+    for t in tasks:
+        for (k, p), (_, rp) in zip(tasks[t].named_parameters(), ref_tasks[t].named_parameters()):
+            assert rel_max(p.grad, rp.grad) < TOL_F32, (t, k)
+    # headline metrics unchanged (utils/meters/ego4d.py): AR top-1, OSCC accuracy, PNR localisation error
+    with torch.no_grad():
+        model.eval(), ref_model.eval()
+        f, rf = model(batches["ar"]), ref_model(ref_batches["ar"])
+        lg = tasks["ar"].forward_logits(tasks["ar"].forward_features(f))
+        rlg = ref_tasks["ar"].forward_logits(ref_tasks["ar"].forward_features(rf))
+        assert eo.metric_ar([l.cpu() for l in lg], ref_batches["ar"].y) == eo.metric_ar(rlg, ref_batches["ar"].y)
+        f, rf = model(batches["oscc"]), ref_model(ref_batches["oscc"])
+        lo = tasks["oscc"].forward_logits(tasks["oscc"].forward_features(f), batches["oscc"].batch)
+        rlo = ref_tasks["oscc"].forward_logits(ref_tasks["oscc"].forward_features(rf), ref_batches["oscc"].batch)
+        assert eo.metric_oscc(lo.cpu(), ref_batches["oscc"].y) == eo.metric_oscc(rlo, ref_batches["oscc"].y)
+        f, rf = model(batches["pnr"]), ref_model(ref_batches["pnr"])
+        lp = tasks["pnr"].forward_logits(tasks["pnr"].forward_features(f))
+        rlp = ref_tasks["pnr"].forward_logits(ref_tasks["pnr"].forward_features(rf))
+        node = ref_batches["pnr"].y.view(V, n).argmax(1)
+        assert eo.metric_pnr_localisation(lp.cpu(), ref_batches["pnr"].batch, node, n) == \
+            eo.metric_pnr_localisation(rlp, ref_batches["pnr"].batch, node, n)
+
+
+def test_egopack_oscc_step_fp32_matches_oracle():
+    """main_egopack.py:45-61: OSCC primary with the frozen AR/LTA/PNR backpack, late fusion, detached secondaries."""
+    egopack_b200.set_precision("fp32")
+    gen = torch.Generator().manual_seed(13)
+    D, S, H, HT, heads, V, n = 48, 3, 64, 72, (7, 11), 6, 9
+    aux = ("ar", "lta", "pnr")
+    ref_model = eo.GraphOracle(D, H, 2, temporal_pooling={"hidden_size": HT}, num_segments=S)
+    ref_tasks = {"oscc": eo.OSCCTaskOracle(H, H, aux_tasks=aux, average_logits=True),
+                 "ar": eo.RecognitionTaskOracle(H, H, heads), "lta": eo.LTATaskOracle(H, H, heads), "pnr": eo.PNRTaskOracle(H, H)}
+    banks = syn.make_banks(aux, 61, H, gen)
+    ref_go = eo.GraphONEOracle(banks, features_size=H, hidden_size=H, k=4, depth=2, residual=True)
+    b = syn.make_batch("oscc", V, n, gen, feature_dim=D, num_segments=S, band_k=1)
+    rb = pyg.Data(x=b.x, pos=b.pos, y=b.y)
+    rb.batch, rb.ptr, rb.edge_index = b.batch, b.ptr, pyg.radius_graph(b.pos, 1.5, b.batch)
+    rfeat = ref_model(rb)
+    rloss = eo.egopack_task_step(rfeat, rb.batch, rb.y, ref_tasks["oscc"], [ref_tasks[t] for t in aux], ref_go)
+    rloss.mean().backward()
+    model = Graph(D, H, 2, temporal_pooling=dict(TP, hidden_size=HT), num_segments=S).to(DEV)
+    model.load_state_dict(ref_model.state_dict())
+    tasks = {"oscc": OSCCTask(H, H, aux_tasks=aux, average_logits=True), "ar": RecognitionTask(H, H, heads),
+             "lta": LTATask(H, H, heads), "pnr": PNRTask(H, H)}
+    for t in tasks:
+        tasks[t].load_state_dict(ref_tasks[t].state_dict())
+        tasks[t].to(DEV)
+    go = GraphONE({t: v.clone() for t, v in banks.items()}, features_size=H, hidden_size=H, k=4, depth=2, residual=True).to(DEV)
+    go.load_state_dict(ref_go.state_dict())
+    nb = RadiusGraph(1.5)(b.to(DEV))
+    loss, per = steps.egopack_losses(model, tasks, {"oscc": nb}, go)
+    loss.backward()
+    assert rel_max(per["oscc"], rloss) < TOL_F32
+    for (k, p), (_, rp) in zip(go.named_parameters(), ref_go.named_parameters()):
+        if rp.grad is not None:
+            assert rel_max(p.grad, rp.grad) < TOL_F32, k
+    for (k, p), (_, rp) in zip(model.named_parameters(), ref_model.named_parameters()):
+        assert rel_max(p.grad, rp.grad) < TOL_F32, k
+    for t in aux:                                               # secondaries are detached: no gradient reaches them
+        assert all(p.grad is None for p in tasks[t].parameters())
