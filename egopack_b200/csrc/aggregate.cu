@@ -5,11 +5,14 @@
 // (2*C*b bytes per node), independent of the window radius, because the adjacency of a temporal graph is a
 // band: consecutive output rows share all but one of their neighbour rows.
 //
-// band kernel: a CTA owns a strip of consecutive rows x a 128-vector (16 B each) column chunk.  Rows stream
-// through a shared-memory ring with cp.async (one commit group per row, P rows in flight); every thread only
-// ever touches its own 16-byte column of the ring, so the pipeline needs no block barrier at all.  Small
-// radii sum the window directly from the ring in ascending neighbour order (bit-identical to a sequential
-// scatter_add); large radii keep a running window sum (add the entering row, subtract the leaving row).
+// band kernels: a CTA owns a strip of consecutive rows x a 128-vector (16 B each) column chunk and a thread only
+// ever touches its own 16-byte column, so no block barrier is needed.
+//   radius <= 4 : the 2k+1-row window is held in registers (sage_mean_band_reg_kernel), summed in ascending
+//                 neighbour order (bit-identical to a sequential scatter_add);
+//   radius  > 4 : rows stream through a shared-memory ring with cp.async (one commit group per row, P rows in
+//                 flight) and a running window sum adds the entering row and subtracts the leaving row.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace egp {
@@ -113,6 +116,106 @@ sage_mean_band_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n, i
   cp_async_wait<0>();
 }
 
+// Small radii (K <= 4): the sliding window lives in REGISTERS.  A thread owns one 16-byte column of a strip of
+// consecutive rows; every row is loaded exactly once (U independent loads in flight per thread), unpacked,
+// optionally pre-scaled, and then reused by the 2K neighbouring outputs straight from registers.  All window
+// indices are compile-time constants (the loops are fully unrolled), so nothing spills to local memory.
+template <typename T, int K, int U>
+__global__ void __launch_bounds__(kAggThreads, 8)
+sage_mean_band_reg_kernel(const T* __restrict__ x, T* __restrict__ out, int n, int64_t channels, int64_t ldx,
+                          int64_t ldo, int rows_per_cta, const int32_t* __restrict__ win_lo,
+                          const int32_t* __restrict__ win_hi, const float* __restrict__ scale_out,
+                          const float* __restrict__ scale_in) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int W = 2 * K + U;
+  const int64_t col = ((int64_t)blockIdx.y * kAggThreads + threadIdx.x) * VN;
+  if (col >= channels) return;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, n);
+  if (r0 >= r1) return;
+  const T* xc = x + col;
+  Raw<T> w[W];  // packed window: rows [g-K, g+U+K)
+#pragma unroll
+  for (int d = 0; d < 2 * K; ++d) {
+    const int j = r0 - K + d;
+    w[d] = (j >= 0 && j < n) ? Raw<T>::load(xc + (int64_t)j * ldx) : Raw<T>::zero();
+  }
+#pragma unroll 1
+  for (int g = r0; g < r1; g += U) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {  // U independent 16-byte loads in flight
+      const int j = g + K + u;
+      w[2 * K + u] = (j < n) ? Raw<T>::load(xc + (int64_t)j * ldx) : Raw<T>::zero();
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = g + u;
+      if (i < r1) {
+        const int lo = win_lo[i], hi = win_hi[i];
+        Vec<T> acc;
+#pragma unroll
+        for (int c = 0; c < VN; ++c) acc.v[c] = 0.f;
+#pragma unroll
+        for (int d = 0; d <= 2 * K; ++d) {
+          if (d == K) continue;
+          const int j = i - K + d;
+          if (j >= lo && j <= hi) {
+            const Vec<T> v = w[u + d].unpack();
+            const float s = scale_in ? scale_in[j] : 1.f;
+#pragma unroll
+            for (int c = 0; c < VN; ++c) acc.v[c] += s * v.v[c];
+          }
+        }
+        const float so = scale_out ? scale_out[i] : 1.f;
+#pragma unroll
+        for (int c = 0; c < VN; ++c) acc.v[c] *= so;
+        acc.store(out + (int64_t)i * ldo + col);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 2 * K; ++d) w[d] = w[d + U];
+  }
+}
+
+// Alternative for small radii: one thread per output vector, neighbours re-read through L1/L2 (a CTA covers
+// ROWS consecutive rows so most neighbour rows are L1 hits).  No sequential dependence at all.
+template <typename T, int K, int ROWS>
+__global__ void __launch_bounds__(kAggThreads * ROWS)
+sage_mean_band_flat_kernel(const T* __restrict__ x, T* __restrict__ out, int n, int64_t channels, int64_t ldx,
+                           int64_t ldo, const int32_t* __restrict__ win_lo, const int32_t* __restrict__ win_hi,
+                           const float* __restrict__ scale_out, const float* __restrict__ scale_in) {
+  constexpr int VN = Vec<T>::N;
+  const int64_t col = ((int64_t)blockIdx.y * kAggThreads + (threadIdx.x % kAggThreads)) * VN;
+  const int i = blockIdx.x * ROWS + threadIdx.x / kAggThreads;
+  if (col >= channels || i >= n) return;
+  const int lo = win_lo[i], hi = win_hi[i];
+  const T* xc = x + col;
+  Vec<T> v[2 * K];
+  float sc[2 * K];
+#pragma unroll
+  for (int d = 0; d < 2 * K; ++d) {
+    const int j = i - K + d + (d >= K ? 1 : 0);
+    const bool ok = j >= lo && j <= hi;
+    sc[d] = ok ? (scale_in ? scale_in[j] : 1.f) : 0.f;
+    if (ok) v[d] = Vec<T>::load(xc + (int64_t)j * ldx);
+    else {
+#pragma unroll
+      for (int c = 0; c < VN; ++c) v[d].v[c] = 0.f;
+    }
+  }
+  Vec<T> acc;
+#pragma unroll
+  for (int c = 0; c < VN; ++c) acc.v[c] = 0.f;
+#pragma unroll
+  for (int d = 0; d < 2 * K; ++d)
+#pragma unroll
+    for (int c = 0; c < VN; ++c) acc.v[c] += sc[d] * v[d].v[c];
+  const float so = scale_out ? scale_out[i] : 1.f;
+#pragma unroll
+  for (int c = 0; c < VN; ++c) acc.v[c] *= so;
+  acc.store(out + (int64_t)i * ldo + col);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kAggThreads)
 sage_mean_csr_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n, int64_t channels, int64_t ldx,
@@ -179,6 +282,35 @@ static int launch_band(const void* x, void* out, int64_t n, int64_t channels, in
   return EGP_OK;
 }
 
+template <typename T, int K, int U>
+static int launch_band_reg(const void* x, void* out, int64_t n, int64_t channels, int64_t ldx, int64_t ldo,
+                           const int32_t* win_lo, const int32_t* win_hi, const float* scale_out, const float* scale_in,
+                           cudaStream_t stream) {
+  constexpr int VN = Vec<T>::N;
+  const unsigned gy = (unsigned)ceil_div(channels, (int64_t)kAggThreads * VN);
+  int64_t rows = (n * gy) / ((int64_t)sm_count() * 16);      // ~2 waves of 8 CTAs per SM
+  rows = rows < 4 * U ? 4 * U : (rows > 512 ? 512 : rows);   // halo re-read <= 2K/(4U)
+  rows = (rows + U - 1) / U * U;
+  dim3 grid((unsigned)ceil_div(n, rows), gy);
+  sage_mean_band_reg_kernel<T, K, U><<<grid, kAggThreads, 0, stream>>>((const T*)x, (T*)out, (int)n, channels, ldx, ldo,
+                                                                       (int)rows, win_lo, win_hi, scale_out, scale_in);
+  EGP_LAUNCH_CHECK();
+  return EGP_OK;
+}
+
+template <typename T, int K>
+static int launch_band_flat(const void* x, void* out, int64_t n, int64_t channels, int64_t ldx, int64_t ldo,
+                            const int32_t* win_lo, const int32_t* win_hi, const float* scale_out, const float* scale_in,
+                            cudaStream_t stream) {
+  constexpr int VN = Vec<T>::N, ROWS = 4;
+  const unsigned gy = (unsigned)ceil_div(channels, (int64_t)kAggThreads * VN);
+  dim3 grid((unsigned)ceil_div(n, ROWS), gy);
+  sage_mean_band_flat_kernel<T, K, ROWS><<<grid, kAggThreads * ROWS, 0, stream>>>(
+      (const T*)x, (T*)out, (int)n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in);
+  EGP_LAUNCH_CHECK();
+  return EGP_OK;
+}
+
 }  // namespace egp
 
 using namespace egp;
@@ -196,7 +328,14 @@ int egp_sage_mean_band(const void* x, void* out, int64_t n, int64_t channels, in
   if (n == 0 || channels == 0) return EGP_OK;
   cudaStream_t s = (cudaStream_t)stream;
   EGP_DISPATCH_DTYPE(dtype, T, {
-    if (k <= 4) return launch_band<T, 8, false>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
+    static const int impl = [] { const char* e = getenv("EGP_BAND_IMPL"); return e ? atoi(e) : 0; }();
+    if (impl == 1 && k <= 1) return launch_band_flat<T, 1>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
+    if (impl == 1 && k == 2) return launch_band_flat<T, 2>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
+    if (impl == 2 && k <= 4) return launch_band<T, 8, false>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
+    if (k <= 1) return launch_band_reg<T, 1, 8>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
+    if (k == 2) return launch_band_reg<T, 2, 8>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
+    if (k == 3) return launch_band_reg<T, 3, 4>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
+    if (k == 4) return launch_band_reg<T, 4, 4>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
     if (k <= 12) return launch_band<T, 16, true>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
     return launch_band<T, 32, true>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
   });

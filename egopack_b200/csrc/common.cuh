@@ -90,6 +90,32 @@ struct Vec<__nv_bfloat16> {
   }
 };
 
+// a 16-byte vector kept PACKED in registers (4 regs) and unpacked only where it is consumed
+template <typename T>
+struct Raw {
+  uint4 u;
+  __device__ __forceinline__ static Raw load(const T* p) { Raw r; r.u = *reinterpret_cast<const uint4*>(p); return r; }
+  __device__ __forceinline__ static Raw zero() { Raw r; r.u = make_uint4(0u, 0u, 0u, 0u); return r; }
+  __device__ __forceinline__ Vec<T> unpack() const;
+};
+template <>
+__device__ __forceinline__ Vec<float> Raw<float>::unpack() const {
+  Vec<float> r;
+  r.v[0] = __uint_as_float(u.x); r.v[1] = __uint_as_float(u.y); r.v[2] = __uint_as_float(u.z); r.v[3] = __uint_as_float(u.w);
+  return r;
+}
+template <>
+__device__ __forceinline__ Vec<__nv_bfloat16> Raw<__nv_bfloat16>::unpack() const {
+  Vec<__nv_bfloat16> r;
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r.v[2 * i] = __uint_as_float(w[i] << 16);
+    r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+  return r;
+}
+
 template <typename T>
 __device__ __forceinline__ float to_float(T x);
 template <>

@@ -11,25 +11,30 @@ static int ew_grid(int64_t nvec) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-// a4: out = x + [sin(pos*f) | cos(pos*f)]  (gnn.PositionalEncoding, models/graph.py:37,63)
+// a4: out = x + [sin(pos*f) | cos(pos*f)]  (gnn.PositionalEncoding, models/graph.py:37,63).  A thread owns one
+// 16-byte vector of the sin half and the matching vector of the cos half, so each argument is reduced once.
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 posenc_add_kernel(const T* __restrict__ x, const int64_t* __restrict__ pos, const float* __restrict__ freq,
-                  T* __restrict__ out, int64_t nvec, int64_t channels) {
+                  T* __restrict__ out, int64_t nwork, int64_t channels) {
   constexpr int VN = Vec<T>::N;
   const int64_t half = channels / 2;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e0 = v * VN;
-    const int64_t row = e0 / channels, c0 = e0 % channels;
+  const int64_t hv = half / VN;  // vectors per half row
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nwork; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = v / hv, c0 = (v % hv) * VN;
     const float p = (float)pos[row];  // int64 * float32 promotes to float32 in the reference
+    const int64_t e0 = row * channels + c0;
     Vec<T> a = Vec<T>::load(x + e0);
+    Vec<T> b = Vec<T>::load(x + e0 + half);
 #pragma unroll
     for (int c = 0; c < VN; ++c) {
-      const int64_t ch = c0 + c;
-      const float pe = ch < half ? sinf(p * freq[ch]) : cosf(p * freq[ch - half]);
-      a.v[c] += pe;
+      float sn, cs;
+      sincosf(p * freq[c0 + c], &sn, &cs);
+      a.v[c] += sn;
+      b.v[c] += cs;
     }
     a.store(out + e0);
+    b.store(out + e0 + half);
   }
 }
 
@@ -171,7 +176,19 @@ colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, int64
   for (int c = 0; c < VN; ++c) acc[c] = 0.f;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
   if (vec_ok && col + VN <= cols) {
-    for (int64_t i = r0; i < r1; ++i) {
+    int64_t i = r0;
+    for (; i + 8 <= r1; i += 8) {  // eight independent 16-byte loads in flight per thread
+      Raw<T> a[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] = Raw<T>::load(x + (i + u) * ldx + col);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const Vec<T> v = a[u].unpack();
+#pragma unroll
+        for (int c = 0; c < VN; ++c) acc[c] += v.v[c];
+      }
+    }
+    for (; i < r1; ++i) {
       const Vec<T> a = Vec<T>::load(x + i * ldx + col);
 #pragma unroll
       for (int c = 0; c < VN; ++c) acc[c] += a.v[c];
@@ -187,13 +204,23 @@ colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, int64
     if (col + c < cols) part[(size_t)blockIdx.x * cols + col + c] = acc[c];
 }
 
+// out[c] = sum_g part[g][c]; block = 32 columns x 8 part-groups so the reduction over parts is parallel
 __global__ void __launch_bounds__(kEwThreads)
 colsum_final_kernel(const float* __restrict__ part, int parts, int64_t cols, float* __restrict__ out) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + tx;
   float a = 0.f;
-  for (int g = 0; g < parts; ++g) a += part[(size_t)g * cols + c];
-  out[c] = a;
+  if (c < cols)
+    for (int g = ty; g < parts; g += 8) a += part[(size_t)g * cols + c];
+  red[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    out[c] = t;
+  }
 }
 
 // 1/||x_i||: one warp per row
@@ -217,7 +244,7 @@ row_inv_norm_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t ro
 
 static int colsum_parts(int64_t rows) {
   int64_t p = ceil_div(rows, 32);
-  const int64_t cap = (int64_t)sm_count() * 2;
+  const int64_t cap = (int64_t)sm_count() * 8;
   return (int)(p < 1 ? 1 : (p > cap ? cap : p));
 }
 
@@ -236,13 +263,13 @@ int egp_posenc_add(const void* x, const int64_t* pos, const float* frequency, vo
                    int64_t channels, int dtype, void* stream) {
   EGP_REQUIRE(x && pos && frequency && out, "posenc_add: null pointer");
   const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
-  EGP_REQUIRE(channels % 2 == 0 && channels % vn == 0 && aligned16(x) && aligned16(out),
-              "posenc_add: channels must be even and a multiple of %d", (int)vn);
+  EGP_REQUIRE(channels % (2 * vn) == 0 && aligned16(x) && aligned16(out),
+              "posenc_add: channels must be a multiple of %d", (int)(2 * vn));
   if (n == 0) return EGP_OK;
   EGP_DISPATCH_DTYPE(dtype, T, {
-    const int64_t nvec = n * channels / Vec<T>::N;
-    posenc_add_kernel<T><<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)x, pos, frequency,
-                                                                                 (T*)out, nvec, channels);
+    const int64_t nwork = n * channels / (2 * Vec<T>::N);
+    posenc_add_kernel<T><<<ew_grid(nwork), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)x, pos, frequency,
+                                                                                  (T*)out, nwork, channels);
     EGP_LAUNCH_CHECK();
   });
   return EGP_OK;
@@ -361,11 +388,13 @@ int egp_colsum(const void* x, float* out, int64_t rows, int64_t cols, int64_t ld
   EGP_DISPATCH_DTYPE(dtype, T, {
     constexpr int VN = Vec<T>::N;
     const int vec_ok = aligned16(x) && (ldx % VN) == 0;
-    const int gy = (int)ceil_div(cols, (int64_t)kEwThreads * VN);
-    colsum_partial_kernel<T><<<dim3(parts, gy), kEwThreads, 0, s>>>((const T*)x, rows, cols, ldx, rows_per, vec_ok, part);
+    const int64_t nvec = ceil_div(cols, (int64_t)VN);
+    const int threads = (int)(nvec >= kEwThreads ? kEwThreads : (nvec + 31) / 32 * 32);   // no idle half-blocks
+    const int gy = (int)ceil_div(nvec, (int64_t)threads);
+    colsum_partial_kernel<T><<<dim3(parts, gy), threads, 0, s>>>((const T*)x, rows, cols, ldx, rows_per, vec_ok, part);
     EGP_LAUNCH_CHECK();
   });
-  colsum_final_kernel<<<(unsigned)ceil_div(cols, kEwThreads), kEwThreads, 0, s>>>(part, parts, cols, out);
+  colsum_final_kernel<<<(unsigned)ceil_div(cols, 32), kEwThreads, 0, s>>>(part, parts, cols, out);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
 }

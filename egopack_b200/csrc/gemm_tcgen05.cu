@@ -75,6 +75,19 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// smem -> global tile store (clips rows/columns outside the tensor); `reduce` adds into global memory instead
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int c1, bool reduce) {
+  if (reduce)
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"((uint64_t)map), "r"(smem_u32(smem)), "r"(c0), "r"(c1) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"((uint64_t)map), "r"(smem_u32(smem)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -146,7 +159,10 @@ struct TcCfg {
   static constexpr int kBBytes = BN * TBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // power of two for BN in {16,...,256}
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiStageBytes = 4 * 32 * 128;   // per epilogue warp: 32 rows x 128 B, 128B-swizzled
+  static constexpr int kEpiBiasBytes = 4 * 256 * 4;     // per epilogue warp: one tile's bias slice
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + kEpiBiasBytes + 1024 /*align slack*/ +
+                                    256 /*barriers*/;
 };
 
 struct TcParams {
@@ -162,6 +178,7 @@ struct TcParams {
   int act;
   float slope;
   int accumulate;      // C += result (fp32 atomics)
+  int tma_store;       // epilogue stages 32x128B boxes in smem and stores them with TMA (coalesced, clipped)
   uint32_t idesc;
 };
 
@@ -169,12 +186,14 @@ template <int BN, bool A_MN, bool B_MN, typename OutT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2,
-               const TcParams p) {
+               const __grid_constant__ CUtensorMap mapC, const TcParams p) {
   using Cfg = TcCfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint8_t* epi_stage = smem + S * Cfg::kStageBytes;                      // 1024-aligned (stage bytes are)
+  float* epi_bias = reinterpret_cast<float*>(epi_stage + Cfg::kEpiStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + Cfg::kEpiStageBytes + Cfg::kEpiBiasBytes);
   uint64_t* full = bars;            // [S]  TMA -> MMA
   uint64_t* empty = bars + S;       // [S]  MMA -> TMA
   uint64_t* tfull = bars + 2 * S;   // [2]  MMA -> epilogue
@@ -186,6 +205,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
     if (p.kb2 > 0) { tma_prefetch_desc(&mapA2); tma_prefetch_desc(&mapB2); }
+    if (p.tma_store) tma_prefetch_desc(&mapC);
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
     fence_barrier_init();
@@ -296,6 +316,72 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const bool row_ok = m < p.M;
       const bool atomic = p.splits > 1 || p.accumulate;
       const bool has_k = kb_e > kb_b;
+      constexpr int CHT = 128 / (int)sizeof(OutT);  // columns per 128-byte staged row: 64 (bf16) / 32 (fp32)
+      if constexpr (BN >= CHT) {
+        if (p.tma_store) {
+          uint8_t* stage_w = epi_stage + quarter * (32 * 128);
+          float* bias_w = epi_bias + quarter * 256;
+          const bool use_bias = p.bias && split == 0;
+          if (use_bias) {  // this warp's copy of the tile's bias slice (no cross-warp barrier needed)
+            __syncwarp();
+            for (int j = lane; j < BN; j += 32) bias_w[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+            __syncwarp();
+          }
+#pragma unroll 1
+          for (int c = 0; c < BN / CHT; ++c) {
+            const int64_t nb = n0 + c * CHT;
+            if (nb >= p.N) break;  // warp-uniform
+            uint32_t r[CHT];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c * CHT);
+            tmem_ld32(taddr, r);
+            if constexpr (CHT == 64) tmem_ld32(taddr + 32, r + 32);
+            tmem_ld_wait();
+            float v[CHT];
+#pragma unroll
+            for (int j = 0; j < CHT; ++j) v[j] = has_k ? __uint_as_float(r[j]) : 0.f;
+            if (use_bias) {
+#pragma unroll
+              for (int j = 0; j < CHT; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_w + c * CHT + j);  // broadcast read
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
+            }
+            if (p.act != EGP_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < CHT; ++j) v[j] = apply_act(v[j], p.act, p.slope);
+            }
+            if (lane == 0) bulk_wait_read0();  // the previous box has been read out of the staging buffer
+            __syncwarp();
+            uint8_t* row = stage_w + lane * 128;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {  // 16-byte pieces, XOR-swizzled with the row index (SWIZZLE_128B)
+              uint4 pk;
+              if constexpr (sizeof(OutT) == 2) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+                pk = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+              } else {
+                pk = make_uint4(__float_as_uint(v[4 * q + 0]), __float_as_uint(v[4 * q + 1]),
+                                __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
+              }
+              *reinterpret_cast<uint4*>(row + ((q ^ (lane & 7)) << 4)) = pk;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&mapC, stage_w, (int)nb, (int)(m0 + quarter * 32), atomic);
+              bulk_commit();
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[as]);
+          continue;
+        }
+      }
       constexpr int CH = BN >= 32 ? 32 : 16;
 #pragma unroll 1
       for (int c = 0; c < BN / CH; ++c) {
@@ -360,6 +446,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
     }
+    if (p.tma_store && lane == 0) bulk_wait0();  // all staged boxes have landed in global memory
   }
 
   tc_fence_before();
@@ -397,25 +484,28 @@ static EncodeTiledFn get_encode() {
 struct MapKey {
   const void* ptr;
   int64_t inner, outer, ld;
-  int box_outer;
+  int box_inner, box_outer, esize;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_outer == o.box_outer;
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
+           box_outer == o.box_outer && esize == o.esize;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr);
     auto mix = [&](int64_t v) { h ^= std::hash<int64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_outer);
+    mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer); mix(k.esize);
     return h;
   }
 };
 
-// 2-D bf16 tensor [outer, inner] (inner contiguous, row stride ld elements), box {64, box_outer}, 128B swizzle
-static int make_map(const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer, CUtensorMap* out) {
+// 2-D tensor [outer, inner] (inner contiguous, row stride ld elements of esize bytes: 2 = bf16, 4 = fp32),
+// box {box_inner, box_outer} with box_inner * esize == 128, 128B swizzle
+static int make_map(const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer, int esize,
+                    CUtensorMap* out) {
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   static std::mutex mu;
-  const MapKey key{ptr, inner, outer, ld, box_outer};
+  const MapKey key{ptr, inner, outer, ld, box_inner, box_outer, esize};
   {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
@@ -427,15 +517,16 @@ static int make_map(const void* ptr, int64_t inner, int64_t outer, int64_t ld, i
     return EGP_ERR_UNSUPPORTED;
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * (cuuint64_t)esize};
+  const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   const cuuint32_t estr[2] = {1u, 1u};
-  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  const CUresult r = enc(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                         const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%lld outer=%lld ld=%lld box=%d", (int)r, ptr,
-              (long long)inner, (long long)outer, (long long)ld, box_outer);
+    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%lld outer=%lld ld=%lld box=%dx%d esize=%d", (int)r, ptr,
+              (long long)inner, (long long)outer, (long long)ld, box_inner, box_outer, esize);
     return EGP_ERR_CUDA;
   }
   std::lock_guard<std::mutex> lock(mu);
@@ -446,8 +537,8 @@ static int make_map(const void* ptr, int64_t inner, int64_t outer, int64_t ld, i
 
 // operand with `rows` (M or N) and `k`: trans=0 -> [rows,k] row-major (K-major); trans=1 -> [k,rows] (MN-major)
 static int operand_map(const void* ptr, int64_t rows, int64_t k, int64_t ld, int trans, int tile_rows, CUtensorMap* out) {
-  if (!trans) return make_map(ptr, k, rows, ld, tile_rows, out);
-  return make_map(ptr, rows, k, ld, 64, out);
+  if (!trans) return make_map(ptr, k, rows, ld, 64, tile_rows, 2, out);
+  return make_map(ptr, rows, k, ld, 64, 64, 2, out);
 }
 
 bool tc_gemm_supported(const void* A, int64_t lda, const void* B, int64_t ldb, const void* A2, int64_t lda2,
@@ -464,7 +555,7 @@ static int tc_launch_inst(const CUtensorMap* maps, const TcParams& p, int grid, 
     EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  kern<<<grid, TC_THREADS, TcCfg<BN>::kSmemBytes, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+  kern<<<grid, TC_THREADS, TcCfg<BN>::kSmemBytes, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
 }
@@ -491,12 +582,16 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
   if (M == 0 || N == 0) return EGP_OK;
   const int sms = sm_count();
   const int m_tiles = (int)ceil_div(M, TBM);
-  // tile N: no wider than N needs; then halve (not below 64: narrower tiles are smem-bandwidth bound) while the
-  // tile count leaves SMs idle.  MN-major B needs >= 64 (one swizzle atom).
+  // tile N: no wider than N needs.  When the epilogue is linear and fp32 (wgrad) SMs are filled by split-K with
+  // the widest tile; otherwise the tile is halved (not below 64: narrower tiles are smem-bandwidth bound) while
+  // the tile count leaves SMs idle.  MN-major B needs >= 64 (one swizzle atom).
   const int bn_min = b_trans ? 64 : 16;
+  const bool can_split = out_dtype == EGP_F32 && act == EGP_ACT_NONE && !residual;
+  const int kb_total = (int)ceil_div(K, TBK) + ((A2 && B2 && K2 > 0) ? (int)ceil_div(K2, TBK) : 0);
   int bn = 256;
   while (bn > bn_min && bn / 2 >= N) bn /= 2;
-  while (bn > 64 && (int64_t)m_tiles * ceil_div(N, bn) < sms) bn /= 2;
+  if (!(can_split && kb_total >= 16))
+    while (bn > 64 && (int64_t)m_tiles * ceil_div(N, bn) < sms) bn /= 2;
   const int n_tiles = (int)ceil_div(N, bn);
   const bool has2 = A2 && B2 && K2 > 0;
   TcParams p;
@@ -511,7 +606,7 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
   // split-K: only for fp32 outputs without a non-linear epilogue (wgrad); keeps >= 4 k-blocks per split
   int splits = 1;
   const int tiles = m_tiles * n_tiles, kb_all = p.kb1 + p.kb2;
-  if (out_dtype == EGP_F32 && act == EGP_ACT_NONE && !residual && tiles * 2 <= sms && kb_all >= 8) {
+  if (can_split && tiles * 2 <= sms && kb_all >= 8) {
     splits = sms / tiles;
     if (splits > kb_all / 4) splits = kb_all / 4;
     if (splits < 1) splits = 1;
@@ -527,7 +622,7 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
     if (ldc == N) EGP_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * (size_t)N, stream));
     else EGP_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, (size_t)M, stream));
   }
-  CUtensorMap maps[4];
+  CUtensorMap maps[5];
   int rc;
   if ((rc = operand_map(A, M, K, lda, a_trans, TBM, &maps[0])) != EGP_OK) return rc;
   if ((rc = operand_map(B, N, K, ldb, b_trans, bn, &maps[1])) != EGP_OK) return rc;
@@ -537,6 +632,15 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
   } else {
     maps[2] = maps[0];
     maps[3] = maps[1];
+  }
+  // TMA-store epilogue: needs a 16-byte-aligned C with 16-byte row pitch, a tile at least one 128-byte staged row
+  // wide, and no residual (the residual form keeps the register-direct epilogue)
+  const int esz = out_dtype == EGP_F32 ? 4 : 2;
+  p.tma_store = (!residual && aligned16(C) && (ldc * esz) % 16 == 0 && bn >= 128 / esz) ? 1 : 0;
+  if (p.tma_store) {
+    if ((rc = make_map(C, N, M, ldc, 128 / esz, 32, esz, &maps[4])) != EGP_OK) return rc;
+  } else {
+    maps[4] = maps[0];
   }
   const int total = tiles * splits;
   const int grid = total < sms ? total : sms;

@@ -68,7 +68,9 @@ gln_stats_kernel(const T* __restrict__ x, int64_t nvec, double inv_count, double
   }
 }
 
-template <typename T>
+// FIXED: the grid stride is a multiple of the row length, so a thread always lands on the same 16-byte column and
+// keeps that column's weight/bias in registers (otherwise they are re-read, vectorised, every iteration).
+template <typename T, bool FIXED>
 __global__ void __launch_bounds__(kNormThreads)
 gln_apply_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                  T* __restrict__ y, const double* __restrict__ stats, int64_t nvec, int64_t channels, float eps,
@@ -76,14 +78,33 @@ gln_apply_kernel(const T* __restrict__ x, const float* __restrict__ w, const flo
   constexpr int VN = Vec<T>::N;
   const float mu = (float)stats[0];
   const float rs = (float)(1.0 / (stats[1] + (double)eps));
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c0 = (v * VN) % channels;
+  const int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float wv[VN], bv[VN];
+  if (FIXED) {
+    const int64_t c0 = (v0 * VN) % channels;
+#pragma unroll
+    for (int c = 0; c < VN; c += 4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(w + c0 + c);
+      const float4 b4 = *reinterpret_cast<const float4*>(b + c0 + c);
+      wv[c] = w4.x; wv[c + 1] = w4.y; wv[c + 2] = w4.z; wv[c + 3] = w4.w;
+      bv[c] = b4.x; bv[c + 1] = b4.y; bv[c + 2] = b4.z; bv[c + 3] = b4.w;
+    }
+  }
+#pragma unroll 2
+  for (int64_t v = v0; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    if (!FIXED) {
+      const int64_t c0 = (v * VN) % channels;
+#pragma unroll
+      for (int c = 0; c < VN; c += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w + c0 + c);
+        const float4 b4 = *reinterpret_cast<const float4*>(b + c0 + c);
+        wv[c] = w4.x; wv[c + 1] = w4.y; wv[c + 2] = w4.z; wv[c + 3] = w4.w;
+        bv[c] = b4.x; bv[c + 1] = b4.y; bv[c + 2] = b4.z; bv[c + 3] = b4.w;
+      }
+    }
     Vec<T> a = Vec<T>::load(x + v * VN);
 #pragma unroll
-    for (int c = 0; c < VN; ++c) {
-      const float xh = (a.v[c] - mu) * rs;
-      a.v[c] = apply_act(xh * w[c0 + c] + b[c0 + c], act, slope);
-    }
+    for (int c = 0; c < VN; ++c) a.v[c] = apply_act((a.v[c] - mu) * rs * wv[c] + bv[c], act, slope);
     a.store(y + v * VN);
   }
 }
@@ -155,23 +176,34 @@ gln_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const f
   }
 }
 
-// blocks [0, colblocks): out0[c] = sum_g colpart[g][0][c], out1[c] = sum_g colpart[g][1][c]
-// block colblocks (if scal != null): scal[0..1] = sum of scalpart pairs
+// blocks [0, colblocks): 32 columns x 8 part-groups each: out0[c] = sum_g colpart[g][0][c], out1[c] likewise.
+// block colblocks (if scal != null): scal[0..1] = sum of the scalpart pairs.
 __global__ void __launch_bounds__(kNormThreads)
 col_finalize_kernel(const float* __restrict__ colpart, int parts, int64_t channels, float* __restrict__ out0,
                     float* __restrict__ out1, const double* __restrict__ scalpart, int scal_parts,
                     double* __restrict__ scal, int colblocks) {
   __shared__ double red[32];
+  __shared__ float r0[8][33], r1[8][33];
   if ((int)blockIdx.x < colblocks) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= channels) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t c = (int64_t)blockIdx.x * 32 + tx;
     float a0 = 0.f, a1 = 0.f;
-    for (int g = 0; g < parts; ++g) {
-      a0 += colpart[(size_t)g * 2 * channels + c];
-      a1 += colpart[(size_t)g * 2 * channels + channels + c];
+    if (c < channels) {
+      for (int g = ty; g < parts; g += 8) {
+        a0 += colpart[(size_t)g * 2 * channels + c];
+        a1 += colpart[(size_t)g * 2 * channels + channels + c];
+      }
     }
-    if (out0) out0[c] = a0;
-    if (out1) out1[c] = a1;
+    r0[ty][tx] = a0;
+    r1[ty][tx] = a1;
+    __syncthreads();
+    if (ty == 0 && c < channels) {
+      float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { t0 += r0[i][tx]; t1 += r1[i][tx]; }
+      if (out0) out0[c] = t0;
+      if (out1) out1[c] = t1;
+    }
   } else {
     double s1 = 0.0, s2 = 0.0;
     for (int p = threadIdx.x; p < scal_parts; p += blockDim.x) {
@@ -184,7 +216,7 @@ col_finalize_kernel(const float* __restrict__ colpart, int parts, int64_t channe
   }
 }
 
-template <typename T>
+template <typename T, bool FIXED>
 __global__ void __launch_bounds__(kNormThreads)
 gln_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ b, const double* __restrict__ stats, const double* __restrict__ scal,
@@ -197,16 +229,28 @@ gln_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
   const float m1 = (float)(scal[0] * inv_count);  // mean(g_hat)
   const double den = sigma * (sigma + (double)eps) * (sigma + (double)eps);
   const float k2 = den > 0.0 ? (float)(scal[1] * inv_count / den) : 0.f;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c0 = (v * VN) % channels;
+  const int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float wv[VN], bv[VN];
+  auto load_params = [&](int64_t c0) {
+#pragma unroll
+    for (int c = 0; c < VN; c += 4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(w + c0 + c);
+      const float4 b4 = *reinterpret_cast<const float4*>(b + c0 + c);
+      wv[c] = w4.x; wv[c + 1] = w4.y; wv[c + 2] = w4.z; wv[c + 3] = w4.w;
+      bv[c] = b4.x; bv[c + 1] = b4.y; bv[c + 2] = b4.z; bv[c + 3] = b4.w;
+    }
+  };
+  if (FIXED) load_params((v0 * VN) % channels);
+#pragma unroll 2
+  for (int64_t v = v0; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    if (!FIXED) load_params((v * VN) % channels);
     const Vec<T> g = Vec<T>::load(dy + v * VN);
     Vec<T> a = Vec<T>::load(x + v * VN);
 #pragma unroll
     for (int c = 0; c < VN; ++c) {
       const float d = a.v[c] - mu;
       const float xh = d * rs;
-      const float wc = w[c0 + c];
-      const float gh = g.v[c] * act_grad(xh * wc + b[c0 + c], act, slope) * wc;
+      const float gh = g.v[c] * act_grad(xh * wv[c] + bv[c], act, slope) * wv[c];
       a.v[c] = (gh - m1) * rs - d * k2;
     }
     a.store(dx + v * VN);
@@ -225,6 +269,20 @@ rln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float
   const int lane = threadIdx.x & 31;
   const int nvec = (int)(channels / VN);
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float wv[NVL][VN], bv[NVL][VN];
+#pragma unroll
+  for (int it = 0; it < NVL; ++it) {
+    const int v = lane + 32 * it;
+    if (v < nvec) {
+#pragma unroll
+      for (int c = 0; c < VN; c += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w + v * VN + c);
+        const float4 b4 = *reinterpret_cast<const float4*>(b + v * VN + c);
+        wv[it][c] = w4.x; wv[it][c + 1] = w4.y; wv[it][c + 2] = w4.z; wv[it][c + 3] = w4.w;
+        bv[it][c] = b4.x; bv[it][c + 1] = b4.y; bv[it][c + 2] = b4.z; bv[it][c + 3] = b4.w;
+      }
+    }
+  }
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
     const T* xr = x + row * channels;
     Vec<T> a[NVL];
@@ -258,7 +316,7 @@ rln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float
         Vec<T> o;
 #pragma unroll
         for (int c = 0; c < VN; ++c)
-          o.v[c] = apply_act((a[it].v[c] - mu) * rs * w[v * VN + c] + b[v * VN + c], act, 0.f);
+          o.v[c] = apply_act((a[it].v[c] - mu) * rs * wv[it][c] + bv[it][c], act, 0.f);
         o.store(yr + (int64_t)v * VN);
       }
     }
@@ -276,11 +334,20 @@ rln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __res
   const int nvec = (int)(channels / VN);
   for (int64_t c = threadIdx.x; c < 2 * channels; c += blockDim.x) cacc[c] = 0.f;
   __syncthreads();
-  float dw[NVL][VN], db[NVL][VN];
+  float dw[NVL][VN], db[NVL][VN], wv[NVL][VN];
 #pragma unroll
-  for (int it = 0; it < NVL; ++it)
+  for (int it = 0; it < NVL; ++it) {
+    const int v = lane + 32 * it;
 #pragma unroll
-    for (int c = 0; c < VN; ++c) { dw[it][c] = 0.f; db[it][c] = 0.f; }
+    for (int c = 0; c < VN; ++c) { dw[it][c] = 0.f; db[it][c] = 0.f; wv[it][c] = 0.f; }
+    if (v < nvec) {
+#pragma unroll
+      for (int c = 0; c < VN; c += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w + v * VN + c);
+        wv[it][c] = w4.x; wv[it][c + 1] = w4.y; wv[it][c + 2] = w4.z; wv[it][c + 3] = w4.w;
+      }
+    }
+  }
 
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
@@ -303,7 +370,7 @@ rln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __res
           if (act == EGP_ACT_RELU && !(yo.v[c] > 0.f)) gp = 0.f;
           dw[it][c] += gp * h;
           db[it][c] += gp;
-          const float t = gp * w[v * VN + c];
+          const float t = gp * wv[it][c];
           gh[it].v[c] = t;
           xh[it].v[c] = h;
           s1 += t;
@@ -338,6 +405,78 @@ rln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __res
   __syncthreads();
   float* cp = colpart + (size_t)blockIdx.x * 2 * channels;
   for (int64_t c = threadIdx.x; c < 2 * channels; c += blockDim.x) cp[c] = cacc[c];
+}
+
+// Row-LN backward, one CTA per row (rows strided over the grid): thread t owns the 16-byte column t of every row its
+// CTA visits, so dweight/dbias accumulate in registers with no atomics, the two row statistics need one
+// __syncthreads per row (double-buffered scratch), and the register footprint stays small enough for full occupancy.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+rln_bwd_block_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+                     const float* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     T* __restrict__ dx, int64_t n, int64_t channels, int act, float* __restrict__ colpart) {
+  constexpr int VN = Vec<T>::N;
+  __shared__ float red[2][32][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int64_t col = (int64_t)threadIdx.x * VN;
+  const bool live = col < channels;
+  float wv[VN], dw[VN], db[VN];
+#pragma unroll
+  for (int c = 0; c < VN; ++c) { wv[c] = 0.f; dw[c] = 0.f; db[c] = 0.f; }
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < VN; c += 4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(w + col + c);
+      wv[c] = w4.x; wv[c + 1] = w4.y; wv[c + 2] = w4.z; wv[c + 3] = w4.w;
+    }
+  }
+  const float inv_c = 1.f / (float)channels;
+  int buf = 0;
+  for (int64_t row = blockIdx.x; row < n; row += gridDim.x, buf ^= 1) {
+    float gh[VN], xh[VN];
+    float s1 = 0.f, s2 = 0.f;
+    const float rs = rstd[row];
+    if (live) {
+      const float mu = mean[row];
+      const int64_t o = row * channels + col;
+      const Vec<T> g = Vec<T>::load(dy + o);
+      const Vec<T> a = Vec<T>::load(x + o);
+      Vec<T> yo;
+      if (act == EGP_ACT_RELU) yo = Vec<T>::load(y + o);
+#pragma unroll
+      for (int c = 0; c < VN; ++c) {
+        const float h = (a.v[c] - mu) * rs;
+        float gp = g.v[c];
+        if (act == EGP_ACT_RELU && !(yo.v[c] > 0.f)) gp = 0.f;
+        dw[c] += gp * h;
+        db[c] += gp;
+        const float t = gp * wv[c];
+        gh[c] = t;
+        xh[c] = h;
+        s1 += t;
+        s2 += t * h;
+      }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) { red[buf][warp][0] = s1; red[buf][warp][1] = s2; }
+    __syncthreads();
+    float c1 = 0.f, c2 = 0.f;
+    for (int i = 0; i < nw; ++i) { c1 += red[buf][i][0]; c2 += red[buf][i][1]; }
+    c1 *= inv_c;
+    c2 *= inv_c;
+    if (live) {
+      Vec<T> o;
+#pragma unroll
+      for (int c = 0; c < VN; ++c) o.v[c] = rs * (gh[c] - c1 - xh[c] * c2);
+      o.store(dx + row * channels + col);
+    }
+  }
+  if (live) {
+    float* cp = colpart + (size_t)blockIdx.x * 2 * channels;
+#pragma unroll
+    for (int c = 0; c < VN; ++c) { cp[col + c] = dw[c]; cp[channels + col + c] = db[c]; }
+  }
 }
 
 // generic fallbacks for very wide rows (no register cache; rows are re-read through L1/L2)
@@ -479,7 +618,9 @@ int egp_graph_layernorm_fwd(const void* x, const float* weight, const float* bia
                                                      &ws->ticket, stats);
     EGP_LAUNCH_CHECK();
     const int g2 = norm_grid(nvec, kNormThreads * 2) * 2;
-    gln_apply_kernel<T><<<g2, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, stats, nvec, channels, eps, act, slope);
+    const bool fixed = ((int64_t)g2 * kNormThreads) % (channels / Vec<T>::N) == 0;
+    if (fixed) gln_apply_kernel<T, true><<<g2, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, stats, nvec, channels, eps, act, slope);
+    else gln_apply_kernel<T, false><<<g2, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, stats, nvec, channels, eps, act, slope);
     EGP_LAUNCH_CHECK();
   });
   return EGP_OK;
@@ -512,15 +653,21 @@ int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, 
     gln_bwd_reduce_kernel<T><<<dim3(parts, gy), kNormThreads, 0, s>>>(
         (const T*)dy, (const T*)x, weight, bias, stats, n, channels, rows_per, eps, act, slope, colpart, scalpart);
     EGP_LAUNCH_CHECK();
-    const int colblocks = (int)ceil_div(channels, kNormThreads);
+    const int colblocks = (int)ceil_div(channels, 32);
     col_finalize_kernel<<<colblocks + 1, kNormThreads, 0, s>>>(colpart, parts, channels, dweight, dbias, scalpart,
                                                                parts * gy, ws->scal, colblocks);
     EGP_LAUNCH_CHECK();
     const int64_t nvec = n * channels / VN;
     const int g2 = norm_grid(nvec, kNormThreads * 2) * 2;
-    gln_bwd_apply_kernel<T><<<g2, kNormThreads, 0, s>>>((const T*)dy, (const T*)x, weight, bias, stats, ws->scal,
-                                                        (T*)dx, nvec, channels, 1.0 / ((double)n * (double)channels),
-                                                        eps, act, slope);
+    const bool fixed = ((int64_t)g2 * kNormThreads) % (channels / VN) == 0;
+    if (fixed)
+      gln_bwd_apply_kernel<T, true><<<g2, kNormThreads, 0, s>>>((const T*)dy, (const T*)x, weight, bias, stats, ws->scal,
+                                                                (T*)dx, nvec, channels,
+                                                                1.0 / ((double)n * (double)channels), eps, act, slope);
+    else
+      gln_bwd_apply_kernel<T, false><<<g2, kNormThreads, 0, s>>>((const T*)dy, (const T*)x, weight, bias, stats, ws->scal,
+                                                                 (T*)dx, nvec, channels,
+                                                                 1.0 / ((double)n * (double)channels), eps, act, slope);
     EGP_LAUNCH_CHECK();
   });
   return EGP_OK;
@@ -528,7 +675,7 @@ int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, 
 
 size_t egp_row_layernorm_workspace(int64_t n, int64_t channels) {
   (void)n;
-  return sizeof(float) * 2 * (size_t)(sm_count() * 4) * (size_t)channels + 64;
+  return sizeof(float) * 2 * (size_t)(sm_count() * 8) * (size_t)channels + 64;
 }
 
 #define EGP_RLN_DISPATCH_NVL(nvec, ...)                                               \
@@ -580,21 +727,29 @@ int egp_row_layernorm_bwd(const void* dy, const void* x, const void* y, const fl
     if (dbias) EGP_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * channels, s));
     return EGP_OK;
   }
-  const int grid = norm_grid(n, kNormThreads / 32);
+  int grid = norm_grid(n, (kNormThreads / 32) * 16);   // warp-per-row kernels: >= 16 rows per warp
   const size_t smem = sizeof(float) * 2 * channels;
   float* colpart = (float*)workspace;
   EGP_DISPATCH_DTYPE(dtype, T, {
     const int64_t nvec = channels / Vec<T>::N;
-    EGP_RLN_DISPATCH_NVL(nvec, {
-      auto kern = rln_bwd_wide_kernel<T>;
-      if constexpr (NVL != 0) kern = rln_bwd_kernel<T, NVL>;
-      if (smem > 48 * 1024) EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<grid, kNormThreads, smem, s>>>((const T*)dy, (const T*)x, (const T*)y, weight, mean, rstd, (T*)dx, n,
-                                            channels, act, colpart);
-    });
+    if (nvec > 32 && nvec <= 1024) {                     // one CTA per row, thread-owned columns
+      const int threads = (int)((nvec + 31) / 32 * 32);
+      const int64_t cap = (int64_t)sm_count() * 8;
+      grid = (int)(n < cap ? n : cap);
+      rln_bwd_block_kernel<T><<<grid, threads, 0, s>>>((const T*)dy, (const T*)x, (const T*)y, weight, mean, rstd, (T*)dx,
+                                                       n, channels, act, colpart);
+    } else {
+      EGP_RLN_DISPATCH_NVL(nvec, {
+        auto kern = rln_bwd_wide_kernel<T>;
+        if constexpr (NVL != 0) kern = rln_bwd_kernel<T, NVL>;
+        if (smem > 48 * 1024) EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kNormThreads, smem, s>>>((const T*)dy, (const T*)x, (const T*)y, weight, mean, rstd, (T*)dx, n,
+                                              channels, act, colpart);
+      });
+    }
     EGP_LAUNCH_CHECK();
   });
-  const int colblocks = (int)ceil_div(channels, kNormThreads);
+  const int colblocks = (int)ceil_div(channels, 32);
   col_finalize_kernel<<<colblocks, kNormThreads, 0, s>>>(colpart, grid, channels, dweight, dbias, nullptr, 0, nullptr, colblocks);
   EGP_LAUNCH_CHECK();
   return EGP_OK;

@@ -123,7 +123,7 @@ def test_segment_max_pool(dtype, tol):
     n, c = batch.numel(), 96
     # distinct small integers per column: exact in bf16 and tie-free (with ties the reference's CPU scatter splits
     # the gradient while its CUDA torch_scatter path -- and this kernel -- credit the first arg-max)
-    x = torch.stack([torch.randperm(n, generator=g) for _ in range(c)], 1).float().sub(70).to(dtype)
+    x = torch.stack([torch.randperm(n, generator=g) for _ in range(c)], 1).float().sub(70.5).to(dtype)
     dy = torch.randn(len(sizes), c, generator=g).to(dtype)
     xr = x.float().clone().requires_grad_(True)
     want = pyg.global_max_pool(xr, batch)
