@@ -159,6 +159,57 @@ __device__ __forceinline__ T block_sum(T v, T* smem) {
   return r;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// counter-based RNG for fused dropout: Philox4x32-10 keyed by (seed), counted by (element-vector index, offset)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+// keep-decisions for the (up to 8) elements of the 16-byte vector with global index `vec`: bit c = keep element c.
+// Drop probability is quantised to 1/65536.
+__device__ __forceinline__ uint32_t dropout_keep_bits(uint64_t vec, uint64_t seed, uint64_t offset, uint32_t thr16) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)vec, (uint32_t)(vec >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t bits = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bits |= ((w[i] & 0xffffu) >= thr16 ? 1u : 0u) << (2 * i);
+    bits |= ((w[i] >> 16) >= thr16 ? 1u : 0u) << (2 * i + 1);
+  }
+  return bits;
+}
+
+// Per-CTA column partial for flat grid-stride kernels whose threads keep a FIXED 16-byte column (the grid stride is
+// a multiple of the row length).  `period` = vectors per row; requires period <= blockDim.x and blockDim.x % period
+// == 0.  Threads sharing a column are combined through shared memory and row `blockIdx.x` of the [gridDim.x, C]
+// partial matrix is written; a col-finalize kernel then reduces the partial rows in a fixed order (deterministic).
+template <int VN>
+__device__ __forceinline__ void block_column_partial(const float (&dsum)[VN], int period, float* __restrict__ part_row,
+                                                     float* smem /* blockDim.x * VN floats */) {
+#pragma unroll
+  for (int c = 0; c < VN; ++c) smem[threadIdx.x * VN + c] = dsum[c];
+  __syncthreads();
+  if ((int)threadIdx.x < period) {
+#pragma unroll
+    for (int c = 0; c < VN; ++c) {
+      float t = 0.f;
+      for (int j = threadIdx.x; j < (int)blockDim.x; j += period) t += smem[j * VN + c];
+      part_row[threadIdx.x * VN + c] = t;
+    }
+  }
+}
+
 // dispatch on the dtype code
 #define EGP_DISPATCH_DTYPE(dtype, T, ...)                         \
   do {                                                            \

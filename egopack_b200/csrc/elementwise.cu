@@ -204,15 +204,22 @@ colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, int64
     if (col + c < cols) part[(size_t)blockIdx.x * cols + col + c] = acc[c];
 }
 
-// out[c] = sum_g part[g][c]; block = 32 columns x 8 part-groups so the reduction over parts is parallel
+// out[c] = sum_g part[g][c]; block = 32 columns x 8 part-groups, 4 loads in flight per thread (deterministic order)
 __global__ void __launch_bounds__(kEwThreads)
 colsum_final_kernel(const float* __restrict__ part, int parts, int64_t cols, float* __restrict__ out) {
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 32 + tx;
   float a = 0.f;
-  if (c < cols)
-    for (int g = ty; g < parts; g += 8) a += part[(size_t)g * cols + c];
+  if (c < cols) {
+    int g = ty;
+    for (; g + 24 < parts; g += 32) {
+      const float v0 = part[(size_t)g * cols + c], v1 = part[(size_t)(g + 8) * cols + c];
+      const float v2 = part[(size_t)(g + 16) * cols + c], v3 = part[(size_t)(g + 24) * cols + c];
+      a += (v0 + v1) + (v2 + v3);
+    }
+    for (; g < parts; g += 8) a += part[(size_t)g * cols + c];
+  }
   red[ty][tx] = a;
   __syncthreads();
   if (ty == 0 && c < cols) {
@@ -242,10 +249,68 @@ row_inv_norm_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t ro
   if (lane == 0) out[row] = 1.0f / sqrtf(q);  // no epsilon, as the reference (graphONE.py:148-151)
 }
 
+// dx = dy * act'(y) fused with the column sums of dx (bias gradient of the producing Linear): threads keep a fixed
+// 16-byte column (grid stride multiple of the row length), CTA partial rows -> colsum_final_kernel.
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+act_bwd_colsum_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t nvec, int period,
+                      int act, float slope, float* __restrict__ part) {
+  constexpr int VN = Vec<T>::N;
+  __shared__ float csum[kEwThreads * VN];
+  float dsum[VN];
+#pragma unroll
+  for (int c = 0; c < VN; ++c) dsum[c] = 0.f;
+#pragma unroll 2
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    Vec<T> g = Vec<T>::load(dy + v * VN);
+    const Vec<T> o = Vec<T>::load(y + v * VN);
+#pragma unroll
+    for (int c = 0; c < VN; ++c) {
+      if (!(o.v[c] > 0.f)) g.v[c] = (act == EGP_ACT_LEAKY_RELU) ? g.v[c] * slope : 0.f;
+      dsum[c] += to_float<T>(from_float<T>(g.v[c]));
+    }
+    g.store(dx + v * VN);
+  }
+  block_column_partial<VN>(dsum, period, part + (size_t)blockIdx.x * period * VN, csum);
+}
+
 static int colsum_parts(int64_t rows) {
   int64_t p = ceil_div(rows, 32);
   const int64_t cap = (int64_t)sm_count() * 8;
   return (int)(p < 1 ? 1 : (p > cap ? cap : p));
+}
+
+size_t colsum_workspace_bytes(int64_t rows, int64_t cols) {
+  return sizeof(float) * (size_t)colsum_parts(rows) * (size_t)cols + 64;
+}
+
+int colsum_launch(const void* x, float* out, int64_t rows, int64_t cols, int64_t ldx, int dtype, void* workspace,
+                  size_t ws_bytes, cudaStream_t s) {
+  EGP_REQUIRE(x && out && workspace, "colsum: null pointer");
+  if (ws_bytes < colsum_workspace_bytes(rows, cols)) {
+    set_error("colsum: workspace too small");
+    return EGP_ERR_WORKSPACE;
+  }
+  if (cols == 0) return EGP_OK;
+  if (rows == 0) {
+    EGP_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, s));
+    return EGP_OK;
+  }
+  const int parts = colsum_parts(rows);
+  const int rows_per = (int)ceil_div(rows, parts);
+  float* part = (float*)workspace;
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    constexpr int VN = Vec<T>::N;
+    const int vec_ok = aligned16(x) && (ldx % VN) == 0;
+    const int64_t nvec = ceil_div(cols, (int64_t)VN);
+    const int threads = (int)(nvec >= kEwThreads ? kEwThreads : (nvec + 31) / 32 * 32);   // no idle half-blocks
+    const int gy = (int)ceil_div(nvec, (int64_t)threads);
+    colsum_partial_kernel<T><<<dim3(parts, gy), threads, 0, s>>>((const T*)x, rows, cols, ldx, rows_per, vec_ok, part);
+    EGP_LAUNCH_CHECK();
+  });
+  colsum_final_kernel<<<(unsigned)ceil_div(cols, 32), kEwThreads, 0, s>>>(part, parts, cols, out);
+  EGP_LAUNCH_CHECK();
+  return EGP_OK;
 }
 
 }  // namespace egp
@@ -365,37 +430,51 @@ int egp_max_combine_bwd(const void* da, const void* f, const void* m, void* df, 
   return EGP_OK;
 }
 
-size_t egp_colsum_workspace(int64_t rows, int64_t cols) {
-  return sizeof(float) * (size_t)colsum_parts(rows) * (size_t)cols + 64;
-}
+size_t egp_colsum_workspace(int64_t rows, int64_t cols) { return colsum_workspace_bytes(rows, cols); }
 
 int egp_colsum(const void* x, float* out, int64_t rows, int64_t cols, int64_t ldx, int dtype, void* workspace,
                size_t ws_bytes, void* stream) {
-  EGP_REQUIRE(x && out && workspace, "colsum: null pointer");
-  if (ws_bytes < egp_colsum_workspace(rows, cols)) {
-    set_error("colsum: workspace too small");
+  return colsum_launch(x, out, rows, cols, ldx, dtype, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+size_t egp_act_bwd_colsum_workspace(int64_t rows, int64_t cols) {
+  return sizeof(float) * (size_t)(sm_count() * 8) * (size_t)cols + colsum_workspace_bytes(rows, cols) + 128;
+}
+
+int egp_act_bwd_colsum(const void* dy, const void* y, void* dx, float* dx_colsum, int64_t rows, int64_t cols, int act,
+                       float slope, int dtype, void* workspace, size_t ws_bytes, void* stream) {
+  EGP_REQUIRE(dy && y && dx && dx_colsum && workspace, "act_bwd_colsum: null pointer");
+  EGP_REQUIRE(act == EGP_ACT_RELU || act == EGP_ACT_LEAKY_RELU, "act_bwd_colsum: act must be relu or leaky relu");
+  const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(cols % vn == 0, "act_bwd_colsum: cols must be a multiple of %d", (int)vn);
+  if (ws_bytes < egp_act_bwd_colsum_workspace(rows, cols)) {
+    set_error("act_bwd_colsum: workspace too small");
     return EGP_ERR_WORKSPACE;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (cols == 0) return EGP_OK;
   if (rows == 0) {
-    EGP_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, s));
+    EGP_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * cols, s));
     return EGP_OK;
   }
-  const int parts = colsum_parts(rows);
-  const int rows_per = (int)ceil_div(rows, parts);
   float* part = (float*)workspace;
+  void* cs_ws = part + (size_t)(sm_count() * 8) * cols;
   EGP_DISPATCH_DTYPE(dtype, T, {
     constexpr int VN = Vec<T>::N;
-    const int vec_ok = aligned16(x) && (ldx % VN) == 0;
-    const int64_t nvec = ceil_div(cols, (int64_t)VN);
-    const int threads = (int)(nvec >= kEwThreads ? kEwThreads : (nvec + 31) / 32 * 32);   // no idle half-blocks
-    const int gy = (int)ceil_div(nvec, (int64_t)threads);
-    colsum_partial_kernel<T><<<dim3(parts, gy), threads, 0, s>>>((const T*)x, rows, cols, ldx, rows_per, vec_ok, part);
-    EGP_LAUNCH_CHECK();
+    const int64_t nvec = rows * cols / VN, period = cols / VN;
+    const int grid = ew_grid(nvec);
+    const bool fuse = ((int64_t)grid * kEwThreads) % period == 0 && period <= kEwThreads && kEwThreads % period == 0;
+    if (fuse) {
+      act_bwd_colsum_kernel<T><<<grid, kEwThreads, 0, s>>>((const T*)dy, (const T*)y, (T*)dx, nvec, (int)period, act, slope, part);
+      EGP_LAUNCH_CHECK();
+      colsum_final_kernel<<<(unsigned)ceil_div(cols, 32), kEwThreads, 0, s>>>(part, grid, cols, dx_colsum);
+      EGP_LAUNCH_CHECK();
+    } else {
+      act_bwd_kernel<T><<<grid, kEwThreads, 0, s>>>((const T*)dy, (const T*)y, (T*)dx, nvec, act, slope);
+      EGP_LAUNCH_CHECK();
+      const int rc = colsum_launch(dx, dx_colsum, rows, cols, cols, dtype, cs_ws, colsum_workspace_bytes(rows, cols), s);
+      if (rc != EGP_OK) return rc;
+    }
   });
-  colsum_final_kernel<<<(unsigned)ceil_div(cols, 32), kEwThreads, 0, s>>>(part, parts, cols, out);
-  EGP_LAUNCH_CHECK();
   return EGP_OK;
 }
 

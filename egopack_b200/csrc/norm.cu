@@ -11,6 +11,11 @@
 
 namespace egp {
 
+// elementwise.cu
+size_t colsum_workspace_bytes(int64_t rows, int64_t cols);
+int colsum_launch(const void* x, float* out, int64_t rows, int64_t cols, int64_t ldx, int dtype, void* workspace,
+                  size_t ws_bytes, cudaStream_t stream);
+
 constexpr int kNormThreads = 256;
 
 // ---------------------------------------------------------------------------------------------------------
@@ -176,33 +181,48 @@ gln_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const f
   }
 }
 
-// blocks [0, colblocks): 32 columns x 8 part-groups each: out0[c] = sum_g colpart[g][0][c], out1[c] likewise.
-// block colblocks (if scal != null): scal[0..1] = sum of the scalpart pairs.
-__global__ void __launch_bounds__(kNormThreads)
-col_finalize_kernel(const float* __restrict__ colpart, int parts, int64_t channels, float* __restrict__ out0,
-                    float* __restrict__ out1, const double* __restrict__ scalpart, int scal_parts,
-                    double* __restrict__ scal, int colblocks) {
+// Deterministic reduction of per-CTA column partials.  colpart is [parts][nout][channels]; block = 32 columns x 32
+// part-groups (1024 threads, 4 loads in flight each): out_k[c] = sum_g colpart[g][k][c].
+// The extra block `colblocks` (if scal != null) reduces the scalar pairs: scal[0..1] = sum scalpart.
+constexpr int kFinThreads = 1024;
+__global__ void __launch_bounds__(kFinThreads)
+col_finalize_kernel(const float* __restrict__ colpart, int parts, int64_t channels, int nout, float* __restrict__ out0,
+                    float* __restrict__ out1, float* __restrict__ out2, const double* __restrict__ scalpart,
+                    int scal_parts, double* __restrict__ scal, int colblocks) {
   __shared__ double red[32];
-  __shared__ float r0[8][33], r1[8][33];
+  __shared__ float rs[3][32][33];
   if ((int)blockIdx.x < colblocks) {
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t c = (int64_t)blockIdx.x * 32 + tx;
-    float a0 = 0.f, a1 = 0.f;
+    float a[3] = {0.f, 0.f, 0.f};
     if (c < channels) {
-      for (int g = ty; g < parts; g += 8) {
-        a0 += colpart[(size_t)g * 2 * channels + c];
-        a1 += colpart[(size_t)g * 2 * channels + channels + c];
-      }
-    }
-    r0[ty][tx] = a0;
-    r1[ty][tx] = a1;
-    __syncthreads();
-    if (ty == 0 && c < channels) {
-      float t0 = 0.f, t1 = 0.f;
+      const size_t stride = (size_t)nout * channels;
+      int g = ty;
+      for (; g + 96 < parts; g += 128) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { t0 += r0[i][tx]; t1 += r1[i][tx]; }
-      if (out0) out0[c] = t0;
-      if (out1) out1[c] = t1;
+        for (int k = 0; k < 3; ++k) {
+          if (k < nout) {
+            const float* p = colpart + (size_t)k * channels + c;
+            const float v0 = p[(size_t)g * stride], v1 = p[(size_t)(g + 32) * stride];
+            const float v2 = p[(size_t)(g + 64) * stride], v3 = p[(size_t)(g + 96) * stride];
+            a[k] += (v0 + v1) + (v2 + v3);
+          }
+        }
+      }
+      for (; g < parts; g += 32)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (k < nout) a[k] += colpart[(size_t)g * stride + (size_t)k * channels + c];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rs[k][ty][tx] = a[k];
+    __syncthreads();
+    if (ty < 3 && ty < nout && c < channels) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t += rs[ty][i][tx];
+      float* o = ty == 0 ? out0 : (ty == 1 ? out1 : out2);
+      if (o) o[c] = t;
     }
   } else {
     double s1 = 0.0, s2 = 0.0;
@@ -221,8 +241,12 @@ __global__ void __launch_bounds__(kNormThreads)
 gln_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ b, const double* __restrict__ stats, const double* __restrict__ scal,
                      T* __restrict__ dx, int64_t nvec, int64_t channels, double inv_count, float eps, int act,
-                     float slope) {
+                     float slope, float* __restrict__ dxpart /* [gridDim.x, C] or null; FIXED only */) {
   constexpr int VN = Vec<T>::N;
+  __shared__ float csum[kNormThreads * VN];
+  float dsum[VN];
+#pragma unroll
+  for (int c = 0; c < VN; ++c) dsum[c] = 0.f;
   const double sigma = stats[1];
   const float mu = (float)stats[0];
   const float rs = (float)(1.0 / (sigma + (double)eps));
@@ -252,9 +276,12 @@ gln_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
       const float xh = d * rs;
       const float gh = g.v[c] * act_grad(xh * wv[c] + bv[c], act, slope) * wv[c];
       a.v[c] = (gh - m1) * rs - d * k2;
+      if (FIXED) dsum[c] += to_float<T>(from_float<T>(a.v[c]));  // column sum of dx as stored
     }
     a.store(dx + v * VN);
   }
+  if (FIXED && dxpart)
+    block_column_partial<VN>(dsum, (int)(channels / VN), dxpart + (size_t)blockIdx.x * channels, csum);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -264,7 +291,7 @@ template <typename T, int NVL>
 __global__ void __launch_bounds__(kNormThreads)
 rln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t n, int64_t channels,
-               float eps, int act) {
+               float eps, int act, uint32_t drop_thr16, float keep_scale, uint64_t seed, uint64_t offset) {
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const int nvec = (int)(channels / VN);
@@ -317,6 +344,11 @@ rln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float
 #pragma unroll
         for (int c = 0; c < VN; ++c)
           o.v[c] = apply_act((a[it].v[c] - mu) * rs * wv[it][c] + bv[it][c], act, 0.f);
+        if (drop_thr16) {  // fused inverted dropout (nn.Dropout after the ReLU, trn_pooling.py:31,36)
+          const uint32_t keep = dropout_keep_bits((uint64_t)row * nvec + v, seed, offset, drop_thr16);
+#pragma unroll
+          for (int c = 0; c < VN; ++c) o.v[c] = ((keep >> c) & 1u) ? o.v[c] * keep_scale : 0.f;
+        }
         o.store(yr + (int64_t)v * VN);
       }
     }
@@ -327,8 +359,10 @@ template <typename T, int NVL>
 __global__ void __launch_bounds__(kNormThreads)
 rln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                const float* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd,
-               T* __restrict__ dx, int64_t n, int64_t channels, int act, float* __restrict__ colpart) {
+               T* __restrict__ dx, int64_t n, int64_t channels, int act, float out_scale,
+               float* __restrict__ colpart) {
   constexpr int VN = Vec<T>::N;
+  const bool use_y = act == EGP_ACT_RELU || out_scale != 1.f;  // mask = output != 0 (ReLU and/or dropout)
   extern __shared__ float cacc[];  // [2][channels] block accumulators for dweight / dbias
   const int lane = threadIdx.x & 31;
   const int nvec = (int)(channels / VN);
@@ -362,12 +396,12 @@ rln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __res
         const Vec<T> g = Vec<T>::load(dy + o);
         const Vec<T> a = Vec<T>::load(x + o);
         Vec<T> yo;
-        if (act == EGP_ACT_RELU) yo = Vec<T>::load(y + o);
+        if (use_y) yo = Vec<T>::load(y + o);
 #pragma unroll
         for (int c = 0; c < VN; ++c) {
           const float h = (a.v[c] - mu) * rs;
-          float gp = g.v[c];
-          if (act == EGP_ACT_RELU && !(yo.v[c] > 0.f)) gp = 0.f;
+          float gp = g.v[c] * out_scale;
+          if (use_y && yo.v[c] == 0.f) gp = 0.f;
           dw[it][c] += gp * h;
           db[it][c] += gp;
           const float t = gp * wv[it][c];
@@ -414,15 +448,17 @@ template <typename T>
 __global__ void __launch_bounds__(1024)
 rln_bwd_block_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                      const float* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd,
-                     T* __restrict__ dx, int64_t n, int64_t channels, int act, float* __restrict__ colpart) {
+                     T* __restrict__ dx, int64_t n, int64_t channels, int act, float out_scale, int nout,
+                     float* __restrict__ colpart) {
   constexpr int VN = Vec<T>::N;
+  const bool use_y = act == EGP_ACT_RELU || out_scale != 1.f;
   __shared__ float red[2][32][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int64_t col = (int64_t)threadIdx.x * VN;
   const bool live = col < channels;
-  float wv[VN], dw[VN], db[VN];
+  float wv[VN], dw[VN], db[VN], dsum[VN];
 #pragma unroll
-  for (int c = 0; c < VN; ++c) { wv[c] = 0.f; dw[c] = 0.f; db[c] = 0.f; }
+  for (int c = 0; c < VN; ++c) { wv[c] = 0.f; dw[c] = 0.f; db[c] = 0.f; dsum[c] = 0.f; }
   if (live) {
 #pragma unroll
     for (int c = 0; c < VN; c += 4) {
@@ -442,12 +478,12 @@ rln_bwd_block_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
       const Vec<T> g = Vec<T>::load(dy + o);
       const Vec<T> a = Vec<T>::load(x + o);
       Vec<T> yo;
-      if (act == EGP_ACT_RELU) yo = Vec<T>::load(y + o);
+      if (use_y) yo = Vec<T>::load(y + o);
 #pragma unroll
       for (int c = 0; c < VN; ++c) {
         const float h = (a.v[c] - mu) * rs;
-        float gp = g.v[c];
-        if (act == EGP_ACT_RELU && !(yo.v[c] > 0.f)) gp = 0.f;
+        float gp = g.v[c] * out_scale;
+        if (use_y && yo.v[c] == 0.f) gp = 0.f;
         dw[c] += gp * h;
         db[c] += gp;
         const float t = gp * wv[c];
@@ -468,14 +504,21 @@ rln_bwd_block_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
     if (live) {
       Vec<T> o;
 #pragma unroll
-      for (int c = 0; c < VN; ++c) o.v[c] = rs * (gh[c] - c1 - xh[c] * c2);
+      for (int c = 0; c < VN; ++c) {
+        o.v[c] = rs * (gh[c] - c1 - xh[c] * c2);
+        dsum[c] += to_float<T>(from_float<T>(o.v[c]));  // column sum of dx AS STORED (bias gradient upstream)
+      }
       o.store(dx + row * channels + col);
     }
   }
   if (live) {
-    float* cp = colpart + (size_t)blockIdx.x * 2 * channels;
+    float* cp = colpart + (size_t)blockIdx.x * nout * channels;
 #pragma unroll
-    for (int c = 0; c < VN; ++c) { cp[col + c] = dw[c]; cp[channels + col + c] = db[c]; }
+    for (int c = 0; c < VN; ++c) {
+      cp[col + c] = dw[c];
+      cp[channels + col + c] = db[c];
+      if (nout == 3) cp[2 * channels + col + c] = dsum[c];
+    }
   }
 }
 
@@ -484,7 +527,8 @@ template <typename T>
 __global__ void __launch_bounds__(kNormThreads)
 rln_fwd_wide_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                     T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t n,
-                    int64_t channels, float eps, int act) {
+                    int64_t channels, float eps, int act, uint32_t drop_thr16, float keep_scale, uint64_t seed,
+                    uint64_t offset) {
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const int nvec = (int)(channels / VN);
@@ -510,6 +554,11 @@ rln_fwd_wide_kernel(const T* __restrict__ x, const float* __restrict__ w, const 
       Vec<T> a = Vec<T>::load(xr + (int64_t)v * VN);
 #pragma unroll
       for (int c = 0; c < VN; ++c) a.v[c] = apply_act((a.v[c] - mu) * rs * w[v * VN + c] + b[v * VN + c], act, 0.f);
+      if (drop_thr16) {
+        const uint32_t keep = dropout_keep_bits((uint64_t)row * nvec + v, seed, offset, drop_thr16);
+#pragma unroll
+        for (int c = 0; c < VN; ++c) a.v[c] = ((keep >> c) & 1u) ? a.v[c] * keep_scale : 0.f;
+      }
       a.store(y + row * channels + (int64_t)v * VN);
     }
   }
@@ -519,8 +568,10 @@ template <typename T>
 __global__ void __launch_bounds__(kNormThreads)
 rln_bwd_wide_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                     const float* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd,
-                    T* __restrict__ dx, int64_t n, int64_t channels, int act, float* __restrict__ colpart) {
+                    T* __restrict__ dx, int64_t n, int64_t channels, int act, float out_scale,
+                    float* __restrict__ colpart) {
   constexpr int VN = Vec<T>::N;
+  const bool use_y = act == EGP_ACT_RELU || out_scale != 1.f;
   extern __shared__ float cacc[];
   const int lane = threadIdx.x & 31;
   const int nvec = (int)(channels / VN);
@@ -535,12 +586,12 @@ rln_bwd_wide_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
       const Vec<T> g = Vec<T>::load(dy + o);
       const Vec<T> a = Vec<T>::load(x + o);
       Vec<T> yo;
-      if (act == EGP_ACT_RELU) yo = Vec<T>::load(y + o);
+      if (use_y) yo = Vec<T>::load(y + o);
 #pragma unroll
       for (int c = 0; c < VN; ++c) {
         const float h = (a.v[c] - mu) * rs;
-        float gp = g.v[c];
-        if (act == EGP_ACT_RELU && !(yo.v[c] > 0.f)) gp = 0.f;
+        float gp = g.v[c] * out_scale;
+        if (use_y && yo.v[c] == 0.f) gp = 0.f;
         atomicAdd(&cacc[v * VN + c], gp * h);
         atomicAdd(&cacc[channels + v * VN + c], gp);
         const float t = gp * w[v * VN + c];
@@ -555,12 +606,12 @@ rln_bwd_wide_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
       const Vec<T> g = Vec<T>::load(dy + o);
       Vec<T> a = Vec<T>::load(x + o);
       Vec<T> yo;
-      if (act == EGP_ACT_RELU) yo = Vec<T>::load(y + o);
+      if (use_y) yo = Vec<T>::load(y + o);
 #pragma unroll
       for (int c = 0; c < VN; ++c) {
         const float h = (a.v[c] - mu) * rs;
-        float gp = g.v[c];
-        if (act == EGP_ACT_RELU && !(yo.v[c] > 0.f)) gp = 0.f;
+        float gp = g.v[c] * out_scale;
+        if (use_y && yo.v[c] == 0.f) gp = 0.f;
         a.v[c] = rs * (gp * w[v * VN + c] - c1 - h * c2);
       }
       a.store(dx + o);
@@ -592,8 +643,10 @@ size_t egp_graph_layernorm_workspace(int64_t n, int64_t channels) {
   size_t bytes = sizeof(GlnWorkspace);
   const size_t np = (size_t)(parts * gy > g_stats ? parts * gy : g_stats);
   bytes += sizeof(double) * 2 * np;
-  bytes += sizeof(float) * 2 * (size_t)parts * (size_t)channels;
-  return bytes + 64;
+  bytes += sizeof(float) * 2 * (size_t)parts * (size_t)channels;            // dweight/dbias partials
+  bytes += sizeof(float) * (size_t)(sm_count() * 8) * (size_t)channels;     // dx column-sum partials
+  const size_t cs = colsum_workspace_bytes(n, channels);                    // fallback column sum of dx
+  return bytes + cs + 128;
 }
 
 int egp_graph_layernorm_fwd(const void* x, const float* weight, const float* bias, void* y, double* stats,
@@ -627,7 +680,7 @@ int egp_graph_layernorm_fwd(const void* x, const float* weight, const float* bia
 }
 
 int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, const float* bias,
-                            const double* stats, void* dx, float* dweight, float* dbias, int64_t n,
+                            const double* stats, void* dx, float* dweight, float* dbias, float* dx_colsum, int64_t n,
                             int64_t channels, float eps, int act, float slope, int dtype, void* workspace,
                             size_t ws_bytes, void* stream) {
   EGP_REQUIRE(dy && x && weight && bias && stats && dx && workspace, "graph_layernorm_bwd: null pointer");
@@ -638,44 +691,61 @@ int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, 
     set_error("graph_layernorm_bwd: workspace too small");
     return EGP_ERR_WORKSPACE;
   }
-  if (n == 0) return EGP_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  if (n == 0) {
+    if (dx_colsum) EGP_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * channels, s));
+    return EGP_OK;
+  }
   GlnWorkspace* ws = (GlnWorkspace*)workspace;
   const int parts = gln_parts(n);
   const int rows_per = (int)ceil_div(n, parts);
   EGP_DISPATCH_DTYPE(dtype, T, {
     constexpr int VN = Vec<T>::N;
-    const int gy = (int)ceil_div(channels, (int64_t)kNormThreads * VN);
+    const int64_t nvec_row = channels / VN;
+    const int rthreads = (int)(nvec_row >= kNormThreads ? kNormThreads : (nvec_row + 31) / 32 * 32);  // no idle lanes
+    const int gy = (int)ceil_div(nvec_row, (int64_t)rthreads);
+    const int gy_ws = (int)ceil_div(channels, (int64_t)kNormThreads * 4);
     const int g_stats = sm_count() * 4;
-    const size_t np = (size_t)(parts * gy > g_stats ? parts * gy : g_stats);
+    const size_t np = (size_t)(parts * gy_ws > g_stats ? parts * gy_ws : g_stats);
     double* scalpart = (double*)(ws + 1);
     float* colpart = (float*)(scalpart + 2 * np);
-    gln_bwd_reduce_kernel<T><<<dim3(parts, gy), kNormThreads, 0, s>>>(
+    float* dxpart = colpart + 2 * (size_t)parts * channels;
+    void* cs_ws = dxpart + (size_t)(sm_count() * 8) * channels;
+    EGP_REQUIRE((size_t)parts * gy <= np, "graph_layernorm_bwd: internal partial sizing");
+    gln_bwd_reduce_kernel<T><<<dim3(parts, gy), rthreads, 0, s>>>(
         (const T*)dy, (const T*)x, weight, bias, stats, n, channels, rows_per, eps, act, slope, colpart, scalpart);
     EGP_LAUNCH_CHECK();
     const int colblocks = (int)ceil_div(channels, 32);
-    col_finalize_kernel<<<colblocks + 1, kNormThreads, 0, s>>>(colpart, parts, channels, dweight, dbias, scalpart,
-                                                               parts * gy, ws->scal, colblocks);
+    col_finalize_kernel<<<colblocks + 1, kFinThreads, 0, s>>>(colpart, parts, channels, 2, dweight, dbias, nullptr,
+                                                              scalpart, parts * gy, ws->scal, colblocks);
     EGP_LAUNCH_CHECK();
     const int64_t nvec = n * channels / VN;
     const int g2 = norm_grid(nvec, kNormThreads * 2) * 2;
-    const bool fixed = ((int64_t)g2 * kNormThreads) % (channels / VN) == 0;
+    const bool fixed = ((int64_t)g2 * kNormThreads) % nvec_row == 0;
+    const bool fuse = dx_colsum && fixed && nvec_row <= kNormThreads && kNormThreads % nvec_row == 0;
+    const double inv_count = 1.0 / ((double)n * (double)channels);
     if (fixed)
       gln_bwd_apply_kernel<T, true><<<g2, kNormThreads, 0, s>>>((const T*)dy, (const T*)x, weight, bias, stats, ws->scal,
-                                                                (T*)dx, nvec, channels,
-                                                                1.0 / ((double)n * (double)channels), eps, act, slope);
+                                                                (T*)dx, nvec, channels, inv_count, eps, act, slope,
+                                                                fuse ? dxpart : nullptr);
     else
       gln_bwd_apply_kernel<T, false><<<g2, kNormThreads, 0, s>>>((const T*)dy, (const T*)x, weight, bias, stats, ws->scal,
-                                                                 (T*)dx, nvec, channels,
-                                                                 1.0 / ((double)n * (double)channels), eps, act, slope);
+                                                                 (T*)dx, nvec, channels, inv_count, eps, act, slope, nullptr);
     EGP_LAUNCH_CHECK();
+    if (fuse) {
+      col_finalize_kernel<<<colblocks, kFinThreads, 0, s>>>(dxpart, g2, channels, 1, dx_colsum, nullptr, nullptr, nullptr, 0,
+                                                            nullptr, colblocks);
+      EGP_LAUNCH_CHECK();
+    } else if (dx_colsum) {
+      const int rc = colsum_launch(dx, dx_colsum, n, channels, channels, dtype, cs_ws, colsum_workspace_bytes(n, channels), s);
+      if (rc != EGP_OK) return rc;
+    }
   });
   return EGP_OK;
 }
 
 size_t egp_row_layernorm_workspace(int64_t n, int64_t channels) {
-  (void)n;
-  return sizeof(float) * 2 * (size_t)(sm_count() * 8) * (size_t)channels + 64;
+  return sizeof(float) * 3 * (size_t)(sm_count() * 8) * (size_t)channels + colsum_workspace_bytes(n, channels) + 128;
 }
 
 #define EGP_RLN_DISPATCH_NVL(nvec, ...)                                               \
@@ -689,21 +759,28 @@ size_t egp_row_layernorm_workspace(int64_t n, int64_t channels) {
   } while (0)
 
 int egp_row_layernorm_fwd(const void* x, const float* weight, const float* bias, void* y, float* mean,
-                          float* rstd, int64_t n, int64_t channels, float eps, int act, int dtype, void* stream) {
+                          float* rstd, int64_t n, int64_t channels, float eps, int act, float dropout_p,
+                          uint64_t seed, uint64_t offset, int dtype, void* stream) {
   EGP_REQUIRE(x && weight && bias && y && mean && rstd, "row_layernorm_fwd: null pointer");
   const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
   EGP_REQUIRE(channels % vn == 0 && aligned16(x) && aligned16(y), "row_layernorm_fwd: channels %% %d != 0 or unaligned", (int)vn);
   EGP_REQUIRE(act == EGP_ACT_NONE || act == EGP_ACT_RELU, "row_layernorm_fwd: act must be none or relu");
+  EGP_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "row_layernorm_fwd: dropout_p must be in [0,1)");
   if (n == 0) return EGP_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = norm_grid(n, kNormThreads / 32);
+  uint32_t thr = (uint32_t)(dropout_p * 65536.0f + 0.5f);
+  if (dropout_p > 0.f && thr == 0) thr = 1;
+  const float keep_scale = dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f;
   EGP_DISPATCH_DTYPE(dtype, T, {
     const int64_t nvec = channels / Vec<T>::N;
     EGP_RLN_DISPATCH_NVL(nvec, {
       if constexpr (NVL == 0)
-        rln_fwd_wide_kernel<T><<<grid, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, mean, rstd, n, channels, eps, act);
+        rln_fwd_wide_kernel<T><<<grid, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, mean, rstd, n, channels, eps,
+                                                             act, thr, keep_scale, seed, offset);
       else
-        rln_fwd_kernel<T, NVL><<<grid, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, mean, rstd, n, channels, eps, act);
+        rln_fwd_kernel<T, NVL><<<grid, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, mean, rstd, n, channels, eps,
+                                                             act, thr, keep_scale, seed, offset);
     });
     EGP_LAUNCH_CHECK();
   });
@@ -711,10 +788,12 @@ int egp_row_layernorm_fwd(const void* x, const float* weight, const float* bias,
 }
 
 int egp_row_layernorm_bwd(const void* dy, const void* x, const void* y, const float* weight, const float* mean,
-                          const float* rstd, void* dx, float* dweight, float* dbias, int64_t n, int64_t channels,
-                          int act, int dtype, void* workspace, size_t ws_bytes, void* stream) {
+                          const float* rstd, void* dx, float* dweight, float* dbias, float* dx_colsum, int64_t n,
+                          int64_t channels, int act, float out_scale, int dtype, void* workspace, size_t ws_bytes,
+                          void* stream) {
   EGP_REQUIRE(dy && x && weight && mean && rstd && dx && workspace, "row_layernorm_bwd: null pointer");
-  EGP_REQUIRE(act == EGP_ACT_NONE || (act == EGP_ACT_RELU && y), "row_layernorm_bwd: relu needs the saved output");
+  EGP_REQUIRE(act == EGP_ACT_NONE || act == EGP_ACT_RELU, "row_layernorm_bwd: act must be none or relu");
+  EGP_REQUIRE(y || (act == EGP_ACT_NONE && out_scale == 1.f), "row_layernorm_bwd: relu/dropout need the saved output");
   const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
   EGP_REQUIRE(channels % vn == 0 && aligned16(x) && aligned16(dy) && aligned16(dx), "row_layernorm_bwd: channels/alignment");
   if (ws_bytes < egp_row_layernorm_workspace(n, channels)) {
@@ -725,33 +804,42 @@ int egp_row_layernorm_bwd(const void* dy, const void* x, const void* y, const fl
   if (n == 0) {
     if (dweight) EGP_CUDA(cudaMemsetAsync(dweight, 0, sizeof(float) * channels, s));
     if (dbias) EGP_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * channels, s));
+    if (dx_colsum) EGP_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * channels, s));
     return EGP_OK;
   }
   int grid = norm_grid(n, (kNormThreads / 32) * 16);   // warp-per-row kernels: >= 16 rows per warp
   const size_t smem = sizeof(float) * 2 * channels;
   float* colpart = (float*)workspace;
+  void* cs_ws = colpart + 3 * (size_t)(sm_count() * 8) * channels;
+  int nout = 2;
   EGP_DISPATCH_DTYPE(dtype, T, {
     const int64_t nvec = channels / Vec<T>::N;
     if (nvec > 32 && nvec <= 1024) {                     // one CTA per row, thread-owned columns
       const int threads = (int)((nvec + 31) / 32 * 32);
       const int64_t cap = (int64_t)sm_count() * 8;
       grid = (int)(n < cap ? n : cap);
+      nout = dx_colsum ? 3 : 2;
       rln_bwd_block_kernel<T><<<grid, threads, 0, s>>>((const T*)dy, (const T*)x, (const T*)y, weight, mean, rstd, (T*)dx,
-                                                       n, channels, act, colpart);
+                                                       n, channels, act, out_scale, nout, colpart);
     } else {
       EGP_RLN_DISPATCH_NVL(nvec, {
         auto kern = rln_bwd_wide_kernel<T>;
         if constexpr (NVL != 0) kern = rln_bwd_kernel<T, NVL>;
         if (smem > 48 * 1024) EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kNormThreads, smem, s>>>((const T*)dy, (const T*)x, (const T*)y, weight, mean, rstd, (T*)dx, n,
-                                              channels, act, colpart);
+                                              channels, act, out_scale, colpart);
       });
     }
     EGP_LAUNCH_CHECK();
   });
   const int colblocks = (int)ceil_div(channels, 32);
-  col_finalize_kernel<<<colblocks, kNormThreads, 0, s>>>(colpart, grid, channels, dweight, dbias, nullptr, 0, nullptr, colblocks);
+  col_finalize_kernel<<<colblocks, kFinThreads, 0, s>>>(colpart, grid, channels, nout, dweight, dbias,
+                                                        nout == 3 ? dx_colsum : nullptr, nullptr, 0, nullptr, colblocks);
   EGP_LAUNCH_CHECK();
+  if (dx_colsum && nout != 3) {
+    const int rc = colsum_launch(dx, dx_colsum, n, channels, channels, dtype, cs_ws, colsum_workspace_bytes(n, channels), s);
+    if (rc != EGP_OK) return rc;
+  }
   return EGP_OK;
 }
 

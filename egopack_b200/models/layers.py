@@ -92,5 +92,8 @@ class GraphLayerNorm(nn.Module):
         return ops.GraphLayerNorm.apply(x, self.weight, self.bias, self.eps, act, slope)
 
 
-def row_layernorm(ln: nn.LayerNorm, x: Tensor, act: int = ACT_NONE) -> Tensor:
-    return ops.RowLayerNorm.apply(x, ln.weight, ln.bias, ln.eps, act)
+def row_layernorm(ln: nn.LayerNorm, x: Tensor, act: int = ACT_NONE, dropout_p: float = 0.0) -> Tensor:
+    """LayerNorm (+ReLU) (+the Dropout that follows, when training) in one kernel."""
+    if dropout_p >= 1.0:
+        return ops.RowLayerNorm.apply(x, ln.weight, ln.bias, ln.eps, act, 0.0) * 0
+    return ops.RowLayerNorm.apply(x, ln.weight, ln.bias, ln.eps, act, float(dropout_p))

@@ -42,6 +42,5 @@ class TRNPooling(TemporalPooling):
         p = self.proj
         for lin, ln, drop in ((p[0], p[1], p[3]), (p[4], p[5], p[7])):
             h = ops.linear(h, lin.weight, lin.bias)
-            h = row_layernorm(ln, h, act=ACT_RELU)
-            h = ops.dropout(h, drop.p, self.training)
+            h = row_layernorm(ln, h, act=ACT_RELU, dropout_p=drop.p if self.training else 0.0)   # LN+ReLU+Dropout fused
         return ops.linear(h, p[8].weight, p[8].bias)

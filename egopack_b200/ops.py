@@ -263,6 +263,43 @@ class Scale(torch.autograd.Function):
         return axpby(g, ctx.alpha), None
 
 
+def _attach_colsum(dx: Tensor, cs: Tensor) -> Tensor:
+    """Remember the column sums of a gradient that a kernel produced as a by-product.  The tag is bound to the
+    tensor's version counter, so an in-place accumulation by autograd invalidates it."""
+    dx._egp_colsum = (dx._version, cs)
+    return dx
+
+
+def _take_colsum(dy: Tensor) -> Optional[Tensor]:
+    tag = getattr(dy, "_egp_colsum", None)
+    if tag is not None and tag[0] == dy._version and tag[1].shape[0] == dy.shape[1]:
+        return tag[1]
+    return None
+
+
+def act_bwd_colsum(dy: Tensor, y: Tensor, act: int, slope: float) -> Tuple[Tensor, Tensor]:
+    """dx = dy * act'(y) and the column sums of dx in one pass."""
+    dy, y = _c(dy), _c(y)
+    rows, cols = dy.shape
+    dx = torch.empty_like(dy)
+    cs = torch.empty(cols, dtype=torch.float32, device=dy.device)
+    nb = L.size("egp_act_bwd_colsum_workspace", rows, cols)
+    ws = L.workspace(nb, dy.device)
+    L.call("egp_act_bwd_colsum", L.ptr(dy), L.ptr(y), L.ptr(dx), L.ptr(cs), rows, cols, act, float(slope), _code(dy),
+           L.ptr(ws), nb, L.stream())
+    return dx, cs
+
+
+_dropout_calls = 0
+
+
+def _dropout_stream() -> Tuple[int, int]:
+    """(seed, offset) of the next fused-dropout call: reproducible under torch.manual_seed and call order."""
+    global _dropout_calls
+    _dropout_calls += 1
+    return int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF, _dropout_calls
+
+
 class _WeightCache:
     """bf16 copies of fp32 parameters, refreshed when the parameter is updated in place (optimizer step).
 
@@ -335,12 +372,21 @@ class Linear(torch.autograd.Function):
         dy = _c(dy)
         dres = dy if ctx.has_res else None
         g = dy
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        db = None
         if ctx.act != ACT_NONE:
             if ctx.has_res:
                 raise RuntimeError("Linear: activation together with a residual is not differentiable here")
-            g = act_bwd(dy, y, ctx.act, ctx.slope)
+            vn = 8 if dy.dtype == torch.bfloat16 else 4
+            if want_db and n % vn == 0:
+                g, db = act_bwd_colsum(dy, y, ctx.act, ctx.slope)      # bias gradient in the same pass
+            else:
+                g = act_bwd(dy, y, ctx.act, ctx.slope)
+        elif want_db:
+            db = _take_colsum(dy)                                     # by-product of the LN backward upstream
         gc = cast(g, cd)                                 # fp32 logits gradients -> bf16 operand
-        db = colsum(g) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        if want_db and db is None:
+            db = colsum(g)
         if cd == torch.bfloat16 and n % 8 != 0:          # TMA needs 16-byte row strides: pad the class dim
             gc = _pad_cols(gc, 8)
         npad = gc.shape[1]
@@ -374,19 +420,24 @@ def linear(x, w, b=None, *, x2=None, w2=None, residual=None, act=ACT_NONE, slope
 # normalisation / elementwise
 # =====================================================================================================
 class RowLayerNorm(torch.autograd.Function):
-    """nn.LayerNorm over the last dim, optionally fused with ReLU (TRNPooling / task nets / GraphONE stages)."""
+    """nn.LayerNorm over the last dim, optionally fused with ReLU and with the Dropout that follows it
+    (TRNPooling: Linear -> LayerNorm -> ReLU -> Dropout; task nets; GraphONE stages).  No dropout mask is stored:
+    a zero in the saved output means "ReLU inactive or dropped".  The backward also returns the column sums of dx
+    (the bias gradient of the Linear that produced x) as a by-product."""
 
     @staticmethod
-    def forward(ctx, x, w, b, eps: float, act: int):
+    def forward(ctx, x, w, b, eps: float, act: int, dropout_p: float = 0.0):
         x = _c(x)
         n, c = x.shape
         y = torch.empty_like(x)
         mean = torch.empty(n, dtype=torch.float32, device=x.device)
         rstd = torch.empty(n, dtype=torch.float32, device=x.device)
+        seed, offset = _dropout_stream() if dropout_p > 0 else (0, 0)
         L.call("egp_row_layernorm_fwd", L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(mean), L.ptr(rstd), n, c,
-               float(eps), act, _code(x), L.stream())
-        ctx.save_for_backward(x, y if act == ACT_RELU else None, w, mean, rstd)
-        ctx.act = act
+               float(eps), act, float(dropout_p), seed, offset, _code(x), L.stream())
+        need_y = act == ACT_RELU or dropout_p > 0
+        ctx.save_for_backward(x, y if need_y else None, w, mean, rstd)
+        ctx.act, ctx.out_scale = act, (1.0 / (1.0 - dropout_p) if dropout_p > 0 else 1.0)
         return y
 
     @staticmethod
@@ -397,11 +448,12 @@ class RowLayerNorm(torch.autograd.Function):
         dx = torch.empty_like(x)
         dw = torch.empty(c, dtype=torch.float32, device=x.device)
         db = torch.empty(c, dtype=torch.float32, device=x.device)
+        dxs = torch.empty(c, dtype=torch.float32, device=x.device)
         nb = L.size("egp_row_layernorm_workspace", n, c)
         ws = L.workspace(nb, x.device)
         L.call("egp_row_layernorm_bwd", L.ptr(dy), L.ptr(x), L.ptr(y), L.ptr(w), L.ptr(mean), L.ptr(rstd), L.ptr(dx),
-               L.ptr(dw), L.ptr(db), n, c, ctx.act, _code(x), L.ptr(ws), nb, L.stream())
-        return dx, dw, db, None, None
+               L.ptr(dw), L.ptr(db), L.ptr(dxs), n, c, ctx.act, float(ctx.out_scale), _code(x), L.ptr(ws), nb, L.stream())
+        return _attach_colsum(dx, dxs), dw, db, None, None, None
 
 
 class GraphLayerNorm(torch.autograd.Function):
@@ -433,9 +485,10 @@ class GraphLayerNorm(torch.autograd.Function):
         db = torch.empty(c, dtype=torch.float32, device=x.device)
         nb = L.size("egp_graph_layernorm_workspace", n, c)
         ws = L.workspace(nb, x.device)
+        dxs = torch.empty(c, dtype=torch.float32, device=x.device)
         L.call("egp_graph_layernorm_bwd", L.ptr(dy), L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(stats), L.ptr(dx), L.ptr(dw),
-               L.ptr(db), n, c, eps, act, slope, _code(x), L.ptr(ws), nb, L.stream())
-        return dx, dw, db, None, None, None
+               L.ptr(db), L.ptr(dxs), n, c, eps, act, slope, _code(x), L.ptr(ws), nb, L.stream())
+        return _attach_colsum(dx, dxs), dw, db, None, None, None
 
 
 class PosEncAdd(torch.autograd.Function):

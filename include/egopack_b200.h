@@ -103,21 +103,27 @@ size_t egp_graph_layernorm_workspace(int64_t num_nodes, int64_t channels);
 int egp_graph_layernorm_fwd(const void* x, const float* weight, const float* bias, void* y, double* stats,
                             int64_t num_nodes, int64_t channels, float eps, int act, float slope, int dtype,
                             void* workspace, size_t ws_bytes, void* stream);
-/* dx, dweight[C], dbias[C] from dy (gradient w.r.t. the activated output), the saved input x and stats. */
+/* dx, dweight[C], dbias[C] from dy (gradient w.r.t. the activated output), the saved input x and stats.
+ * dx_colsum (optional, float[C]) receives the column sums of dx -- the bias gradient of the Linear that produced x,
+ * computed in the same pass instead of by a separate egp_colsum. */
 int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, const float* bias,
-                            const double* stats, void* dx, float* dweight, float* dbias, int64_t num_nodes,
-                            int64_t channels, float eps, int act, float slope, int dtype, void* workspace,
-                            size_t ws_bytes, void* stream);
+                            const double* stats, void* dx, float* dweight, float* dbias, float* dx_colsum,
+                            int64_t num_nodes, int64_t channels, float eps, int act, float slope, int dtype,
+                            void* workspace, size_t ws_bytes, void* stream);
 
-/* ---- row LayerNorm (+ReLU) (nn.LayerNorm in TRNPooling trn_pooling.py:30,35; tasks task.py:20; GraphONE
- *      graphONE.py:61) ; mean/rstd float [N] are saved for the backward ------------------------------------ */
+/* ---- row LayerNorm (+ReLU) (+Dropout) (nn.LayerNorm -> ReLU -> Dropout in TRNPooling trn_pooling.py:30-37; tasks
+ *      task.py:20; GraphONE graphONE.py:61); mean/rstd float [N] are saved for the backward ---------------------
+ * fwd: y = dropout_p(act(LN(x))); the keep decisions come from Philox4x32-10(seed; element-vector index, offset), so
+ *      no mask is stored.  bwd: a zero in the saved output y means "ReLU inactive or dropped"; the incoming gradient
+ *      is scaled by out_scale = 1/(1-p).  dx_colsum (optional) as in egp_graph_layernorm_bwd. */
 size_t egp_row_layernorm_workspace(int64_t num_nodes, int64_t channels);
 int egp_row_layernorm_fwd(const void* x, const float* weight, const float* bias, void* y, float* mean,
-                          float* rstd, int64_t num_nodes, int64_t channels, float eps, int act, int dtype,
-                          void* stream);
+                          float* rstd, int64_t num_nodes, int64_t channels, float eps, int act, float dropout_p,
+                          uint64_t seed, uint64_t offset, int dtype, void* stream);
 int egp_row_layernorm_bwd(const void* dy, const void* x, const void* y, const float* weight, const float* mean,
-                          const float* rstd, void* dx, float* dweight, float* dbias, int64_t num_nodes,
-                          int64_t channels, int act, int dtype, void* workspace, size_t ws_bytes, void* stream);
+                          const float* rstd, void* dx, float* dweight, float* dbias, float* dx_colsum,
+                          int64_t num_nodes, int64_t channels, int act, float out_scale, int dtype, void* workspace,
+                          size_t ws_bytes, void* stream);
 
 /* ---- a4: out = x + [sin(pos*f) | cos(pos*f)]  (gnn.PositionalEncoding, models/graph.py:37,63) ---------- */
 int egp_posenc_add(const void* x, const int64_t* pos, const float* frequency, void* out, int64_t num_nodes,
@@ -131,6 +137,10 @@ int egp_add(const void* a, const void* b, void* out, int64_t n, int dtype, void*
 int egp_axpby(const void* a, float alpha, const void* b, float beta, void* out, int64_t n, int dtype, void* stream);
 /* dx = dy * act'(y) with y the activated output (ReLU / LeakyReLU) */
 int egp_act_bwd(const void* dy, const void* y, void* dx, int64_t n, int act, float slope, int dtype, void* stream);
+/* act_bwd fused with the column sums of dx (bias gradient of the Linear whose epilogue applied the activation) */
+size_t egp_act_bwd_colsum_workspace(int64_t rows, int64_t cols);
+int egp_act_bwd_colsum(const void* dy, const void* y, void* dx, float* dx_colsum, int64_t rows, int64_t cols, int act,
+                       float slope, int dtype, void* workspace, size_t ws_bytes, void* stream);
 /* out[c] = sum_i x[i,c] (bias gradients); workspace float [blocks*C], see egp_colsum_workspace */
 size_t egp_colsum_workspace(int64_t rows, int64_t cols);
 int egp_colsum(const void* x, float* out, int64_t rows, int64_t cols, int64_t ldx, int dtype, void* workspace,

@@ -203,7 +203,7 @@ def check_kernels():
             xx = torch.randn(n, cc, generator=g).to(dt).to(dev).requires_grad_(True)
             ww = (torch.randn(cc, generator=g) * 0.5 + 1).to(dev).requires_grad_(True)
             bb = (torch.randn(cc, generator=g) * 0.1).to(dev).requires_grad_(True)
-            y = ops.RowLayerNorm.apply(xx, ww, bb, 1e-5, ACT_RELU)
+            y = ops.RowLayerNorm.apply(xx, ww, bb, 1e-5, ACT_RELU, 0.0)
             wv = torch.randn(n, cc, generator=g).to(dt).to(dev)
             y.backward(wv)
             xd = xx.detach().double().requires_grad_(True)

@@ -115,13 +115,13 @@ def main():
 
     def build_rln_fwd():
         x, w, b = rnd(N, H), rnd(H, dt=torch.float32), rnd(H, dt=torch.float32)
-        return lambda: ops.RowLayerNorm.apply(x, w, b, 1e-5, ACT_RELU)
+        return lambda: ops.RowLayerNorm.apply(x, w, b, 1e-5, ACT_RELU, 0.0)
     mem_case("row_ln_relu_fwd_bf16", build_rln_fwd, 2 * N * H * 2)
 
     def build_rln_bwd():
         x = rnd(N, H).requires_grad_(True)
         w, b = rnd(H, dt=torch.float32).requires_grad_(True), rnd(H, dt=torch.float32).requires_grad_(True)
-        y = ops.RowLayerNorm.apply(x, w, b, 1e-5, ACT_RELU)
+        y = ops.RowLayerNorm.apply(x, w, b, 1e-5, ACT_RELU, 0.0)
         dy = rnd(N, H)
         return lambda: torch.autograd.grad(y, (x, w, b), dy, retain_graph=True)
     mem_case("row_ln_relu_bwd_bf16", build_rln_bwd, 4 * N * H * 2)

@@ -174,3 +174,88 @@ def test_colsum_cast_axpby_dropout():
     assert 0.45 < float(keep.float().mean()) < 0.55
     assert torch.equal(out, keep.float() * 2.0) and torch.equal(xd.grad, keep.float() * 2.0)
     assert ops.dropout(xd, 0.5, False) is xd
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_row_layernorm_fused_dropout_and_colsum_byproduct(dtype, tol):
+    """LN -> ReLU -> Dropout in one kernel (TRNPooling, trn_pooling.py:30-37): the mask is never stored, the
+    backward infers it from the zeros of the saved output, and dx's column sums come out as a by-product."""
+    g = torch.Generator().manual_seed(5)
+    n, c, p = 512, 1024, 0.5
+    x = (torch.randn(n, c, generator=g) * 2 - 0.5).to(dtype)
+    dy = torch.randn(n, c, generator=g).to(dtype)
+    w = (torch.randn(c, generator=g) * 0.5 + 1)
+    b = (torch.randn(c, generator=g) * 0.1)
+    xd = x.to(DEV).requires_grad_(True)
+    wd, bd = w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    torch.manual_seed(123)
+    y = ops.RowLayerNorm.apply(xd, wd, bd, 1e-5, ACT_RELU, p)
+    torch.manual_seed(123)
+    y2 = ops.RowLayerNorm.apply(xd, wd, bd, 1e-5, ACT_RELU, p)
+    assert not torch.equal(y, y2), "every call draws a fresh mask"
+    xr = x.float().clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    base = F.layer_norm(xr, (c,), wr, br, 1e-5).relu()
+    keep = (y.float().cpu() != 0)
+    active = base.detach() > 1e-3
+    frac = float(keep[active].float().mean())
+    assert 0.47 < frac < 0.53, frac
+    want = base * keep.float() / (1 - p)
+    assert rel_max(y, want) < tol
+    y.backward(dy.to(DEV))
+    want.backward(dy.float())
+    assert rel_max(xd.grad, xr.grad) < tol
+    gtol = tol if dtype == torch.float32 else 5 * tol
+    assert rel_max(wd.grad, wr.grad) < gtol and rel_max(bd.grad, br.grad) < gtol
+    tag = ops._take_colsum(xd.grad) if hasattr(xd.grad, "_egp_colsum") else None
+    # the by-product rides on the tensor autograd hands upstream; check the kernel output directly as well
+    dx = torch.empty_like(xd)
+    dxs = torch.empty(c, dtype=torch.float32, device=DEV)
+    from egopack_b200 import _lib as L
+    mean = torch.empty(n, dtype=torch.float32, device=DEV)
+    rstd = torch.empty(n, dtype=torch.float32, device=DEV)
+    yy = torch.empty_like(xd)
+    code = 0 if dtype == torch.float32 else 1
+    L.call("egp_row_layernorm_fwd", xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), yy.data_ptr(), mean.data_ptr(),
+           rstd.data_ptr(), n, c, 1e-5, ACT_RELU, 0.0, 0, 0, code, L.stream())
+    nb = L.size("egp_row_layernorm_workspace", n, c)
+    ws = L.workspace(nb, xd.device)
+    dwt, dbt = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+    dyd = dy.to(DEV)
+    L.call("egp_row_layernorm_bwd", dyd.data_ptr(), xd.data_ptr(), yy.data_ptr(), wd.data_ptr(), mean.data_ptr(),
+           rstd.data_ptr(), dx.data_ptr(), dwt.data_ptr(), dbt.data_ptr(), dxs.data_ptr(), n, c, ACT_RELU, 1.0, code,
+           ws.data_ptr(), nb, L.stream())
+    assert rel_max(dxs, dx.double().sum(0)) < 1e-5
+    if tag is not None:
+        assert rel_max(tag, xd.grad.double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_colsum_byproducts_feed_bias_gradients(dtype, tol):
+    """Linear -> graph-LN/LeakyReLU and Linear(ReLU epilogue): the bias gradient comes from the fused column sums."""
+    g = torch.Generator().manual_seed(9)
+    n, c = 640, 1024
+    x = torch.randn(n, c, generator=g).to(dtype)
+    wl = (torch.randn(c, c, generator=g) / 32)
+    bl = torch.randn(c, generator=g) * 0.1
+    gw, gb = torch.randn(c, generator=g) * 0.3 + 1, torch.randn(c, generator=g) * 0.1
+    dy = torch.randn(n, c, generator=g).to(dtype)
+    q = (lambda t: t.to(dtype).float()) if dtype == torch.bfloat16 else (lambda t: t)
+    xr = x.float()
+    wr, br = wl.clone().requires_grad_(True), bl.clone().requires_grad_(True)
+    h = F.linear(xr, q(wr), br)
+    ln = pyg.LayerNorm(c)
+    with torch.no_grad():
+        ln.weight.copy_(gw), ln.bias.copy_(gb)
+    out = F.leaky_relu(ln(q(h) if dtype == torch.bfloat16 else h), 0.2) + F.linear(xr, q(wr), br).relu()
+    out.backward(dy.float())
+    xd = x.to(DEV)
+    wd, bd = wl.to(DEV).requires_grad_(True), bl.to(DEV).requires_grad_(True)
+    gwd, gbd = gw.to(DEV).requires_grad_(True), gb.to(DEV).requires_grad_(True)
+    hd = ops.linear(xd, wd, bd)
+    o1 = ops.GraphLayerNorm.apply(hd, gwd, gbd, 1e-5, ACT_LEAKY, 0.2)
+    o2 = ops.linear(xd, wd, bd, act=ACT_RELU)
+    ops.Add.apply(o1, o2).backward(dy.to(DEV))
+    btol = 1e-4 if dtype == torch.float32 else 6e-2
+    assert rel_max(bd.grad, br.grad) < btol, rel_max(bd.grad, br.grad)
+    assert rel_max(wd.grad, wr.grad) < btol
