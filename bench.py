@@ -122,8 +122,11 @@ def cpu_oracle_run(videos: int, nodes: int, steps: int, warmup: int):
 # clocks
 # ------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """`nvidia-smi -lms` in the background (started BEFORE the warm-up so it is already streaming); `window()` keeps
+    the samples whose timestamps fall inside the timed region (padded by one sampling period)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 20
 
     def __init__(self, index: int):
         self.rows, self.proc, self.index = [], None, index
@@ -131,32 +134,39 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", str(self.PERIOD_MS)],
+                                         stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0: float, t1: float):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(2 * self.PERIOD_MS / 1e3)
         self.proc.terminate()
+        pad = 2 * self.PERIOD_MS / 1e3
+        inside = [r for t, r in self.rows if t0 - pad <= t <= t1 + pad]
+        scope = "timed region"
+        if len(inside) < 3:                                  # very short timed regions: fall back to the whole run
+            inside, scope = [r for _, r in self.rows], "warm-up + timed region"
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-                for nme, v in zip(names, r[3:7]):
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for nme, v in zip(names, r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
             except (ValueError, IndexError):
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "scope": scope}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -232,20 +242,22 @@ def native_run(args, rank: int, world: int, local_rank: int):
 
     # ---- device-resident timing ------------------------------------------------------------------------
     resident = upload()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for _ in range(args.warmup):
         step(resident)
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     _lib.CALL_COUNTS.clear()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         loss = step(resident)
     e1.record()
     barrier()
+    t_end = time.time()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clock_info = clocks.stop()
+    clock_info = clocks.stop(t_begin, t_end)
     launches = _lib.kernel_launches()
     ms_per_step = ms_total / args.steps
     value = world * n_nodes / (ms_per_step / 1e3)

@@ -56,6 +56,8 @@ SIGNATURES: Dict[str, tuple] = {
     "egp_cos_topk_workspace": (SZ, [I64, I64, I64]),
     "egp_cos_topk": (I, [P, P, P, P, I64, I64, I64, I, P, P, SZ, P]),
     "egp_proto_max_gather": (I, [P, P, P, I64, I64, I64, I, I, P]),
+    "egp_proto_max_scatter_bwd": (I, [P, P, P, P, P, I64, I64, I64, I, P]),
+    "egp_class_sum_f64": (I, [P, P, P, I64, I64, I64, I, P]),
     "egp_max_combine_fwd": (I, [P, P, P, I64, I, P]),
     "egp_max_combine_bwd": (I, [P, P, P, P, I64, I, P]),
     "egp_segment_max_pool_fwd": (I, [P, P, P, P, I64, I64, I, P]),

@@ -9,8 +9,10 @@
 // ever touches its own 16-byte column, so no block barrier is needed.
 //   radius <= 4 : the 2k+1-row window is held in registers (sage_mean_band_reg_kernel), summed in ascending
 //                 neighbour order (bit-identical to a sequential scatter_add);
-//   radius  > 4 : rows stream through a shared-memory ring with cp.async (one commit group per row, P rows in
-//                 flight) and a running window sum adds the entering row and subtracts the leaving row.
+//   radius  > 4 : a running window sum adds the entering row and subtracts the leaving row; both variants exist:
+//                 register-resident (sage_mean_band_run_kernel, default: entering row from HBM, leaving/self rows
+//                 from L1/L2) and a cp.async shared-memory ring (sage_mean_band_kernel, EGP_BAND_IMPL=3), which
+//                 measured slower on B200 because the ring caps occupancy at 1-2 CTAs per SM.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -177,6 +179,89 @@ sage_mean_band_reg_kernel(const T* __restrict__ x, T* __restrict__ out, int n, i
   }
 }
 
+// Large radii (K > 4): running window sum held in REGISTERS.  A thread owns one 16-byte column of a strip of rows.
+// For every output row it needs three rows: the one entering the window (first touch -> HBM), the one leaving it
+// and the row itself (both touched <= 2K+1 rows ago by the same CTA -> L1/L2 hits), so DRAM traffic stays at one
+// read + one write of the tensor while no shared-memory ring limits occupancy.  The 3*U loads of U consecutive
+// output rows are issued together.  At a graph boundary (or strip start) the sum restarts from scratch, so no
+// cancellation residue survives a graph.
+template <typename T, int U>
+__global__ void __launch_bounds__(kAggThreads, 8)
+sage_mean_band_run_kernel(const T* __restrict__ x, T* __restrict__ out, int n, int64_t channels, int64_t ldx,
+                          int64_t ldo, int rows_per_cta, int k, const int32_t* __restrict__ win_lo,
+                          const int32_t* __restrict__ win_hi, const float* __restrict__ scale_out,
+                          const float* __restrict__ scale_in) {
+  constexpr int VN = Vec<T>::N;
+  const int64_t col = ((int64_t)blockIdx.y * kAggThreads + threadIdx.x) * VN;
+  if (col >= channels) return;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, n);
+  if (r0 >= r1) return;
+  const T* xc = x + col;
+  float acc[VN];
+#pragma unroll
+  for (int c = 0; c < VN; ++c) acc[c] = 0.f;
+  int plo = 0, phi = -1;  // window currently summed in acc: [plo, phi] (empty)
+  auto add_row = [&](int j, float sign) {
+    const Vec<T> v = Vec<T>::load(xc + (int64_t)j * ldx);
+    const float s = sign * (scale_in ? scale_in[j] : 1.f);
+#pragma unroll
+    for (int c = 0; c < VN; ++c) acc[c] += s * v.v[c];
+  };
+#pragma unroll 1
+  for (int g = r0; g < r1; g += U) {
+    // speculative loads for U rows: entering (i+k), leaving (i-k-1), self (i); clamped, applied under masks
+    Raw<T> en[U], lv[U], sf[U];
+    int lo[U], hi[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = min(g + u, r1 - 1);
+      lo[u] = win_lo[i];
+      hi[u] = win_hi[i];
+      en[u] = Raw<T>::load(xc + (int64_t)min(i + k, n - 1) * ldx);
+      lv[u] = Raw<T>::load(xc + (int64_t)max(i - k - 1, 0) * ldx);
+      sf[u] = Raw<T>::load(xc + (int64_t)i * ldx);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = g + u;
+      if (i < r1) {
+        if (lo[u] > phi || phi < plo) {  // new graph / strip start: rebuild the window sum
+#pragma unroll
+          for (int c = 0; c < VN; ++c) acc[c] = 0.f;
+          for (int j = lo[u]; j <= hi[u]; ++j) add_row(j, 1.f);
+        } else {
+          if (hi[u] == phi + 1 && hi[u] == i + k) {  // the common case: one row enters ...
+            const Vec<T> v = en[u].unpack();
+            const float s = scale_in ? scale_in[hi[u]] : 1.f;
+#pragma unroll
+            for (int c = 0; c < VN; ++c) acc[c] += s * v.v[c];
+          } else {
+            for (int j = phi + 1; j <= hi[u]; ++j) add_row(j, 1.f);
+          }
+          if (lo[u] == plo + 1 && plo == i - k - 1) {  // ... and one row leaves
+            const Vec<T> v = lv[u].unpack();
+            const float s = scale_in ? scale_in[plo] : 1.f;
+#pragma unroll
+            for (int c = 0; c < VN; ++c) acc[c] -= s * v.v[c];
+          } else {
+            for (int j = plo; j < lo[u]; ++j) add_row(j, -1.f);
+          }
+        }
+        plo = lo[u];
+        phi = hi[u];
+        const Vec<T> self = sf[u].unpack();
+        const float ss = scale_in ? scale_in[i] : 1.f;
+        const float so = scale_out ? scale_out[i] : 1.f;
+        Vec<T> res;
+#pragma unroll
+        for (int c = 0; c < VN; ++c) res.v[c] = (acc[c] - ss * self.v[c]) * so;
+        res.store(out + (int64_t)i * ldo + col);
+      }
+    }
+  }
+}
+
 // Alternative for small radii: one thread per output vector, neighbours re-read through L1/L2 (a CTA covers
 // ROWS consecutive rows so most neighbour rows are L1 hits).  No sequential dependence at all.
 template <typename T, int K, int ROWS>
@@ -298,6 +383,23 @@ static int launch_band_reg(const void* x, void* out, int64_t n, int64_t channels
   return EGP_OK;
 }
 
+template <typename T>
+static int launch_band_run(const void* x, void* out, int64_t n, int64_t channels, int64_t ldx, int64_t ldo, int k,
+                           const int32_t* win_lo, const int32_t* win_hi, const float* scale_out, const float* scale_in,
+                           cudaStream_t stream) {
+  constexpr int VN = Vec<T>::N, U = 4;
+  const unsigned gy = (unsigned)ceil_div(channels, (int64_t)kAggThreads * VN);
+  int64_t rows = (n * gy) / ((int64_t)sm_count() * 16);
+  const int64_t min_rows = 2 * (2 * k + 1);                    // restart (2k+1 rows, L2 hits) <= half a strip's loads
+  rows = rows < min_rows ? min_rows : (rows > 2048 ? 2048 : rows);
+  rows = (rows + U - 1) / U * U;
+  dim3 grid((unsigned)ceil_div(n, rows), gy);
+  sage_mean_band_run_kernel<T, U><<<grid, kAggThreads, 0, stream>>>((const T*)x, (T*)out, (int)n, channels, ldx, ldo,
+                                                                    (int)rows, k, win_lo, win_hi, scale_out, scale_in);
+  EGP_LAUNCH_CHECK();
+  return EGP_OK;
+}
+
 template <typename T, int K>
 static int launch_band_flat(const void* x, void* out, int64_t n, int64_t channels, int64_t ldx, int64_t ldo,
                             const int32_t* win_lo, const int32_t* win_hi, const float* scale_out, const float* scale_in,
@@ -336,6 +438,7 @@ int egp_sage_mean_band(const void* x, void* out, int64_t n, int64_t channels, in
     if (k == 2) return launch_band_reg<T, 2, 8>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
     if (k == 3) return launch_band_reg<T, 3, 4>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
     if (k == 4) return launch_band_reg<T, 4, 4>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
+    if (impl != 3) return launch_band_run<T>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
     if (k <= 12) return launch_band<T, 16, true>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
     return launch_band<T, 32, true>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
   });

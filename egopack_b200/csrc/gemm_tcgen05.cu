@@ -14,6 +14,7 @@
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile t overlaps the mainloop
 // of tile t+1.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -85,7 +86,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                  ::"l"((uint64_t)map), "r"(smem_u32(smem)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
@@ -152,17 +154,22 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
+// Shared-memory budget (227 KB): a ring of TMA stages for A/B, then the epilogue's staging ring (each epilogue warp
+// owns kEpiBufs buffers of 32 rows x 128 B so that a tile's boxes are written back-to-back without waiting for the
+// previous TMA store to drain), the per-warp bias slices and the mbarriers.
+constexpr int kEpiBufs = 2;
 template <int BN>
 struct TcCfg {
-  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int kABytes = TBM * TBK * 2;
   static constexpr int kBBytes = BN * TBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // power of two for BN in {16,...,256}
-  static constexpr int kEpiStageBytes = 4 * 32 * 128;   // per epilogue warp: 32 rows x 128 B, 128B-swizzled
-  static constexpr int kEpiBiasBytes = 4 * 256 * 4;     // per epilogue warp: one tile's bias slice
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + kEpiBiasBytes + 1024 /*align slack*/ +
-                                    256 /*barriers*/;
+  static constexpr int kEpiStageBytes = 4 * kEpiBufs * 32 * 128;   // 32 KB
+  static constexpr int kEpiBiasBytes = 2 * 256 * 4;                // one bias slice per accumulator stage
+  static constexpr int kFixedBytes = kEpiStageBytes + kEpiBiasBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagesFit = (232448 - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;  // 4 for BN=256, 6 for BN=128, up to 8 below
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;      // power of two for BN in {16,...,256}
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
 };
 
 struct TcParams {
@@ -179,6 +186,7 @@ struct TcParams {
   float slope;
   int accumulate;      // C += result (fp32 atomics)
   int tma_store;       // epilogue stages 32x128B boxes in smem and stores them with TMA (coalesced, clipped)
+  int debug;           // EGP_TC_DEBUG bit 0: skip the stores, bit 1: skip the TMEM loads too (timing experiments)
   uint32_t idesc;
 };
 
@@ -303,6 +311,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     OutT* C = reinterpret_cast<OutT*>(p.C);
     const OutT* R = reinterpret_cast<const OutT*>(p.residual);
     int it = 0;
+    int ebuf = 0;  // next staging buffer of this warp's ring
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int split = t / tiles_mn, mn = t % tiles_mn;
       const int64_t m0 = (int64_t)(mn / p.n_tiles) * TBM, n0 = (int64_t)(mn % p.n_tiles) * BN;
@@ -319,13 +328,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       constexpr int CHT = 128 / (int)sizeof(OutT);  // columns per 128-byte staged row: 64 (bf16) / 32 (fp32)
       if constexpr (BN >= CHT) {
         if (p.tma_store) {
-          uint8_t* stage_w = epi_stage + quarter * (32 * 128);
-          float* bias_w = epi_bias + quarter * 256;
-          const bool use_bias = p.bias && split == 0;
-          if (use_bias) {  // this warp's copy of the tile's bias slice (no cross-warp barrier needed)
-            __syncwarp();
-            for (int j = lane; j < BN; j += 32) bias_w[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
-            __syncwarp();
+          uint8_t* stage_w0 = epi_stage + quarter * (kEpiBufs * 32 * 128);
+          float* bias_w = epi_bias + as * 256;
+          const bool use_bias = p.bias != nullptr;   // every tile stages (zeros for split > 0): barrier stays uniform
+          if (use_bias) {
+            // the tile's bias slice, staged once by the 128 epilogue threads.  Double-buffered by accumulator
+            // stage: a warp can only reach the tile that reuses this buffer after every warp passed the barrier
+            // of the tile in between, i.e. finished reading it.
+            const int et = (int)threadIdx.x - 64;
+            for (int j = et; j < BN; j += 128)
+              bias_w[j] = (split == 0 && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
           }
 #pragma unroll 1
           for (int c = 0; c < BN / CHT; ++c) {
@@ -333,9 +346,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (nb >= p.N) break;  // warp-uniform
             uint32_t r[CHT];
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c * CHT);
-            tmem_ld32(taddr, r);
-            if constexpr (CHT == 64) tmem_ld32(taddr + 32, r + 32);
-            tmem_ld_wait();
+            if (!(p.debug & 2)) {
+              tmem_ld32(taddr, r);
+              if constexpr (CHT == 64) tmem_ld32(taddr + 32, r + 32);
+              tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int j = 0; j < CHT; ++j) r[j] = 0u;
+            }
+            if (p.debug & 1) continue;
             float v[CHT];
 #pragma unroll
             for (int j = 0; j < CHT; ++j) v[j] = has_k ? __uint_as_float(r[j]) : 0.f;
@@ -350,7 +369,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < CHT; ++j) v[j] = apply_act(v[j], p.act, p.slope);
             }
-            if (lane == 0) bulk_wait_read0();  // the previous box has been read out of the staging buffer
+            // staging ring: buffer `ebuf` is free once all but the newest kEpiBufs-1 stores have been read out
+            uint8_t* stage_w = stage_w0 + ebuf * (32 * 128);
+            ebuf = (ebuf + 1) % kEpiBufs;
+            if (lane == 0) bulk_wait_read<kEpiBufs - 1>();
             __syncwarp();
             uint8_t* row = stage_w + lane * 128;
 #pragma unroll
@@ -601,6 +623,8 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
   p.m_tiles = m_tiles; p.n_tiles = n_tiles;
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.C = C; p.ldc = ldc;
   p.act = act; p.slope = slope; p.accumulate = accumulate;
+  static const int tc_debug = [] { const char* e = getenv("EGP_TC_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug = tc_debug;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_trans ? 1 : 0) << 15) |
             ((uint32_t)(b_trans ? 1 : 0) << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
   // split-K: only for fp32 outputs without a non-linear epilogue (wgrad); keeps >= 4 k-blocks per split

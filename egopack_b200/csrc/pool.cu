@@ -72,6 +72,53 @@ proto_max_gather_kernel(const T* __restrict__ protos, const int64_t* __restrict_
   }
 }
 
+// gradient of a = max(f, max_j P[idx[:,j]]) w.r.t. the bank (GraphONE(freeze=False)): where the prototype maximum
+// wins, da goes to the FIRST of the k gathered prototypes that attains it (torch_scatter arg-max semantics).
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+proto_max_scatter_bwd_kernel(const T* __restrict__ da, const T* __restrict__ f, const T* __restrict__ protos,
+                             const int64_t* __restrict__ idx, float* __restrict__ dbank, int64_t nvec, int64_t k,
+                             int64_t channels) {
+  constexpr int VN = Vec<T>::N;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = v * VN;
+    const int64_t row = e0 / channels, c0 = e0 % channels;
+    const Vec<T> g = Vec<T>::load(da + e0);
+    const Vec<T> fv = Vec<T>::load(f + e0);
+    float best[VN];
+    int64_t who[VN];
+#pragma unroll
+    for (int c = 0; c < VN; ++c) { best[c] = -FLT_MAX; who[c] = -1; }
+    for (int64_t j = 0; j < k; ++j) {
+      const int64_t pj = idx[row * k + j];
+      const Vec<T> a = Vec<T>::load(protos + pj * channels + c0);
+#pragma unroll
+      for (int c = 0; c < VN; ++c)
+        if (a.v[c] > best[c]) { best[c] = a.v[c]; who[c] = pj; }
+    }
+#pragma unroll
+    for (int c = 0; c < VN; ++c)
+      if (!(fv.v[c] >= best[c]) && who[c] >= 0 && g.v[c] != 0.f) atomicAdd(dbank + who[c] * channels + c0 + c, g.v[c]);
+  }
+}
+
+// class-conditional feature sums in fp64 (prototype-bank builder, graphone.py:53): out[label[i], :] += x[i, :]
+template <typename T>
+__global__ void __launch_bounds__(kPoolThreads)
+class_sum_kernel(const T* __restrict__ x, const int64_t* __restrict__ label, double* __restrict__ out, int64_t nvec,
+                 int64_t channels, int64_t num_classes) {
+  constexpr int VN = Vec<T>::N;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = v * VN;
+    const int64_t row = e0 / channels, c0 = e0 % channels;
+    const int64_t l = label[row];
+    if (l < 0 || l >= num_classes) continue;
+    const Vec<T> a = Vec<T>::load(x + e0);
+#pragma unroll
+    for (int c = 0; c < VN; ++c) atomicAdd(out + l * channels + c0 + c, (double)a.v[c]);
+  }
+}
+
 static int pool_grid(int64_t nvec) {
   int64_t g = ceil_div(nvec, (int64_t)kPoolThreads * 2);
   const int64_t cap = (int64_t)sm_count() * 16;
@@ -126,6 +173,36 @@ int egp_proto_max_gather(const void* protos, const int64_t* idx, void* m, int64_
     const int64_t nvec = num_nodes * channels / Vec<T>::N;
     proto_max_gather_kernel<T><<<pool_grid(nvec), kPoolThreads, 0, (cudaStream_t)stream>>>(
         (const T*)protos, idx, (T*)m, nvec, k, channels);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+int egp_proto_max_scatter_bwd(const void* da, const void* f, const void* protos, const int64_t* idx, float* dbank,
+                              int64_t num_nodes, int64_t k, int64_t channels, int dtype, void* stream) {
+  EGP_REQUIRE(da && f && protos && idx && dbank, "proto_max_scatter_bwd: null pointer");
+  const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(channels % vn == 0 && k >= 1, "proto_max_scatter_bwd: channels %% %d", (int)vn);
+  if (num_nodes == 0) return EGP_OK;
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    const int64_t nvec = num_nodes * channels / Vec<T>::N;
+    proto_max_scatter_bwd_kernel<T><<<pool_grid(nvec), kPoolThreads, 0, (cudaStream_t)stream>>>(
+        (const T*)da, (const T*)f, (const T*)protos, idx, dbank, nvec, k, channels);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+int egp_class_sum_f64(const void* x, const int64_t* label, double* out, int64_t rows, int64_t channels,
+                      int64_t num_classes, int dtype, void* stream) {
+  EGP_REQUIRE(x && label && out, "class_sum_f64: null pointer");
+  const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(channels % vn == 0 && aligned16(x), "class_sum_f64: channels %% %d", (int)vn);
+  if (rows == 0) return EGP_OK;
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    const int64_t nvec = rows * channels / Vec<T>::N;
+    class_sum_kernel<T><<<pool_grid(nvec), kPoolThreads, 0, (cudaStream_t)stream>>>((const T*)x, label, out, nvec, channels,
+                                                                                    num_classes);
     EGP_LAUNCH_CHECK();
   });
   return EGP_OK;

@@ -38,8 +38,10 @@ class _Stage(nn.Module):
         self.module_2 = nn.ReLU()
         self.module_3 = nn.Linear(hidden_size, features_size)
 
-    def forward(self, f: torch.Tensor, m: torch.Tensor, residual: bool) -> torch.Tensor:
-        a = ops.MaxCombine.apply(f, m)                       # max over {self} U {k nearest prototypes}
+    def forward(self, f: torch.Tensor, m, residual: bool) -> torch.Tensor:
+        # max over {self} U {k nearest prototypes}; `m` is the gathered maximum (frozen bank) or a closure that
+        # differentiates through the gather (trainable bank)
+        a = m(f) if callable(m) else ops.MaxCombine.apply(f, m)
         u = ops.linear(a, self.module_0.lin_l.weight, None, x2=f, w2=self.module_0.lin_r.weight)
         g = row_layernorm(self.module_1, u, act=ACT_RELU)
         return ops.linear(g, self.module_3.weight, self.module_3.bias, residual=f if residual else None)
@@ -102,12 +104,14 @@ class GraphONE(nn.Module):
     def _task_interaction(self, task: str, features: torch.Tensor):
         if not features.is_cuda:
             raise RuntimeError("egopack_b200.GraphONE runs on CUDA only (no CPU fallback)")
-        if not self.freeze and self.embeddings[task].weight.requires_grad:
-            raise NotImplementedError("trainable prototype banks (freeze=False) are not built yet")
         f = ops.Cast.apply(features, config.compute_dtype())
         idx = self.nearest_prototypes(task, f)                # constant across stages: matched on the inputs
         _, _, bank = self._bank(task)
-        m = ops.proto_max_gather(bank, idx)
+        weight = self.embeddings[task].weight
+        if weight.requires_grad and torch.is_grad_enabled():  # freeze=False: gradients reach the arg-max prototypes
+            m = lambda cur: ops.ProtoMaxCombine.apply(cur, weight, bank, idx)
+        else:
+            m = ops.proto_max_gather(bank, idx)
         for stage in self.conv_stages[task]:
             f = stage(f, m, self.residual)
         return f, [idx[:, 0]] * self.depth

@@ -356,8 +356,14 @@ class Linear(torch.autograd.Function):
         wc = weight_cache.get(w, cd)
         w2c = weight_cache.get(w2, cd) if w2 is not None else None
         out_dtype = out_dtype or cd
+        out = None
+        per16 = 16 // (4 if out_dtype == torch.float32 else 2)
+        if n % per16 and residual is None and n > per16:
+            # classifier heads (115 / 478 classes): pad the row pitch to 16 bytes so the TMA-store epilogue applies;
+            # the caller sees the [m, n] view
+            out = torch.empty((m, (n + per16 - 1) // per16 * per16), dtype=out_dtype, device=x.device)[:, :n]
         y = gemm(x, False, wc, False, m, n, k, a2=x2, b2=w2c, k2=(x2.shape[1] if x2 is not None else 0), bias=b,
-                 residual=residual, act=act, slope=slope, out_dtype=out_dtype)
+                 residual=residual, act=act, slope=slope, out_dtype=out_dtype, out=out)
         ctx.save_for_backward(x, w, x2, w2, y if act != ACT_NONE else None)
         ctx.act, ctx.slope, ctx.has_bias, ctx.has_res = act, slope, b is not None, residual is not None
         ctx.res_dtype = residual.dtype if residual is not None else None
@@ -604,6 +610,43 @@ class MaxCombine(torch.autograd.Function):
         df = torch.empty_like(f)
         L.call("egp_max_combine_bwd", L.ptr(da), L.ptr(f), L.ptr(m), L.ptr(df), f.numel(), _code(f), L.stream())
         return df, None
+
+
+class ProtoMaxCombine(torch.autograd.Function):
+    """a = max(f, max_j bank[idx[:, j]]) with a TRAINABLE bank (GraphONE(freeze=False)): the gradient reaches f where
+    f wins and the arg-max prototype otherwise.  `bank_cd` is the compute-dtype copy of `bank` the forward reads."""
+
+    @staticmethod
+    def forward(ctx, f, bank, bank_cd, idx):
+        f = _c(f)
+        m = proto_max_gather(bank_cd, idx)
+        a = torch.empty_like(f)
+        L.call("egp_max_combine_fwd", L.ptr(f), L.ptr(m), L.ptr(a), f.numel(), _code(f), L.stream())
+        ctx.save_for_backward(f, m, bank_cd, idx)
+        ctx.bank_shape = tuple(bank.shape)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        f, m, bank_cd, idx = ctx.saved_tensors
+        da = _c(da)
+        df = torch.empty_like(f)
+        L.call("egp_max_combine_bwd", L.ptr(da), L.ptr(f), L.ptr(m), L.ptr(df), f.numel(), _code(f), L.stream())
+        dbank = None
+        if ctx.needs_input_grad[1]:
+            dbank = torch.zeros(ctx.bank_shape, dtype=torch.float32, device=f.device)
+            L.call("egp_proto_max_scatter_bwd", L.ptr(da), L.ptr(f), L.ptr(bank_cd), L.ptr(_c(idx)), L.ptr(dbank),
+                   f.shape[0], idx.shape[1], f.shape[1], _code(f), L.stream())
+        return df, dbank, None, None
+
+
+def class_sum_f64(x: Tensor, labels: Tensor, num_classes: int, out: Optional[Tensor] = None) -> Tensor:
+    """out[label[i]] += x[i] in fp64 (rows with label < 0 are skipped)."""
+    x, labels = _c(x), _c(labels)
+    if out is None:
+        out = torch.zeros((num_classes, x.shape[1]), dtype=torch.float64, device=x.device)
+    L.call("egp_class_sum_f64", L.ptr(x), L.ptr(labels), L.ptr(out), x.shape[0], x.shape[1], num_classes, _code(x), L.stream())
+    return out
 
 
 def row_normalize(x: Tensor, out_dtype: torch.dtype = torch.float32) -> Tensor:

@@ -186,6 +186,16 @@ int egp_proto_max_gather(const void* protos, const int64_t* idx, void* m, int64_
 int egp_max_combine_fwd(const void* f, const void* m, void* a, int64_t n, int dtype, void* stream);
 int egp_max_combine_bwd(const void* da, const void* f, const void* m, void* df, int64_t n, int dtype, void* stream);
 
+/* gradient of the combine w.r.t. a TRAINABLE bank (GraphONE(freeze=False), graphONE.py:47-49): where the prototype
+ * maximum beats f, da[i,c] is added (fp32 atomics) to dbank[idx[i,j*],c], j* = first of the k that attains the max. */
+int egp_proto_max_scatter_bwd(const void* da, const void* f, const void* protos, const int64_t* idx, float* dbank,
+                              int64_t num_nodes, int64_t k, int64_t channels, int dtype, void* stream);
+
+/* ---- (f)-1: prototype-bank builder (graphone.py:16-63): out[label[i], :] += x[i, :] accumulated in fp64;
+ *      rows with a label outside [0, num_classes) are skipped.  out is double [num_classes, C], caller-zeroed. */
+int egp_class_sum_f64(const void* x, const int64_t* label, double* out, int64_t rows, int64_t channels,
+                      int64_t num_classes, int dtype, void* stream);
+
 /* ---- a12: per-graph channel-wise max pooling (gnn.pool.global_max_pool, models/tasks/oscc.py:68,85) ------
  * out[g,c] = max_{i in [ptr[g],ptr[g+1])} x[i,c] (0 for an empty graph); arg int32 [G,C] (-1 if empty).     */
 int egp_segment_max_pool_fwd(const void* x, const int64_t* ptr, void* out, int32_t* arg, int64_t num_graphs,

@@ -267,3 +267,56 @@ def test_egopack_oscc_step_fp32_matches_oracle():
         assert rel_max(p.grad, rp.grad) < TOL_F32, k
     for t in aux:                                               # secondaries are detached: no gradient reaches them
         assert all(p.grad is None for p in tasks[t].parameters())
+
+
+def test_graphone_trainable_banks_fp32_matches_oracle():
+    """GraphONE(freeze=False) (graphONE.py:19,47-49): gradients reach the arg-max prototypes."""
+    egopack_b200.set_precision("fp32")
+    gen = torch.Generator().manual_seed(21)
+    C, B = 64, 50
+    banks = syn.make_banks(("ar", "pnr"), 33, C, gen)
+    ref = eo.GraphONEOracle({t: b.clone() for t, b in banks.items()}, features_size=C, hidden_size=48, k=3, depth=2,
+                            residual=True, freeze=False)
+    go = GraphONE({t: b.clone() for t, b in banks.items()}, features_size=C, hidden_size=48, k=3, depth=2, residual=True,
+                  freeze=False).to(DEV)
+    go.load_state_dict(ref.state_dict())
+    feats = {t: torch.randn(B, C, generator=gen) for t in ("pnr", "ar")}
+    w = {t: torch.randn(B, C, generator=gen) for t in feats}
+    ro, _ = ref.interact({t: f.clone().requires_grad_(True) for t, f in feats.items()})
+    sum((ro[t] * w[t]).sum() for t in ro).backward()
+    no, _ = go.interact({t: f.clone().to(DEV).requires_grad_(True) for t, f in feats.items()})
+    sum((no[t] * w[t].to(DEV)).sum() for t in no).backward()
+    for t in ro:
+        assert rel_max(no[t], ro[t]) < TOL_F32
+    rp = dict(ref.named_parameters())
+    for k, p in go.named_parameters():
+        assert p.grad is not None and rel_max(p.grad, rp[k].grad) < TOL_F32, k
+    assert float(go.embeddings["ar"].weight.grad.abs().sum()) > 0
+
+
+def test_prototype_bank_builder_matches_reference_golden(golden):
+    """graphone.py:16-63 incl. the len(tasks)x bincount quirk, against banks built by the reference's own function."""
+    from egopack_b200.graphone_builder import build_graphone
+    egopack_b200.set_precision("fp32")
+    g = golden("bank_builder.pt")
+    st = g["graph_state"]
+    D, H, HT = st["temporal_pooling.proj.0.weight"].shape[1] // 3, st["temporal_pooling.proj.8.weight"].shape[0], \
+        st["temporal_pooling.proj.0.weight"].shape[0]
+    depth = sum(1 for k in st if k.endswith("lin_r.weight"))
+    m = Graph(D, H, depth, temporal_pooling=dict(TP, hidden_size=HT), num_segments=3).to(DEV)
+    m.load_state_dict(st)
+    C = g["ar"]["net.4.weight"].shape[0]
+    ar, lta, pnr = RecognitionTask(H, C, g["heads"]), LTATask(H, C, g["heads"]), PNRTask(H, C)
+    ar.load_state_dict(g["ar"]), lta.load_state_dict(g["lta"]), pnr.load_state_dict(g["pnr"])
+    for t in (ar, lta, pnr):
+        t.to(DEV)
+    loader = []
+    for b in g["batches"]:
+        d = Data(x=b["x"], pos=b["pos"], edge_index=b["edge_index"], y=b["y"])
+        d.batch, d.ptr = b["batch"], b["ptr"]
+        loader.append(d)
+    banks = build_graphone(m, ar, [ar, lta, pnr], loader, device=DEV)
+    assert set(banks) == set(g["banks"])
+    for t in banks:
+        assert banks[t].shape == g["banks"][t].shape and banks[t].dtype == torch.float32
+        assert rel_max(banks[t], g["banks"][t]) < TOL_F32
