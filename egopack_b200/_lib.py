@@ -40,6 +40,7 @@ SIGNATURES: Dict[str, tuple] = {
     "egp_row_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I64, I64, I, F, I, P, SZ, P]),
     "egp_posenc_add": (I, [P, P, P, P, I64, I64, I, P]),
     "egp_cast": (I, [P, P, I64, I, I, P]),
+    "egp_cast_pad": (I, [P, I64, P, I64, I64, I64, I, I, P]),
     "egp_add": (I, [P, P, P, I64, I, P]),
     "egp_axpby": (I, [P, F, P, F, P, I64, I, P]),
     "egp_act_bwd": (I, [P, P, P, I64, I, F, I, P]),

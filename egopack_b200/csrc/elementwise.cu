@@ -204,29 +204,43 @@ colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, int64
     if (col + c < cols) part[(size_t)blockIdx.x * cols + col + c] = acc[c];
 }
 
-// out[c] = sum_g part[g][c]; block = 32 columns x 8 part-groups, 4 loads in flight per thread (deterministic order)
-__global__ void __launch_bounds__(kEwThreads)
+// out[c] = sum_g part[g][c]; block = 32 columns x 32 part-groups (1024 threads), 4 loads in flight per thread,
+// fixed summation order (deterministic)
+constexpr int kFinalThreads = 1024;
+__global__ void __launch_bounds__(kFinalThreads)
 colsum_final_kernel(const float* __restrict__ part, int parts, int64_t cols, float* __restrict__ out) {
-  __shared__ float red[8][33];
+  __shared__ float red[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 32 + tx;
   float a = 0.f;
   if (c < cols) {
     int g = ty;
-    for (; g + 24 < parts; g += 32) {
-      const float v0 = part[(size_t)g * cols + c], v1 = part[(size_t)(g + 8) * cols + c];
-      const float v2 = part[(size_t)(g + 16) * cols + c], v3 = part[(size_t)(g + 24) * cols + c];
+    for (; g + 96 < parts; g += 128) {
+      const float v0 = part[(size_t)g * cols + c], v1 = part[(size_t)(g + 32) * cols + c];
+      const float v2 = part[(size_t)(g + 64) * cols + c], v3 = part[(size_t)(g + 96) * cols + c];
       a += (v0 + v1) + (v2 + v3);
     }
-    for (; g < parts; g += 8) a += part[(size_t)g * cols + c];
+    for (; g < parts; g += 32) a += part[(size_t)g * cols + c];
   }
   red[ty][tx] = a;
   __syncthreads();
   if (ty == 0 && c < cols) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    for (int i = 0; i < 32; ++i) t += red[i][tx];
     out[c] = t;
+  }
+}
+
+// dst[m, ldd] (bf16/fp32) = cast(src[m, n]) with the columns n..ldd-1 zero-filled: gives classifier-width gradients
+// (115 / 478 columns) the 16-byte row pitch TMA needs, in one pass
+template <typename S, typename D>
+__global__ void __launch_bounds__(kEwThreads)
+cast_pad_kernel(const S* __restrict__ src, int64_t lds, D* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols) {
+  const int64_t total = rows * ldd;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / ldd, c = e % ldd;
+    dst[e] = c < cols ? from_float<D>(to_float<S>(src[r * lds + c])) : from_float<D>(0.f);
   }
 }
 
@@ -308,7 +322,7 @@ int colsum_launch(const void* x, float* out, int64_t rows, int64_t cols, int64_t
     colsum_partial_kernel<T><<<dim3(parts, gy), threads, 0, s>>>((const T*)x, rows, cols, ldx, rows_per, vec_ok, part);
     EGP_LAUNCH_CHECK();
   });
-  colsum_final_kernel<<<(unsigned)ceil_div(cols, 32), kEwThreads, 0, s>>>(part, parts, cols, out);
+  colsum_final_kernel<<<(unsigned)ceil_div(cols, 32), kFinalThreads, 0, s>>>(part, parts, cols, out);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
 }
@@ -355,6 +369,29 @@ int egp_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype
     return EGP_OK;
   } else {
     set_error("cast: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
+    return EGP_ERR_INVALID;
+  }
+  EGP_LAUNCH_CHECK();
+  return EGP_OK;
+}
+
+int egp_cast_pad(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols, int src_dtype,
+                 int dst_dtype, void* stream) {
+  EGP_REQUIRE(src && dst, "cast_pad: null pointer");
+  EGP_REQUIRE(ldd >= cols && lds >= cols, "cast_pad: row pitches must cover the columns");
+  if (rows == 0 || ldd == 0) return EGP_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = ew_grid(ceil_div(rows * ldd, 4));
+  if (src_dtype == EGP_F32 && dst_dtype == EGP_BF16)
+    cast_pad_kernel<float, __nv_bfloat16><<<grid, kEwThreads, 0, s>>>((const float*)src, lds, (__nv_bfloat16*)dst, ldd, rows, cols);
+  else if (src_dtype == EGP_BF16 && dst_dtype == EGP_BF16)
+    cast_pad_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kEwThreads, 0, s>>>((const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, rows, cols);
+  else if (src_dtype == EGP_F32 && dst_dtype == EGP_F32)
+    cast_pad_kernel<float, float><<<grid, kEwThreads, 0, s>>>((const float*)src, lds, (float*)dst, ldd, rows, cols);
+  else if (src_dtype == EGP_BF16 && dst_dtype == EGP_F32)
+    cast_pad_kernel<__nv_bfloat16, float><<<grid, kEwThreads, 0, s>>>((const __nv_bfloat16*)src, lds, (float*)dst, ldd, rows, cols);
+  else {
+    set_error("cast_pad: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
     return EGP_ERR_INVALID;
   }
   EGP_LAUNCH_CHECK();
@@ -466,7 +503,7 @@ int egp_act_bwd_colsum(const void* dy, const void* y, void* dx, float* dx_colsum
     if (fuse) {
       act_bwd_colsum_kernel<T><<<grid, kEwThreads, 0, s>>>((const T*)dy, (const T*)y, (T*)dx, nvec, (int)period, act, slope, part);
       EGP_LAUNCH_CHECK();
-      colsum_final_kernel<<<(unsigned)ceil_div(cols, 32), kEwThreads, 0, s>>>(part, grid, cols, dx_colsum);
+      colsum_final_kernel<<<(unsigned)ceil_div(cols, 32), kFinalThreads, 0, s>>>(part, grid, cols, dx_colsum);
       EGP_LAUNCH_CHECK();
     } else {
       act_bwd_kernel<T><<<grid, kEwThreads, 0, s>>>((const T*)dy, (const T*)y, (T*)dx, nvec, act, slope);

@@ -15,6 +15,7 @@
 // of tile t+1.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -27,6 +28,10 @@ constexpr int TBM = 128;     // tile M (UMMA_M)
 constexpr int TBK = 64;      // k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;   // bf16
 constexpr int TC_THREADS = 192;
+// fused top-k kernels run kTopkGroups epilogue warps per TMEM lane quarter (each takes every kTopkGroups-th 32-column
+// chunk and keeps its own candidate set), so every scheduler has several epilogue warps to interleave
+constexpr int kTopkGroups = 2;
+constexpr int TC_THREADS_TOPK = 64 + 128 * kTopkGroups;
 
 // ------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -90,6 +95,11 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// L2 prefetch of a tile that a later TMA load will fetch (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -186,12 +196,14 @@ struct TcParams {
   float slope;
   int accumulate;      // C += result (fp32 atomics)
   int tma_store;       // epilogue stages 32x128B boxes in smem and stores them with TMA (coalesced, clipped)
-  int debug;           // EGP_TC_DEBUG bit 0: skip the stores, bit 1: skip the TMEM loads too (timing experiments)
+  int topk;            // TOPK kernels: candidates kept per row (8 or 16); 0 otherwise
+  int32_t* cand;       // TOPK kernels: [M, TOPK] column indices of the largest entries of each row (unordered)
+  int debug;           // EGP_TC_DEBUG bit 0: skip the stores, bit 1: skip the TMEM loads too, bit 2: enable the L2 look-ahead (timing experiments)
   uint32_t idesc;
 };
 
-template <int BN, bool A_MN, bool B_MN, typename OutT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BN, bool A_MN, bool B_MN, typename OutT, int TOPK = 0>
+__global__ void __launch_bounds__(TOPK > 0 ? TC_THREADS_TOPK : TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2,
                const __grid_constant__ CUtensorMap mapC, const TcParams p) {
@@ -215,7 +227,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (p.kb2 > 0) { tma_prefetch_desc(&mapA2); tma_prefetch_desc(&mapB2); }
     if (p.tma_store) tma_prefetch_desc(&mapC);
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], TOPK > 0 ? 4 * kTopkGroups : 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -235,13 +247,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     e = min(b + per, kb_all);
   };
 
+  // The i-th tile of this CTA.  Normal GEMMs stride the linear tile index by the grid (n fastest, so CTAs running
+  // side by side share an A row block).  TOPK kernels give a CTA whole row blocks and walk all of its n tiles in
+  // order, so a row's running top-k stays in the registers of one epilogue thread.
+  auto tile_at = [&](int iter, int& split, int& m_blk, int& n_blk) -> bool {
+    if (TOPK) {
+      const int mb = blockIdx.x + (iter / p.n_tiles) * gridDim.x;
+      if (mb >= p.m_tiles) return false;
+      split = 0; m_blk = mb; n_blk = iter % p.n_tiles;
+      return true;
+    }
+    const int t = blockIdx.x + iter * gridDim.x;
+    if (t >= total) return false;
+    split = t / tiles_mn;
+    const int mn = t % tiles_mn;
+    m_blk = mn / p.n_tiles; n_blk = mn % p.n_tiles;
+    return true;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int split = t / tiles_mn, mn = t % tiles_mn;
-        const int m0 = (mn / p.n_tiles) * TBM, n0 = (mn % p.n_tiles) * BN;
+      int split, m_blk, n_blk;
+      for (int it = 0; tile_at(it, split, m_blk, n_blk); ++it) {
+        const int m0 = m_blk * TBM, n0 = n_blk * BN;
         int kb_b, kb_e;
         split_range(split, kb_b, kb_e);
         for (int kb = kb_b; kb < kb_e; ++kb) {
@@ -275,9 +305,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const int split = t / tiles_mn;
+      int split, m_blk, n_blk;
+      for (int it = 0; tile_at(it, split, m_blk, n_blk); ++it) {
         int kb_b, kb_e;
         split_range(split, kb_b, kb_e);
         const int as = it & 1;
@@ -310,11 +339,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int quarter = warp & 3;
     OutT* C = reinterpret_cast<OutT*>(p.C);
     const OutT* R = reinterpret_cast<const OutT*>(p.residual);
-    int it = 0;
     int ebuf = 0;  // next staging buffer of this warp's ring
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-      const int split = t / tiles_mn, mn = t % tiles_mn;
-      const int64_t m0 = (int64_t)(mn / p.n_tiles) * TBM, n0 = (int64_t)(mn % p.n_tiles) * BN;
+    constexpr int KK = TOPK > 0 ? TOPK : 1;
+    float tv[KK];   // fused top-k: the KK largest entries of this thread's row so far (unsorted)
+    int ti[KK];
+    float tmin = -3.0e38f;
+    int smin = 0;
+    int split, m_blk, n_blk;
+    for (int it = 0; tile_at(it, split, m_blk, n_blk); ++it) {
+      const int64_t m0 = (int64_t)m_blk * TBM, n0 = (int64_t)n_blk * BN;
       int kb_b, kb_e;
       split_range(split, kb_b, kb_e);
       const int as = it & 1;
@@ -323,6 +356,64 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_after();
       const int64_t m = m0 + quarter * 32 + lane;
       const bool row_ok = m < p.M;
+      if constexpr (TOPK > 0) {
+        // similarity tile -> running set of the KK largest entries of the row; nothing is written to C.
+        // The set is UNSORTED (the exact re-rank orders it): an insertion overwrites the slot holding the current
+        // minimum and re-derives (minimum, slot) with a tournament -- ~40 short-dependency selects instead of a
+        // sorted shift, which matters because an epilogue warp has its scheduler to itself (no latency hiding).
+        // Ties keep the earlier (lower) column: only a strictly larger value evicts.
+        if (n_blk == 0) {
+#pragma unroll
+          for (int q = 0; q < KK; ++q) { tv[q] = -3.0e38f; ti[q] = 0x7fffffff; }
+          tmin = -3.0e38f;
+          smin = 0;
+        }
+        const int group = (warp - 2) >> 2;  // which of the kTopkGroups column groups this warp scans
+#pragma unroll 1
+        for (int c = group; c < BN / 32; c += kTopkGroups) {
+          const int64_t nb = n0 + c * 32;
+          if (nb >= p.N) break;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = __uint_as_float(r[j]);
+            if (v > tmin && nb + j < p.N) {
+#pragma unroll
+              for (int q = 0; q < KK; ++q) {
+                const bool here = q == smin;
+                tv[q] = here ? v : tv[q];
+                ti[q] = here ? (int)(nb + j) : ti[q];
+              }
+              // tournament for the new (minimum, slot)
+              float mv[KK];
+              int ms[KK];
+#pragma unroll
+              for (int q = 0; q < KK; ++q) { mv[q] = tv[q]; ms[q] = q; }
+#pragma unroll
+              for (int w = KK / 2; w >= 1; w /= 2) {
+#pragma unroll
+                for (int q = 0; q < w; ++q) {
+                  const bool lt = mv[q + w] < mv[q];
+                  mv[q] = lt ? mv[q + w] : mv[q];
+                  ms[q] = lt ? ms[q + w] : ms[q];
+                }
+              }
+              tmin = mv[0];
+              smin = ms[0];
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+        if (n_blk == p.n_tiles - 1 && row_ok) {
+#pragma unroll
+          for (int q = 0; q < KK; ++q) p.cand[(m * kTopkGroups + group) * KK + q] = ti[q];
+        }
+        continue;
+      }
       const bool atomic = p.splits > 1 || p.accumulate;
       const bool has_k = kb_e > kb_b;
       constexpr int CHT = 128 / (int)sizeof(OutT);  // columns per 128-byte staged row: 64 (bf16) / 32 (fp32)
@@ -623,6 +714,7 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
   p.m_tiles = m_tiles; p.n_tiles = n_tiles;
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.C = C; p.ldc = ldc;
   p.act = act; p.slope = slope; p.accumulate = accumulate;
+  p.topk = 0; p.cand = nullptr;
   static const int tc_debug = [] { const char* e = getenv("EGP_TC_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = tc_debug;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_trans ? 1 : 0) << 15) |
@@ -682,6 +774,55 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
 #undef EGP_TC_BN
   set_error("tc_gemm: no kernel for tile N %d", bn);
   return EGP_ERR_INVALID;
+}
+
+// Fused similarity + top-k: S = A[M,K] B[N,K]^T on the tensor cores, the `keep` (8 or 16) largest entries of every row
+// are selected in the epilogue (registers of the thread that owns the row) and only their column indices leave the
+// chip: cand int32 [M, kTopkGroups * keep], unordered (the re-rank scores and sorts them).  Replaces the [M,N] fp32 similarity round trip through HBM.
+template <int KEEP>
+static int tc_gemm_topk_inst(const CUtensorMap* maps, const TcParams& p, int grid, cudaStream_t stream) {
+  constexpr int BN = 256;
+  auto kern = tc_gemm_kernel<BN, false, false, float, KEEP>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  kern<<<grid, TC_THREADS_TOPK, TcCfg<BN>::kSmemBytes, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  EGP_LAUNCH_CHECK();
+  return EGP_OK;
+}
+
+int tc_topk_groups() { return kTopkGroups; }
+
+int tc_gemm_topk_launch(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K, int keep,
+                        int32_t* cand, cudaStream_t stream) {
+  if (M == 0) return EGP_OK;
+  if (keep != 8 && keep != 16) {
+    set_error("tc_gemm_topk: keep must be 8 or 16");
+    return EGP_ERR_INVALID;
+  }
+  constexpr int BN = 256;
+  const int sms = sm_count();
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N;
+  p.kb1 = (int)ceil_div(K, TBK);
+  p.kb2 = 0;
+  p.splits = 1;
+  p.m_tiles = (int)ceil_div(M, TBM);
+  p.n_tiles = (int)ceil_div(N, BN);
+  p.act = EGP_ACT_NONE;
+  p.topk = keep;
+  p.cand = cand;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+  CUtensorMap maps[5];
+  int rc;
+  if ((rc = operand_map(A, M, K, lda, 0, TBM, &maps[0])) != EGP_OK) return rc;
+  if ((rc = operand_map(B, N, K, ldb, 0, BN, &maps[1])) != EGP_OK) return rc;
+  maps[2] = maps[0]; maps[3] = maps[1]; maps[4] = maps[0];
+  const int grid = p.m_tiles < sms ? p.m_tiles : sms;
+  return keep == 8 ? tc_gemm_topk_inst<8>(maps, p, grid, stream) : tc_gemm_topk_inst<16>(maps, p, grid, stream);
 }
 
 }  // namespace egp

@@ -9,6 +9,7 @@
 //                    on bf16 rounding as long as the true top-k is inside the candidate set.
 #include <float.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -22,6 +23,9 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
                    int64_t lda2, const void* B2, int64_t ldb2, int64_t K2, const float* bias, const void* residual,
                    int64_t ldr, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int act, float slope,
                    int out_dtype, int accumulate, cudaStream_t stream);
+int tc_gemm_topk_launch(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K, int keep,
+                        int32_t* cand, cudaStream_t stream);
+int tc_topk_groups();
 bool tc_gemm_supported(const void* A, int64_t lda, const void* B, int64_t ldb, const void* A2, int64_t lda2,
                        const void* B2, int64_t ldb2);
 
@@ -172,8 +176,7 @@ static int topk_kk(int k) { return k + 8 <= 16 ? 16 : (k + 8 <= 32 ? 32 : 0); }
 
 size_t egp_cos_topk_workspace(int64_t num_nodes, int64_t num_protos, int64_t k) {
   const int64_t rows = num_nodes < kTopkChunkRows ? num_nodes : kTopkChunkRows;
-  const int kk = topk_kk((int)k);
-  return (size_t)rows * (size_t)num_protos * sizeof(float) + (size_t)rows * (size_t)(kk ? kk : 1) * sizeof(int32_t) + 256;
+  return (size_t)rows * (size_t)num_protos * sizeof(float) + (size_t)rows * 32 * sizeof(int32_t) + 512;
 }
 
 int egp_cos_topk(const float* fn, const float* pn, const void* fn16, const void* pn16, int64_t num_nodes,
@@ -198,7 +201,21 @@ int egp_cos_topk(const float* fn, const float* pn, const void* fn16, const void*
     const int64_t rows = (num_nodes - r0) < chunk ? (num_nodes - r0) : chunk;
     const unsigned grid = (unsigned)ceil_div(rows, kTopkThreads / 32);
     int rc;
-    if (tensor) {
+    static const bool unfused = [] { const char* e = getenv("EGP_TOPK_UNFUSED"); return e && e[0] == '1'; }();
+    if (tensor && kk == 16 && !unfused) {
+      // fused path: similarity GEMM with the best candidates selected in its epilogue (k+4 <= 8 -> keep 8, else 16),
+      // then the exact fp32 re-rank of those candidates
+      const __nv_bfloat16* a = (const __nv_bfloat16*)fn16 + r0 * channels;
+      // every column group keeps its own set: keep 8 per group when k+4 <= 8 (k+4 covered the true top-k on every
+      // row in SURVEY app. B), else 16; the re-rank sees groups*keep candidates (unused slots hold INT_MAX)
+      const int keep = (k + 4 <= 8) ? 8 : 16;
+      rc = tc_gemm_topk_launch(a, channels, pn16, channels, rows, num_protos, channels, keep, cand, s);
+      if (rc != EGP_OK) return rc;
+      if (keep * tc_topk_groups() == 16)
+        rerank_kernel<16><<<grid, kTopkThreads, 0, s>>>(fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k);
+      else
+        rerank_kernel<32><<<grid, kTopkThreads, 0, s>>>(fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k);
+    } else if (tensor) {
       const __nv_bfloat16* a = (const __nv_bfloat16*)fn16 + r0 * channels;
       rc = tc_gemm_launch(a, channels, 0, pn16, channels, 0, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, 0, S,
                           num_protos, rows, num_protos, channels, EGP_ACT_NONE, 0.f, EGP_F32, 0, s);

@@ -309,16 +309,20 @@ class _WeightCache:
     def __init__(self):
         self._store = {}
 
-    def get(self, w: Tensor, dtype: torch.dtype) -> Tensor:
-        if w.dtype == dtype:
+    def get(self, w: Tensor, dtype: torch.dtype, pad_rows: int = 0) -> Tensor:
+        """`pad_rows` > rows appends zero rows (dgrad of a classifier whose gradient had its class dim padded)."""
+        pad_rows = pad_rows if pad_rows > w.shape[0] else 0
+        if w.dtype == dtype and not pad_rows:
             return w
-        key = (w.data_ptr(), tuple(w.shape), dtype)
+        key = (w.data_ptr(), tuple(w.shape), dtype, pad_rows)
         hit = self._store.get(key)
         if hit is not None:
             src = hit[0]()
             if src is not None and src.data_ptr() == w.data_ptr() and hit[1] == w._version:
                 return hit[2]
         c = cast(w.detach(), dtype)
+        if pad_rows:
+            c = torch.cat([c, c.new_zeros((pad_rows - w.shape[0], w.shape[1]))], 0)
         if len(self._store) > 4096:
             self._store = {k: v for k, v in self._store.items() if v[0]() is not None}
         self._store[key] = (weakref.ref(w), w._version, c)
@@ -328,14 +332,17 @@ class _WeightCache:
 weight_cache = _WeightCache()
 
 
-def _pad_cols(x: Tensor, mult: int) -> Tensor:
-    """Zero-pad the last dim up to a multiple of `mult` (bf16 operands must have 16-byte row strides for TMA)."""
-    c = x.shape[1]
-    if c % mult == 0:
-        return x
+def cast_pad(x: Tensor, dtype: torch.dtype, mult: int) -> Tensor:
+    """cast + zero-pad the last dim up to a multiple of `mult` in one kernel (bf16 operands need 16-byte row
+    pitches for TMA; classifier gradients have 115 / 478 columns)."""
+    r, c = x.shape
     cp = (c + mult - 1) // mult * mult
-    out = torch.zeros((x.shape[0], cp), dtype=x.dtype, device=x.device)
-    out[:, :c].copy_(x)
+    if cp == c:
+        return cast(x, dtype)
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    out = torch.empty((r, cp), dtype=dtype, device=x.device)
+    L.call("egp_cast_pad", L.ptr(x), x.stride(0), L.ptr(out), cp, r, c, _code(x), L.DTYPE_CODE[dtype], L.stream())
     return out
 
 
@@ -390,25 +397,20 @@ class Linear(torch.autograd.Function):
                 g = act_bwd(dy, y, ctx.act, ctx.slope)
         elif want_db:
             db = _take_colsum(dy)                                     # by-product of the LN backward upstream
-        gc = cast(g, cd)                                 # fp32 logits gradients -> bf16 operand
         if want_db and db is None:
             db = colsum(g)
-        if cd == torch.bfloat16 and n % 8 != 0:          # TMA needs 16-byte row strides: pad the class dim
-            gc = _pad_cols(gc, 8)
+        # fp32 logits gradients -> bf16 operand; TMA needs 16-byte row pitches, so the class dim is zero-padded
+        gc = cast_pad(g, cd, 8) if cd == torch.bfloat16 else cast(g, cd)
         npad = gc.shape[1]
         dx = dx2 = dw = dw2 = None
-        wc = weight_cache.get(w, cd)
-        if npad != n:
-            wc = torch.cat([wc, wc.new_zeros((npad - n, k))], 0)
+        wc = weight_cache.get(w, cd, pad_rows=npad)
         if ctx.needs_input_grad[0]:
             dx = gemm(gc, False, wc, True, m, k, npad)                           # dx = g W
         if ctx.needs_input_grad[1]:
             dw = gemm(gc, True, x, True, n, k, m, out_dtype=torch.float32)       # dW = g^T x
         if x2 is not None:
             k2 = x2.shape[1]
-            w2c = weight_cache.get(w2, cd)
-            if npad != n:
-                w2c = torch.cat([w2c, w2c.new_zeros((npad - n, k2))], 0)
+            w2c = weight_cache.get(w2, cd, pad_rows=npad)
             if ctx.needs_input_grad[3]:
                 dx2 = gemm(gc, False, w2c, True, m, k2, npad)
             if ctx.needs_input_grad[4]:

@@ -131,6 +131,9 @@ int egp_posenc_add(const void* x, const int64_t* pos, const float* frequency, vo
 
 /* ---- elementwise helpers ------------------------------------------------------------------------------- */
 int egp_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
+/* dst[rows, ldd] = cast(src[rows, cols] with pitch lds), columns cols..ldd-1 zero-filled (16-byte pitch for TMA) */
+int egp_cast_pad(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols, int src_dtype,
+                 int dst_dtype, void* stream);
 /* out = a + b (same dtype) */
 int egp_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
 /* out = alpha*a + beta*b (b may be NULL: out = alpha*a) */
