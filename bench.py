@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-videos", type=int, default=16, help="graphs per task batch of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2 = MTL AR+LTA+PNR (the BASELINE metric's config); c3 = EgoPack OSCC + AR/LTA/PNR prototype backpack")
+    ap.add_argument("--protos", type=int, default=4096, help="prototypes per bank (c3)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (for profiler runs)")
     ap.add_argument("--trace-out", default=None, help="write the per-launch trace summary to this JSON file")
     return ap.parse_args()
@@ -178,7 +181,8 @@ def native_run(args, rank: int, world: int, local_rank: int):
     from egopack_b200 import synthetic as syn
     from egopack_b200.dp import GradientAllReduce
     from egopack_b200.models.graph import Graph
-    from egopack_b200.models.tasks import LTATask, PNRTask, RecognitionTask
+    from egopack_b200.models.graphONE.graphONE import GraphONE
+    from egopack_b200.models.tasks import LTATask, OSCCTask, PNRTask, RecognitionTask
     from egopack_b200.models.transforms import LTATemporalConnectivity
 
     dev = torch.device("cuda", local_rank)
@@ -188,19 +192,36 @@ def native_run(args, rank: int, world: int, local_rank: int):
     model = Graph(syn.FEATURE_DIM, HIDDEN, DEPTH, temporal_pooling={"hidden_size": TRN_HIDDEN, "dropout": DROPOUT},
                   num_segments=syn.NUM_SEGMENTS).to(dev)
     heads = (syn.N_VERBS, syn.N_NOUNS)
-    tasks = {"ar": RecognitionTask(HIDDEN, HIDDEN, heads).to(dev), "lta": LTATask(HIDDEN, HIDDEN, heads).to(dev),
-             "pnr": PNRTask(HIDDEN, HIDDEN).to(dev)}
+    c3 = args.workload == "c3"
+    graphone = None
+    if c3:
+        # EgoPack novel task (experiments/egopack/oscc.yaml): OSCC primary, frozen AR/LTA/PNR banks, k=4, depth 3,
+        # residual, late fusion with averaged logits, Graph trainable
+        aux = ("ar", "lta", "pnr")
+        tasks = {"oscc": OSCCTask(HIDDEN, HIDDEN, aux_tasks=aux, average_logits=True, head_dropout=0.5).to(dev),
+                 "ar": RecognitionTask(HIDDEN, HIDDEN, heads).to(dev), "lta": LTATask(HIDDEN, HIDDEN, heads).to(dev),
+                 "pnr": PNRTask(HIDDEN, HIDDEN).to(dev)}
+        banks = syn.make_banks(aux, args.protos, HIDDEN, syn.generator(SEED, 3, 0))
+        graphone = GraphONE(banks, features_size=HIDDEN, hidden_size=HIDDEN, k=4, depth=3, residual=True).to(dev)
+        graphone.train()
+        task_names = ("oscc",)
+    else:
+        tasks = {"ar": RecognitionTask(HIDDEN, HIDDEN, heads).to(dev), "lta": LTATask(HIDDEN, HIDDEN, heads).to(dev),
+                 "pnr": PNRTask(HIDDEN, HIDDEN).to(dev)}
+        task_names = TASKS
     model.train()
     for t in tasks.values():
         t.train()
     params = list(model.parameters()) + [p for t in tasks.values() for p in t.parameters()]
+    if graphone is not None:
+        params += [p for p in graphone.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5, fused=True)
     sync = GradientAllReduce(params) if world > 1 else None
     lta_edges = LTATemporalConnectivity(r=K_RADIUS + 0.5)
 
     gen = syn.generator(SEED, 2, rank)                        # every rank draws its own shard of graphs
-    host = {t: syn.make_batch(t, args.videos, args.nodes, gen, band_k=K_RADIUS, pin=True) for t in TASKS}
-    n_nodes = args.videos * args.nodes * len(TASKS)
+    host = {t: syn.make_batch(t, args.videos, args.nodes, gen, band_k=K_RADIUS, pin=True) for t in task_names}
+    n_nodes = args.videos * args.nodes * len(task_names)
     h2d_bytes = sum(v.numel() * v.element_size() for b in host.values() for v in (b.x, b.pos, b.y, b.batch, b.ptr))
 
     def upload(stream=None):
@@ -220,7 +241,10 @@ def native_run(args, rank: int, world: int, local_rank: int):
 
     def step(batches):
         opt.zero_grad(set_to_none=True)
-        loss, _ = steps.mtl_losses(model, tasks, batches)
+        if c3:
+            loss, _ = steps.egopack_losses(model, tasks, batches, graphone)
+        else:
+            loss, _ = steps.mtl_losses(model, tasks, batches)
         loss.backward()
         if sync is not None:
             sync.finish()
@@ -291,6 +315,64 @@ def native_run(args, rank: int, world: int, local_rank: int):
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e_value = world * n_nodes / (e2e_ms / 1e3)
 
+    # ---- launch-bound regime: the reference's own batch size (16 graphs/task), eager vs one CUDA graph per step ------
+    small = None
+    if world == 1 and not c3:
+        try:
+            import gc
+            from egopack_b200.graphs import GraphedStep
+            # AccumulateGrad nodes created on the default stream by the eager steps above must not survive into the
+            # capture stream: drop every reference to the old autograd graphs first
+            loss = None
+            nxt = cur = None
+            gc.collect()
+            sv, sn = 16, 16
+            sgen = syn.generator(SEED, 9, rank)
+            shost = {t: syn.make_batch(t, sv, sn, sgen, band_k=K_RADIUS) for t in task_names}
+            sdev = {}
+            for t, hb in shost.items():
+                d = egopack_b200.Batch()
+                for k in ("x", "pos", "y", "batch", "ptr"):
+                    setattr(d, k, getattr(hb, k).to(dev))
+                if t == "lta":
+                    lta_edges(d)
+                else:
+                    d.band_k = K_RADIUS
+                sdev[t] = d
+            opt2 = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5, fused=True, capturable=True)
+
+            def small_step(b):
+                opt2.zero_grad(set_to_none=True)
+                l, _ = steps.mtl_losses(model, tasks, b)
+                l.backward()
+                opt2.step()
+                return l
+
+            def time_it(fn, n=30):
+                for _ in range(5):
+                    fn()
+                torch.cuda.synchronize()
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(n):
+                    fn()
+                b_.record()
+                torch.cuda.synchronize()
+                return a.elapsed_time(b_) / n
+
+            eager_ms = time_it(lambda: small_step(sdev))
+            gc.collect()
+            runner = GraphedStep(small_step, sdev)
+            graph_ms = time_it(lambda: runner())
+            nn_small = sv * sn * len(task_names)
+            small = {"graphs_per_task": sv, "nodes_per_graph": sn, "nodes_per_step": nn_small,
+                     "eager_ms_per_step": round(eager_ms, 3), "cuda_graph_ms_per_step": round(graph_ms, 3),
+                     "eager_nodes_per_s": round(nn_small / eager_ms * 1e3, 1),
+                     "cuda_graph_nodes_per_s": round(nn_small / graph_ms * 1e3, 1),
+                     "note": "reference-scale batch (launch-bound): whole step (fwd+bwd+Adam) replayed as ONE CUDA graph"}
+        except Exception as ex:  # noqa: BLE001 -- a probe; never let it take the bench line down
+            small = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+
     # ---- per-launch trace for the roofline (separate, untimed steps) ---------------------------------------
     pk = peaks()
     ops.TRACE = []
@@ -330,8 +412,11 @@ def native_run(args, rank: int, world: int, local_rank: int):
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": "c2: MTL AR+LTA+PNR shared temporal GNN (experiments/mtl.yaml: k=1, hidden 1024, depth 3, "
-                               "TRN hidden 1024, dropout 0.5), full train step = zero_grad+fwd+loss+bwd+grad-allreduce+Adam",
+        "config": {"workload": ("c3: EgoPack OSCC primary + frozen AR/LTA/PNR prototype backpack (k=4, depth 3, residual, "
+                                f"{args.protos} prototypes/bank, late fusion), Graph trainable, full train step"
+                                if c3 else
+                                "c2: MTL AR+LTA+PNR shared temporal GNN (experiments/mtl.yaml: k=1, hidden 1024, depth 3, "
+                                "TRN hidden 1024, dropout 0.5), full train step = zero_grad+fwd+loss+bwd+grad-allreduce+Adam"),
                    "graphs_per_task_per_gpu": args.videos, "nodes_per_graph": args.nodes,
                    "nodes_per_step_per_gpu": n_nodes, "features": "[N,3,1536] fp32 N(0,1)", "parallelism": f"dp{world}",
                    "l2": f"inputs larger than L2 ({h2d_bytes / 2**20:.0f} MiB of features per step)",
@@ -345,6 +430,8 @@ def native_run(args, rank: int, world: int, local_rank: int):
     }
     if roof_hbm:
         out["roofline_hbm"] = roof_hbm
+    if small is not None:
+        out["small_batch"] = small
     return out
 
 

@@ -36,7 +36,7 @@ SIGNATURES: Dict[str, tuple] = {
     "egp_graph_layernorm_fwd": (I, [P, P, P, P, P, I64, I64, F, I, F, I, P, SZ, P]),
     "egp_graph_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, I64, I64, F, I, F, I, P, SZ, P]),
     "egp_row_layernorm_workspace": (SZ, [I64, I64]),
-    "egp_row_layernorm_fwd": (I, [P, P, P, P, P, P, I64, I64, F, I, F, C.c_uint64, C.c_uint64, I, P]),
+    "egp_row_layernorm_fwd": (I, [P, P, P, P, P, P, I64, I64, F, I, F, C.c_uint64, C.c_uint64, P, I, P]),
     "egp_row_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I64, I64, I, F, I, P, SZ, P]),
     "egp_posenc_add": (I, [P, P, P, P, I64, I64, I, P]),
     "egp_cast": (I, [P, P, I64, I, I, P]),

@@ -291,7 +291,11 @@ template <typename T, int NVL>
 __global__ void __launch_bounds__(kNormThreads)
 rln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t n, int64_t channels,
-               float eps, int act, uint32_t drop_thr16, float keep_scale, uint64_t seed, uint64_t offset) {
+               float eps, int act, uint32_t drop_thr16, float keep_scale, uint64_t seed, uint64_t offset,
+               const uint64_t* __restrict__ rng_state) {
+  // CUDA-graph replays cannot change kernel arguments, so the per-step part of the Philox stream may come from device
+  // memory: rng_state = {seed, step}; the call-site index stays in `offset`
+  if (rng_state) { seed = rng_state[0]; offset += rng_state[1] << 20; }
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const int nvec = (int)(channels / VN);
@@ -528,7 +532,8 @@ __global__ void __launch_bounds__(kNormThreads)
 rln_fwd_wide_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                     T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t n,
                     int64_t channels, float eps, int act, uint32_t drop_thr16, float keep_scale, uint64_t seed,
-                    uint64_t offset) {
+                    uint64_t offset, const uint64_t* __restrict__ rng_state) {
+  if (rng_state) { seed = rng_state[0]; offset += rng_state[1] << 20; }
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const int nvec = (int)(channels / VN);
@@ -760,7 +765,7 @@ size_t egp_row_layernorm_workspace(int64_t n, int64_t channels) {
 
 int egp_row_layernorm_fwd(const void* x, const float* weight, const float* bias, void* y, float* mean,
                           float* rstd, int64_t n, int64_t channels, float eps, int act, float dropout_p,
-                          uint64_t seed, uint64_t offset, int dtype, void* stream) {
+                          uint64_t seed, uint64_t offset, const uint64_t* rng_state, int dtype, void* stream) {
   EGP_REQUIRE(x && weight && bias && y && mean && rstd, "row_layernorm_fwd: null pointer");
   const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
   EGP_REQUIRE(channels % vn == 0 && aligned16(x) && aligned16(y), "row_layernorm_fwd: channels %% %d != 0 or unaligned", (int)vn);
@@ -777,10 +782,10 @@ int egp_row_layernorm_fwd(const void* x, const float* weight, const float* bias,
     EGP_RLN_DISPATCH_NVL(nvec, {
       if constexpr (NVL == 0)
         rln_fwd_wide_kernel<T><<<grid, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, mean, rstd, n, channels, eps,
-                                                             act, thr, keep_scale, seed, offset);
+                                                             act, thr, keep_scale, seed, offset, rng_state);
       else
         rln_fwd_kernel<T, NVL><<<grid, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, mean, rstd, n, channels, eps,
-                                                             act, thr, keep_scale, seed, offset);
+                                                             act, thr, keep_scale, seed, offset, rng_state);
     });
     EGP_LAUNCH_CHECK();
   });

@@ -291,6 +291,9 @@ def act_bwd_colsum(dy: Tensor, y: Tensor, act: int, slope: float) -> Tuple[Tenso
 
 
 _dropout_calls = 0
+# Set by egopack_b200.graphs while a training step is captured into a CUDA graph: a device uint64[2] = {seed, step}
+# that the replayed kernels read, because their scalar arguments are frozen at capture time.
+RNG_STATE: Optional[Tensor] = None
 
 
 def _dropout_stream() -> Tuple[int, int]:
@@ -442,7 +445,8 @@ class RowLayerNorm(torch.autograd.Function):
         rstd = torch.empty(n, dtype=torch.float32, device=x.device)
         seed, offset = _dropout_stream() if dropout_p > 0 else (0, 0)
         L.call("egp_row_layernorm_fwd", L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(mean), L.ptr(rstd), n, c,
-               float(eps), act, float(dropout_p), seed, offset, _code(x), L.stream())
+               float(eps), act, float(dropout_p), seed, offset & 0xFFFFF, L.ptr(RNG_STATE) if dropout_p > 0 else None,
+               _code(x), L.stream())
         need_y = act == ACT_RELU or dropout_p > 0
         ctx.save_for_backward(x, y if need_y else None, w, mean, rstd)
         ctx.act, ctx.out_scale = act, (1.0 / (1.0 - dropout_p) if dropout_p > 0 else 1.0)

@@ -114,12 +114,13 @@ int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, 
 /* ---- row LayerNorm (+ReLU) (+Dropout) (nn.LayerNorm -> ReLU -> Dropout in TRNPooling trn_pooling.py:30-37; tasks
  *      task.py:20; GraphONE graphONE.py:61); mean/rstd float [N] are saved for the backward ---------------------
  * fwd: y = dropout_p(act(LN(x))); the keep decisions come from Philox4x32-10(seed; element-vector index, offset), so
- *      no mask is stored.  bwd: a zero in the saved output y means "ReLU inactive or dropped"; the incoming gradient
+ *      no mask is stored; rng_state (optional, device uint64[2] = {seed, step}) overrides the seed and adds step<<20 to
+ *      the offset so that CUDA-graph replays draw fresh masks.  bwd: a zero in the saved output y means "ReLU inactive or dropped"; the incoming gradient
  *      is scaled by out_scale = 1/(1-p).  dx_colsum (optional) as in egp_graph_layernorm_bwd. */
 size_t egp_row_layernorm_workspace(int64_t num_nodes, int64_t channels);
 int egp_row_layernorm_fwd(const void* x, const float* weight, const float* bias, void* y, float* mean,
                           float* rstd, int64_t num_nodes, int64_t channels, float eps, int act, float dropout_p,
-                          uint64_t seed, uint64_t offset, int dtype, void* stream);
+                          uint64_t seed, uint64_t offset, const uint64_t* rng_state, int dtype, void* stream);
 int egp_row_layernorm_bwd(const void* dy, const void* x, const void* y, const float* weight, const float* mean,
                           const float* rstd, void* dx, float* dweight, float* dbias, float* dx_colsum,
                           int64_t num_nodes, int64_t channels, int act, float out_scale, int dtype, void* workspace,

@@ -217,7 +217,7 @@ def test_row_layernorm_fused_dropout_and_colsum_byproduct(dtype, tol):
     yy = torch.empty_like(xd)
     code = 0 if dtype == torch.float32 else 1
     L.call("egp_row_layernorm_fwd", xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), yy.data_ptr(), mean.data_ptr(),
-           rstd.data_ptr(), n, c, 1e-5, ACT_RELU, 0.0, 0, 0, code, L.stream())
+           rstd.data_ptr(), n, c, 1e-5, ACT_RELU, 0.0, 0, 0, None, code, L.stream())
     nb = L.size("egp_row_layernorm_workspace", n, c)
     ws = L.workspace(nb, xd.device)
     dwt, dbt = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
