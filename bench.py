@@ -436,6 +436,9 @@ def native_run(args, rank: int, world: int, local_rank: int):
 
 
 def main():
+    # some images export NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout next to the JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

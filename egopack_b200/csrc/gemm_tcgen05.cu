@@ -75,11 +75,37 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
+// `bar_addr` is a shared-window address; with CG == 2 it may name the mbarrier of the pair's leader CTA
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar_addr, void* smem, int c0, int c1) {
+  if constexpr (CG == 2)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(bar_addr), "r"(c0), "r"(c1)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(bar_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// thread-block-cluster plumbing for the CTA-pair (cta_group::2) kernels
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 // smem -> global tile store (clips rows/columns outside the tensor); `reduce` adds into global memory instead
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int c1, bool reduce) {
@@ -104,27 +130,58 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
 
+// CG == 2: executed by the same warp of BOTH CTAs of the pair (each gets the address in its own shared memory)
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if constexpr (CG == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  if constexpr (CG == 2)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// CG == 2: issued by the leader CTA only; multiplies the pair's 256 x BN tile (A rows and B columns split over the
+// two CTAs' shared memories, accumulator rows split over their TMEMs)
+template <int CG>
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (CG == 2)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
-// arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed
+// arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed; CG == 2 arrives on
+// the barrier at the same shared-memory offset in BOTH CTAs of the pair
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  if constexpr (CG == 2)
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+        : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -167,17 +224,22 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 // Shared-memory budget (227 KB): a ring of TMA stages for A/B, then the epilogue's staging ring (each epilogue warp
 // owns kEpiBufs buffers of 32 rows x 128 B so that a tile's boxes are written back-to-back without waiting for the
 // previous TMA store to drain), the per-warp bias slices and the mbarriers.
+//
+// CG == 2 (CTA pair, cta_group::2): the pair computes a 256 x BN tile; each CTA stages its own 128 rows of A and
+// HALF of the B tile, so a k-block costs 32 KB per SM instead of 48 KB (BN = 256) -- 6 stages instead of 4 and a
+// third less L2 -> shared-memory traffic per flop.
 constexpr int kEpiBufs = 2;
-template <int BN>
+template <int BN, int CG = 1>
 struct TcCfg {
   static constexpr int kABytes = TBM * TBK * 2;
-  static constexpr int kBBytes = BN * TBK * 2;
+  static constexpr int kBBytes = (BN / CG) * TBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiStageBytes = 4 * kEpiBufs * 32 * 128;   // 32 KB
   static constexpr int kEpiBiasBytes = 2 * 256 * 4;                // one bias slice per accumulator stage
-  static constexpr int kFixedBytes = kEpiStageBytes + kEpiBiasBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // the dynamic shared-memory window is declared 1024-byte aligned (checked at kernel entry), no slack needed
+  static constexpr int kFixedBytes = kEpiStageBytes + kEpiBiasBytes + 256 /*barriers*/;
   static constexpr int kStagesFit = (232448 - kFixedBytes) / kStageBytes;
-  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;  // 4 for BN=256, 6 for BN=128, up to 8 below
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;  // 4 for BN=256 (6 as a CTA pair), 6 for BN=128
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;      // power of two for BN in {16,...,256}
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
 };
@@ -202,15 +264,28 @@ struct TcParams {
   uint32_t idesc;
 };
 
-template <int BN, bool A_MN, bool B_MN, typename OutT, int TOPK = 0>
+// CG = 2 (launched as clusters of two CTAs): the pair owns a 256 x BN tile.  CTA `rank` stages rows
+// [rank*128, rank*128+128) of A and columns [rank*BN/2, (rank+1)*BN/2) of B; the leader (rank 0) issues
+// tcgen05.mma.cta_group::2, which reads both shared memories and writes each CTA's 128 accumulator rows into its
+// own TMEM; each CTA runs its own epilogue.  Barriers: `full` lives in the leader (both producers' TMA bytes land
+// on it), `empty` / `tfull` are signalled in both CTAs by a multicast tcgen05.commit, `tempty` lives in the leader
+// and collects the (remote) arrivals of both CTAs' epilogue warps.
+template <int BN, bool A_MN, bool B_MN, typename OutT, int TOPK = 0, int CG = 1>
 __global__ void __launch_bounds__(TOPK > 0 ? TC_THREADS_TOPK : TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2,
                const __grid_constant__ CUtensorMap mapC, const TcParams p) {
-  using Cfg = TcCfg<BN>;
+  static_assert(CG == 1 || (TOPK == 0 && BN >= 128), "CTA pairs: plain GEMM with BN >= 128 only");
+  using Cfg = TcCfg<BN, CG>;
   constexpr int S = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;   // 128-byte-swizzled TMA boxes and UMMA descriptors need 1024-byte alignment
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("egopack_b200: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   uint8_t* epi_stage = smem + S * Cfg::kStageBytes;                      // 1024-aligned (stage bytes are)
   float* epi_bias = reinterpret_cast<float*>(epi_stage + Cfg::kEpiStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + Cfg::kEpiStageBytes + Cfg::kEpiBiasBytes);
@@ -227,17 +302,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (p.kb2 > 0) { tma_prefetch_desc(&mapA2); tma_prefetch_desc(&mapB2); }
     if (p.tma_store) tma_prefetch_desc(&mapC);
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], TOPK > 0 ? 4 * kTopkGroups : 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], (TOPK > 0 ? 4 * kTopkGroups : 4) * CG); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  __syncwarp();
+  if (warp == 1) tmem_alloc<CG>(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_mn = p.m_tiles * p.n_tiles;
+  // CTA pairs tile M in units of 256 rows: m_units pair-rows, this CTA taking the `cta_rank`-th half of each
+  const int m_units = CG == 2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int tiles_mn = m_units * p.n_tiles;
   const int total = tiles_mn * p.splits;
+  const int worker = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int workers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int kb_all = p.kb1 + p.kb2;
 
   // k-block range of split s: contiguous chunks of the concatenated [pair1 | pair2] k-block list
@@ -257,11 +337,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       split = 0; m_blk = mb; n_blk = iter % p.n_tiles;
       return true;
     }
-    const int t = blockIdx.x + iter * gridDim.x;
+    const int t = worker + iter * workers;
     if (t >= total) return false;
     split = t / tiles_mn;
     const int mn = t % tiles_mn;
-    m_blk = mn / p.n_tiles; n_blk = mn % p.n_tiles;
+    m_blk = (mn / p.n_tiles) * CG + (int)cta_rank; n_blk = mn % p.n_tiles;
     return true;
   };
 
@@ -271,12 +351,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       uint32_t phase = 0;
       int split, m_blk, n_blk;
       for (int it = 0; tile_at(it, split, m_blk, n_blk); ++it) {
-        const int m0 = m_blk * TBM, n0 = n_blk * BN;
+        const int m0 = m_blk * TBM, n0 = n_blk * BN + (int)cta_rank * (BN / CG);
         int kb_b, kb_e;
         split_range(split, kb_b, kb_e);
         for (int kb = kb_b; kb < kb_e; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
-          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          if (leader) mbar_expect_tx(&full[stage], CG * Cfg::kStageBytes);
+          const uint32_t full_bar = CG == 2 ? mapa_u32(smem_u32(&full[stage]), 0u) : smem_u32(&full[stage]);
           const bool second = kb >= p.kb1;
           const CUtensorMap* ma = second ? &mapA2 : &mapA;
           const CUtensorMap* mb = second ? &mapB2 : &mapB;
@@ -284,25 +365,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           if (!A_MN) {
-            tma_load_2d(ma, &full[stage], sa, k0, m0);              // box {64 k, 128 rows}
+            tma_load_2d<CG>(ma, full_bar, sa, k0, m0);               // box {64 k, 128 rows}
           } else {
 #pragma unroll
             for (int a = 0; a < TBM / 64; ++a)                       // box {64 m, 64 k} per MN atom
-              tma_load_2d(ma, &full[stage], sa + a * (TBK * 128), m0 + a * 64, k0);
+              tma_load_2d<CG>(ma, full_bar, sa + a * (TBK * 128), m0 + a * 64, k0);
           }
           if (!B_MN) {
-            tma_load_2d(mb, &full[stage], sb, k0, n0);              // box {64 k, BN rows}
+            tma_load_2d<CG>(mb, full_bar, sb, k0, n0);               // box {64 k, BN / CG rows}
           } else {
 #pragma unroll
-            for (int a = 0; a < BN / 64; ++a)
-              tma_load_2d(mb, &full[stage], sb + a * (TBK * 128), n0 + a * 64, k0);
+            for (int a = 0; a < BN / CG / 64; ++a)
+              tma_load_2d<CG>(mb, full_bar, sb + a * (TBK * 128), n0 + a * 64, k0);
           }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0;
       int split, m_blk, n_blk;
@@ -326,12 +407,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // advance the 14-bit start-address field: 32 B per UMMA_K step (K-major) or 16 rows x 128 B (MN-major)
             const uint64_t ao = (uint64_t)((A_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
             const uint64_t bo = (uint64_t)((B_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
-            umma_bf16(d_tmem, adesc + ao, bdesc + bo, p.idesc, (kb > kb_b || k > 0) ? 1u : 0u);
+            umma_bf16<CG>(d_tmem, adesc + ao, bdesc + bo, p.idesc, (kb > kb_b || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          umma_commit<CG>(&empty[stage]);
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull[as]);
+        umma_commit<CG>(&tfull[as]);
       }
     }
   } else {
@@ -345,6 +426,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     int ti[KK];
     float tmin = -3.0e38f;
     int smin = 0;
+    // release accumulator stage `as` to the MMA issuer (CTA pairs: the leader's barrier, from both CTAs)
+    auto tempty_arrive = [&](int as) {
+      if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0u));
+      else mbar_arrive(&tempty[as]);
+    };
     int split, m_blk, n_blk;
     for (int it = 0; tile_at(it, split, m_blk, n_blk); ++it) {
       const int64_t m0 = (int64_t)m_blk * TBM, n0 = (int64_t)n_blk * BN;
@@ -407,7 +493,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[as]);
+        if (lane == 0) tempty_arrive(as);
         if (n_blk == p.n_tiles - 1 && row_ok) {
 #pragma unroll
           for (int q = 0; q < KK; ++q) p.cand[(m * kTopkGroups + group) * KK + q] = ti[q];
@@ -491,7 +577,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[as]);
+          if (lane == 0) tempty_arrive(as);
           continue;
         }
       }
@@ -557,16 +643,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) tempty_arrive(as);
     }
     if (p.tma_store && lane == 0) bulk_wait0();  // all staged boxes have landed in global memory
   }
 
+  // teardown.  CTA pairs: neither CTA may exit (or free TMEM) while its partner can still touch its shared memory
+  // or barriers, so the whole cluster meets here first.
+  __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    tmem_dealloc<CG>(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -660,29 +749,57 @@ bool tc_gemm_supported(const void* A, int64_t lda, const void* B, int64_t ldb, c
   return ok(A, lda) && ok(B, ldb) && ok(A2, lda2) && ok(B2, ldb2);
 }
 
-template <int BN, bool A_MN, bool B_MN, typename OutT>
-static int tc_launch_inst(const CUtensorMap* maps, const TcParams& p, int grid, cudaStream_t stream) {
-  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, OutT>;
+// `work` = tiles (CG == 1) or pair tiles (CG == 2) to distribute; the grid is min(work, resident CTAs / clusters)
+template <int BN, bool A_MN, bool B_MN, typename OutT, int CG>
+static int tc_launch_inst(const CUtensorMap* maps, const TcParams& p, int work, cudaStream_t stream) {
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, OutT, 0, CG>;
+  constexpr int kSmem = TcCfg<BN, CG>::kSmemBytes;
   static bool attr_set = false;
+  static int max_clusters = 0;
   if (!attr_set) {
-    EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes));
+    EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    if (CG == 2) {
+      cudaLaunchConfig_t q = {};
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.gridDim = dim3(2 * (unsigned)sm_count()); q.blockDim = dim3(TC_THREADS); q.dynamicSmemBytes = kSmem;
+      q.attrs = qa; q.numAttrs = 1;
+      EGP_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q));
+      if (max_clusters < 1) {
+        set_error("tc_gemm: no CTA pair of the cta_group::2 kernel fits on this device");
+        return EGP_ERR_UNSUPPORTED;
+      }
+    }
     attr_set = true;
   }
-  kern<<<grid, TC_THREADS, TcCfg<BN>::kSmemBytes, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  if constexpr (CG == 2) {
+    const int clusters = work < max_clusters ? work : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(2 * (unsigned)clusters); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = kSmem;
+    cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 1;
+    EGP_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], p));
+  } else {
+    const int sms = sm_count();
+    kern<<<work < sms ? work : sms, TC_THREADS, kSmem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  }
   EGP_LAUNCH_CHECK();
   return EGP_OK;
 }
 
-template <int BN, typename OutT>
-static int tc_launch_major(int a_trans, int b_trans, const CUtensorMap* maps, const TcParams& p, int grid,
+template <int BN, typename OutT, int CG>
+static int tc_launch_major(int a_trans, int b_trans, const CUtensorMap* maps, const TcParams& p, int work,
                            cudaStream_t stream) {
-  if (!a_trans && !b_trans) return tc_launch_inst<BN, false, false, OutT>(maps, p, grid, stream);
+  if (!a_trans && !b_trans) return tc_launch_inst<BN, false, false, OutT, CG>(maps, p, work, stream);
   if (!a_trans && b_trans) {
-    if constexpr (BN >= 64) return tc_launch_inst<BN, false, true, OutT>(maps, p, grid, stream);
+    if constexpr (BN >= 64) return tc_launch_inst<BN, false, true, OutT, CG>(maps, p, work, stream);
   }
-  if (a_trans && !b_trans) return tc_launch_inst<BN, true, false, OutT>(maps, p, grid, stream);
+  if (a_trans && !b_trans) return tc_launch_inst<BN, true, false, OutT, CG>(maps, p, work, stream);
   if (a_trans && b_trans) {
-    if constexpr (BN >= 64) return tc_launch_inst<BN, true, true, OutT>(maps, p, grid, stream);
+    if constexpr (BN >= 64) return tc_launch_inst<BN, true, true, OutT, CG>(maps, p, work, stream);
   }
   set_error("tc_gemm: MN-major B needs a tile N of at least 64");
   return EGP_ERR_INVALID;
@@ -707,6 +824,9 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
     while (bn > 64 && (int64_t)m_tiles * ceil_div(N, bn) < sms) bn /= 2;
   const int n_tiles = (int)ceil_div(N, bn);
   const bool has2 = A2 && B2 && K2 > 0;
+  // CTA pairs (cta_group::2) for the widest tile whenever there are at least two row blocks; EGP_TC_CG=1 disables
+  static const int tc_cg = [] { const char* e = getenv("EGP_TC_CG"); return e ? atoi(e) : 2; }();
+  const int cg = (tc_cg == 2 && bn == 256 && m_tiles >= 2) ? 2 : 1;
   TcParams p;
   p.M = M; p.N = N;
   p.kb1 = (int)ceil_div(K, TBK);
@@ -718,12 +838,13 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
   static const int tc_debug = [] { const char* e = getenv("EGP_TC_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = tc_debug;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_trans ? 1 : 0) << 15) |
-            ((uint32_t)(b_trans ? 1 : 0) << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+            ((uint32_t)(b_trans ? 1 : 0) << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((TBM * cg) >> 4) << 24);
   // split-K: only for fp32 outputs without a non-linear epilogue (wgrad); keeps >= 4 k-blocks per split
   int splits = 1;
-  const int tiles = m_tiles * n_tiles, kb_all = p.kb1 + p.kb2;
-  if (can_split && tiles * 2 <= sms && kb_all >= 8) {
-    splits = sms / tiles;
+  const int tiles = (cg == 2 ? (m_tiles + 1) / 2 : m_tiles) * n_tiles, kb_all = p.kb1 + p.kb2;
+  const int slots = sms / cg;  // concurrently running tiles (CTAs, or CTA pairs)
+  if (can_split && tiles * 2 <= slots && kb_all >= 8) {
+    splits = slots / tiles;
     if (splits > kb_all / 4) splits = kb_all / 4;
     if (splits < 1) splits = 1;
     const int per = (kb_all + splits - 1) / splits;
@@ -741,10 +862,10 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
   CUtensorMap maps[5];
   int rc;
   if ((rc = operand_map(A, M, K, lda, a_trans, TBM, &maps[0])) != EGP_OK) return rc;
-  if ((rc = operand_map(B, N, K, ldb, b_trans, bn, &maps[1])) != EGP_OK) return rc;
+  if ((rc = operand_map(B, N, K, ldb, b_trans, bn / cg, &maps[1])) != EGP_OK) return rc;
   if (has2) {
     if ((rc = operand_map(A2, M, K2, lda2, a_trans, TBM, &maps[2])) != EGP_OK) return rc;
-    if ((rc = operand_map(B2, N, K2, ldb2, b_trans, bn, &maps[3])) != EGP_OK) return rc;
+    if ((rc = operand_map(B2, N, K2, ldb2, b_trans, bn / cg, &maps[3])) != EGP_OK) return rc;
   } else {
     maps[2] = maps[0];
     maps[3] = maps[1];
@@ -759,11 +880,13 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
     maps[4] = maps[0];
   }
   const int total = tiles * splits;
-  const int grid = total < sms ? total : sms;
+  if (cg == 2)
+    return out_dtype == EGP_F32 ? tc_launch_major<256, float, 2>(a_trans, b_trans, maps, p, total, stream)
+                                : tc_launch_major<256, __nv_bfloat16, 2>(a_trans, b_trans, maps, p, total, stream);
 #define EGP_TC_BN(BNV)                                                                                          \
   case BNV:                                                                                                     \
-    return out_dtype == EGP_F32 ? tc_launch_major<BNV, float>(a_trans, b_trans, maps, p, grid, stream)          \
-                                : tc_launch_major<BNV, __nv_bfloat16>(a_trans, b_trans, maps, p, grid, stream);
+    return out_dtype == EGP_F32 ? tc_launch_major<BNV, float, 1>(a_trans, b_trans, maps, p, total, stream)      \
+                                : tc_launch_major<BNV, __nv_bfloat16, 1>(a_trans, b_trans, maps, p, total, stream);
   switch (bn) {
     EGP_TC_BN(256)
     EGP_TC_BN(128)
