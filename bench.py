@@ -381,11 +381,18 @@ def native_run(args, rank: int, world: int, local_rank: int):
     torch.cuda.synchronize()
     trace, ops.TRACE = ops.TRACE, None
     agg = {}
-    for name, work, unit, a, b in trace:
+    shapes = {}
+    for name, work, unit, a, b, detail in trace:
+        ms = a.elapsed_time(b)
         r = agg.setdefault(name, {"work": 0.0, "ms": 0.0, "n": 0, "unit": unit})
         r["work"] += work
-        r["ms"] += a.elapsed_time(b)
+        r["ms"] += ms
         r["n"] += 1
+        if detail:
+            d = shapes.setdefault(f"{name} {detail}", {"work": 0.0, "ms": 0.0, "n": 0})
+            d["work"] += work
+            d["ms"] += ms
+            d["n"] += 1
     roof, roof_hbm = None, None
     if "gemm_tcgen05" in agg or "gemm_ffma" in agg:
         g = agg.get("gemm_tcgen05") or agg["gemm_ffma"]
@@ -406,7 +413,11 @@ def native_run(args, rank: int, world: int, local_rank: int):
             roof_hbm.append(r)
     if args.trace_out and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.trace_out)), exist_ok=True)
-        json.dump({k: {**v, "ms_per_step": v["ms"] / 2} for k, v in agg.items()}, open(args.trace_out, "w"), indent=1)
+        summary = {k: {**v, "ms_per_step": v["ms"] / 2} for k, v in agg.items()}
+        summary["gemm_shapes"] = {k: {"launches_per_step": v["n"] // 2, "ms_per_step": round(v["ms"] / 2, 4),
+                                      "tflops": round(v["work"] / (v["ms"] / 1e3) / 1e12, 1)}
+                                  for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])}
+        json.dump(summary, open(args.trace_out, "w"), indent=1)
 
     out = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,

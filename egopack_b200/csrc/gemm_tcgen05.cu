@@ -274,7 +274,8 @@ template <int BN, bool A_MN, bool B_MN, typename OutT, int TOPK = 0, int CG = 1>
 __global__ void __launch_bounds__(TOPK > 0 ? TC_THREADS_TOPK : TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2,
-               const __grid_constant__ CUtensorMap mapC, const TcParams p) {
+               const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapR,
+               const TcParams p) {
   static_assert(CG == 1 || (TOPK == 0 && BN >= 128), "CTA pairs: plain GEMM with BN >= 128 only");
   using Cfg = TcCfg<BN, CG>;
   constexpr int S = Cfg::kStages;
@@ -294,6 +295,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* tfull = bars + 2 * S;   // [2]  MMA -> epilogue
   uint64_t* tempty = tfull + 2;     // [2]  epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rbar = bars + 24;       // [4 warps][kEpiBufs]  residual box landed in the warp's staging buffer
+  static_assert((2 * S + 4) * 8 + 4 <= 192 && (24 + 4 * kEpiBufs) * 8 <= 256, "barrier area layout");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -301,6 +304,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     tma_prefetch_desc(&mapB);
     if (p.kb2 > 0) { tma_prefetch_desc(&mapA2); tma_prefetch_desc(&mapB2); }
     if (p.tma_store) tma_prefetch_desc(&mapC);
+    if (p.tma_store && p.residual) tma_prefetch_desc(&mapR);
+    for (int s = 0; s < 4 * kEpiBufs; ++s) mbar_init(&rbar[s], 1);
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], (TOPK > 0 ? 4 * kTopkGroups : 4) * CG); }
     fence_barrier_init();
@@ -421,6 +426,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     OutT* C = reinterpret_cast<OutT*>(p.C);
     const OutT* R = reinterpret_cast<const OutT*>(p.residual);
     int ebuf = 0;  // next staging buffer of this warp's ring
+    uint32_t rphase = 0;  // parity bit per staging buffer of this warp's residual barriers
     constexpr int KK = TOPK > 0 ? TOPK : 1;
     float tv[KK];   // fused top-k: the KK largest entries of this thread's row so far (unsorted)
     int ti[KK];
@@ -508,6 +514,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           uint8_t* stage_w0 = epi_stage + quarter * (kEpiBufs * 32 * 128);
           float* bias_w = epi_bias + as * 256;
           const bool use_bias = p.bias != nullptr;   // every tile stages (zeros for split > 0): barrier stays uniform
+          // residual: the matching 32 x 128 B box of R is TMA-loaded INTO the staging buffer one chunk ahead, the
+          // accumulator is added onto it in place and the same buffer is stored
+          const bool has_res = p.residual != nullptr;
+          uint64_t* rbar_w = rbar + quarter * kEpiBufs;
+          auto load_residual = [&](int buf, int64_t col) {
+            mbar_expect_tx(&rbar_w[buf], 32 * 128);
+            tma_load_2d<1>(&mapR, smem_u32(&rbar_w[buf]), stage_w0 + buf * (32 * 128), (int)col, (int)(m0 + quarter * 32));
+          };
+          if (has_res && lane == 0) {
+            bulk_wait_read<kEpiBufs - 1>();
+            load_residual(ebuf, n0);
+          }
           if (use_bias) {
             // the tile's bias slice, staged once by the 128 epilogue threads.  Double-buffered by accumulator
             // stage: a warp can only reach the tile that reuses this buffer after every warp passed the barrier
@@ -548,12 +566,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
             // staging ring: buffer `ebuf` is free once all but the newest kEpiBufs-1 stores have been read out
             uint8_t* stage_w = stage_w0 + ebuf * (32 * 128);
+            const int cur = ebuf;
             ebuf = (ebuf + 1) % kEpiBufs;
-            if (lane == 0) bulk_wait_read<kEpiBufs - 1>();
-            __syncwarp();
+            if (!has_res) {
+              if (lane == 0) bulk_wait_read<kEpiBufs - 1>();
+              __syncwarp();
+            } else {
+              if (lane == 0 && c + 1 < BN / CHT && nb + CHT < p.N) {
+                bulk_wait_read<0>();       // the other buffer's store (previous chunk) has been read out
+                load_residual(ebuf, nb + CHT);
+              }
+              mbar_wait(&rbar_w[cur], (rphase >> cur) & 1u);
+              rphase ^= 1u << cur;
+            }
             uint8_t* row = stage_w + lane * 128;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {  // 16-byte pieces, XOR-swizzled with the row index (SWIZZLE_128B)
+              if (has_res) {
+                const Vec<OutT> rr = Vec<OutT>::load(reinterpret_cast<const OutT*>(row + ((q ^ (lane & 7)) << 4)));
+#pragma unroll
+                for (int e = 0; e < Vec<OutT>::N; ++e) v[q * Vec<OutT>::N + e] += rr.v[e];
+              }
               uint4 pk;
               if constexpr (sizeof(OutT) == 2) {
                 __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
@@ -781,10 +814,10 @@ static int tc_launch_inst(const CUtensorMap* maps, const TcParams& p, int work, 
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.gridDim = dim3(2 * (unsigned)clusters); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = kSmem;
     cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 1;
-    EGP_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], p));
+    EGP_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p));
   } else {
     const int sms = sm_count();
-    kern<<<work < sms ? work : sms, TC_THREADS, kSmem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+    kern<<<work < sms ? work : sms, TC_THREADS, kSmem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   }
   EGP_LAUNCH_CHECK();
   return EGP_OK;
@@ -859,7 +892,7 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
     if (ldc == N) EGP_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * (size_t)N, stream));
     else EGP_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, (size_t)M, stream));
   }
-  CUtensorMap maps[5];
+  CUtensorMap maps[6];
   int rc;
   if ((rc = operand_map(A, M, K, lda, a_trans, TBM, &maps[0])) != EGP_OK) return rc;
   if ((rc = operand_map(B, N, K, ldb, b_trans, bn / cg, &maps[1])) != EGP_OK) return rc;
@@ -870,14 +903,16 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
     maps[2] = maps[0];
     maps[3] = maps[1];
   }
-  // TMA-store epilogue: needs a 16-byte-aligned C with 16-byte row pitch, a tile at least one 128-byte staged row
-  // wide, and no residual (the residual form keeps the register-direct epilogue)
+  // TMA-store epilogue: needs a 16-byte-aligned C (and residual) with 16-byte row pitch and a tile at least one
+  // 128-byte staged row wide; anything else keeps the register-direct epilogue
   const int esz = out_dtype == EGP_F32 ? 4 : 2;
-  p.tma_store = (!residual && aligned16(C) && (ldc * esz) % 16 == 0 && bn >= 128 / esz) ? 1 : 0;
+  p.tma_store = (aligned16(C) && (ldc * esz) % 16 == 0 && bn >= 128 / esz &&
+                 (!residual || (aligned16(residual) && (ldr * esz) % 16 == 0))) ? 1 : 0;
+  maps[4] = maps[0];
+  maps[5] = maps[0];
   if (p.tma_store) {
     if ((rc = make_map(C, N, M, ldc, 128 / esz, 32, esz, &maps[4])) != EGP_OK) return rc;
-  } else {
-    maps[4] = maps[0];
+    if (residual && (rc = make_map(residual, N, M, ldr, 128 / esz, 32, esz, &maps[5])) != EGP_OK) return rc;
   }
   const int total = tiles * splits;
   if (cg == 2)
@@ -911,7 +946,7 @@ static int tc_gemm_topk_inst(const CUtensorMap* maps, const TcParams& p, int gri
     EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  kern<<<grid, TC_THREADS_TOPK, TcCfg<BN>::kSmemBytes, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  kern<<<grid, TC_THREADS_TOPK, TcCfg<BN>::kSmemBytes, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[4], p);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
 }

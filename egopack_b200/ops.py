@@ -19,15 +19,15 @@ F32, BF16 = 0, 1
 
 
 # Optional per-launch tracing for bench.py's roofline numbers: when TRACE is a list, traced ops append
-# (name, work, unit, start_event, end_event) with CUDA events recorded on the launching (current) stream.
+# (name, work, unit, start_event, end_event, detail) with CUDA events recorded on the launching (current) stream.
 TRACE = None
 
 
 class _Traced:
-    def __init__(self, name: str, work: float, unit: str):
+    def __init__(self, name: str, work: float, unit: str, detail: str = ""):
         self.on = TRACE is not None
         if self.on:
-            self.name, self.work, self.unit = name, work, unit
+            self.name, self.work, self.unit, self.detail = name, work, unit, detail
             self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def __enter__(self):
@@ -38,7 +38,7 @@ class _Traced:
     def __exit__(self, *exc):
         if self.on:
             self.e1.record()
-            TRACE.append((self.name, self.work, self.unit, self.e0, self.e1))
+            TRACE.append((self.name, self.work, self.unit, self.e0, self.e1, self.detail))
         return False
 
 
@@ -190,7 +190,12 @@ def gemm(a: Tensor, a_trans: bool, b: Tensor, b_trans: bool, m: int, n: int, k: 
     if residual is not None:
         assert residual.dtype == out.dtype and residual.shape == out.shape
     name = "gemm_tcgen05" if a.dtype == torch.bfloat16 else "gemm_ffma"
-    with _Traced(name, 2.0 * m * n * (k + k2), "FLOP"):
+    detail = ""
+    if TRACE is not None:
+        detail = (f"{m}x{n}x{k}" + (f"+{k2}" if k2 else "") + f" {'T' if a_trans else 'N'}{'T' if b_trans else 'N'}"
+                  f" -> {'f32' if out.dtype == torch.float32 else 'bf16'}" + (" +bias" if bias is not None else "")
+                  + (f" act{act}" if act else "") + (" +res" if residual is not None else "") + (" acc" if accumulate else ""))
+    with _Traced(name, 2.0 * m * n * (k + k2), "FLOP", detail):
         _gemm_launch(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate)
     return out
 

@@ -87,6 +87,21 @@ def main():
     gemm_case("gemm_small_batch_fwd", 2048, H, H, bias=True)
     gemm_case("gemm_small_batch_wgrad", H, H, 2048, a_trans=True, b_trans=True, out_dtype=torch.float32)
 
+    # the library baseline at the same shapes (cuBLAS through torch.mm, bias / activation NOT included)
+    def cublas_case(name, m, n, k, a_trans=False, b_trans=False, out_dtype=BF):
+        def build():
+            A = rnd(k, m).t() if a_trans else rnd(m, k)
+            B = rnd(k, n) if b_trans else rnd(n, k).t()
+            out = torch.empty(m, n, dtype=BF, device=DEV)
+            return lambda: torch.mm(A, B, out=out)
+        cases.append((name, build, 2.0 * m * n * k, "TFLOP/s"))
+
+    cublas_case("cublas_fwd_k1024", N, H, H)
+    cublas_case("cublas_fwd_k4608", N, H, K0)
+    cublas_case("cublas_dgrad_k1024", N, H, H, b_trans=True)
+    cublas_case("cublas_wgrad_1024x1024 (bf16 out)", H, H, N, a_trans=True, b_trans=True)
+    cublas_case("cublas_wgrad_1024x4608 (bf16 out)", H, K0, N, a_trans=True, b_trans=True)
+
     def mem_case(name, build, nbytes):
         cases.append((name, build, float(nbytes), "GB/s"))
 

@@ -70,6 +70,26 @@ def test_tc_dual_and_epilogues():
     run_case(BF, 128, 128, 256, a_trans=True, out_dtype=F32)
 
 
+# 256-wide tiles run as CTA pairs (cta_group::2): odd number of 128-row blocks (the last pair's second CTA is all
+# padding), ragged N inside the second CTA's half of B, every operand layout, dual operands, split-K
+@pytest.mark.parametrize("kw", [dict(m=4728, n=1000, k=320, bias=True, act=2),
+                                dict(m=4728, n=1000, k=320, out_dtype=F32, bias=True),
+                                dict(m=4728, n=1000, k=320, b_trans=True),
+                                dict(m=4728, n=1000, k=200, a_trans=True, bias=True, act=1),
+                                dict(m=4728, n=1000, k=192, k2=320, bias=True),
+                                dict(m=4728, n=1000, k=192, k2=128, b_trans=True, out_dtype=F32),
+                                dict(m=384, n=520, k=4096, a_trans=True, b_trans=True, out_dtype=F32),
+                                dict(m=384, n=520, k=1100, k2=2048, a_trans=True, b_trans=True, out_dtype=F32),
+                                dict(m=32768, n=1024, k=1024, bias=True),
+                                # residual boxes TMA-loaded into the epilogue's staging buffers (ragged N, fp32 too)
+                                dict(m=4728, n=1000, k=320, bias=True, residual=True),
+                                dict(m=4728, n=1000, k=320, bias=True, act=1, residual=True, out_dtype=F32),
+                                dict(m=4728, n=72, k=320, residual=True),
+                                dict(m=32768, n=1024, k=1024, bias=True, residual=True)])
+def test_tc_cta_pair_tiles(kw):
+    run_case(BF, **kw)
+
+
 @pytest.mark.parametrize("kw", [dict(m=100, n=70, k=50), dict(m=300, n=130, k=77, b_trans=True, bias=True, act=1),
                                 dict(m=64, n=200, k=300, a_trans=True, b_trans=True),
                                 dict(m=256, n=128, k=96, k2=64, bias=True, residual=True), dict(m=1024, n=1024, k=1024)])
