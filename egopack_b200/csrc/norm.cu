@@ -35,7 +35,23 @@ gln_stats_kernel(const T* __restrict__ x, int64_t nvec, double inv_count, double
   __shared__ double red[32];
   __shared__ bool is_last;
   double s = 0.0, q = 0.0;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; v + 3 * stride < nvec; v += 4 * stride) {  // four independent 16-byte loads in flight per thread
+    Raw<T> r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = Raw<T>::load(x + (v + u * stride) * VN);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const Vec<T> a = r[u].unpack();
+      float ls = 0.f, lq = 0.f;
+#pragma unroll
+      for (int c = 0; c < VN; ++c) { ls += a.v[c]; lq += a.v[c] * a.v[c]; }
+      s += (double)ls;
+      q += (double)lq;
+    }
+  }
+  for (; v < nvec; v += stride) {
     const Vec<T> a = Vec<T>::load(x + v * VN);
     float ls = 0.f, lq = 0.f;
 #pragma unroll
@@ -147,9 +163,7 @@ gln_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const f
   double s1 = 0.0, s2 = 0.0;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(r0 + rows_per_cta, n);
   if (live) {
-    for (int64_t i = r0; i < r1; ++i) {
-      const Vec<T> g = Vec<T>::load(dy + i * channels + col);
-      const Vec<T> a = Vec<T>::load(x + i * channels + col);
+    auto row_update = [&](const Vec<T>& g, const Vec<T>& a) {
       float l1 = 0.f, l2 = 0.f;
 #pragma unroll
       for (int c = 0; c < VN; ++c) {
@@ -164,7 +178,19 @@ gln_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const f
       }
       s1 += (double)l1;
       s2 += (double)l2;
+    };
+    int64_t i = r0;
+    for (; i + 4 <= r1; i += 4) {  // four rows = eight independent 16-byte loads in flight per thread
+      Raw<T> gr[4], ar[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        gr[u] = Raw<T>::load(dy + (i + u) * channels + col);
+        ar[u] = Raw<T>::load(x + (i + u) * channels + col);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) row_update(gr[u].unpack(), ar[u].unpack());
     }
+    for (; i < r1; ++i) row_update(Vec<T>::load(dy + i * channels + col), Vec<T>::load(x + i * channels + col));
     float* cp = colpart + (size_t)blockIdx.x * 2 * channels;
 #pragma unroll
     for (int c = 0; c < VN; ++c) {
@@ -287,8 +313,10 @@ gln_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
 // ---------------------------------------------------------------------------------------------------------
 // row LayerNorm: one warp per row, lane owns vectors lane, lane+32, ...  (NVL of them, cached in registers)
 // ---------------------------------------------------------------------------------------------------------
+// weight / bias live in shared memory as float4, laid out [NVL][VN/4][lane] so a warp's reads are conflict-free;
+// the NEXT row of the warp is already in flight (packed registers) while the current one is reduced and written.
 template <typename T, int NVL>
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(kNormThreads, NVL * (16 / (int)sizeof(T)) <= 16 ? 4 : (NVL * (16 / (int)sizeof(T)) <= 32 ? 3 : 2))
 rln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t n, int64_t channels,
                float eps, int act, uint32_t drop_thr16, float keep_scale, uint64_t seed, uint64_t offset,
@@ -297,57 +325,70 @@ rln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float
   // memory: rng_state = {seed, step}; the call-site index stays in `offset`
   if (rng_state) { seed = rng_state[0]; offset += rng_state[1] << 20; }
   constexpr int VN = Vec<T>::N;
+  constexpr int Q = VN / 4;  // float4 pieces per 16-byte vector of T
+  __shared__ float4 sw[NVL * Q * 32], sb[NVL * Q * 32];
   const int lane = threadIdx.x & 31;
   const int nvec = (int)(channels / VN);
-  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  float wv[NVL][VN], bv[NVL][VN];
-#pragma unroll
-  for (int it = 0; it < NVL; ++it) {
-    const int v = lane + 32 * it;
+  for (int i = threadIdx.x; i < NVL * Q * 32; i += blockDim.x) {
+    const int ln = i & 31, h = (i >> 5) % Q, it = (i >> 5) / Q;
+    const int v = ln + 32 * it;
+    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = w4;
     if (v < nvec) {
-#pragma unroll
-      for (int c = 0; c < VN; c += 4) {
-        const float4 w4 = *reinterpret_cast<const float4*>(w + v * VN + c);
-        const float4 b4 = *reinterpret_cast<const float4*>(b + v * VN + c);
-        wv[it][c] = w4.x; wv[it][c + 1] = w4.y; wv[it][c + 2] = w4.z; wv[it][c + 3] = w4.w;
-        bv[it][c] = b4.x; bv[it][c + 1] = b4.y; bv[it][c + 2] = b4.z; bv[it][c + 3] = b4.w;
-      }
+      w4 = *reinterpret_cast<const float4*>(w + v * VN + 4 * h);
+      b4 = *reinterpret_cast<const float4*>(b + v * VN + 4 * h);
     }
+    sw[i] = w4;
+    sb[i] = b4;
   }
-  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
-    const T* xr = x + row * channels;
-    Vec<T> a[NVL];
+  __syncthreads();
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float inv_c = 1.f / (float)channels;
+  Raw<T> cur[NVL], nxt[NVL];
+  auto load_row = [&](Raw<T>* dst, int64_t r) {
+#pragma unroll
+    for (int it = 0; it < NVL; ++it) {
+      const int v = lane + 32 * it;
+      dst[it] = v < nvec ? Raw<T>::load(x + r * channels + (int64_t)v * VN) : Raw<T>::zero();
+    }
+  };
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row < n) load_row(cur, row);
+  for (; row < n; row += warps) {
+    if (row + warps < n) load_row(nxt, row + warps);
     float s = 0.f;
 #pragma unroll
     for (int it = 0; it < NVL; ++it) {
-      const int v = lane + 32 * it;
-      if (v < nvec) {
-        a[it] = Vec<T>::load(xr + (int64_t)v * VN);
+      const Vec<T> a = cur[it].unpack();   // lanes past the row end hold zeros
 #pragma unroll
-        for (int c = 0; c < VN; ++c) s += a[it].v[c];
-      }
+      for (int c = 0; c < VN; ++c) s += a.v[c];
     }
-    const float mu = warp_sum(s) / (float)channels;
+    const float mu = warp_sum(s) * inv_c;
     float q = 0.f;
 #pragma unroll
     for (int it = 0; it < NVL; ++it) {
-      const int v = lane + 32 * it;
-      if (v < nvec) {
+      if (lane + 32 * it < nvec) {
+        const Vec<T> a = cur[it].unpack();
 #pragma unroll
-        for (int c = 0; c < VN; ++c) { const float d = a[it].v[c] - mu; q += d * d; }
+        for (int c = 0; c < VN; ++c) { const float d = a.v[c] - mu; q += d * d; }
       }
     }
-    const float rs = rsqrtf(warp_sum(q) / (float)channels + eps);
+    const float rs = rsqrtf(warp_sum(q) * inv_c + eps);
     if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
     T* yr = y + row * channels;
 #pragma unroll
     for (int it = 0; it < NVL; ++it) {
       const int v = lane + 32 * it;
       if (v < nvec) {
+        const Vec<T> a = cur[it].unpack();
         Vec<T> o;
 #pragma unroll
-        for (int c = 0; c < VN; ++c)
-          o.v[c] = apply_act((a[it].v[c] - mu) * rs * wv[it][c] + bv[it][c], act, 0.f);
+        for (int h = 0; h < Q; ++h) {
+          const float4 w4 = sw[(it * Q + h) * 32 + lane], b4 = sb[(it * Q + h) * 32 + lane];
+          o.v[4 * h + 0] = apply_act((a.v[4 * h + 0] - mu) * rs * w4.x + b4.x, act, 0.f);
+          o.v[4 * h + 1] = apply_act((a.v[4 * h + 1] - mu) * rs * w4.y + b4.y, act, 0.f);
+          o.v[4 * h + 2] = apply_act((a.v[4 * h + 2] - mu) * rs * w4.z + b4.z, act, 0.f);
+          o.v[4 * h + 3] = apply_act((a.v[4 * h + 3] - mu) * rs * w4.w + b4.w, act, 0.f);
+        }
         if (drop_thr16) {  // fused inverted dropout (nn.Dropout after the ReLU, trn_pooling.py:31,36)
           const uint32_t keep = dropout_keep_bits((uint64_t)row * nvec + v, seed, offset, drop_thr16);
 #pragma unroll
@@ -356,6 +397,8 @@ rln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float
         o.store(yr + (int64_t)v * VN);
       }
     }
+#pragma unroll
+    for (int it = 0; it < NVL; ++it) cur[it] = nxt[it];
   }
 }
 
@@ -448,8 +491,8 @@ rln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __res
 // Row-LN backward, one CTA per row (rows strided over the grid): thread t owns the 16-byte column t of every row its
 // CTA visits, so dweight/dbias accumulate in registers with no atomics, the two row statistics need one
 // __syncthreads per row (double-buffered scratch), and the register footprint stays small enough for full occupancy.
-template <typename T>
-__global__ void __launch_bounds__(1024)
+template <typename T, int MAXT>
+__global__ void __launch_bounds__(MAXT)
 rln_bwd_block_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                      const float* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd,
                      T* __restrict__ dx, int64_t n, int64_t channels, int act, float out_scale, int nout,
@@ -472,17 +515,27 @@ rln_bwd_block_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
   }
   const float inv_c = 1.f / (float)channels;
   int buf = 0;
+  // the next row's operands (and statistics) are requested before the current row is reduced
+  Raw<T> ng = Raw<T>::zero(), na = ng, ny = ng;
+  float nmu = 0.f, nrs = 0.f;
+  auto prefetch = [&](int64_t r) {
+    nrs = rstd[r];
+    if (live) {
+      nmu = mean[r];
+      const int64_t o = r * channels + col;
+      ng = Raw<T>::load(dy + o);
+      na = Raw<T>::load(x + o);
+      if (use_y) ny = Raw<T>::load(y + o);
+    }
+  };
+  if ((int64_t)blockIdx.x < n) prefetch(blockIdx.x);
   for (int64_t row = blockIdx.x; row < n; row += gridDim.x, buf ^= 1) {
     float gh[VN], xh[VN];
     float s1 = 0.f, s2 = 0.f;
-    const float rs = rstd[row];
+    const float rs = nrs, mu = nmu;
+    const Vec<T> g = ng.unpack(), a = na.unpack(), yo = ny.unpack();
+    if (row + gridDim.x < n) prefetch(row + gridDim.x);
     if (live) {
-      const float mu = mean[row];
-      const int64_t o = row * channels + col;
-      const Vec<T> g = Vec<T>::load(dy + o);
-      const Vec<T> a = Vec<T>::load(x + o);
-      Vec<T> yo;
-      if (use_y) yo = Vec<T>::load(y + o);
 #pragma unroll
       for (int c = 0; c < VN; ++c) {
         const float h = (a.v[c] - mu) * rs;
@@ -633,7 +686,10 @@ static int norm_grid(int64_t work_items, int per_block) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-static int gln_parts(int64_t n) { return norm_grid(n, 16); }  // row strips of >= 16 rows, <= 4 per SM
+static int gln_parts(int64_t n) {  // row strips of >= 16 rows, <= 8 per SM
+  const int64_t g = ceil_div(n, 16), cap = (int64_t)sm_count() * 8;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
 
 }  // namespace egp
 
@@ -784,8 +840,16 @@ int egp_row_layernorm_fwd(const void* x, const float* weight, const float* bias,
         rln_fwd_wide_kernel<T><<<grid, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, mean, rstd, n, channels, eps,
                                                              act, thr, keep_scale, seed, offset, rng_state);
       else
-        rln_fwd_kernel<T, NVL><<<grid, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, mean, rstd, n, channels, eps,
-                                                             act, thr, keep_scale, seed, offset, rng_state);
+      {
+        static int resident = 0;   // CTAs per SM of this instantiation (rows are strided over whatever grid runs)
+        if (!resident) {
+          EGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, rln_fwd_kernel<T, (NVL ? NVL : 1)>, kNormThreads, 0));
+          if (resident < 1) resident = 1;
+        }
+        const int64_t want = ceil_div(n, kNormThreads / 32), cap = (int64_t)sm_count() * resident;
+        rln_fwd_kernel<T, (NVL ? NVL : 1)><<<(int)(want < cap ? want : cap), kNormThreads, 0, s>>>(
+            (const T*)x, weight, bias, (T*)y, mean, rstd, n, channels, eps, act, thr, keep_scale, seed, offset, rng_state);
+      }
     });
     EGP_LAUNCH_CHECK();
   });
@@ -821,11 +885,25 @@ int egp_row_layernorm_bwd(const void* dy, const void* x, const void* y, const fl
     const int64_t nvec = channels / Vec<T>::N;
     if (nvec > 32 && nvec <= 1024) {                     // one CTA per row, thread-owned columns
       const int threads = (int)((nvec + 31) / 32 * 32);
-      const int64_t cap = (int64_t)sm_count() * 8;
+      // one wave of resident CTAs (rows are strided over the grid); the partial workspace holds 8 per SM
+      static int resident[2] = {0, 0};
+      int& res = resident[threads <= 256 ? 0 : 1];
+      if (!res) {
+        if (threads <= 256) EGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, rln_bwd_block_kernel<T, 256>, 128, 0));
+        else EGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, rln_bwd_block_kernel<T, 1024>, 1024, 0));
+        res = res < 1 ? 1 : (res > 8 ? 8 : res);
+      }
+      int per_sm = res;
+      if (threads > 128 && threads <= 256) per_sm = res / 2 > 0 ? res / 2 : 1;
+      const int64_t cap = (int64_t)sm_count() * per_sm;
       grid = (int)(n < cap ? n : cap);
       nout = dx_colsum ? 3 : 2;
-      rln_bwd_block_kernel<T><<<grid, threads, 0, s>>>((const T*)dy, (const T*)x, (const T*)y, weight, mean, rstd, (T*)dx,
-                                                       n, channels, act, out_scale, nout, colpart);
+      if (threads <= 256)
+        rln_bwd_block_kernel<T, 256><<<grid, threads, 0, s>>>((const T*)dy, (const T*)x, (const T*)y, weight, mean, rstd,
+                                                              (T*)dx, n, channels, act, out_scale, nout, colpart);
+      else
+        rln_bwd_block_kernel<T, 1024><<<grid, threads, 0, s>>>((const T*)dy, (const T*)x, (const T*)y, weight, mean, rstd,
+                                                               (T*)dx, n, channels, act, out_scale, nout, colpart);
     } else {
       EGP_RLN_DISPATCH_NVL(nvec, {
         auto kern = rln_bwd_wide_kernel<T>;
