@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--protos", type=int, default=4096, help="prototypes per bank (c3)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (for profiler runs)")
     ap.add_argument("--trace-out", default=None, help="write the per-launch trace summary to this JSON file")
+    ap.add_argument("--gap-profile", default=None,
+                    help="(with --quick) profile two more steps with torch.profiler and write kernel busy/idle statistics here")
     return ap.parse_args()
 
 
@@ -286,6 +288,30 @@ def native_run(args, rank: int, world: int, local_rank: int):
     ms_per_step = ms_total / args.steps
     value = world * n_nodes / (ms_per_step / 1e3)
 
+    if args.quick and args.gap_profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(2):
+                step(resident)
+            torch.cuda.synchronize()
+        ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events()
+                     if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda t: t[0])
+        busy = sum(b - a for a, b, _ in ks)
+        gaps, end = [], ks[0][1]
+        for a, b, nme in ks[1:]:
+            if a > end:
+                gaps.append((a - end, nme))
+            end = max(end, b)
+        span = end - ks[0][0]
+        gaps.sort(reverse=True)
+        hist = {"<1us": 0, "1-2us": 0, "2-5us": 0, "5-20us": 0, ">20us": 0}
+        for g, _ in gaps:
+            hist["<1us" if g < 1 else "1-2us" if g < 2 else "2-5us" if g < 5 else "5-20us" if g < 20 else ">20us"] += 1
+        os.makedirs(os.path.dirname(os.path.abspath(args.gap_profile)), exist_ok=True)
+        json.dump({"steps": 2, "kernels": len(ks), "span_us": span, "busy_us": busy, "idle_us": span - busy,
+                   "idle_frac": (span - busy) / span, "gap_hist": hist,
+                   "largest_gaps_us_before": [(round(g, 1), n[:80]) for g, n in gaps[:25]]},
+                  open(args.gap_profile, "w"), indent=1)
     if args.quick:
         return {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "gpu_launches": int(launches), "quick": True}

@@ -260,7 +260,7 @@ struct TcParams {
   int tma_store;       // epilogue stages 32x128B boxes in smem and stores them with TMA (coalesced, clipped)
   int topk;            // TOPK kernels: candidates kept per row (8 or 16); 0 otherwise
   int32_t* cand;       // TOPK kernels: [M, TOPK] column indices of the largest entries of each row (unordered)
-  int debug;           // EGP_TC_DEBUG bit 0: skip the stores, bit 1: skip the TMEM loads too, bit 2: enable the L2 look-ahead (timing experiments)
+  int debug;           // EGP_TC_DEBUG (timing experiments) bit 0: skip the stores, bit 1: skip the TMEM loads too, bit 2: all CTAs load tile (0,0)
   uint32_t idesc;
 };
 
@@ -356,7 +356,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       uint32_t phase = 0;
       int split, m_blk, n_blk;
       for (int it = 0; tile_at(it, split, m_blk, n_blk); ++it) {
-        const int m0 = m_blk * TBM, n0 = n_blk * BN + (int)cta_rank * (BN / CG);
+        int m0 = m_blk * TBM, n0 = n_blk * BN + (int)cta_rank * (BN / CG);
+        if (p.debug & 4) { m0 = 0; n0 = 0; }   // timing experiment: every CTA streams the SAME operand tiles
         int kb_b, kb_e;
         split_range(split, kb_b, kb_e);
         for (int kb = kb_b; kb < kb_e; ++kb) {

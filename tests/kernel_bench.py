@@ -84,6 +84,8 @@ def main():
     gemm_case("gemm_wgrad_1024x4608", H, K0, N, a_trans=True, b_trans=True, out_dtype=torch.float32)
     gemm_case("gemm_head_478_f32out", N, 478, H, bias=True, out_dtype=torch.float32)
     gemm_case("gemm_head_115_f32out", N, 115, H, bias=True, out_dtype=torch.float32)
+    gemm_case("gemm_epilogue_only_k64", N, H, 64, bias=True)          # one k-block: launch + epilogue cost of a fwd tile sweep
+    gemm_case("gemm_one_tile_256x256x64 (launch + prologue + drain)", 256, 256, 64, bias=True)
     gemm_case("gemm_small_batch_fwd", 2048, H, H, bias=True)
     gemm_case("gemm_small_batch_wgrad", H, H, 2048, a_trans=True, b_trans=True, out_dtype=torch.float32)
 
@@ -163,6 +165,11 @@ def main():
         x = rnd(N, K0, dt=torch.float32)
         return lambda: ops.cast(x, BF)
     mem_case("cast_f32_bf16_4608", build_cast, N * K0 * 6)
+
+    def build_tiny():
+        x = rnd(8, 8, dt=torch.float32)
+        return lambda: ops.cast(x, BF)
+    mem_case("cast_64_elements (launch floor of this harness)", build_tiny, 64 * 6)
 
     def build_actbwd():
         dy, y = rnd(N, H), rnd(N, H)
