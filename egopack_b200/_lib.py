@@ -63,6 +63,9 @@ SIGNATURES: Dict[str, tuple] = {
     "egp_max_combine_bwd": (I, [P, P, P, P, I64, I, P]),
     "egp_segment_max_pool_fwd": (I, [P, P, P, P, I64, I64, I, P]),
     "egp_segment_max_pool_bwd": (I, [P, P, P, P, I64, I64, I, P]),
+    "egp_label_rank": (I, [P, I64, P, I64, I64, I64, I64, P, P]),
+    "egp_segment_argmax": (I, [P, P, I64, I, P, P]),
+    "egp_edit_distance_min": (I, [P, P, I64, I64, I64, P, P]),
 }
 
 _lib = None
@@ -124,6 +127,7 @@ KERNELS_PER_CALL = {
     "egp_axpby": 1, "egp_act_bwd": 1, "egp_act_bwd_colsum": 2, "egp_colsum": 2, "egp_mask_scale": 1, "egp_gemm": 1, "egp_row_normalize": 1,
     "egp_row_inv_norm": 1, "egp_cos_topk": 3, "egp_proto_max_gather": 1, "egp_max_combine_fwd": 1,
     "egp_max_combine_bwd": 1, "egp_segment_max_pool_fwd": 1, "egp_segment_max_pool_bwd": 1,
+    "egp_label_rank": 1, "egp_segment_argmax": 1, "egp_edit_distance_min": 1,
 }
 
 

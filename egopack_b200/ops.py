@@ -660,6 +660,44 @@ def class_sum_f64(x: Tensor, labels: Tensor, num_classes: int, out: Optional[Ten
     return out
 
 
+def label_rank(logits: Tensor, labels: Tensor, ignore_index: int = -1) -> Tensor:
+    """int32 [N]: how many classes beat the label's logit (ties: lower class index wins); -1 for ignored rows.
+    ``0 <= rank < k`` is a top-k hit (utils/meters/ego4d.py MulticlassAccuracy(top_k=k, ignore_index=-1))."""
+    assert logits.dim() == 2 and labels.dim() == 1 and labels.shape[0] == logits.shape[0]
+    logits = logits.detach()
+    if logits.dtype != torch.float32:
+        logits = logits.float()
+    if logits.stride(1) != 1:
+        logits = logits.contiguous()
+    labels = labels.detach()
+    assert labels.dtype == torch.int64
+    rank = torch.empty(logits.shape[0], dtype=torch.int32, device=logits.device)
+    if logits.shape[0]:
+        L.call("egp_label_rank", L.ptr(logits), logits.stride(0), L.ptr(labels), labels.stride(0), logits.shape[0],
+               logits.shape[1], int(ignore_index), L.ptr(rank), L.stream())
+    return rank
+
+
+def segment_argmax(values: Tensor, ptr: Tensor, apply_sigmoid: bool = False) -> Tensor:
+    """int64 [G]: first arg-max of (sigmoid of) values inside every graph [ptr[g], ptr[g+1]), relative to ptr[g]."""
+    values, ptr = _c(values.detach().float()), _c(ptr)
+    out = torch.empty(ptr.shape[0] - 1, dtype=torch.int64, device=values.device)
+    if out.shape[0]:
+        L.call("egp_segment_argmax", L.ptr(values), L.ptr(ptr), out.shape[0], int(apply_sigmoid), L.ptr(out), L.stream())
+    return out
+
+
+def edit_distance_min(preds: Tensor, labels: Tensor) -> Tensor:
+    """int32 [N]: min over the K samples of Levenshtein(preds[n, :, k], labels[n, :]); preds int64 [N, Z, K]."""
+    assert preds.dim() == 3 and labels.shape == preds.shape[:2]
+    preds, labels = _c(preds.detach().long()), _c(labels.detach().long())
+    out = torch.empty(preds.shape[0], dtype=torch.int32, device=preds.device)
+    if preds.shape[0]:
+        L.call("egp_edit_distance_min", L.ptr(preds), L.ptr(labels), preds.shape[0], preds.shape[1], preds.shape[2],
+               L.ptr(out), L.stream())
+    return out
+
+
 def row_normalize(x: Tensor, out_dtype: torch.dtype = torch.float32) -> Tensor:
     x = _c(x)
     out = torch.empty(x.shape, dtype=out_dtype, device=x.device)

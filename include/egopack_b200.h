@@ -207,6 +207,23 @@ int egp_segment_max_pool_fwd(const void* x, const int64_t* ptr, void* out, int32
 int egp_segment_max_pool_bwd(const void* dout, const int32_t* arg, const int64_t* batch, void* dx,
                              int64_t num_nodes, int64_t channels, int dtype, void* stream);
 
+/* ---- a-M / (f)-4: headline metrics (utils/meters/ego4d.py) -- integer results, bit-exact ----------------------
+ * The reference computes these on the host through torchmetrics 1.0.1 / editdistance 0.6.2 (environment.yml:308,247).
+ *
+ * egp_label_rank: rank[i] = #{c : logits[i,c] > logits[i,t] or (== and c < t)}, t = labels[i*label_stride]; -1 when
+ * t == ignore_index or t outside [0, classes).  top-k hit <=> 0 <= rank < k; k = 1 is the first-arg-max rule of
+ * MulticlassAccuracy(top_k=1) (utils/meters/ego4d.py:46-49,60-63,93-96,107-110,306,432-433).  logits fp32 [n, ld]. */
+int egp_label_rank(const float* logits, int64_t ld, const int64_t* labels, int64_t label_stride, int64_t n,
+                   int64_t classes, int64_t ignore_index, int32_t* rank, void* stream);
+/* PNR key-frame localisation (utils/meters/ego4d.py:356-358): out[g] = first arg-max, relative to ptr[g], of
+ * sigmoid(values) (apply_sigmoid != 0; fp32 1/(1+exp(-v))) or of values over nodes [ptr[g], ptr[g+1]); -1 if empty. */
+int egp_segment_argmax(const float* values, const int64_t* ptr, int64_t num_graphs, int apply_sigmoid, int64_t* out,
+                       void* stream);
+/* LTA edit distance (utils/meters/ego4d.py:410-422): out[i] = min_k Levenshtein(preds[i,:,k], labels[i,:]) with
+ * editdistance.eval's unit costs; preds int64 [n, seq_len, num_samples], labels int64 [n, seq_len], seq_len <= 64. */
+int egp_edit_distance_min(const int64_t* preds, const int64_t* labels, int64_t n, int64_t seq_len, int64_t num_samples,
+                          int32_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -385,6 +385,57 @@ def metric_pnr_localisation(logits: Tensor, batch: Tensor, pnr_node: Tensor, n_p
     return float(((pred - pnr_node).abs().float() * clip_frames / n_per_graph / fps).mean())
 
 
+def topk_accuracy(logits: Tensor, target: Tensor, k: int, ignore_index: int = -1) -> float:
+    """MulticlassAccuracy(top_k=k, average='micro', ignore_index=-1) (utils/meters/ego4d.py:46-49 etc.; torchmetrics
+    1.0.1, third party, absent).  A row is a hit when fewer than k classes beat the label's logit; an equal logit
+    beats it only from a lower class index -- for k=1 this is torch.argmax (first maximum), which is what torchmetrics
+    uses; for k>1 torchmetrics inherits torch.topk's unspecified tie order and this rule is the deterministic choice."""
+    hits = tot = 0
+    for row, t in zip(logits.tolist(), target.tolist()):
+        if t == ignore_index:
+            continue
+        tot += 1
+        beat = sum(1 for c, v in enumerate(row) if v > row[t] or (v == row[t] and c < t))
+        hits += beat < k
+    return hits / tot if tot else 0.0
+
+
+def macro_accuracy(logits: Tensor, target: Tensor, ignore_index: int = -1) -> float:
+    """MulticlassAccuracy(top_k=1, average='macro', ignore_index=-1): mean over classes of tp/(tp+fn), classes with
+    tp+fp+fn == 0 excluded (torchmetrics 1.0.1 `_adjust_weights_safe_divide`)."""
+    c = logits.shape[1]
+    tp, sup, pred = [0] * c, [0] * c, [0] * c
+    for row, t in zip(logits.tolist(), target.tolist()):
+        if t == ignore_index:
+            continue
+        p = max(range(c), key=lambda j: (row[j], -j))
+        sup[t] += 1
+        pred[p] += 1
+        tp[t] += p == t
+    seen = [j for j in range(c) if sup[j] + pred[j] > 0]
+    return sum((tp[j] / sup[j]) if sup[j] else 0.0 for j in seen) / len(seen) if seen else 0.0
+
+
+def pnr_meter(logits: Tensor, labels: Tensor, batch: Tensor, start_frame: Tensor, end_frame: Tensor,
+              pnr_frame: Tensor) -> Dict[str, float]:
+    """Ego4dPNRMeter.update + get_logs (utils/meters/ego4d.py:347-389), literal: per-graph loop with .item()s."""
+    probs = torch.sigmoid(logits)
+    pred, tgt = probs > 0.5, labels > 0.5
+    tp, fp = int((pred & tgt).sum()), int((pred & ~tgt).sum())
+    tn, fn = int((~pred & ~tgt).sum()), int((~pred & tgt).sum())
+    errs = []
+    for g, (sf, ef, pf) in enumerate(zip(start_frame, end_frame, pnr_frame)):
+        p = probs[batch == g]
+        loc = torch.argmax(p).item()
+        mapped = ((ef - sf) / 16 * loc).item()
+        errs.append(abs(mapped - (pf.item() - sf.item())) / 30)
+    # BinaryAUROC(thresholds=None): area under the exact ROC curve = P(score_pos > score_neg) + 0.5 P(equal)
+    pos, neg = probs[tgt].tolist(), probs[~tgt].tolist()
+    auc = (sum((a > b) + 0.5 * (a == b) for a in pos for b in neg) / (len(pos) * len(neg))) if pos and neg else 0.0
+    return {"accuracy": (tp + tn) / max(tp + fp + tn + fn, 1), "recall": tp / max(tp + fn, 1), "auroc": auc,
+            "localization_error": sum(errs) / max(len(errs), 1)}
+
+
 def levenshtein(a: Sequence[int], b: Sequence[int]) -> int:
     """``editdistance.eval`` (third party, absent): classic two-row DP."""
     prev = list(range(len(b) + 1))

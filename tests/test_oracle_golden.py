@@ -1,4 +1,5 @@
 """Pins the oracle against fixtures produced by the reference's own model code (tests/golden/make_golden.py)."""
+import pytest
 import torch
 
 from oracle import egopack_oracle as eo
@@ -136,3 +137,28 @@ def test_bank_builder_matches_reference(golden):
     banks = eo.build_graphone(m, ar, [ar, lta, pnr], [_data(b) for b in g["batches"]])
     for t in banks:
         close(banks[t], g["banks"][t])
+
+
+# ---- headline metrics: hand-derived known answers (utils/meters/ego4d.py has no tests of its own) -------------------
+def test_oracle_meters_known_answers():
+    from oracle import egopack_oracle as eo
+    assert eo.levenshtein([1, 2, 3], [1, 2, 3]) == 0
+    assert eo.levenshtein([1, 2, 3], [1, 3]) == 1                       # one deletion
+    assert eo.levenshtein([1, 2, 3, 4], [2, 3, 4, 5]) == 2              # delete front, insert back
+    assert eo.levenshtein(list("kitten"), list("sitting")) == 3        # the textbook pair
+    assert eo.levenshtein([], [7, 7]) == 2
+    logits = torch.tensor([[0.1, 0.9, 0.0], [0.5, 0.5, 0.2], [0.3, 0.2, 0.9], [1.0, 0.0, 0.0]])
+    y = torch.tensor([1, 1, 0, -1])
+    # row 0: label is the arg-max; row 1: tie with class 0, lower index wins -> label ranks 2nd; row 2: label ranks 2nd
+    assert eo.topk_accuracy(logits, y, 1) == pytest.approx(1 / 3)
+    assert eo.topk_accuracy(logits, y, 2) == pytest.approx(1.0)
+    # classes: 0 -> support 1, tp 0; 1 -> support 2, tp 1; 2 -> predicted once, never a target -> counted with score 0
+    assert eo.macro_accuracy(logits, y) == pytest.approx((0.0 + 0.5 + 0.0) / 3)
+    # PNR: graph 0 arg-max node 2 of 4; (ef - sf) / 16 * 2 = 20 frames vs pnr offset 25 -> 5 / 30 s
+    lg = torch.tensor([-1.0, 0.0, 2.0, 1.0, 3.0, -3.0])
+    lab = torch.tensor([0.0, 0.0, 1.0, 0.0, 0.0, 1.0])
+    out = eo.pnr_meter(lg, lab, torch.tensor([0, 0, 0, 0, 1, 1]), torch.tensor([100, 0]), torch.tensor([260, 32]),
+                       torch.tensor([125, 10]))
+    assert out["localization_error"] == pytest.approx((5 / 30 + 10 / 30) / 2)
+    assert out["accuracy"] == pytest.approx(3 / 6) and out["recall"] == pytest.approx(1 / 2)
+    assert out["auroc"] == pytest.approx(3 / 8)   # positives {2, -3} vs negatives {-1, 0, 1, 3}: 2 beats three of them
