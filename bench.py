@@ -317,29 +317,49 @@ def native_run(args, rank: int, world: int, local_rank: int):
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "gpu_launches": int(launches), "quick": True}
 
     # ---- end-to-end timing: pinned host -> device every step, loss read back every step -------------------
-    copy_stream = torch.cuda.Stream()
-    for _ in range(2):
-        b = upload(copy_stream)
-        torch.cuda.current_stream().wait_stream(copy_stream)
+    # step i+1's inputs are uploaded on a copy stream (and its edges built on the device) while step i computes
+    from egopack_b200.feed import DeviceFeeder
+    from egopack_b200.models.transforms import RadiusGraph
+    feed_tf = {t: (lta_edges if t == "lta" else RadiusGraph(r=K_RADIUS + 0.5)) for t in task_names}
+
+    def host_loader(n):
+        for _ in range(n):
+            yield host
+
+    for b in DeviceFeeder(host_loader(2), dev, feed_tf):
         float(step(b).item())
     barrier()
+    feeder = DeviceFeeder(host_loader(args.steps), dev, feed_tf)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    nxt = upload(copy_stream)
-    for i in range(args.steps):
-        torch.cuda.current_stream().wait_stream(copy_stream)
-        cur = nxt
-        for d in cur.values():                                 # keep the allocator honest across streams
-            for k in ("x", "pos", "y", "batch", "ptr"):
-                getattr(d, k).record_stream(torch.cuda.current_stream())
-        loss = step(cur)                                       # enqueue this step's kernels first ...
-        if i + 1 < args.steps:
-            nxt = upload(copy_stream)                          # ... so the next step's copy overlaps them
-        last = float(loss.item())                              # D2H of the loss every step
-    e1.record()
+    if os.environ.get("EGP_BENCH_E2E") != "feeder":
+        # default: single-thread ordering -- enqueue step i, THEN upload i+1 on the copy stream, then read the loss.
+        # EGP_BENCH_E2E=feeder runs the same loop through the threaded DeviceFeeder instead; at this batch size its
+        # worker loses ~10 ms/step to GIL hand-offs around the edge-count read-backs (A/B on one box: 48 vs 39 ms)
+        copy_stream = torch.cuda.Stream()
+        e0.record()
+        nxt = upload(copy_stream)
+        for i in range(args.steps):
+            torch.cuda.current_stream().wait_stream(copy_stream)
+            cur = nxt
+            for d in cur.values():
+                for k in ("x", "pos", "y", "batch", "ptr"):
+                    getattr(d, k).record_stream(torch.cuda.current_stream())
+            loss = step(cur)
+            if i + 1 < args.steps:
+                nxt = upload(copy_stream)
+            last = float(loss.item())
+        e1.record()
+        feeder.h2d_bytes = h2d_bytes * args.steps
+    else:
+        e0.record()
+        for b in feeder:
+            loss = step(b)
+            last = float(loss.item())                          # D2H of the loss every step
+        e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e_value = world * n_nodes / (e2e_ms / 1e3)
+    assert feeder.h2d_bytes == h2d_bytes * args.steps, (feeder.h2d_bytes, h2d_bytes)
 
     # ---- launch-bound regime: the reference's own batch size (16 graphs/task), eager vs one CUDA graph per step ------
     small = None

@@ -108,3 +108,35 @@ def test_csr_structure_is_deterministic_and_complete():
             assert col[rowptr[i]:rowptr[i + 1]].tolist() == want
     deg = torch.bincount(ei[1], minlength=n).clamp(min=1).float()
     assert torch.allclose(gs.inv_deg.cpu(), 1.0 / deg)
+
+
+def test_device_feeder_uploads_and_builds_edges_on_device():
+    """egopack_b200.feed.DeviceFeeder: values survive the pinned async copy, edges are built on the device behind it,
+    and match the oracle's radius graph / LTA connectivity (bit-exact after canonical ordering)."""
+    from egopack_b200 import synthetic as syn
+    from egopack_b200.feed import DeviceFeeder
+    from egopack_b200.models.transforms import LTATemporalConnectivity, RadiusGraph
+    gen = torch.Generator().manual_seed(5)
+    host = [{"ar": syn.make_batch("ar", 3, 9, gen, feature_dim=8, num_segments=2, band_k=1, n_verbs=5, n_nouns=7),
+             "lta": syn.make_batch("lta", 2, 22, gen, feature_dim=8, num_segments=2, band_k=1, n_verbs=5, n_nouns=7)}
+            for _ in range(3)]
+    tf = {"ar": RadiusGraph(r=1.5), "lta": LTATemporalConnectivity(r=1.5)}
+    feeder = DeviceFeeder(host, DEV, tf)
+    n = 0
+    for hb, db in zip(host, feeder):
+        n += 1
+        for t in ("ar", "lta"):
+            assert db[t].x.is_cuda and torch.equal(db[t].x.cpu(), hb[t].x) and torch.equal(db[t].y.cpu(), hb[t].y)
+            assert hb[t].x.device.type == "cpu"                      # the host batch is left alone
+        want = pyg.radius_graph(hb["ar"].pos, 1.5, hb["ar"].batch)
+        assert canon_edges(db["ar"].edge_index) == canon_edges(want) and db["ar"].band_k == 1
+        want_lta = []
+        off = 0
+        for g in range(2):
+            sl = slice(int(hb["lta"].ptr[g]), int(hb["lta"].ptr[g + 1]))
+            d = pyg.Data(pos=hb["lta"].pos[sl], y=hb["lta"].y[sl])
+            want_lta.append(eo.lta_temporal_connectivity(d, 1.5).edge_index + off)
+            off += sl.stop - sl.start
+        assert canon_edges(db["lta"].edge_index) == canon_edges(torch.cat(want_lta, 1))
+    assert n == 3 and feeder.h2d_bytes == 3 * sum(v.numel() * v.element_size() for b in host[0].values()
+                                                 for v in (b.x, b.pos, b.y, b.batch, b.ptr))

@@ -73,3 +73,39 @@ def test_batch_collation_matches_oracle_collate():
     assert a.band_k == 1 and a.num_graphs == 3
     scalar = Batch.from_data_list([Data(x=torch.zeros(2, 1), y=torch.tensor(1)), Data(x=torch.zeros(3, 1), y=torch.tensor(0))])
     assert scalar.y.tolist() == [1, 0]
+
+
+# ---- feed: multi-task loader interleaving (utils/dataloading.py:8-47) and the device feeder's host-side behaviour ----
+def test_multiloader_restarts_short_loaders_until_all_completed():
+    from egopack_b200.feed import multiloader
+    a, b = [1, 2, 3], ["x", "y"]
+    # b runs out first and is restarted; the epoch ends when a (the last one still pending) is exhausted
+    assert list(multiloader([a, b, None], [1, 1, 1])) == [(1, "x", None), (2, "y", None), (3, "x", None)]
+    # weight 0 disables a loader
+    assert list(multiloader([a, b], [1, 0])) == [(1, None), (2, None), (3, None)]
+    # equal lengths: one pass
+    assert list(multiloader([[1, 2], [3, 4]], [1, 1])) == [(1, 3), (2, 4)]
+    # (with no active loader at all the reference yields tuples of None forever; mirrored, not exercised)
+
+
+def test_device_feeder_preserves_order_structure_and_errors():
+    from egopack_b200 import Batch, Data
+    from egopack_b200.feed import DeviceFeeder
+    mk = lambda i: Batch.from_data_list([Data(x=torch.full((3, 2), float(i)), pos=torch.arange(3))])
+    items = [{"ar": mk(i), "lta": mk(10 + i), "pnr": None} for i in range(4)]
+    seen = []
+    tf = {"ar": lambda b: (seen.append("ar"), b)[1], "lta": lambda b: (setattr(b, "tag", 7), b)[1]}
+    out = list(DeviceFeeder(items, "cpu", transforms=tf))
+    assert [float(o["ar"].x[0, 0]) for o in out] == [0.0, 1.0, 2.0, 3.0]
+    assert [float(o["lta"].x[0, 0]) for o in out] == [10.0, 11.0, 12.0, 13.0]
+    assert all(o["pnr"] is None and o["lta"].tag == 7 for o in out) and seen == ["ar"] * 4
+    assert out[0]["ar"] is not items[0]["ar"] and out[0]["ar"].ptr.tolist() == [0, 3]     # a fresh Batch per step
+    for i, _ in enumerate(DeviceFeeder(items, "cpu")):                                        # early exit stops the worker
+        if i == 1:
+            break
+
+    def broken():
+        yield items[0]
+        raise ValueError("loader failed")
+    with pytest.raises(ValueError, match="loader failed"):
+        list(DeviceFeeder(broken(), "cpu"))
