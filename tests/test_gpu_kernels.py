@@ -112,7 +112,10 @@ def test_positional_encoding_add(dtype, tol):
     pe = pyg.PositionalEncoding(c)
     want = x.float() + pe(pos)
     y = ops.PosEncAdd.apply(x.to(DEV), pos.to(DEV), pe.frequency.to(DEV))
-    assert rel_max(y, want) < (1e-6 if dtype == torch.float32 else tol)
+    # fp32: CUDA sincosf (2 ulp) against the host libm/Sleef build of whichever box runs the oracle -- a few 1e-7
+    # absolute on values up to ~5; 1e-5 relative keeps a wide margin below the 1e-4 parity bar
+    err = rel_max(y, want)
+    assert err < (1e-5 if dtype == torch.float32 else tol), err
 
 
 @pytest.mark.parametrize("dtype,tol", DTYPES)
