@@ -493,9 +493,9 @@ def native_run(args, rank: int, world: int, local_rank: int):
 
 
 def main():
-    # some images export NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout next to the JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly one JSON line: NCCL's own log (the "NCCL version ..." banner that any NCCL_DEBUG level
+    # >= VERSION prints, warnings) goes to stderr instead
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
