@@ -226,20 +226,30 @@ def native_run(args, rank: int, world: int, local_rank: int):
     n_nodes = args.videos * args.nodes * len(task_names)
     h2d_bytes = sum(v.numel() * v.element_size() for b in host.values() for v in (b.x, b.pos, b.y, b.batch, b.ptr))
 
-    def upload(stream=None):
-        """H2D of one step's inputs + device-side edge/structure construction (what a DataLoader hands over)."""
+    def upload_copies(stream=None):
+        """Phase 1 of the feed: enqueue the pinned H2D copies of one step's inputs (no host waits)."""
         out = {}
         with torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
             for t, hb in host.items():
                 d = egopack_b200.Batch()
                 for k in ("x", "pos", "y", "batch", "ptr"):
                     setattr(d, k, getattr(hb, k).to(dev, non_blocking=True))
+                out[t] = d
+        return out
+
+    def upload_structure(out, stream=None):
+        """Phase 2: device-side edge / structure construction behind the copies (reads edge counts back: host waits)."""
+        with torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
+            for t, d in out.items():
                 if t == "lta":
                     lta_edges(d)                               # band + star edges, on the device
                 else:
                     d.band_k = K_RADIUS                        # unit-spaced pos: the band needs no edge_index
-                out[t] = d
         return out
+
+    def upload(stream=None):
+        """H2D of one step's inputs + device-side edge/structure construction (what a DataLoader hands over)."""
+        return upload_structure(upload_copies(stream), stream)
 
     def step(batches):
         opt.zero_grad(set_to_none=True)
@@ -332,7 +342,8 @@ def native_run(args, rank: int, world: int, local_rank: int):
     feeder = DeviceFeeder(host_loader(args.steps), dev, feed_tf)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if os.environ.get("EGP_BENCH_E2E") != "feeder":
-        # default: single-thread ordering -- enqueue step i, THEN upload i+1 on the copy stream, then read the loss.
+        # default: single-thread ordering -- enqueue the copies of step i+1, then step i, then i+1's edge construction
+        # (which waits on the host for edge counts), then read the loss.
         # EGP_BENCH_E2E=feeder runs the same loop through the threaded DeviceFeeder instead; at this batch size its
         # worker loses ~10 ms/step to GIL hand-offs around the edge-count read-backs (A/B on one box: 48 vs 39 ms)
         copy_stream = torch.cuda.Stream()
@@ -344,9 +355,12 @@ def native_run(args, rank: int, world: int, local_rank: int):
             for d in cur.values():
                 for k in ("x", "pos", "y", "batch", "ptr"):
                     getattr(d, k).record_stream(torch.cuda.current_stream())
-            loss = step(cur)
-            if i + 1 < args.steps:
-                nxt = upload(copy_stream)
+            more = i + 1 < args.steps
+            if more:
+                nxt = upload_copies(copy_stream)               # the bus starts on step i+1 before step i is enqueued,
+            loss = step(cur)                                   # so host waits inside the step cannot delay the copy
+            if more:
+                upload_structure(nxt, copy_stream)             # its edges are built (host waits) behind the step's launches
             last = float(loss.item())
         e1.record()
         feeder.h2d_bytes = h2d_bytes * args.steps
@@ -440,12 +454,21 @@ def native_run(args, rank: int, world: int, local_rank: int):
             d["ms"] += ms
             d["n"] += 1
     roof, roof_hbm = None, None
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")     # measured once under ncu, per launch
+    if os.path.exists(tpath):
+        traffic = {k: v for k, v in json.load(open(tpath)).items() if isinstance(v, dict)}
+
+    def traffic_of(kernel):
+        t = traffic.get(kernel)
+        return (int(t["bytes"]), f"ncu dram bytes of one launch: {t['launch']} ({t['source']})") if t else (None, None)
     if "gemm_tcgen05" in agg or "gemm_ffma" in agg:
         g = agg.get("gemm_tcgen05") or agg["gemm_ffma"]
         ach = g["work"] / (g["ms"] / 1e3) / 1e12
         peak = pk["tensor_sustained"]
         roof = {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05/TMEM/TMA)" if "gemm_tcgen05" in agg else "sgemm_kernel",
-                "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None,
+                "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
+                "traffic": traffic_of("tc_gemm_kernel")[0], "traffic_note": traffic_of("tc_gemm_kernel")[1],
                 "launches_per_step": g["n"] // 2, "ms_per_step": round(g["ms"] / 2, 3),
                 "share_of_step": round(g["ms"] / 2 / ms_per_step, 3), "peak_source": f"{pk['source']} (sustained bf16 GEMM)"}
     for nme in ("sage_mean_band", "sage_mean_csr"):
@@ -453,7 +476,8 @@ def native_run(args, rank: int, world: int, local_rank: int):
             a = agg[nme]
             ach = a["work"] / (a["ms"] / 1e3) / 1e9
             r = {"bound": "hbm", "kernel": nme, "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
-                 "frac": round(ach / pk["hbm"], 4), "traffic": None, "launches_per_step": a["n"] // 2,
+                 "frac": round(ach / pk["hbm"], 4), "traffic": traffic_of(nme)[0], "traffic_note": traffic_of(nme)[1],
+                 "launches_per_step": a["n"] // 2,
                  "ms_per_step": round(a["ms"] / 2, 3), "peak_source": pk["source"]}
             roof_hbm = roof_hbm or []
             roof_hbm.append(r)

@@ -1,0 +1,38 @@
+"""Extract the judged metrics of one kernel from an `ncu --set full` report into a small CSV (not a pytest file).
+
+    python tests/extract_ncu.py report.ncu-rep > profiles/rN_ncu_<kernel>.csv
+"""
+import csv
+import subprocess
+import sys
+
+WANT = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__grid_size", "launch__block_size",
+    "launch__cluster_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+    "sm__cycles_elapsed.max", "sm__cycles_active.avg", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_op_hmma.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+]
+
+
+def main():
+    raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    head, units, vals = rows[0], rows[1], rows[2]
+    w = csv.writer(sys.stdout)
+    w.writerow(["metric", "unit", "value"])
+    w.writerow(["Kernel Name", "", vals[head.index("Kernel Name")]])
+    for m in WANT:
+        if m in head:
+            i = head.index(m)
+            w.writerow([m, units[i], vals[i]])
+
+
+if __name__ == "__main__":
+    main()
