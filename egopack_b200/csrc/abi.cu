@@ -1,5 +1,6 @@
 // Library-level entry points: version, per-thread error string, device info.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -25,6 +26,11 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("EGP_PDL"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 }  // namespace egp

@@ -41,6 +41,7 @@ sage_mean_band_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n, i
                       int64_t ldo, int rows_per_cta, int ring_rows, const int32_t* __restrict__ win_lo,
                       const int32_t* __restrict__ win_hi, const float* __restrict__ scale_out,
                       const float* __restrict__ scale_in) {
+  pdl_enter();
   extern __shared__ uint4 ring[];
   constexpr int VN = Vec<T>::N;
   const int64_t col = ((int64_t)blockIdx.y * kAggThreads + threadIdx.x) * VN;
@@ -128,6 +129,7 @@ sage_mean_band_reg_kernel(const T* __restrict__ x, T* __restrict__ out, int n, i
                           int64_t ldo, int rows_per_cta, const int32_t* __restrict__ win_lo,
                           const int32_t* __restrict__ win_hi, const float* __restrict__ scale_out,
                           const float* __restrict__ scale_in) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   constexpr int W = 2 * K + U;
   const int64_t col = ((int64_t)blockIdx.y * kAggThreads + threadIdx.x) * VN;
@@ -191,6 +193,7 @@ sage_mean_band_run_kernel(const T* __restrict__ x, T* __restrict__ out, int n, i
                           int64_t ldo, int rows_per_cta, int k, const int32_t* __restrict__ win_lo,
                           const int32_t* __restrict__ win_hi, const float* __restrict__ scale_out,
                           const float* __restrict__ scale_in) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   const int64_t col = ((int64_t)blockIdx.y * kAggThreads + threadIdx.x) * VN;
   if (col >= channels) return;
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(kAggThreads * ROWS)
 sage_mean_band_flat_kernel(const T* __restrict__ x, T* __restrict__ out, int n, int64_t channels, int64_t ldx,
                            int64_t ldo, const int32_t* __restrict__ win_lo, const int32_t* __restrict__ win_hi,
                            const float* __restrict__ scale_out, const float* __restrict__ scale_in) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   const int64_t col = ((int64_t)blockIdx.y * kAggThreads + (threadIdx.x % kAggThreads)) * VN;
   const int i = blockIdx.x * ROWS + threadIdx.x / kAggThreads;
@@ -307,6 +311,7 @@ sage_mean_csr_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n, in
                      int64_t ldo, int rows_per_cta, const int32_t* __restrict__ rowptr,
                      const int32_t* __restrict__ colidx, const float* __restrict__ scale_out,
                      const float* __restrict__ scale_in) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   const int64_t col = ((int64_t)blockIdx.y * kAggThreads + threadIdx.x) * VN;
   if (col >= channels) return;
@@ -361,7 +366,7 @@ static int launch_band(const void* x, void* out, int64_t n, int64_t channels, in
   auto kern = sage_mean_band_kernel<T, P, SLIDING>;
   if (smem > 48 * 1024) EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(n, rows), gy);
-  kern<<<grid, kAggThreads, smem, stream>>>((const T*)x, (T*)out, n, channels, ldx, ldo, (int)rows, ring_rows,
+  (void)launch_kernel(kern, grid, kAggThreads, smem, stream, (const T*)x, (T*)out, n, channels, ldx, ldo, (int)rows, ring_rows,
                                             win_lo, win_hi, scale_out, scale_in);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
@@ -377,7 +382,7 @@ static int launch_band_reg(const void* x, void* out, int64_t n, int64_t channels
   rows = rows < 4 * U ? 4 * U : (rows > 512 ? 512 : rows);   // halo re-read <= 2K/(4U)
   rows = (rows + U - 1) / U * U;
   dim3 grid((unsigned)ceil_div(n, rows), gy);
-  sage_mean_band_reg_kernel<T, K, U><<<grid, kAggThreads, 0, stream>>>((const T*)x, (T*)out, (int)n, channels, ldx, ldo,
+  (void)launch_kernel(sage_mean_band_reg_kernel<T, K, U>, grid, kAggThreads, 0, stream, (const T*)x, (T*)out, (int)n, channels, ldx, ldo,
                                                                        (int)rows, win_lo, win_hi, scale_out, scale_in);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
@@ -394,7 +399,7 @@ static int launch_band_run(const void* x, void* out, int64_t n, int64_t channels
   rows = rows < min_rows ? min_rows : (rows > 2048 ? 2048 : rows);
   rows = (rows + U - 1) / U * U;
   dim3 grid((unsigned)ceil_div(n, rows), gy);
-  sage_mean_band_run_kernel<T, U><<<grid, kAggThreads, 0, stream>>>((const T*)x, (T*)out, (int)n, channels, ldx, ldo,
+  (void)launch_kernel(sage_mean_band_run_kernel<T, U>, grid, kAggThreads, 0, stream, (const T*)x, (T*)out, (int)n, channels, ldx, ldo,
                                                                     (int)rows, k, win_lo, win_hi, scale_out, scale_in);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
@@ -407,7 +412,7 @@ static int launch_band_flat(const void* x, void* out, int64_t n, int64_t channel
   constexpr int VN = Vec<T>::N, ROWS = 4;
   const unsigned gy = (unsigned)ceil_div(channels, (int64_t)kAggThreads * VN);
   dim3 grid((unsigned)ceil_div(n, ROWS), gy);
-  sage_mean_band_flat_kernel<T, K, ROWS><<<grid, kAggThreads * ROWS, 0, stream>>>(
+  (void)launch_kernel(sage_mean_band_flat_kernel<T, K, ROWS>, grid, kAggThreads * ROWS, 0, stream, 
       (const T*)x, (T*)out, (int)n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
@@ -459,7 +464,7 @@ int egp_sage_mean_csr(const void* x, void* out, int64_t n, int64_t channels, int
     int64_t rows = (n * gy) / ((int64_t)sm_count() * 16);
     rows = rows < 4 ? 4 : (rows > 256 ? 256 : rows);
     dim3 grid((unsigned)ceil_div(n, rows), gy);
-    sage_mean_csr_kernel<T><<<grid, kAggThreads, 0, (cudaStream_t)stream>>>(
+    (void)launch_kernel(sage_mean_csr_kernel<T>, grid, kAggThreads, 0, (cudaStream_t)stream, 
         (const T*)x, (T*)out, n, channels, ldx, ldo, (int)rows, rowptr, col, scale_out, scale_in);
     EGP_LAUNCH_CHECK();
   });

@@ -40,6 +40,35 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 int sm_count();
+bool pdl_enabled();   // EGP_PDL=0 turns programmatic dependent launch off (abi.cu)
+
+// ------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of the library starts with pdl_enter(): it lets the NEXT kernel in the
+// stream be scheduled early (its CTAs become resident and run up to their own pdl_enter as SMs free up) and then waits
+// until the PREVIOUS kernel has completed and flushed its memory -- so the data dependencies are exactly those of
+// plain stream order, but the 1-3 us between the end of one kernel and the first CTA of the next are hidden.
+// Kernels launched without the attribute (or after a non-kernel stream operation) see both instructions as no-ops.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                        Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -44,6 +44,7 @@ __device__ __forceinline__ int enumerate_band(const int64_t* __restrict__ pos, i
 __global__ void band_edge_count_kernel(const int64_t* __restrict__ pos, const int64_t* __restrict__ batch,
                                        const int64_t* __restrict__ ptr, int64_t n, float r2, int cap,
                                        int monotone, int32_t* __restrict__ deg) {
+  pdl_enter();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t g = batch[i];
@@ -54,6 +55,7 @@ __global__ void band_edge_fill_kernel(const int64_t* __restrict__ pos, const int
                                       const int64_t* __restrict__ ptr, int64_t n, float r2, int cap,
                                       int monotone, const int64_t* __restrict__ rowptr, int64_t num_edges,
                                       int64_t* __restrict__ edge_index) {
+  pdl_enter();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t g = batch[i];
@@ -102,6 +104,7 @@ __global__ void lta_edge_count_kernel(const int64_t* __restrict__ pos, const int
                                       int64_t y_cols, const int64_t* __restrict__ batch,
                                       const int64_t* __restrict__ ptr, int64_t n, float r,
                                       int32_t* __restrict__ deg) {
+  pdl_enter();
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   const int64_t g = batch[s];
@@ -113,6 +116,7 @@ __global__ void lta_edge_fill_kernel(const int64_t* __restrict__ pos, const int6
                                      const int64_t* __restrict__ ptr, int64_t n, float r,
                                      const int64_t* __restrict__ rowptr, int64_t num_edges,
                                      int64_t* __restrict__ edge_index) {
+  pdl_enter();
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   const int64_t g = batch[s];
@@ -131,6 +135,7 @@ __global__ void lta_edge_fill_kernel(const int64_t* __restrict__ pos, const int6
 // ---------------------------------------------------------------------------------------------------------
 template <typename Out>
 __global__ void exclusive_scan_kernel(const int32_t* __restrict__ in, int64_t n, Out* __restrict__ out) {
+  pdl_enter();
   __shared__ long long warp_tot[32];
   __shared__ long long carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -172,6 +177,7 @@ __global__ void exclusive_scan_kernel(const int32_t* __restrict__ in, int64_t n,
 __global__ void band_windows_kernel(const int64_t* __restrict__ batch, const int64_t* __restrict__ ptr,
                                     int64_t n, int k, int32_t* __restrict__ win_lo,
                                     int32_t* __restrict__ win_hi, float* __restrict__ inv_deg) {
+  pdl_enter();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t g = batch[i];
@@ -187,6 +193,7 @@ __global__ void band_windows_kernel(const int64_t* __restrict__ batch, const int
 // CSR build
 // ---------------------------------------------------------------------------------------------------------
 __global__ void csr_count_kernel(const int64_t* __restrict__ key, int64_t e_count, int32_t* __restrict__ deg) {
+  pdl_enter();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < e_count) atomicAdd(&deg[key[e]], 1);
 }
@@ -194,6 +201,7 @@ __global__ void csr_count_kernel(const int64_t* __restrict__ key, int64_t e_coun
 __global__ void csr_fill_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t e_count,
                                 const int32_t* __restrict__ rowptr, int32_t* __restrict__ cursor,
                                 int32_t* __restrict__ col) {
+  pdl_enter();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= e_count) return;
   const int64_t r = key[e];
@@ -202,6 +210,7 @@ __global__ void csr_fill_kernel(const int64_t* __restrict__ key, const int64_t* 
 }
 
 __global__ void csr_sort_rows_kernel(const int32_t* __restrict__ rowptr, int64_t n, int32_t* __restrict__ col) {
+  pdl_enter();
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const int b = rowptr[r], e = rowptr[r + 1];
@@ -214,6 +223,7 @@ __global__ void csr_sort_rows_kernel(const int32_t* __restrict__ rowptr, int64_t
 }
 
 __global__ void csr_inv_degree_kernel(const int32_t* __restrict__ rowptr, int64_t n, float* __restrict__ inv_deg) {
+  pdl_enter();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int d = rowptr[i + 1] - rowptr[i];
@@ -231,7 +241,7 @@ int egp_band_edge_count(const int64_t* pos, const int64_t* batch, const int64_t*
   EGP_REQUIRE(pos && batch && ptr && deg, "band_edge_count: null pointer");
   EGP_REQUIRE(n >= 0 && r > 0.f && max_num_neighbors > 0, "band_edge_count: bad size/radius");
   if (n == 0) return EGP_OK;
-  band_edge_count_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_kernel(band_edge_count_kernel, (unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream, 
       pos, batch, ptr, n, r * r, max_num_neighbors + 1, monotone, deg);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
@@ -243,7 +253,7 @@ int egp_band_edge_fill(const int64_t* pos, const int64_t* batch, const int64_t* 
   EGP_REQUIRE(pos && batch && ptr && rowptr, "band_edge_fill: null pointer");
   EGP_REQUIRE(edge_index || num_edges == 0, "band_edge_fill: null edge_index");
   if (n == 0 || num_edges == 0) return EGP_OK;
-  band_edge_fill_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_kernel(band_edge_fill_kernel, (unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream, 
       pos, batch, ptr, n, r * r, max_num_neighbors + 1, monotone, rowptr, num_edges, edge_index);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
@@ -251,7 +261,7 @@ int egp_band_edge_fill(const int64_t* pos, const int64_t* batch, const int64_t* 
 
 int egp_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* out, void* stream) {
   EGP_REQUIRE(out && (in || n == 0), "exclusive_scan: null pointer");
-  exclusive_scan_kernel<int64_t><<<1, 1024, 0, (cudaStream_t)stream>>>(in, n, out);
+  (void)launch_kernel(exclusive_scan_kernel<int64_t>, 1, 1024, 0, (cudaStream_t)stream, in, n, out);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
 }
@@ -267,7 +277,7 @@ int egp_lta_edge_count(const int64_t* pos, const int64_t* y, int64_t y_cols, con
     return EGP_ERR_UNSUPPORTED;
   }
   if (n == 0) return EGP_OK;
-  lta_edge_count_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(pos, y, y_cols, batch,
+  (void)launch_kernel(lta_edge_count_kernel, (unsigned)ceil_div(n, 128), 128, 0, (cudaStream_t)stream, pos, y, y_cols, batch,
                                                                                       ptr, n, r, deg);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
@@ -280,7 +290,7 @@ int egp_lta_edge_fill(const int64_t* pos, const int64_t* y, int64_t y_cols, cons
   EGP_REQUIRE(pos && y && batch && ptr && rowptr, "lta_edge_fill: null pointer");
   EGP_REQUIRE(edge_index || num_edges == 0, "lta_edge_fill: null edge_index");
   if (n == 0 || num_edges == 0) return EGP_OK;
-  lta_edge_fill_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(
+  (void)launch_kernel(lta_edge_fill_kernel, (unsigned)ceil_div(n, 128), 128, 0, (cudaStream_t)stream, 
       pos, y, y_cols, batch, ptr, n, r, rowptr, num_edges, edge_index);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
@@ -291,7 +301,7 @@ int egp_band_windows(const int64_t* batch, const int64_t* ptr, int64_t n, int k,
   EGP_REQUIRE(batch && ptr && win_lo && win_hi && inv_deg, "band_windows: null pointer");
   EGP_REQUIRE(k >= 0 && n < (int64_t)INT32_MAX, "band_windows: bad k or too many nodes");
   if (n == 0) return EGP_OK;
-  band_windows_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(batch, ptr, n, k, win_lo,
+  (void)launch_kernel(band_windows_kernel, (unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream, batch, ptr, n, k, win_lo,
                                                                                     win_hi, inv_deg);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
@@ -307,16 +317,16 @@ int egp_csr_build(const int64_t* edge_index, int64_t num_edges, int64_t n, int g
   const int64_t* val = group_by_dst ? edge_index : edge_index + num_edges;
   if (n > 0) EGP_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * n, s));
   if (num_edges > 0) {
-    csr_count_kernel<<<(unsigned)ceil_div(num_edges, 256), 256, 0, s>>>(key, num_edges, cursor);
+    (void)launch_kernel(csr_count_kernel, (unsigned)ceil_div(num_edges, 256), 256, 0, s, key, num_edges, cursor);
     EGP_LAUNCH_CHECK();
   }
-  exclusive_scan_kernel<int32_t><<<1, 1024, 0, s>>>(cursor, n, rowptr);
+  (void)launch_kernel(exclusive_scan_kernel<int32_t>, 1, 1024, 0, s, cursor, n, rowptr);
   EGP_LAUNCH_CHECK();
   if (num_edges > 0) {
     EGP_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * n, s));
-    csr_fill_kernel<<<(unsigned)ceil_div(num_edges, 256), 256, 0, s>>>(key, val, num_edges, rowptr, cursor, col);
+    (void)launch_kernel(csr_fill_kernel, (unsigned)ceil_div(num_edges, 256), 256, 0, s, key, val, num_edges, rowptr, cursor, col);
     EGP_LAUNCH_CHECK();
-    csr_sort_rows_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, s>>>(rowptr, n, col);
+    (void)launch_kernel(csr_sort_rows_kernel, (unsigned)ceil_div(n, 128), 128, 0, s, rowptr, n, col);
     EGP_LAUNCH_CHECK();
   }
   return EGP_OK;
@@ -325,7 +335,7 @@ int egp_csr_build(const int64_t* edge_index, int64_t num_edges, int64_t n, int g
 int egp_csr_inv_degree(const int32_t* rowptr, int64_t n, float* inv_deg, void* stream) {
   EGP_REQUIRE(rowptr && inv_deg, "csr_inv_degree: null pointer");
   if (n == 0) return EGP_OK;
-  csr_inv_degree_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(rowptr, n, inv_deg);
+  (void)launch_kernel(csr_inv_degree_kernel, (unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream, rowptr, n, inv_deg);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
 }

@@ -17,6 +17,7 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 posenc_add_kernel(const T* __restrict__ x, const int64_t* __restrict__ pos, const float* __restrict__ freq,
                   T* __restrict__ out, int64_t nwork, int64_t channels) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   const int64_t half = channels / 2;
   const int64_t hv = half / VN;  // vectors per half row
@@ -41,6 +42,7 @@ posenc_add_kernel(const T* __restrict__ x, const int64_t* __restrict__ pos, cons
 template <typename S, typename D>
 __global__ void __launch_bounds__(kEwThreads)
 cast_kernel(const S* __restrict__ src, D* __restrict__ dst, int64_t n) {
+  pdl_enter();
   // 8 elements per thread-iteration: 2x16B loads for fp32 sources, 1x16B for bf16
   const int64_t n8 = n / 8;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n8; v += (int64_t)gridDim.x * blockDim.x) {
@@ -76,6 +78,7 @@ cast_kernel(const S* __restrict__ src, D* __restrict__ dst, int64_t n) {
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t nvec) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
     Vec<T> x = Vec<T>::load(a + v * VN);
@@ -90,6 +93,7 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 axpby_kernel(const T* __restrict__ a, float alpha, const T* __restrict__ b, float beta, T* __restrict__ out,
              int64_t nvec) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
     Vec<T> x = Vec<T>::load(a + v * VN);
@@ -109,6 +113,7 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t nvec, int act,
                float slope) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
     Vec<T> g = Vec<T>::load(dy + v * VN);
@@ -125,6 +130,7 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 mask_scale_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mask, T* __restrict__ out, int64_t nvec,
                   float scale) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
     Vec<T> a = Vec<T>::load(x + v * VN);
@@ -138,6 +144,7 @@ mask_scale_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mask, T* 
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 max_combine_fwd_kernel(const T* __restrict__ f, const T* __restrict__ m, T* __restrict__ a, int64_t nvec) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
     Vec<T> x = Vec<T>::load(f + v * VN);
@@ -152,6 +159,7 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 max_combine_bwd_kernel(const T* __restrict__ da, const T* __restrict__ f, const T* __restrict__ m,
                        T* __restrict__ df, int64_t nvec) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
     Vec<T> g = Vec<T>::load(da + v * VN);
@@ -168,6 +176,7 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, int64_t ldx, int rows_per_cta,
                       int vec_ok, float* __restrict__ part) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   const int64_t col = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * VN;
   if (col >= cols) return;
@@ -209,6 +218,7 @@ colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, int64
 constexpr int kFinalThreads = 1024;
 __global__ void __launch_bounds__(kFinalThreads)
 colsum_final_kernel(const float* __restrict__ part, int parts, int64_t cols, float* __restrict__ out) {
+  pdl_enter();
   __shared__ float red[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 32 + tx;
@@ -237,6 +247,7 @@ colsum_final_kernel(const float* __restrict__ part, int parts, int64_t cols, flo
 template <typename S, typename D>
 __global__ void __launch_bounds__(kEwThreads)
 cast_pad_kernel(const S* __restrict__ src, int64_t lds, D* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols) {
+  pdl_enter();
   const int64_t total = rows * ldd;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = e / ldd, c = e % ldd;
@@ -248,6 +259,7 @@ cast_pad_kernel(const S* __restrict__ src, int64_t lds, D* __restrict__ dst, int
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 row_inv_norm_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t rows, int64_t cols, int64_t ldx) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -269,6 +281,7 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 act_bwd_colsum_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t nvec, int period,
                       int act, float slope, float* __restrict__ part) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   __shared__ float csum[kEwThreads * VN];
   float dsum[VN];
@@ -319,10 +332,10 @@ int colsum_launch(const void* x, float* out, int64_t rows, int64_t cols, int64_t
     const int64_t nvec = ceil_div(cols, (int64_t)VN);
     const int threads = (int)(nvec >= kEwThreads ? kEwThreads : (nvec + 31) / 32 * 32);   // no idle half-blocks
     const int gy = (int)ceil_div(nvec, (int64_t)threads);
-    colsum_partial_kernel<T><<<dim3(parts, gy), threads, 0, s>>>((const T*)x, rows, cols, ldx, rows_per, vec_ok, part);
+    (void)launch_kernel(colsum_partial_kernel<T>, dim3(parts, gy), threads, 0, s, (const T*)x, rows, cols, ldx, rows_per, vec_ok, part);
     EGP_LAUNCH_CHECK();
   });
-  colsum_final_kernel<<<(unsigned)ceil_div(cols, 32), kFinalThreads, 0, s>>>(part, parts, cols, out);
+  (void)launch_kernel(colsum_final_kernel, (unsigned)ceil_div(cols, 32), kFinalThreads, 0, s, part, parts, cols, out);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
 }
@@ -347,7 +360,7 @@ int egp_posenc_add(const void* x, const int64_t* pos, const float* frequency, vo
   if (n == 0) return EGP_OK;
   EGP_DISPATCH_DTYPE(dtype, T, {
     const int64_t nwork = n * channels / (2 * Vec<T>::N);
-    posenc_add_kernel<T><<<ew_grid(nwork), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)x, pos, frequency,
+    (void)launch_kernel(posenc_add_kernel<T>, ew_grid(nwork), kEwThreads, 0, (cudaStream_t)stream, (const T*)x, pos, frequency,
                                                                                   (T*)out, nwork, channels);
     EGP_LAUNCH_CHECK();
   });
@@ -361,9 +374,9 @@ int egp_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = ew_grid(ceil_div(n, 8));
   if (src_dtype == EGP_F32 && dst_dtype == EGP_BF16)
-    cast_kernel<float, __nv_bfloat16><<<grid, kEwThreads, 0, s>>>((const float*)src, (__nv_bfloat16*)dst, n);
+    (void)launch_kernel(cast_kernel<float, __nv_bfloat16>, grid, kEwThreads, 0, s, (const float*)src, (__nv_bfloat16*)dst, n);
   else if (src_dtype == EGP_BF16 && dst_dtype == EGP_F32)
-    cast_kernel<__nv_bfloat16, float><<<grid, kEwThreads, 0, s>>>((const __nv_bfloat16*)src, (float*)dst, n);
+    (void)launch_kernel(cast_kernel<__nv_bfloat16, float>, grid, kEwThreads, 0, s, (const __nv_bfloat16*)src, (float*)dst, n);
   else if (src_dtype == dst_dtype && (src_dtype == EGP_F32 || src_dtype == EGP_BF16)) {
     EGP_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * (src_dtype == EGP_F32 ? 4 : 2), cudaMemcpyDeviceToDevice, s));
     return EGP_OK;
@@ -383,13 +396,13 @@ int egp_cast_pad(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t r
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = ew_grid(ceil_div(rows * ldd, 4));
   if (src_dtype == EGP_F32 && dst_dtype == EGP_BF16)
-    cast_pad_kernel<float, __nv_bfloat16><<<grid, kEwThreads, 0, s>>>((const float*)src, lds, (__nv_bfloat16*)dst, ldd, rows, cols);
+    (void)launch_kernel(cast_pad_kernel<float, __nv_bfloat16>, grid, kEwThreads, 0, s, (const float*)src, lds, (__nv_bfloat16*)dst, ldd, rows, cols);
   else if (src_dtype == EGP_BF16 && dst_dtype == EGP_BF16)
-    cast_pad_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kEwThreads, 0, s>>>((const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, rows, cols);
+    (void)launch_kernel(cast_pad_kernel<__nv_bfloat16, __nv_bfloat16>, grid, kEwThreads, 0, s, (const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, rows, cols);
   else if (src_dtype == EGP_F32 && dst_dtype == EGP_F32)
-    cast_pad_kernel<float, float><<<grid, kEwThreads, 0, s>>>((const float*)src, lds, (float*)dst, ldd, rows, cols);
+    (void)launch_kernel(cast_pad_kernel<float, float>, grid, kEwThreads, 0, s, (const float*)src, lds, (float*)dst, ldd, rows, cols);
   else if (src_dtype == EGP_BF16 && dst_dtype == EGP_F32)
-    cast_pad_kernel<__nv_bfloat16, float><<<grid, kEwThreads, 0, s>>>((const __nv_bfloat16*)src, lds, (float*)dst, ldd, rows, cols);
+    (void)launch_kernel(cast_pad_kernel<__nv_bfloat16, float>, grid, kEwThreads, 0, s, (const __nv_bfloat16*)src, lds, (float*)dst, ldd, rows, cols);
   else {
     set_error("cast_pad: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
     return EGP_ERR_INVALID;
@@ -403,7 +416,7 @@ int egp_add(const void* a, const void* b, void* out, int64_t n, int dtype, void*
   EGP_EW_CHECK("add", n, dtype);
   EGP_DISPATCH_DTYPE(dtype, T, {
     const int64_t nvec = n / Vec<T>::N;
-    add_kernel<T><<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, (T*)out, nvec);
+    (void)launch_kernel(add_kernel<T>, ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream, (const T*)a, (const T*)b, (T*)out, nvec);
     EGP_LAUNCH_CHECK();
   });
   return EGP_OK;
@@ -414,7 +427,7 @@ int egp_axpby(const void* a, float alpha, const void* b, float beta, void* out, 
   EGP_EW_CHECK("axpby", n, dtype);
   EGP_DISPATCH_DTYPE(dtype, T, {
     const int64_t nvec = n / Vec<T>::N;
-    axpby_kernel<T><<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)a, alpha, (const T*)b, beta, (T*)out, nvec);
+    (void)launch_kernel(axpby_kernel<T>, ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream, (const T*)a, alpha, (const T*)b, beta, (T*)out, nvec);
     EGP_LAUNCH_CHECK();
   });
   return EGP_OK;
@@ -426,7 +439,7 @@ int egp_act_bwd(const void* dy, const void* y, void* dx, int64_t n, int act, flo
   EGP_EW_CHECK("act_bwd", n, dtype);
   EGP_DISPATCH_DTYPE(dtype, T, {
     const int64_t nvec = n / Vec<T>::N;
-    act_bwd_kernel<T><<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)y, (T*)dx,
+    (void)launch_kernel(act_bwd_kernel<T>, ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream, (const T*)dy, (const T*)y, (T*)dx,
                                                                               nvec, act, slope);
     EGP_LAUNCH_CHECK();
   });
@@ -438,7 +451,7 @@ int egp_mask_scale(const void* x, const uint8_t* mask, void* out, int64_t n, flo
   EGP_EW_CHECK("mask_scale", n, dtype);
   EGP_DISPATCH_DTYPE(dtype, T, {
     const int64_t nvec = n / Vec<T>::N;
-    mask_scale_kernel<T><<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)x, mask, (T*)out, nvec, scale);
+    (void)launch_kernel(mask_scale_kernel<T>, ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream, (const T*)x, mask, (T*)out, nvec, scale);
     EGP_LAUNCH_CHECK();
   });
   return EGP_OK;
@@ -449,7 +462,7 @@ int egp_max_combine_fwd(const void* f, const void* m, void* a, int64_t n, int dt
   EGP_EW_CHECK("max_combine_fwd", n, dtype);
   EGP_DISPATCH_DTYPE(dtype, T, {
     const int64_t nvec = n / Vec<T>::N;
-    max_combine_fwd_kernel<T><<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)f, (const T*)m, (T*)a, nvec);
+    (void)launch_kernel(max_combine_fwd_kernel<T>, ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream, (const T*)f, (const T*)m, (T*)a, nvec);
     EGP_LAUNCH_CHECK();
   });
   return EGP_OK;
@@ -460,7 +473,7 @@ int egp_max_combine_bwd(const void* da, const void* f, const void* m, void* df, 
   EGP_EW_CHECK("max_combine_bwd", n, dtype);
   EGP_DISPATCH_DTYPE(dtype, T, {
     const int64_t nvec = n / Vec<T>::N;
-    max_combine_bwd_kernel<T><<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)da, (const T*)f,
+    (void)launch_kernel(max_combine_bwd_kernel<T>, ew_grid(nvec), kEwThreads, 0, (cudaStream_t)stream, (const T*)da, (const T*)f,
                                                                                       (const T*)m, (T*)df, nvec);
     EGP_LAUNCH_CHECK();
   });
@@ -501,12 +514,12 @@ int egp_act_bwd_colsum(const void* dy, const void* y, void* dx, float* dx_colsum
     const int grid = ew_grid(nvec);
     const bool fuse = ((int64_t)grid * kEwThreads) % period == 0 && period <= kEwThreads && kEwThreads % period == 0;
     if (fuse) {
-      act_bwd_colsum_kernel<T><<<grid, kEwThreads, 0, s>>>((const T*)dy, (const T*)y, (T*)dx, nvec, (int)period, act, slope, part);
+      (void)launch_kernel(act_bwd_colsum_kernel<T>, grid, kEwThreads, 0, s, (const T*)dy, (const T*)y, (T*)dx, nvec, (int)period, act, slope, part);
       EGP_LAUNCH_CHECK();
-      colsum_final_kernel<<<(unsigned)ceil_div(cols, 32), kFinalThreads, 0, s>>>(part, grid, cols, dx_colsum);
+      (void)launch_kernel(colsum_final_kernel, (unsigned)ceil_div(cols, 32), kFinalThreads, 0, s, part, grid, cols, dx_colsum);
       EGP_LAUNCH_CHECK();
     } else {
-      act_bwd_kernel<T><<<grid, kEwThreads, 0, s>>>((const T*)dy, (const T*)y, (T*)dx, nvec, act, slope);
+      (void)launch_kernel(act_bwd_kernel<T>, grid, kEwThreads, 0, s, (const T*)dy, (const T*)y, (T*)dx, nvec, act, slope);
       EGP_LAUNCH_CHECK();
       const int rc = colsum_launch(dx, dx_colsum, rows, cols, cols, dtype, cs_ws, colsum_workspace_bytes(rows, cols), s);
       if (rc != EGP_OK) return rc;
@@ -521,7 +534,7 @@ int egp_row_inv_norm(const void* x, float* out, int64_t rows, int64_t cols, int6
   EGP_REQUIRE(cols % vn == 0 && ldx % vn == 0 && aligned16(x), "row_inv_norm: cols/ld must be multiples of %d", (int)vn);
   if (rows == 0) return EGP_OK;
   EGP_DISPATCH_DTYPE(dtype, T, {
-    row_inv_norm_kernel<T><<<(unsigned)ceil_div(rows, kEwThreads / 32), kEwThreads, 0, (cudaStream_t)stream>>>(
+    (void)launch_kernel(row_inv_norm_kernel<T>, (unsigned)ceil_div(rows, kEwThreads / 32), kEwThreads, 0, (cudaStream_t)stream, 
         (const T*)x, out, rows, cols, ldx);
     EGP_LAUNCH_CHECK();
   });

@@ -64,6 +64,7 @@ sgemm_kernel(const InT* __restrict__ A, int64_t lda, const InT* __restrict__ B, 
              const float* __restrict__ bias, const OutT* __restrict__ residual, int64_t ldr, OutT* __restrict__ C,
              int64_t ldc, int64_t M, int64_t N, int64_t K, int act, float slope, int accumulate, int vec_a,
              int vec_b, int vec_a2, int vec_b2) {
+  pdl_enter();
   __shared__ __align__(16) float As[SBK][SBM + 4];
   __shared__ __align__(16) float Bs[SBK][SBN + 4];
   const int64_t m0 = (int64_t)blockIdx.y * SBM, n0 = (int64_t)blockIdx.x * SBN;
@@ -131,7 +132,7 @@ static int sgemm_launch_t(const InT* A, int64_t lda, int a_trans, const InT* B, 
   constexpr int VE = 16 / (int)sizeof(InT);  // elements per 16-byte load
   const int va = vec_ok(A, lda, VE), vb = vec_ok(B, ldb, VE), va2 = vec_ok(A2, lda2, VE), vb2 = vec_ok(B2, ldb2, VE);
 #define EGP_SGEMM(AT, BT, OT)                                                                                       \
-  sgemm_kernel<AT, BT, InT, OT><<<grid, STHREADS, 0, stream>>>(A, lda, B, ldb, A2, lda2, B2, ldb2, K2, bias,       \
+  (void)launch_kernel(sgemm_kernel<AT, BT, InT, OT>, grid, STHREADS, 0, stream, A, lda, B, ldb, A2, lda2, B2, ldb2, K2, bias,       \
                                                                (const OT*)residual, ldr, (OT*)C, ldc, M, N, K, act, \
                                                                slope, accumulate, va, vb, va2, vb2)
 #define EGP_SGEMM_T(OT)                                       \

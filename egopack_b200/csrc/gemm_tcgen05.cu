@@ -312,6 +312,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
   __syncwarp();
   if (warp == 1) tmem_alloc<CG>(tmem_slot, Cfg::kTmemCols);
+  // everything above touches only this CTA's shared memory / TMEM and the kernel parameters, so it may overlap the
+  // tail of the previous kernel; global memory is first read below
+  pdl_enter();
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -810,15 +813,17 @@ static int tc_launch_inst(const CUtensorMap* maps, const TcParams& p, int work, 
   if constexpr (CG == 2) {
     const int clusters = work < max_clusters ? work : max_clusters;
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.gridDim = dim3(2 * (unsigned)clusters); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = kSmem;
-    cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     EGP_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p));
   } else {
     const int sms = sm_count();
-    kern<<<work < sms ? work : sms, TC_THREADS, kSmem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+    (void)launch_kernel(kern, work < sms ? work : sms, TC_THREADS, kSmem, stream, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   }
   EGP_LAUNCH_CHECK();
   return EGP_OK;
@@ -947,7 +952,7 @@ static int tc_gemm_topk_inst(const CUtensorMap* maps, const TcParams& p, int gri
     EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  kern<<<grid, TC_THREADS_TOPK, TcCfg<BN>::kSmemBytes, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[4], p);
+  (void)launch_kernel(kern, grid, TC_THREADS_TOPK, TcCfg<BN>::kSmemBytes, stream, maps[0], maps[1], maps[2], maps[3], maps[4], maps[4], p);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
 }

@@ -15,6 +15,7 @@ constexpr int kMetricThreads = 256;
 __global__ void __launch_bounds__(kMetricThreads)
 label_rank_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels, int64_t label_stride,
                   int64_t n, int64_t classes, int64_t ignore_index, int32_t* __restrict__ rank) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (kMetricThreads / 32) + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -40,6 +41,7 @@ label_rank_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* _
 __global__ void __launch_bounds__(kMetricThreads)
 segment_argmax_kernel(const float* __restrict__ values, const int64_t* __restrict__ ptr, int64_t num_graphs,
                       int apply_sigmoid, int64_t* __restrict__ out) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t g = (int64_t)blockIdx.x * (kMetricThreads / 32) + (threadIdx.x >> 5);
   if (g >= num_graphs) return;
@@ -67,6 +69,7 @@ constexpr int kMaxSeq = 64;
 __global__ void __launch_bounds__(kMetricThreads)
 edit_distance_min_kernel(const int64_t* __restrict__ preds, const int64_t* __restrict__ labels, int64_t n, int z, int k,
                          int32_t* __restrict__ out) {
+  pdl_enter();
   __shared__ int32_t res[kMetricThreads];
   const int per = kMetricThreads / k;              // rows per block
   const int local_row = threadIdx.x / k, s = threadIdx.x % k;
@@ -111,7 +114,7 @@ int egp_label_rank(const float* logits, int64_t ld, const int64_t* labels, int64
   EGP_REQUIRE(logits && labels && rank, "label_rank: null pointer");
   EGP_REQUIRE(classes >= 1 && ld >= classes && label_stride >= 1, "label_rank: bad sizes");
   if (n == 0) return EGP_OK;
-  label_rank_kernel<<<(unsigned)ceil_div(n, kMetricThreads / 32), kMetricThreads, 0, (cudaStream_t)stream>>>(
+  (void)launch_kernel(label_rank_kernel, (unsigned)ceil_div(n, kMetricThreads / 32), kMetricThreads, 0, (cudaStream_t)stream, 
       logits, ld, labels, label_stride, n, classes, ignore_index, rank);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
@@ -121,7 +124,7 @@ int egp_segment_argmax(const float* values, const int64_t* ptr, int64_t num_grap
                        void* stream) {
   EGP_REQUIRE(values && ptr && out, "segment_argmax: null pointer");
   if (num_graphs == 0) return EGP_OK;
-  segment_argmax_kernel<<<(unsigned)ceil_div(num_graphs, kMetricThreads / 32), kMetricThreads, 0, (cudaStream_t)stream>>>(
+  (void)launch_kernel(segment_argmax_kernel, (unsigned)ceil_div(num_graphs, kMetricThreads / 32), kMetricThreads, 0, (cudaStream_t)stream, 
       values, ptr, num_graphs, apply_sigmoid, out);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
@@ -134,7 +137,7 @@ int egp_edit_distance_min(const int64_t* preds, const int64_t* labels, int64_t n
   EGP_REQUIRE(num_samples >= 1 && num_samples <= kMetricThreads, "edit_distance_min: 1 <= K <= %d", kMetricThreads);
   if (n == 0) return EGP_OK;
   const int per = kMetricThreads / (int)num_samples;
-  edit_distance_min_kernel<<<(unsigned)ceil_div(n, per), kMetricThreads, 0, (cudaStream_t)stream>>>(
+  (void)launch_kernel(edit_distance_min_kernel, (unsigned)ceil_div(n, per), kMetricThreads, 0, (cudaStream_t)stream, 
       preds, labels, n, (int)seq_len, (int)num_samples, out);
   EGP_LAUNCH_CHECK();
   return EGP_OK;

@@ -31,6 +31,7 @@ template <typename T>
 __global__ void __launch_bounds__(kNormThreads)
 gln_stats_kernel(const T* __restrict__ x, int64_t nvec, double inv_count, double* __restrict__ partial,
                  unsigned int* __restrict__ ticket, double* __restrict__ stats) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   __shared__ double red[32];
   __shared__ bool is_last;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(kNormThreads)
 gln_apply_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                  T* __restrict__ y, const double* __restrict__ stats, int64_t nvec, int64_t channels, float eps,
                  int act, float slope) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   const float mu = (float)stats[0];
   const float rs = (float)(1.0 / (stats[1] + (double)eps));
@@ -146,6 +148,7 @@ gln_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const f
                       const float* __restrict__ b, const double* __restrict__ stats, int64_t n, int64_t channels,
                       int rows_per_cta, float eps, int act, float slope, float* __restrict__ colpart,
                       double* __restrict__ scalpart) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   __shared__ double red[32];
   const int64_t col = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * VN;
@@ -215,6 +218,7 @@ __global__ void __launch_bounds__(kFinThreads)
 col_finalize_kernel(const float* __restrict__ colpart, int parts, int64_t channels, int nout, float* __restrict__ out0,
                     float* __restrict__ out1, float* __restrict__ out2, const double* __restrict__ scalpart,
                     int scal_parts, double* __restrict__ scal, int colblocks) {
+  pdl_enter();
   __shared__ double red[32];
   __shared__ float rs[3][32][33];
   if ((int)blockIdx.x < colblocks) {
@@ -268,6 +272,7 @@ gln_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
                      const float* __restrict__ b, const double* __restrict__ stats, const double* __restrict__ scal,
                      T* __restrict__ dx, int64_t nvec, int64_t channels, double inv_count, float eps, int act,
                      float slope, float* __restrict__ dxpart /* [gridDim.x, C] or null; FIXED only */) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   __shared__ float csum[kNormThreads * VN];
   float dsum[VN];
@@ -321,6 +326,7 @@ rln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float
                T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t n, int64_t channels,
                float eps, int act, uint32_t drop_thr16, float keep_scale, uint64_t seed, uint64_t offset,
                const uint64_t* __restrict__ rng_state) {
+  pdl_enter();
   // CUDA-graph replays cannot change kernel arguments, so the per-step part of the Philox stream may come from device
   // memory: rng_state = {seed, step}; the call-site index stays in `offset`
   if (rng_state) { seed = rng_state[0]; offset += rng_state[1] << 20; }
@@ -408,6 +414,7 @@ rln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __res
                const float* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd,
                T* __restrict__ dx, int64_t n, int64_t channels, int act, float out_scale,
                float* __restrict__ colpart) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   const bool use_y = act == EGP_ACT_RELU || out_scale != 1.f;  // mask = output != 0 (ReLU and/or dropout)
   extern __shared__ float cacc[];  // [2][channels] block accumulators for dweight / dbias
@@ -497,6 +504,7 @@ rln_bwd_block_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
                      const float* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd,
                      T* __restrict__ dx, int64_t n, int64_t channels, int act, float out_scale, int nout,
                      float* __restrict__ colpart) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   const bool use_y = act == EGP_ACT_RELU || out_scale != 1.f;
   __shared__ float red[2][32][2];
@@ -586,6 +594,7 @@ rln_fwd_wide_kernel(const T* __restrict__ x, const float* __restrict__ w, const 
                     T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t n,
                     int64_t channels, float eps, int act, uint32_t drop_thr16, float keep_scale, uint64_t seed,
                     uint64_t offset, const uint64_t* __restrict__ rng_state) {
+  pdl_enter();
   if (rng_state) { seed = rng_state[0]; offset += rng_state[1] << 20; }
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31;
@@ -628,6 +637,7 @@ rln_bwd_wide_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
                     const float* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd,
                     T* __restrict__ dx, int64_t n, int64_t channels, int act, float out_scale,
                     float* __restrict__ colpart) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   const bool use_y = act == EGP_ACT_RELU || out_scale != 1.f;
   extern __shared__ float cacc[];
@@ -728,13 +738,13 @@ int egp_graph_layernorm_fwd(const void* x, const float* weight, const float* bia
   EGP_DISPATCH_DTYPE(dtype, T, {
     const int64_t nvec = n * channels / Vec<T>::N;
     const int g1 = norm_grid(nvec, kNormThreads * 4);
-    gln_stats_kernel<T><<<g1, kNormThreads, 0, s>>>((const T*)x, nvec, 1.0 / ((double)n * (double)channels), partial,
+    (void)launch_kernel(gln_stats_kernel<T>, g1, kNormThreads, 0, s, (const T*)x, nvec, 1.0 / ((double)n * (double)channels), partial,
                                                      &ws->ticket, stats);
     EGP_LAUNCH_CHECK();
     const int g2 = norm_grid(nvec, kNormThreads * 2) * 2;
     const bool fixed = ((int64_t)g2 * kNormThreads) % (channels / Vec<T>::N) == 0;
-    if (fixed) gln_apply_kernel<T, true><<<g2, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, stats, nvec, channels, eps, act, slope);
-    else gln_apply_kernel<T, false><<<g2, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, stats, nvec, channels, eps, act, slope);
+    if (fixed) (void)launch_kernel(gln_apply_kernel<T, true>, g2, kNormThreads, 0, s, (const T*)x, weight, bias, (T*)y, stats, nvec, channels, eps, act, slope);
+    else (void)launch_kernel(gln_apply_kernel<T, false>, g2, kNormThreads, 0, s, (const T*)x, weight, bias, (T*)y, stats, nvec, channels, eps, act, slope);
     EGP_LAUNCH_CHECK();
   });
   return EGP_OK;
@@ -773,11 +783,11 @@ int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, 
     float* dxpart = colpart + 2 * (size_t)parts * channels;
     void* cs_ws = dxpart + (size_t)(sm_count() * 8) * channels;
     EGP_REQUIRE((size_t)parts * gy <= np, "graph_layernorm_bwd: internal partial sizing");
-    gln_bwd_reduce_kernel<T><<<dim3(parts, gy), rthreads, 0, s>>>(
+    (void)launch_kernel(gln_bwd_reduce_kernel<T>, dim3(parts, gy), rthreads, 0, s, 
         (const T*)dy, (const T*)x, weight, bias, stats, n, channels, rows_per, eps, act, slope, colpart, scalpart);
     EGP_LAUNCH_CHECK();
     const int colblocks = (int)ceil_div(channels, 32);
-    col_finalize_kernel<<<colblocks + 1, kFinThreads, 0, s>>>(colpart, parts, channels, 2, dweight, dbias, nullptr,
+    (void)launch_kernel(col_finalize_kernel, colblocks + 1, kFinThreads, 0, s, colpart, parts, channels, 2, dweight, dbias, nullptr,
                                                               scalpart, parts * gy, ws->scal, colblocks);
     EGP_LAUNCH_CHECK();
     const int64_t nvec = n * channels / VN;
@@ -786,15 +796,15 @@ int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, 
     const bool fuse = dx_colsum && fixed && nvec_row <= kNormThreads && kNormThreads % nvec_row == 0;
     const double inv_count = 1.0 / ((double)n * (double)channels);
     if (fixed)
-      gln_bwd_apply_kernel<T, true><<<g2, kNormThreads, 0, s>>>((const T*)dy, (const T*)x, weight, bias, stats, ws->scal,
+      (void)launch_kernel(gln_bwd_apply_kernel<T, true>, g2, kNormThreads, 0, s, (const T*)dy, (const T*)x, weight, bias, stats, ws->scal,
                                                                 (T*)dx, nvec, channels, inv_count, eps, act, slope,
                                                                 fuse ? dxpart : nullptr);
     else
-      gln_bwd_apply_kernel<T, false><<<g2, kNormThreads, 0, s>>>((const T*)dy, (const T*)x, weight, bias, stats, ws->scal,
+      (void)launch_kernel(gln_bwd_apply_kernel<T, false>, g2, kNormThreads, 0, s, (const T*)dy, (const T*)x, weight, bias, stats, ws->scal,
                                                                  (T*)dx, nvec, channels, inv_count, eps, act, slope, nullptr);
     EGP_LAUNCH_CHECK();
     if (fuse) {
-      col_finalize_kernel<<<colblocks, kFinThreads, 0, s>>>(dxpart, g2, channels, 1, dx_colsum, nullptr, nullptr, nullptr, 0,
+      (void)launch_kernel(col_finalize_kernel, colblocks, kFinThreads, 0, s, dxpart, g2, channels, 1, dx_colsum, nullptr, nullptr, nullptr, 0,
                                                             nullptr, colblocks);
       EGP_LAUNCH_CHECK();
     } else if (dx_colsum) {
@@ -837,7 +847,7 @@ int egp_row_layernorm_fwd(const void* x, const float* weight, const float* bias,
     const int64_t nvec = channels / Vec<T>::N;
     EGP_RLN_DISPATCH_NVL(nvec, {
       if constexpr (NVL == 0)
-        rln_fwd_wide_kernel<T><<<grid, kNormThreads, 0, s>>>((const T*)x, weight, bias, (T*)y, mean, rstd, n, channels, eps,
+        (void)launch_kernel(rln_fwd_wide_kernel<T>, grid, kNormThreads, 0, s, (const T*)x, weight, bias, (T*)y, mean, rstd, n, channels, eps,
                                                              act, thr, keep_scale, seed, offset, rng_state);
       else
       {
@@ -847,7 +857,7 @@ int egp_row_layernorm_fwd(const void* x, const float* weight, const float* bias,
           if (resident < 1) resident = 1;
         }
         const int64_t want = ceil_div(n, kNormThreads / 32), cap = (int64_t)sm_count() * resident;
-        rln_fwd_kernel<T, (NVL ? NVL : 1)><<<(int)(want < cap ? want : cap), kNormThreads, 0, s>>>(
+        (void)launch_kernel(rln_fwd_kernel<T, (NVL ? NVL : 1)>, (int)(want < cap ? want : cap), kNormThreads, 0, s, 
             (const T*)x, weight, bias, (T*)y, mean, rstd, n, channels, eps, act, thr, keep_scale, seed, offset, rng_state);
       }
     });
@@ -899,24 +909,24 @@ int egp_row_layernorm_bwd(const void* dy, const void* x, const void* y, const fl
       grid = (int)(n < cap ? n : cap);
       nout = dx_colsum ? 3 : 2;
       if (threads <= 256)
-        rln_bwd_block_kernel<T, 256><<<grid, threads, 0, s>>>((const T*)dy, (const T*)x, (const T*)y, weight, mean, rstd,
+        (void)launch_kernel(rln_bwd_block_kernel<T, 256>, grid, threads, 0, s, (const T*)dy, (const T*)x, (const T*)y, weight, mean, rstd,
                                                               (T*)dx, n, channels, act, out_scale, nout, colpart);
       else
-        rln_bwd_block_kernel<T, 1024><<<grid, threads, 0, s>>>((const T*)dy, (const T*)x, (const T*)y, weight, mean, rstd,
+        (void)launch_kernel(rln_bwd_block_kernel<T, 1024>, grid, threads, 0, s, (const T*)dy, (const T*)x, (const T*)y, weight, mean, rstd,
                                                                (T*)dx, n, channels, act, out_scale, nout, colpart);
     } else {
       EGP_RLN_DISPATCH_NVL(nvec, {
         auto kern = rln_bwd_wide_kernel<T>;
         if constexpr (NVL != 0) kern = rln_bwd_kernel<T, NVL>;
         if (smem > 48 * 1024) EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kNormThreads, smem, s>>>((const T*)dy, (const T*)x, (const T*)y, weight, mean, rstd, (T*)dx, n,
+        (void)launch_kernel(kern, grid, kNormThreads, smem, s, (const T*)dy, (const T*)x, (const T*)y, weight, mean, rstd, (T*)dx, n,
                                               channels, act, out_scale, colpart);
       });
     }
     EGP_LAUNCH_CHECK();
   });
   const int colblocks = (int)ceil_div(channels, 32);
-  col_finalize_kernel<<<colblocks, kFinThreads, 0, s>>>(colpart, grid, channels, nout, dweight, dbias,
+  (void)launch_kernel(col_finalize_kernel, colblocks, kFinThreads, 0, s, colpart, grid, channels, nout, dweight, dbias,
                                                         nout == 3 ? dx_colsum : nullptr, nullptr, 0, nullptr, colblocks);
   EGP_LAUNCH_CHECK();
   if (dx_colsum && nout != 3) {

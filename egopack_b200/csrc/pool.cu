@@ -13,6 +13,7 @@ template <typename T>
 __global__ void __launch_bounds__(kPoolThreads)
 segment_max_fwd_kernel(const T* __restrict__ x, const int64_t* __restrict__ ptr, T* __restrict__ out,
                        int32_t* __restrict__ arg, int64_t channels) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   const int64_t g = blockIdx.x;
   const int64_t col = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * VN;
@@ -41,6 +42,7 @@ template <typename T>
 __global__ void __launch_bounds__(kPoolThreads)
 segment_max_bwd_kernel(const T* __restrict__ dout, const int32_t* __restrict__ arg,
                        const int64_t* __restrict__ batch, T* __restrict__ dx, int64_t nvec, int64_t channels) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e0 = v * VN;
@@ -58,6 +60,7 @@ template <typename T>
 __global__ void __launch_bounds__(kPoolThreads)
 proto_max_gather_kernel(const T* __restrict__ protos, const int64_t* __restrict__ idx, T* __restrict__ m,
                         int64_t nvec, int64_t k, int64_t channels) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e0 = v * VN;
@@ -79,6 +82,7 @@ __global__ void __launch_bounds__(kPoolThreads)
 proto_max_scatter_bwd_kernel(const T* __restrict__ da, const T* __restrict__ f, const T* __restrict__ protos,
                              const int64_t* __restrict__ idx, float* __restrict__ dbank, int64_t nvec, int64_t k,
                              int64_t channels) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e0 = v * VN;
@@ -107,6 +111,7 @@ template <typename T>
 __global__ void __launch_bounds__(kPoolThreads)
 class_sum_kernel(const T* __restrict__ x, const int64_t* __restrict__ label, double* __restrict__ out, int64_t nvec,
                  int64_t channels, int64_t num_classes) {
+  pdl_enter();
   constexpr int VN = Vec<T>::N;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e0 = v * VN;
@@ -139,7 +144,7 @@ int egp_segment_max_pool_fwd(const void* x, const int64_t* ptr, void* out, int32
   if (num_graphs == 0 || channels == 0) return EGP_OK;
   EGP_DISPATCH_DTYPE(dtype, T, {
     const unsigned gy = (unsigned)ceil_div(channels, (int64_t)kPoolThreads * Vec<T>::N);
-    segment_max_fwd_kernel<T><<<dim3((unsigned)num_graphs, gy), kPoolThreads, 0, (cudaStream_t)stream>>>(
+    (void)launch_kernel(segment_max_fwd_kernel<T>, dim3((unsigned)num_graphs, gy), kPoolThreads, 0, (cudaStream_t)stream, 
         (const T*)x, ptr, (T*)out, arg, channels);
     EGP_LAUNCH_CHECK();
   });
@@ -154,7 +159,7 @@ int egp_segment_max_pool_bwd(const void* dout, const int32_t* arg, const int64_t
   if (num_nodes == 0 || channels == 0) return EGP_OK;
   EGP_DISPATCH_DTYPE(dtype, T, {
     const int64_t nvec = num_nodes * channels / Vec<T>::N;
-    segment_max_bwd_kernel<T><<<pool_grid(nvec), kPoolThreads, 0, (cudaStream_t)stream>>>(
+    (void)launch_kernel(segment_max_bwd_kernel<T>, pool_grid(nvec), kPoolThreads, 0, (cudaStream_t)stream, 
         (const T*)dout, arg, batch, (T*)dx, nvec, channels);
     EGP_LAUNCH_CHECK();
   });
@@ -171,7 +176,7 @@ int egp_proto_max_gather(const void* protos, const int64_t* idx, void* m, int64_
   if (num_nodes == 0 || channels == 0) return EGP_OK;
   EGP_DISPATCH_DTYPE(out_dtype, T, {
     const int64_t nvec = num_nodes * channels / Vec<T>::N;
-    proto_max_gather_kernel<T><<<pool_grid(nvec), kPoolThreads, 0, (cudaStream_t)stream>>>(
+    (void)launch_kernel(proto_max_gather_kernel<T>, pool_grid(nvec), kPoolThreads, 0, (cudaStream_t)stream, 
         (const T*)protos, idx, (T*)m, nvec, k, channels);
     EGP_LAUNCH_CHECK();
   });
@@ -186,7 +191,7 @@ int egp_proto_max_scatter_bwd(const void* da, const void* f, const void* protos,
   if (num_nodes == 0) return EGP_OK;
   EGP_DISPATCH_DTYPE(dtype, T, {
     const int64_t nvec = num_nodes * channels / Vec<T>::N;
-    proto_max_scatter_bwd_kernel<T><<<pool_grid(nvec), kPoolThreads, 0, (cudaStream_t)stream>>>(
+    (void)launch_kernel(proto_max_scatter_bwd_kernel<T>, pool_grid(nvec), kPoolThreads, 0, (cudaStream_t)stream, 
         (const T*)da, (const T*)f, (const T*)protos, idx, dbank, nvec, k, channels);
     EGP_LAUNCH_CHECK();
   });
@@ -201,7 +206,7 @@ int egp_class_sum_f64(const void* x, const int64_t* label, double* out, int64_t 
   if (rows == 0) return EGP_OK;
   EGP_DISPATCH_DTYPE(dtype, T, {
     const int64_t nvec = rows * channels / Vec<T>::N;
-    class_sum_kernel<T><<<pool_grid(nvec), kPoolThreads, 0, (cudaStream_t)stream>>>((const T*)x, label, out, nvec, channels,
+    (void)launch_kernel(class_sum_kernel<T>, pool_grid(nvec), kPoolThreads, 0, (cudaStream_t)stream, (const T*)x, label, out, nvec, channels,
                                                                                     num_classes);
     EGP_LAUNCH_CHECK();
   });

@@ -41,6 +41,7 @@ __device__ __forceinline__ bool key_less(float ka, int ia, float kb, int ib) {
 template <int KK, bool DIST, typename IdxT>
 __global__ void __launch_bounds__(kTopkThreads)
 row_topk_kernel(const float* __restrict__ S, int64_t rows, int64_t cols, int nout, IdxT* __restrict__ out) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -88,6 +89,7 @@ template <int KK>
 __global__ void __launch_bounds__(kTopkThreads)
 rerank_kernel(const float* __restrict__ fn, const float* __restrict__ pn, const int32_t* __restrict__ cand,
               int64_t rows, int64_t protos, int64_t channels, int k, int64_t* __restrict__ idx) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -135,6 +137,7 @@ rerank_kernel(const float* __restrict__ fn, const float* __restrict__ pn, const 
 template <typename T, typename O>
 __global__ void __launch_bounds__(kTopkThreads)
 row_normalize_kernel(const T* __restrict__ x, O* __restrict__ out, int64_t rows, int64_t cols) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -157,13 +160,13 @@ int egp_row_normalize(const void* x, void* out, int64_t rows, int64_t cols, int 
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned grid = (unsigned)ceil_div(rows, kTopkThreads / 32);
   if (in_dtype == EGP_F32 && out_dtype == EGP_F32)
-    row_normalize_kernel<float, float><<<grid, kTopkThreads, 0, s>>>((const float*)x, (float*)out, rows, cols);
+    (void)launch_kernel(row_normalize_kernel<float, float>, grid, kTopkThreads, 0, s, (const float*)x, (float*)out, rows, cols);
   else if (in_dtype == EGP_F32 && out_dtype == EGP_BF16)
-    row_normalize_kernel<float, __nv_bfloat16><<<grid, kTopkThreads, 0, s>>>((const float*)x, (__nv_bfloat16*)out, rows, cols);
+    (void)launch_kernel(row_normalize_kernel<float, __nv_bfloat16>, grid, kTopkThreads, 0, s, (const float*)x, (__nv_bfloat16*)out, rows, cols);
   else if (in_dtype == EGP_BF16 && out_dtype == EGP_F32)
-    row_normalize_kernel<__nv_bfloat16, float><<<grid, kTopkThreads, 0, s>>>((const __nv_bfloat16*)x, (float*)out, rows, cols);
+    (void)launch_kernel(row_normalize_kernel<__nv_bfloat16, float>, grid, kTopkThreads, 0, s, (const __nv_bfloat16*)x, (float*)out, rows, cols);
   else if (in_dtype == EGP_BF16 && out_dtype == EGP_BF16)
-    row_normalize_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kTopkThreads, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, rows, cols);
+    (void)launch_kernel(row_normalize_kernel<__nv_bfloat16, __nv_bfloat16>, grid, kTopkThreads, 0, s, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, rows, cols);
   else {
     set_error("row_normalize: bad dtype pair %d -> %d", in_dtype, out_dtype);
     return EGP_ERR_INVALID;
@@ -212,29 +215,29 @@ int egp_cos_topk(const float* fn, const float* pn, const void* fn16, const void*
       rc = tc_gemm_topk_launch(a, channels, pn16, channels, rows, num_protos, channels, keep, cand, s);
       if (rc != EGP_OK) return rc;
       if (keep * tc_topk_groups() == 16)
-        rerank_kernel<16><<<grid, kTopkThreads, 0, s>>>(fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k);
+        (void)launch_kernel(rerank_kernel<16>, grid, kTopkThreads, 0, s, fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k);
       else
-        rerank_kernel<32><<<grid, kTopkThreads, 0, s>>>(fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k);
+        (void)launch_kernel(rerank_kernel<32>, grid, kTopkThreads, 0, s, fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k);
     } else if (tensor) {
       const __nv_bfloat16* a = (const __nv_bfloat16*)fn16 + r0 * channels;
       rc = tc_gemm_launch(a, channels, 0, pn16, channels, 0, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, 0, S,
                           num_protos, rows, num_protos, channels, EGP_ACT_NONE, 0.f, EGP_F32, 0, s);
       if (rc != EGP_OK) return rc;
       if (kk == 16) {
-        row_topk_kernel<16, false, int32_t><<<grid, kTopkThreads, 0, s>>>(S, rows, num_protos, 16, cand);
-        rerank_kernel<16><<<grid, kTopkThreads, 0, s>>>(fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k);
+        (void)launch_kernel(row_topk_kernel<16, false, int32_t>, grid, kTopkThreads, 0, s, S, rows, num_protos, 16, cand);
+        (void)launch_kernel(rerank_kernel<16>, grid, kTopkThreads, 0, s, fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k);
       } else {
-        row_topk_kernel<32, false, int32_t><<<grid, kTopkThreads, 0, s>>>(S, rows, num_protos, 32, cand);
-        rerank_kernel<32><<<grid, kTopkThreads, 0, s>>>(fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k);
+        (void)launch_kernel(row_topk_kernel<32, false, int32_t>, grid, kTopkThreads, 0, s, S, rows, num_protos, 32, cand);
+        (void)launch_kernel(rerank_kernel<32>, grid, kTopkThreads, 0, s, fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k);
       }
     } else {
       rc = sgemm_launch(fn + r0 * channels, channels, 0, pn, channels, 0, nullptr, 0, nullptr, 0, 0, nullptr, nullptr,
                         0, S, num_protos, rows, num_protos, channels, EGP_ACT_NONE, 0.f, EGP_F32, EGP_F32, 0, s);
       if (rc != EGP_OK) return rc;
-      if (k <= 4) row_topk_kernel<4, true, int64_t><<<grid, kTopkThreads, 0, s>>>(S, rows, num_protos, k, idx + r0 * k);
-      else if (k <= 8) row_topk_kernel<8, true, int64_t><<<grid, kTopkThreads, 0, s>>>(S, rows, num_protos, k, idx + r0 * k);
-      else if (k <= 16) row_topk_kernel<16, true, int64_t><<<grid, kTopkThreads, 0, s>>>(S, rows, num_protos, k, idx + r0 * k);
-      else row_topk_kernel<32, true, int64_t><<<grid, kTopkThreads, 0, s>>>(S, rows, num_protos, k, idx + r0 * k);
+      if (k <= 4) (void)launch_kernel(row_topk_kernel<4, true, int64_t>, grid, kTopkThreads, 0, s, S, rows, num_protos, k, idx + r0 * k);
+      else if (k <= 8) (void)launch_kernel(row_topk_kernel<8, true, int64_t>, grid, kTopkThreads, 0, s, S, rows, num_protos, k, idx + r0 * k);
+      else if (k <= 16) (void)launch_kernel(row_topk_kernel<16, true, int64_t>, grid, kTopkThreads, 0, s, S, rows, num_protos, k, idx + r0 * k);
+      else (void)launch_kernel(row_topk_kernel<32, true, int64_t>, grid, kTopkThreads, 0, s, S, rows, num_protos, k, idx + r0 * k);
     }
     EGP_LAUNCH_CHECK();
   }
