@@ -517,9 +517,12 @@ def native_run(args, rank: int, world: int, local_rank: int):
 
 
 def main():
-    # stdout carries exactly one JSON line: NCCL's own log (the "NCCL version ..." banner that any NCCL_DEBUG level
-    # >= VERSION prints, warnings) goes to stderr instead
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly one JSON line.  Libraries write to file descriptor 1 on their own (NCCL prints a
+    # "NCCL version ..." banner there at any NCCL_DEBUG level >= VERSION), so fd 1 is pointed at stderr for the whole run
+    # and the result line goes to a private duplicate of the original stdout.
+    sys.stdout.flush()
+    result_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -537,7 +540,7 @@ def main():
                        "graphs_per_task": args.cpu_videos, "nodes_per_graph": args.nodes},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": round(r["value"], 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
+        }), file=result_out, flush=True)
         return
 
     if not torch.cuda.is_available():
@@ -553,7 +556,7 @@ def main():
             out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         elif not args.no_cpu_baseline:
             out["cpu_baseline"] = None
-        print(json.dumps(out))
+        print(json.dumps(out), file=result_out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

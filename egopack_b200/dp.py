@@ -54,6 +54,7 @@ class GradientAllReduce:
             self.buckets.append(_Bucket(cur))
         self._owner = {}
         self._handles = []
+        self._avg = False
         if overlap and self.world > 1:
             for b in self.buckets:
                 for p in b.params:
@@ -63,7 +64,10 @@ class GradientAllReduce:
     def _launch(self, b: _Bucket):
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in b.params]
         b.flat = torch.cat([g.reshape(-1) for g in grads])
-        b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        # NCCL averages inside the collective; gloo (CPU tests) has no AVG, so it sums and finish() divides
+        self._avg = b.flat.is_cuda
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
 
     def _on_grad(self, p):
         b = self._owner[p]
@@ -72,7 +76,8 @@ class GradientAllReduce:
             self._launch(b)
 
     def finish(self):
-        """Wait for every bucket and scatter the averaged gradients back into ``p.grad``."""
+        """Wait for every bucket; afterwards every ``p.grad`` IS its slice of the averaged bucket (a view: no copy-back
+        kernels; ``zero_grad(set_to_none=True)`` drops the views before the next backward)."""
         if self.world == 1:
             return
         for b in self.buckets:
@@ -80,14 +85,12 @@ class GradientAllReduce:
                 self._launch(b)
         for b in self.buckets:
             b.work.wait()
-            b.flat.div_(self.world)
+            if not self._avg:
+                b.flat.div_(self.world)
             off = 0
             for p in b.params:
                 n = p.numel()
-                if p.grad is None:
-                    p.grad = b.flat[off:off + n].view_as(p).clone()
-                else:
-                    p.grad.copy_(b.flat[off:off + n].view_as(p))
+                p.grad = b.flat[off:off + n].view_as(p)
                 off += n
             b.pending, b.flat, b.work = len(b.params), None, None
 
