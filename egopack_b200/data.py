@@ -7,7 +7,7 @@ along dim 0 (0-dim tensors are stacked), ``edge_index`` along dim -1 with cumula
 """
 from __future__ import annotations
 
-from typing import Any, Dict, Iterable, List, Sequence
+from typing import Any, Dict, List, Sequence
 
 import torch
 

@@ -10,7 +10,7 @@ what matters; the edges never cross the bus.
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Iterable, Iterator, Mapping, Optional, Sequence, Tuple, Union
+from typing import Iterable, Iterator, Mapping, Optional, Sequence, Tuple, Union
 
 import queue
 import threading

@@ -16,9 +16,8 @@ fixed sequence of sm_100a kernels:
 from __future__ import annotations
 
 import importlib
-from typing import Any, Optional
+from typing import Any
 
-import torch
 import torch.nn as nn
 
 from .. import config, ops

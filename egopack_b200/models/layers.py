@@ -4,15 +4,13 @@ their kernel-backed forwards.  Nothing here depends on torch_geometric.
 """
 from __future__ import annotations
 
-import math
-from typing import List, Optional
 
 import torch
 import torch.nn as nn
 from torch import Tensor
 
 from .. import ops
-from ..ops import ACT_LEAKY, ACT_NONE, ACT_RELU, GraphStructure
+from ..ops import ACT_NONE, ACT_RELU, GraphStructure
 
 
 def structure_for(data, n: int) -> GraphStructure:

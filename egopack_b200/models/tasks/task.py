@@ -8,7 +8,7 @@ classifier GEMMs: each auxiliary classifier takes the running sum of logits as i
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, Literal, Optional, Sequence
+from typing import Literal, Optional
 
 import torch
 import torch.nn as nn

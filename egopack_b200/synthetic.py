@@ -6,7 +6,7 @@ is part of the end-to-end measurement).
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+from typing import Dict, Optional
 
 import torch
 

@@ -23,7 +23,6 @@ Assumption tags A1..A9 follow SURVEY.md §8c.
 from __future__ import annotations
 
 import math
-import re
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import torch

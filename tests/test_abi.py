@@ -1,6 +1,5 @@
 """CPU: the C-ABI library builds/loads and exports every symbol ``include/egopack_b200.h`` declares, and the
 ctypes prototypes agree with the header's argument counts.  No compute call is made (no GPU here)."""
-import ctypes
 import os
 import re
 

@@ -6,7 +6,7 @@ import torch.nn.functional as F
 from egopack_b200 import ops
 from egopack_b200.ops import ACT_LEAKY, ACT_NONE, ACT_RELU
 from oracle import pyg_restated as pyg
-from tests.gpu_util import DEV, TOL_BF16, TOL_F32, graph_sizes_to_index, rel_l2, rel_max
+from tests.gpu_util import DEV, TOL_BF16, TOL_F32, graph_sizes_to_index, rel_max
 
 pytestmark = pytest.mark.gpu
 DTYPES = [(torch.float32, TOL_F32), (torch.bfloat16, TOL_BF16)]

@@ -12,7 +12,7 @@ from egopack_b200.models.tasks import LTATask, OSCCTask, PNRTask, RecognitionTas
 from egopack_b200.models.transforms import LTATemporalConnectivity, RadiusGraph
 from oracle import egopack_oracle as eo
 from oracle import pyg_restated as pyg
-from tests.gpu_util import DEV, TOL_BF16, TOL_F32, grads_close, rel_l2, rel_max
+from tests.gpu_util import DEV, TOL_BF16, TOL_F32, rel_l2, rel_max
 
 pytestmark = pytest.mark.gpu
 TP = {"_target_": "models.temporal_pooling.trn_pooling.TRNPooling", "dropout": 0.0}
