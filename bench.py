@@ -50,8 +50,9 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-videos", type=int, default=16, help="graphs per task batch of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
-                    help="c2 = MTL AR+LTA+PNR (the BASELINE metric's config); c3 = EgoPack OSCC + AR/LTA/PNR prototype backpack")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+                    help="c2 = MTL AR+LTA+PNR (the BASELINE metric's config); c3 = EgoPack OSCC + AR/LTA/PNR prototype backpack; "
+                         "c4 = long-video stress (AR, 256 graphs x 2048 segments, radius 16, 4 GNN layers)")
     ap.add_argument("--protos", type=int, default=4096, help="prototypes per bank (c3)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (for profiler runs)")
     ap.add_argument("--trace-out", default=None, help="write the per-launch trace summary to this JSON file")
@@ -191,10 +192,13 @@ def native_run(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(dev)
     egopack_b200.set_precision(args.precision)
     torch.manual_seed(SEED)                                   # identical replicas on every rank
-    model = Graph(syn.FEATURE_DIM, HIDDEN, DEPTH, temporal_pooling={"hidden_size": TRN_HIDDEN, "dropout": DROPOUT},
+    c3, c4 = args.workload == "c3", args.workload == "c4"
+    k_radius, depth = (16, 4) if c4 else (K_RADIUS, DEPTH)
+    if c4 and (args.videos, args.nodes) == (256, 128):        # BASELINE configs[3]: 256 videos x 2048 segments
+        args.nodes = 2048
+    model = Graph(syn.FEATURE_DIM, HIDDEN, depth, temporal_pooling={"hidden_size": TRN_HIDDEN, "dropout": DROPOUT},
                   num_segments=syn.NUM_SEGMENTS).to(dev)
     heads = (syn.N_VERBS, syn.N_NOUNS)
-    c3 = args.workload == "c3"
     graphone = None
     if c3:
         # EgoPack novel task (experiments/egopack/oscc.yaml): OSCC primary, frozen AR/LTA/PNR banks, k=4, depth 3,
@@ -207,6 +211,9 @@ def native_run(args, rank: int, world: int, local_rank: int):
         graphone = GraphONE(banks, features_size=HIDDEN, hidden_size=HIDDEN, k=4, depth=3, residual=True).to(dev)
         graphone.train()
         task_names = ("oscc",)
+    elif c4:
+        tasks = {"ar": RecognitionTask(HIDDEN, HIDDEN, heads).to(dev)}
+        task_names = ("ar",)
     else:
         tasks = {"ar": RecognitionTask(HIDDEN, HIDDEN, heads).to(dev), "lta": LTATask(HIDDEN, HIDDEN, heads).to(dev),
                  "pnr": PNRTask(HIDDEN, HIDDEN).to(dev)}
@@ -219,10 +226,10 @@ def native_run(args, rank: int, world: int, local_rank: int):
         params += [p for p in graphone.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5, fused=True)
     sync = GradientAllReduce(params) if world > 1 else None
-    lta_edges = LTATemporalConnectivity(r=K_RADIUS + 0.5)
+    lta_edges = LTATemporalConnectivity(r=k_radius + 0.5)
 
     gen = syn.generator(SEED, 2, rank)                        # every rank draws its own shard of graphs
-    host = {t: syn.make_batch(t, args.videos, args.nodes, gen, band_k=K_RADIUS, pin=True) for t in task_names}
+    host = {t: syn.make_batch(t, args.videos, args.nodes, gen, band_k=k_radius, pin=True) for t in task_names}
     n_nodes = args.videos * args.nodes * len(task_names)
     h2d_bytes = sum(v.numel() * v.element_size() for b in host.values() for v in (b.x, b.pos, b.y, b.batch, b.ptr))
 
@@ -244,7 +251,7 @@ def native_run(args, rank: int, world: int, local_rank: int):
                 if t == "lta":
                     lta_edges(d)                               # band + star edges, on the device
                 else:
-                    d.band_k = K_RADIUS                        # unit-spaced pos: the band needs no edge_index
+                    d.band_k = k_radius                        # unit-spaced pos: the band needs no edge_index
         return out
 
     def upload(stream=None):
@@ -330,7 +337,7 @@ def native_run(args, rank: int, world: int, local_rank: int):
     # step i+1's inputs are uploaded on a copy stream (and its edges built on the device) while step i computes
     from egopack_b200.feed import DeviceFeeder
     from egopack_b200.models.transforms import RadiusGraph
-    feed_tf = {t: (lta_edges if t == "lta" else RadiusGraph(r=K_RADIUS + 0.5)) for t in task_names}
+    feed_tf = {t: (lta_edges if t == "lta" else RadiusGraph(r=k_radius + 0.5)) for t in task_names}
 
     def host_loader(n):
         for _ in range(n):
@@ -377,7 +384,7 @@ def native_run(args, rank: int, world: int, local_rank: int):
 
     # ---- launch-bound regime: the reference's own batch size (16 graphs/task), eager vs one CUDA graph per step ------
     small = None
-    if world == 1 and not c3:
+    if world == 1 and not c3 and not c4:
         try:
             import gc
             from egopack_b200.graphs import GraphedStep
@@ -388,7 +395,7 @@ def native_run(args, rank: int, world: int, local_rank: int):
             gc.collect()
             sv, sn = 16, 16
             sgen = syn.generator(SEED, 9, rank)
-            shost = {t: syn.make_batch(t, sv, sn, sgen, band_k=K_RADIUS) for t in task_names}
+            shost = {t: syn.make_batch(t, sv, sn, sgen, band_k=k_radius) for t in task_names}
             sdev = {}
             for t, hb in shost.items():
                 d = egopack_b200.Batch()
@@ -397,7 +404,7 @@ def native_run(args, rank: int, world: int, local_rank: int):
                 if t == "lta":
                     lta_edges(d)
                 else:
-                    d.band_k = K_RADIUS
+                    d.band_k = k_radius
                 sdev[t] = d
             opt2 = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5, fused=True, capturable=True)
 
@@ -496,6 +503,9 @@ def native_run(args, rank: int, world: int, local_rank: int):
         "config": {"workload": ("c3: EgoPack OSCC primary + frozen AR/LTA/PNR prototype backpack (k=4, depth 3, residual, "
                                 f"{args.protos} prototypes/bank, late fusion), Graph trainable, full train step"
                                 if c3 else
+                                "c4: long-video stress (BASELINE configs[3]): AR over 2048-segment graphs, temporal radius 16 "
+                                "(33-wide band), 4 GNN layers, hidden 1024, full train step"
+                                if c4 else
                                 "c2: MTL AR+LTA+PNR shared temporal GNN (experiments/mtl.yaml: k=1, hidden 1024, depth 3, "
                                 "TRN hidden 1024, dropout 0.5), full train step = zero_grad+fwd+loss+bwd+grad-allreduce+Adam"),
                    "graphs_per_task_per_gpu": args.videos, "nodes_per_graph": args.nodes,
