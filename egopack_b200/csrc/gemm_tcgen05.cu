@@ -260,7 +260,7 @@ struct TcParams {
   int tma_store;       // epilogue stages 32x128B boxes in smem and stores them with TMA (coalesced, clipped)
   int topk;            // TOPK kernels: candidates kept per row (8 or 16); 0 otherwise
   int32_t* cand;       // TOPK kernels: [M, TOPK] column indices of the largest entries of each row (unordered)
-  int debug;           // EGP_TC_DEBUG (timing experiments) bit 0: skip the stores, bit 1: skip the TMEM loads too, bit 2: all CTAs load tile (0,0)
+  int debug;           // EGP_TC_DEBUG (timing experiments) bit 0: skip the stores, bit 1: skip the TMEM loads too, bit 2: all CTAs load tile (0,0), bit 3: skip the B loads of odd k-blocks
   uint32_t idesc;
 };
 
@@ -365,7 +365,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         split_range(split, kb_b, kb_e);
         for (int kb = kb_b; kb < kb_e; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
-          if (leader) mbar_expect_tx(&full[stage], CG * Cfg::kStageBytes);
+          const bool skip_b = (p.debug & 8) && (kb & 1);   // timing experiment: 25 % less operand traffic (stale B)
+          if (leader) mbar_expect_tx(&full[stage], CG * (skip_b ? Cfg::kABytes : Cfg::kStageBytes));
           const uint32_t full_bar = CG == 2 ? mapa_u32(smem_u32(&full[stage]), 0u) : smem_u32(&full[stage]);
           const bool second = kb >= p.kb1;
           const CUtensorMap* ma = second ? &mapA2 : &mapA;
@@ -380,7 +381,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int a = 0; a < TBM / 64; ++a)                       // box {64 m, 64 k} per MN atom
               tma_load_2d<CG>(ma, full_bar, sa + a * (TBK * 128), m0 + a * 64, k0);
           }
-          if (!B_MN) {
+          if (skip_b) {
+          } else if (!B_MN) {
             tma_load_2d<CG>(mb, full_bar, sb, k0, n0);               // box {64 k, BN / CG rows}
           } else {
 #pragma unroll
@@ -807,6 +809,8 @@ static int tc_launch_inst(const CUtensorMap* maps, const TcParams& p, int work, 
         set_error("tc_gemm: no CTA pair of the cta_group::2 kernel fits on this device");
         return EGP_ERR_UNSUPPORTED;
       }
+      // timing experiment: run on fewer SMs (is the kernel bound per SM, or by a chip-wide L2 limit?)
+      if (const char* e = getenv("EGP_TC_MAX_CLUSTERS")) { const int lim = atoi(e); if (lim >= 1 && lim < max_clusters) max_clusters = lim; }
     }
     attr_set = true;
   }
