@@ -187,8 +187,15 @@ sage_mean_band_reg_kernel(const T* __restrict__ x, T* __restrict__ out, int n, i
 // read + one write of the tensor while no shared-memory ring limits occupancy.  The 3*U loads of U consecutive
 // output rows are issued together.  At a graph boundary (or strip start) the sum restarts from scratch, so no
 // cancellation residue survives a graph.
+// Software-pipelined: the 3*U loads of the NEXT group of U rows are in flight while the current group is summed
+// and stored, so a thread keeps loads outstanding all the time and a few CTAs per SM saturate HBM.  That matters
+// because the combined windows of all RESIDENT threads ((2k+1) rows x 16 B each) must stay in L2 for the leaving / own
+// rows to be re-read from there instead of DRAM: strips are strided over a grid of kBandRunCtasPerSm CTAs per SM
+// (148 x 3 x 128 threads x 33 rows x 16 B = 30 MB at radius 16; with every strip resident it was 78 MB, L2 hit rate 2 %,
+// every row read from DRAM three times).
+constexpr int kBandRunCtasPerSm = 3;
 template <typename T, int U>
-__global__ void __launch_bounds__(kAggThreads, 8)
+__global__ void __launch_bounds__(kAggThreads, kBandRunCtasPerSm)
 sage_mean_band_run_kernel(const T* __restrict__ x, T* __restrict__ out, int n, int64_t channels, int64_t ldx,
                           int64_t ldo, int rows_per_cta, int k, const int32_t* __restrict__ win_lo,
                           const int32_t* __restrict__ win_hi, const float* __restrict__ scale_out,
@@ -197,78 +204,87 @@ sage_mean_band_run_kernel(const T* __restrict__ x, T* __restrict__ out, int n, i
   constexpr int VN = Vec<T>::N;
   const int64_t col = ((int64_t)blockIdx.y * kAggThreads + threadIdx.x) * VN;
   if (col >= channels) return;
-  const int r0 = blockIdx.x * rows_per_cta;
-  const int r1 = min(r0 + rows_per_cta, n);
-  if (r0 >= r1) return;
   const T* xc = x + col;
-  float acc[VN];
+  struct Group {  // speculative loads for U rows: entering (i+k), leaving (i-k-1), self (i); clamped, applied under masks
+    Raw<T> en[U], lv[U], sf[U];
+    int lo[U], hi[U];
+  };
+  auto load_group = [&](Group& q, int g, int r1) {
 #pragma unroll
-  for (int c = 0; c < VN; ++c) acc[c] = 0.f;
-  int plo = 0, phi = -1;  // window currently summed in acc: [plo, phi] (empty)
+    for (int u = 0; u < U; ++u) {
+      const int i = min(g + u, r1 - 1);
+      q.lo[u] = win_lo[i];
+      q.hi[u] = win_hi[i];
+      q.en[u] = Raw<T>::load(xc + (int64_t)min(i + k, n - 1) * ldx);
+      q.lv[u] = Raw<T>::load(xc + (int64_t)max(i - k - 1, 0) * ldx);
+      q.sf[u] = Raw<T>::load(xc + (int64_t)i * ldx);
+    }
+  };
+  float acc[VN];
   auto add_row = [&](int j, float sign) {
     const Vec<T> v = Vec<T>::load(xc + (int64_t)j * ldx);
     const float s = sign * (scale_in ? scale_in[j] : 1.f);
 #pragma unroll
     for (int c = 0; c < VN; ++c) acc[c] += s * v.v[c];
   };
+  const int stride = (int)gridDim.x * rows_per_cta;
+  int r0 = (int)blockIdx.x * rows_per_cta;
+  if (r0 >= n) return;
+  Group cur, nxt;
+  load_group(cur, r0, min(r0 + rows_per_cta, n));
 #pragma unroll 1
-  for (int g = r0; g < r1; g += U) {
-    // speculative loads for U rows: entering (i+k), leaving (i-k-1), self (i); clamped, applied under masks
-    Raw<T> en[U], lv[U], sf[U];
-    int lo[U], hi[U];
+  for (; r0 < n; r0 += stride) {
+    const int r1 = min(r0 + rows_per_cta, n);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = min(g + u, r1 - 1);
-      lo[u] = win_lo[i];
-      hi[u] = win_hi[i];
-      en[u] = Raw<T>::load(xc + (int64_t)min(i + k, n - 1) * ldx);
-      lv[u] = Raw<T>::load(xc + (int64_t)max(i - k - 1, 0) * ldx);
-      sf[u] = Raw<T>::load(xc + (int64_t)i * ldx);
-    }
+    for (int c = 0; c < VN; ++c) acc[c] = 0.f;
+    int plo = 0, phi = -1;  // window currently summed in acc: [plo, phi] (empty)
+#pragma unroll 1
+    for (int g = r0; g < r1; g += U) {
+      // next group: the following rows of this strip, or the first rows of this CTA's next strip
+      if (g + U < r1) load_group(nxt, g + U, r1);
+      else if (r0 + stride < n) load_group(nxt, r0 + stride, min(r0 + stride + rows_per_cta, n));
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = g + u;
-      if (i < r1) {
-        if (lo[u] > phi || phi < plo) {  // new graph / strip start: rebuild the window sum
+      for (int u = 0; u < U; ++u) {
+        const int i = g + u;
+        if (i < r1) {
+          const int lo = cur.lo[u], hi = cur.hi[u];
+          if (lo > phi || phi < plo) {  // new graph / strip start: rebuild the window sum
 #pragma unroll
-          for (int c = 0; c < VN; ++c) acc[c] = 0.f;
-          for (int j = lo[u]; j <= hi[u]; ++j) add_row(j, 1.f);
-        } else {
-          if (hi[u] == phi + 1 && hi[u] == i + k) {  // the common case: one row enters ...
-            const Vec<T> v = en[u].unpack();
-            const float s = scale_in ? scale_in[hi[u]] : 1.f;
-#pragma unroll
-            for (int c = 0; c < VN; ++c) acc[c] += s * v.v[c];
+            for (int c = 0; c < VN; ++c) acc[c] = 0.f;
+            for (int j = lo; j <= hi; ++j) add_row(j, 1.f);
           } else {
-            for (int j = phi + 1; j <= hi[u]; ++j) add_row(j, 1.f);
-          }
-          if (lo[u] == plo + 1 && plo == i - k - 1) {  // ... and one row leaves
-            const Vec<T> v = lv[u].unpack();
-            const float s = scale_in ? scale_in[plo] : 1.f;
+            if (hi == phi + 1 && hi == i + k) {  // the common case: one row enters ...
+              const Vec<T> v = cur.en[u].unpack();
+              const float s = scale_in ? scale_in[hi] : 1.f;
 #pragma unroll
-            for (int c = 0; c < VN; ++c) acc[c] -= s * v.v[c];
-          } else {
-            for (int j = plo; j < lo[u]; ++j) add_row(j, -1.f);
-          }
-        }
-        plo = lo[u];
-        phi = hi[u];
-        const Vec<T> self = sf[u].unpack();
-        const float ss = scale_in ? scale_in[i] : 1.f;
-        const float so = scale_out ? scale_out[i] : 1.f;
-        Vec<T> res;
+              for (int c = 0; c < VN; ++c) acc[c] += s * v.v[c];
+            } else {
+              for (int j = phi + 1; j <= hi; ++j) add_row(j, 1.f);
+            }
+            if (lo == plo + 1 && plo == i - k - 1) {  // ... and one row leaves
+              const Vec<T> v = cur.lv[u].unpack();
+              const float s = scale_in ? scale_in[plo] : 1.f;
 #pragma unroll
-        for (int c = 0; c < VN; ++c) res.v[c] = (acc[c] - ss * self.v[c]) * so;
-        // streaming store: the output must not push the window rows (re-read up to 2k+1 rows later) out of L2.
-        // ncu at 524 288 nodes: with plain stores the leaving / own rows missed L2 (hit rate 2 %) and every row was
-        // read from DRAM three times; with streaming stores radius 8 runs 0.99 -> 0.71 ms (radius 16's combined
-        // windows, 78 MB over the resident CTAs, still overflow L2)
-        {
+              for (int c = 0; c < VN; ++c) acc[c] -= s * v.v[c];
+            } else {
+              for (int j = plo; j < lo; ++j) add_row(j, -1.f);
+            }
+          }
+          plo = lo;
+          phi = hi;
+          const Vec<T> self = cur.sf[u].unpack();
+          const float ss = scale_in ? scale_in[i] : 1.f;
+          const float so = scale_out ? scale_out[i] : 1.f;
+          Vec<T> res;
+#pragma unroll
+          for (int c = 0; c < VN; ++c) res.v[c] = (acc[c] - ss * self.v[c]) * so;
+          // streaming store: the output must not push the window rows out of L2 either
           T tmp[VN];
           res.store(tmp);
           __stcs(reinterpret_cast<uint4*>(out + (int64_t)i * ldo + col), *reinterpret_cast<const uint4*>(tmp));
         }
       }
+      cur = nxt;
     }
   }
 }
@@ -402,11 +418,18 @@ static int launch_band_run(const void* x, void* out, int64_t n, int64_t channels
                            cudaStream_t stream) {
   constexpr int VN = Vec<T>::N, U = 4;
   const unsigned gy = (unsigned)ceil_div(channels, (int64_t)kAggThreads * VN);
-  int64_t rows = (n * gy) / ((int64_t)sm_count() * 16);
+  static const int per_sm_env = [] { const char* e = getenv("EGP_BAND_RUN_CTAS"); return e ? atoi(e) : 0; }();
+  const int per_sm = per_sm_env > 0 && per_sm_env < kBandRunCtasPerSm ? per_sm_env : kBandRunCtasPerSm;
+  const int64_t cap = ceil_div((int64_t)sm_count() * per_sm, (int64_t)gy);   // resident CTAs along the row dimension
+  // strips: as long as possible (every strip start rebuilds a 2k+1-row window sum) while every resident CTA gets the
+  // same number of them -- one strip each unless that would exceed 2048 rows
   const int64_t min_rows = 2 * (2 * k + 1);                    // restart (2k+1 rows, L2 hits) <= half a strip's loads
-  rows = rows < min_rows ? min_rows : (rows > 2048 ? 2048 : rows);
+  const int64_t waves = ceil_div(n, cap * 2048);
+  int64_t rows = ceil_div(n, cap * waves);
+  rows = rows < min_rows ? min_rows : rows;
   rows = (rows + U - 1) / U * U;
-  dim3 grid((unsigned)ceil_div(n, rows), gy);
+  const int64_t strips = ceil_div(n, rows);
+  dim3 grid((unsigned)(strips < cap ? strips : cap), gy);
   (void)launch_kernel(sage_mean_band_run_kernel<T, U>, grid, kAggThreads, 0, stream, (const T*)x, (T*)out, (int)n, channels, ldx, ldo,
                                                                     (int)rows, k, win_lo, win_hi, scale_out, scale_in);
   EGP_LAUNCH_CHECK();
