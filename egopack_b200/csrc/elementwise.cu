@@ -213,32 +213,43 @@ colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, int64
     if (col + c < cols) part[(size_t)blockIdx.x * cols + col + c] = acc[c];
 }
 
-// out[c] = sum_g part[g][c]; block = 32 columns x 32 part-groups (1024 threads), 4 loads in flight per thread,
-// fixed summation order (deterministic)
+// out[c] = sum_g part[g][c]; a block owns kFinalCols columns and splits the part rows over 1024 / kFinalCols groups
+// (latency-bound: few serial iterations per thread, ~128 CTAs for 1024 columns), combined in a fixed order
+// (deterministic): shuffles inside a warp, shared memory across warps
 constexpr int kFinalThreads = 1024;
+constexpr int kFinalCols = 8;
+constexpr int kFinalGroups = kFinalThreads / kFinalCols;
 __global__ void __launch_bounds__(kFinalThreads)
 colsum_final_kernel(const float* __restrict__ part, int parts, int64_t cols, float* __restrict__ out) {
   pdl_enter();
-  __shared__ float red[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int64_t c = (int64_t)blockIdx.x * 32 + tx;
+  __shared__ float red[32][kFinalCols];
+  const int tx = threadIdx.x % kFinalCols, ty = threadIdx.x / kFinalCols;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * kFinalCols + tx;
   float a = 0.f;
   if (c < cols) {
     int g = ty;
-    for (; g + 96 < parts; g += 128) {
-      const float v0 = part[(size_t)g * cols + c], v1 = part[(size_t)(g + 32) * cols + c];
-      const float v2 = part[(size_t)(g + 64) * cols + c], v3 = part[(size_t)(g + 96) * cols + c];
+    for (; g + 3 * kFinalGroups < parts; g += 4 * kFinalGroups) {
+      const float v0 = part[(size_t)g * cols + c], v1 = part[(size_t)(g + kFinalGroups) * cols + c];
+      const float v2 = part[(size_t)(g + 2 * kFinalGroups) * cols + c], v3 = part[(size_t)(g + 3 * kFinalGroups) * cols + c];
       a += (v0 + v1) + (v2 + v3);
     }
-    for (; g < parts; g += 32) a += part[(size_t)g * cols + c];
+    for (; g < parts; g += kFinalGroups) a += part[(size_t)g * cols + c];
   }
-  red[ty][tx] = a;
+#pragma unroll
+  for (int o = kFinalCols; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane < kFinalCols) red[warp][lane] = a;
   __syncthreads();
-  if (ty == 0 && c < cols) {
+  if (warp == 0) {
+    constexpr int kPer = 32 / (32 / kFinalCols);  // warp partials summed per lane
+    const int col = lane % kFinalCols, part0 = (lane / kFinalCols) * kPer;
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) t += red[i][tx];
-    out[c] = t;
+    for (int i = 0; i < kPer; ++i) t += red[part0 + i][col];
+#pragma unroll
+    for (int o = kFinalCols; o < 32; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    const int64_t cc = (int64_t)blockIdx.x * kFinalCols + col;
+    if (lane < kFinalCols && cc < cols) out[cc] = t;
   }
 }
 
@@ -335,7 +346,7 @@ int colsum_launch(const void* x, float* out, int64_t rows, int64_t cols, int64_t
     (void)launch_kernel(colsum_partial_kernel<T>, dim3(parts, gy), threads, 0, s, (const T*)x, rows, cols, ldx, rows_per, vec_ok, part);
     EGP_LAUNCH_CHECK();
   });
-  (void)launch_kernel(colsum_final_kernel, (unsigned)ceil_div(cols, 32), kFinalThreads, 0, s, part, parts, cols, out);
+  (void)launch_kernel(colsum_final_kernel, (unsigned)ceil_div(cols, kFinalCols), kFinalThreads, 0, s, part, parts, cols, out);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
 }
@@ -516,7 +527,7 @@ int egp_act_bwd_colsum(const void* dy, const void* y, void* dx, float* dx_colsum
     if (fuse) {
       (void)launch_kernel(act_bwd_colsum_kernel<T>, grid, kEwThreads, 0, s, (const T*)dy, (const T*)y, (T*)dx, nvec, (int)period, act, slope, part);
       EGP_LAUNCH_CHECK();
-      (void)launch_kernel(colsum_final_kernel, (unsigned)ceil_div(cols, 32), kFinalThreads, 0, s, part, grid, cols, dx_colsum);
+      (void)launch_kernel(colsum_final_kernel, (unsigned)ceil_div(cols, kFinalCols), kFinalThreads, 0, s, part, grid, cols, dx_colsum);
       EGP_LAUNCH_CHECK();
     } else {
       (void)launch_kernel(act_bwd_kernel<T>, grid, kEwThreads, 0, s, (const T*)dy, (const T*)y, (T*)dx, nvec, act, slope);

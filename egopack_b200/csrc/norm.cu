@@ -210,49 +210,63 @@ gln_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const f
   }
 }
 
-// Deterministic reduction of per-CTA column partials.  colpart is [parts][nout][channels]; block = 32 columns x 32
-// part-groups (1024 threads, 4 loads in flight each): out_k[c] = sum_g colpart[g][k][c].
+// Deterministic reduction of per-CTA column partials.  colpart is [parts][nout][channels]; a block owns kFinCols
+// columns and splits the part rows over 1024 / kFinCols groups (few serial iterations per thread, ~128 CTAs for 1024
+// channels: the kernel is pure latency), then combines the groups in a fixed order: shuffles inside a warp, shared
+// memory across warps.  out_k[c] = sum_g colpart[g][k][c].
 // The extra block `colblocks` (if scal != null) reduces the scalar pairs: scal[0..1] = sum scalpart.
 constexpr int kFinThreads = 1024;
+constexpr int kFinCols = 8;                       // columns per block: 32-byte segments of a partial row
+constexpr int kFinGroups = kFinThreads / kFinCols;
 __global__ void __launch_bounds__(kFinThreads)
 col_finalize_kernel(const float* __restrict__ colpart, int parts, int64_t channels, int nout, float* __restrict__ out0,
                     float* __restrict__ out1, float* __restrict__ out2, const double* __restrict__ scalpart,
                     int scal_parts, double* __restrict__ scal, int colblocks) {
   pdl_enter();
   __shared__ double red[32];
-  __shared__ float rs[3][32][33];
+  __shared__ float rs[3][32][kFinCols];
   if ((int)blockIdx.x < colblocks) {
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int64_t c = (int64_t)blockIdx.x * 32 + tx;
+    const int tx = threadIdx.x % kFinCols, ty = threadIdx.x / kFinCols;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t c = (int64_t)blockIdx.x * kFinCols + tx;
     float a[3] = {0.f, 0.f, 0.f};
     if (c < channels) {
       const size_t stride = (size_t)nout * channels;
       int g = ty;
-      for (; g + 96 < parts; g += 128) {
+      for (; g + 3 * kFinGroups < parts; g += 4 * kFinGroups) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           if (k < nout) {
             const float* p = colpart + (size_t)k * channels + c;
-            const float v0 = p[(size_t)g * stride], v1 = p[(size_t)(g + 32) * stride];
-            const float v2 = p[(size_t)(g + 64) * stride], v3 = p[(size_t)(g + 96) * stride];
+            const float v0 = p[(size_t)g * stride], v1 = p[(size_t)(g + kFinGroups) * stride];
+            const float v2 = p[(size_t)(g + 2 * kFinGroups) * stride], v3 = p[(size_t)(g + 3 * kFinGroups) * stride];
             a[k] += (v0 + v1) + (v2 + v3);
           }
         }
       }
-      for (; g < parts; g += 32)
+      for (; g < parts; g += kFinGroups)
 #pragma unroll
         for (int k = 0; k < 3; ++k)
           if (k < nout) a[k] += colpart[(size_t)g * stride + (size_t)k * channels + c];
     }
+    // a warp holds 32 / kFinCols consecutive groups of the same kFinCols columns
 #pragma unroll
-    for (int k = 0; k < 3; ++k) rs[k][ty][tx] = a[k];
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int o = kFinCols; o < 32; o <<= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+      if (lane < kFinCols) rs[k][warp][lane] = a[k];
+    }
     __syncthreads();
-    if (ty < 3 && ty < nout && c < channels) {
+    if (warp < 3 && warp < nout) {  // warp k finishes output k: lane = (quarter of the 32 warp partials, column)
+      const int col = lane % kFinCols, part0 = (lane / kFinCols) * (32 / (32 / kFinCols));
       float t = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) t += rs[ty][i][tx];
-      float* o = ty == 0 ? out0 : (ty == 1 ? out1 : out2);
-      if (o) o[c] = t;
+      for (int i = 0; i < 32 / (32 / kFinCols); ++i) t += rs[warp][part0 + i][col];
+#pragma unroll
+      for (int o = kFinCols; o < 32; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      const int64_t cc = (int64_t)blockIdx.x * kFinCols + col;
+      float* o = warp == 0 ? out0 : (warp == 1 ? out1 : out2);
+      if (lane < kFinCols && cc < channels && o) o[cc] = t;
     }
   } else {
     double s1 = 0.0, s2 = 0.0;
@@ -786,7 +800,7 @@ int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, 
     (void)launch_kernel(gln_bwd_reduce_kernel<T>, dim3(parts, gy), rthreads, 0, s, 
         (const T*)dy, (const T*)x, weight, bias, stats, n, channels, rows_per, eps, act, slope, colpart, scalpart);
     EGP_LAUNCH_CHECK();
-    const int colblocks = (int)ceil_div(channels, 32);
+    const int colblocks = (int)ceil_div(channels, kFinCols);
     (void)launch_kernel(col_finalize_kernel, colblocks + 1, kFinThreads, 0, s, colpart, parts, channels, 2, dweight, dbias, nullptr,
                                                               scalpart, parts * gy, ws->scal, colblocks);
     EGP_LAUNCH_CHECK();
@@ -925,7 +939,7 @@ int egp_row_layernorm_bwd(const void* dy, const void* x, const void* y, const fl
     }
     EGP_LAUNCH_CHECK();
   });
-  const int colblocks = (int)ceil_div(channels, 32);
+  const int colblocks = (int)ceil_div(channels, kFinCols);
   (void)launch_kernel(col_finalize_kernel, colblocks, kFinThreads, 0, s, colpart, grid, channels, nout, dweight, dbias,
                                                         nout == 3 ? dx_colsum : nullptr, nullptr, 0, nullptr, colblocks);
   EGP_LAUNCH_CHECK();
