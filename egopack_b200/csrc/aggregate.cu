@@ -9,115 +9,17 @@
 // ever touches its own 16-byte column, so no block barrier is needed.
 //   radius <= 4 : the 2k+1-row window is held in registers (sage_mean_band_reg_kernel), summed in ascending
 //                 neighbour order (bit-identical to a sequential scatter_add);
-//   radius  > 4 : a running window sum adds the entering row and subtracts the leaving row; both variants exist:
-//                 register-resident (sage_mean_band_run_kernel, default: entering row from HBM, leaving/self rows
-//                 from L1/L2) and a cp.async shared-memory ring (sage_mean_band_kernel, EGP_BAND_IMPL=3), which
-//                 measured slower on B200 because the ring caps occupancy at 1-2 CTAs per SM.
+//   radius  > 4 : a running window sum adds the entering row (from HBM) and subtracts the leaving row (re-read from
+//                 L2), software-pipelined over few resident CTAs per SM (sage_mean_band_run_kernel).  Variants that
+//                 measured slower and were removed: a cp.async shared-memory ring (occupancy 1-2 CTAs per SM, 3.5 ms
+//                 at 524 288 nodes against 0.56 ms) and one thread per output vector with L1 re-reads.
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace egp {
 
-__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
-  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
 constexpr int kAggThreads = 128;
-
-template <typename T>
-__device__ __forceinline__ Vec<T> ring_load(const uint4* ring, int slot) {
-  return Vec<T>::load(reinterpret_cast<const T*>(ring + (size_t)slot * kAggThreads + threadIdx.x));
-}
-
-// P = prefetch distance in rows (compile time so cp.async.wait_group gets an immediate)
-template <typename T, int P, bool SLIDING>
-__global__ void __launch_bounds__(kAggThreads)
-sage_mean_band_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n, int64_t channels, int64_t ldx,
-                      int64_t ldo, int rows_per_cta, int ring_rows, const int32_t* __restrict__ win_lo,
-                      const int32_t* __restrict__ win_hi, const float* __restrict__ scale_out,
-                      const float* __restrict__ scale_in) {
-  pdl_enter();
-  extern __shared__ uint4 ring[];
-  constexpr int VN = Vec<T>::N;
-  const int64_t col = ((int64_t)blockIdx.y * kAggThreads + threadIdx.x) * VN;
-  if (col >= channels) return;  // no block-level barrier below: safe to drop out
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
-  const int64_t r1 = min(r0 + rows_per_cta, n);
-  if (r0 >= r1) return;
-
-  const T* xc = x + col;
-  int64_t issued = (int64_t)win_lo[r0] - 1;  // last row whose copy has been issued
-  auto issue_upto = [&](int64_t last) {
-    for (int64_t j = issued + 1; j <= last; ++j)
-      cp_async_16(ring + (size_t)((int)j % ring_rows) * kAggThreads + threadIdx.x, xc + j * ldx);
-    if (last > issued) issued = last;
-  };
-#pragma unroll 1
-  for (int p = 0; p < P; ++p) {
-    if (r0 + p < r1) issue_upto(win_hi[r0 + p]);
-    cp_async_commit();
-  }
-
-  Vec<T> acc;
-#pragma unroll
-  for (int c = 0; c < VN; ++c) acc.v[c] = 0.f;
-  int64_t cl = win_lo[r0], ch = cl - 1;  // rows currently summed in acc (SLIDING only)
-
-#pragma unroll 1
-  for (int64_t i = r0; i < r1; ++i) {
-    if (i + P < r1) issue_upto(win_hi[i + P]);
-    cp_async_commit();
-    cp_async_wait<P>();  // everything but the newest P groups has landed => rows <= win_hi[i] are in the ring
-    const int64_t lo = win_lo[i], hi = win_hi[i];
-    Vec<T> res;
-    if (!SLIDING) {
-#pragma unroll
-      for (int c = 0; c < VN; ++c) res.v[c] = 0.f;
-      for (int64_t j = lo; j <= hi; ++j) {
-        if (j == i) continue;
-        const Vec<T> v = ring_load<T>(ring, ((int)j % ring_rows));
-        const float s = scale_in ? scale_in[j] : 1.f;
-#pragma unroll
-        for (int c = 0; c < VN; ++c) res.v[c] += s * v.v[c];
-      }
-    } else {
-      if (lo > ch) {  // window left the previous graph entirely: restart (no cancellation residue)
-#pragma unroll
-        for (int c = 0; c < VN; ++c) acc.v[c] = 0.f;
-        cl = lo;
-        ch = lo - 1;
-      }
-      while (ch < hi) {
-        ++ch;
-        const Vec<T> v = ring_load<T>(ring, ((int)ch % ring_rows));
-        const float s = scale_in ? scale_in[ch] : 1.f;
-#pragma unroll
-        for (int c = 0; c < VN; ++c) acc.v[c] += s * v.v[c];
-      }
-      while (cl < lo) {
-        const Vec<T> v = ring_load<T>(ring, ((int)cl % ring_rows));
-        const float s = scale_in ? scale_in[cl] : 1.f;
-#pragma unroll
-        for (int c = 0; c < VN; ++c) acc.v[c] -= s * v.v[c];
-        ++cl;
-      }
-      const Vec<T> self = ring_load<T>(ring, ((int)i % ring_rows));
-      const float s = scale_in ? scale_in[i] : 1.f;
-#pragma unroll
-      for (int c = 0; c < VN; ++c) res.v[c] = acc.v[c] - s * self.v[c];
-    }
-    const float so = scale_out ? scale_out[i] : 1.f;
-#pragma unroll
-    for (int c = 0; c < VN; ++c) res.v[c] *= so;
-    res.store(out + i * ldo + col);
-  }
-  cp_async_wait<0>();
-}
 
 // Small radii (K <= 4): the sliding window lives in REGISTERS.  A thread owns one 16-byte column of a strip of
 // consecutive rows; every row is loaded exactly once (U independent loads in flight per thread), unpacked,
@@ -289,46 +191,6 @@ sage_mean_band_run_kernel(const T* __restrict__ x, T* __restrict__ out, int n, i
   }
 }
 
-// Alternative for small radii: one thread per output vector, neighbours re-read through L1/L2 (a CTA covers
-// ROWS consecutive rows so most neighbour rows are L1 hits).  No sequential dependence at all.
-template <typename T, int K, int ROWS>
-__global__ void __launch_bounds__(kAggThreads * ROWS)
-sage_mean_band_flat_kernel(const T* __restrict__ x, T* __restrict__ out, int n, int64_t channels, int64_t ldx,
-                           int64_t ldo, const int32_t* __restrict__ win_lo, const int32_t* __restrict__ win_hi,
-                           const float* __restrict__ scale_out, const float* __restrict__ scale_in) {
-  pdl_enter();
-  constexpr int VN = Vec<T>::N;
-  const int64_t col = ((int64_t)blockIdx.y * kAggThreads + (threadIdx.x % kAggThreads)) * VN;
-  const int i = blockIdx.x * ROWS + threadIdx.x / kAggThreads;
-  if (col >= channels || i >= n) return;
-  const int lo = win_lo[i], hi = win_hi[i];
-  const T* xc = x + col;
-  Vec<T> v[2 * K];
-  float sc[2 * K];
-#pragma unroll
-  for (int d = 0; d < 2 * K; ++d) {
-    const int j = i - K + d + (d >= K ? 1 : 0);
-    const bool ok = j >= lo && j <= hi;
-    sc[d] = ok ? (scale_in ? scale_in[j] : 1.f) : 0.f;
-    if (ok) v[d] = Vec<T>::load(xc + (int64_t)j * ldx);
-    else {
-#pragma unroll
-      for (int c = 0; c < VN; ++c) v[d].v[c] = 0.f;
-    }
-  }
-  Vec<T> acc;
-#pragma unroll
-  for (int c = 0; c < VN; ++c) acc.v[c] = 0.f;
-#pragma unroll
-  for (int d = 0; d < 2 * K; ++d)
-#pragma unroll
-    for (int c = 0; c < VN; ++c) acc.v[c] += sc[d] * v[d].v[c];
-  const float so = scale_out ? scale_out[i] : 1.f;
-#pragma unroll
-  for (int c = 0; c < VN; ++c) acc.v[c] *= so;
-  acc.store(out + (int64_t)i * ldo + col);
-}
-
 template <typename T>
 __global__ void __launch_bounds__(kAggThreads)
 sage_mean_csr_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n, int64_t channels, int64_t ldx,
@@ -376,26 +238,6 @@ sage_mean_csr_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n, in
   }
 }
 
-template <typename T, int P, bool SLIDING>
-static int launch_band(const void* x, void* out, int64_t n, int64_t channels, int64_t ldx, int64_t ldo, int k,
-                       const int32_t* win_lo, const int32_t* win_hi, const float* scale_out,
-                       const float* scale_in, cudaStream_t stream) {
-  constexpr int VN = Vec<T>::N;
-  const int ring_rows = P + 2 * k + 2;
-  const size_t smem = (size_t)ring_rows * kAggThreads * sizeof(uint4);
-  const unsigned gy = (unsigned)ceil_div(channels, (int64_t)kAggThreads * VN);
-  int64_t rows = (n * gy) / ((int64_t)sm_count() * 8);
-  rows = rows < 4 * P ? 4 * P : rows;
-  rows = rows > 1024 ? 1024 : rows;
-  auto kern = sage_mean_band_kernel<T, P, SLIDING>;
-  if (smem > 48 * 1024) EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div(n, rows), gy);
-  (void)launch_kernel(kern, grid, kAggThreads, smem, stream, (const T*)x, (T*)out, n, channels, ldx, ldo, (int)rows, ring_rows,
-                                            win_lo, win_hi, scale_out, scale_in);
-  EGP_LAUNCH_CHECK();
-  return EGP_OK;
-}
-
 template <typename T, int K, int U>
 static int launch_band_reg(const void* x, void* out, int64_t n, int64_t channels, int64_t ldx, int64_t ldo,
                            const int32_t* win_lo, const int32_t* win_hi, const float* scale_out, const float* scale_in,
@@ -436,19 +278,6 @@ static int launch_band_run(const void* x, void* out, int64_t n, int64_t channels
   return EGP_OK;
 }
 
-template <typename T, int K>
-static int launch_band_flat(const void* x, void* out, int64_t n, int64_t channels, int64_t ldx, int64_t ldo,
-                            const int32_t* win_lo, const int32_t* win_hi, const float* scale_out, const float* scale_in,
-                            cudaStream_t stream) {
-  constexpr int VN = Vec<T>::N, ROWS = 4;
-  const unsigned gy = (unsigned)ceil_div(channels, (int64_t)kAggThreads * VN);
-  dim3 grid((unsigned)ceil_div(n, ROWS), gy);
-  (void)launch_kernel(sage_mean_band_flat_kernel<T, K, ROWS>, grid, kAggThreads * ROWS, 0, stream, 
-      (const T*)x, (T*)out, (int)n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in);
-  EGP_LAUNCH_CHECK();
-  return EGP_OK;
-}
-
 }  // namespace egp
 
 using namespace egp;
@@ -466,17 +295,11 @@ int egp_sage_mean_band(const void* x, void* out, int64_t n, int64_t channels, in
   if (n == 0 || channels == 0) return EGP_OK;
   cudaStream_t s = (cudaStream_t)stream;
   EGP_DISPATCH_DTYPE(dtype, T, {
-    static const int impl = [] { const char* e = getenv("EGP_BAND_IMPL"); return e ? atoi(e) : 0; }();
-    if (impl == 1 && k <= 1) return launch_band_flat<T, 1>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
-    if (impl == 1 && k == 2) return launch_band_flat<T, 2>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
-    if (impl == 2 && k <= 4) return launch_band<T, 8, false>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
     if (k <= 1) return launch_band_reg<T, 1, 8>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
     if (k == 2) return launch_band_reg<T, 2, 8>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
     if (k == 3) return launch_band_reg<T, 3, 4>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
     if (k == 4) return launch_band_reg<T, 4, 4>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
-    if (impl != 3) return launch_band_run<T>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
-    if (k <= 12) return launch_band<T, 16, true>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
-    return launch_band<T, 32, true>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
+    return launch_band_run<T>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
   });
   return EGP_OK;
 }
