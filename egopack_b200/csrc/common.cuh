@@ -39,6 +39,8 @@ void set_error(const char* fmt, ...);
     }                                                                                        \
   } while (0)
 
+constexpr int kMaxDevices = 64;
+int current_device();  // cudaGetDevice(), clamped to [0, kMaxDevices): index for per-device one-time state
 int sm_count();
 bool pdl_enabled();   // EGP_PDL=0 turns programmatic dependent launch off (abi.cu)
 

@@ -192,21 +192,28 @@ __global__ void band_windows_kernel(const int64_t* __restrict__ batch, const int
 // ---------------------------------------------------------------------------------------------------------
 // CSR build
 // ---------------------------------------------------------------------------------------------------------
-__global__ void csr_count_kernel(const int64_t* __restrict__ key, int64_t e_count, int32_t* __restrict__ deg) {
+// Edges whose endpoints fall outside [0, n) are dropped (count and fill apply the same test), so a malformed
+// edge_index can never index the CSR arrays out of bounds.
+__global__ void csr_count_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t e_count,
+                                 int64_t n, int32_t* __restrict__ deg) {
   pdl_enter();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < e_count) atomicAdd(&deg[key[e]], 1);
+  if (e >= e_count) return;
+  const int64_t r = key[e], c = val[e];
+  if (r < 0 || r >= n || c < 0 || c >= n) return;
+  atomicAdd(&deg[r], 1);
 }
 
 __global__ void csr_fill_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t e_count,
-                                const int32_t* __restrict__ rowptr, int32_t* __restrict__ cursor,
+                                int64_t n, const int32_t* __restrict__ rowptr, int32_t* __restrict__ cursor,
                                 int32_t* __restrict__ col) {
   pdl_enter();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= e_count) return;
-  const int64_t r = key[e];
+  const int64_t r = key[e], c = val[e];
+  if (r < 0 || r >= n || c < 0 || c >= n) return;
   const int slot = atomicAdd(&cursor[r], 1);
-  col[rowptr[r] + slot] = (int32_t)val[e];
+  col[rowptr[r] + slot] = (int32_t)c;
 }
 
 __global__ void csr_sort_rows_kernel(const int32_t* __restrict__ rowptr, int64_t n, int32_t* __restrict__ col) {
@@ -317,14 +324,14 @@ int egp_csr_build(const int64_t* edge_index, int64_t num_edges, int64_t n, int g
   const int64_t* val = group_by_dst ? edge_index : edge_index + num_edges;
   if (n > 0) EGP_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * n, s));
   if (num_edges > 0) {
-    (void)launch_kernel(csr_count_kernel, (unsigned)ceil_div(num_edges, 256), 256, 0, s, key, num_edges, cursor);
+    (void)launch_kernel(csr_count_kernel, (unsigned)ceil_div(num_edges, 256), 256, 0, s, key, val, num_edges, n, cursor);
     EGP_LAUNCH_CHECK();
   }
   (void)launch_kernel(exclusive_scan_kernel<int32_t>, 1, 1024, 0, s, cursor, n, rowptr);
   EGP_LAUNCH_CHECK();
   if (num_edges > 0) {
     EGP_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * n, s));
-    (void)launch_kernel(csr_fill_kernel, (unsigned)ceil_div(num_edges, 256), 256, 0, s, key, val, num_edges, rowptr, cursor, col);
+    (void)launch_kernel(csr_fill_kernel, (unsigned)ceil_div(num_edges, 256), 256, 0, s, key, val, num_edges, n, rowptr, cursor, col);
     EGP_LAUNCH_CHECK();
     (void)launch_kernel(csr_sort_rows_kernel, (unsigned)ceil_div(n, 128), 128, 0, s, rowptr, n, col);
     EGP_LAUNCH_CHECK();

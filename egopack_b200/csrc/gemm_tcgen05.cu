@@ -793,8 +793,15 @@ template <int BN, bool A_MN, bool B_MN, typename OutT, int CG>
 static int tc_launch_inst(const CUtensorMap* maps, const TcParams& p, int work, cudaStream_t stream) {
   auto kern = tc_gemm_kernel<BN, A_MN, B_MN, OutT, 0, CG>;
   constexpr int kSmem = TcCfg<BN, CG>::kSmemBytes;
-  static bool attr_set = false;
-  static int max_clusters = 0;
+  // cudaFuncSetAttribute is per DEVICE: a process that drives several GPUs (or a feeder thread racing the training
+  // thread) must set it once on each of them
+  static std::mutex attr_mu;
+  static bool attr_done[kMaxDevices] = {};
+  static int max_clusters_dev[kMaxDevices] = {};
+  const int dev = current_device();
+  std::unique_lock<std::mutex> attr_lock(attr_mu);
+  bool& attr_set = attr_done[dev];
+  int& max_clusters = max_clusters_dev[dev];
   if (!attr_set) {
     EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     if (CG == 2) {
@@ -814,8 +821,10 @@ static int tc_launch_inst(const CUtensorMap* maps, const TcParams& p, int work, 
     }
     attr_set = true;
   }
+  const int max_clusters_now = max_clusters;
+  attr_lock.unlock();
   if constexpr (CG == 2) {
-    const int clusters = work < max_clusters ? work : max_clusters;
+    const int clusters = work < max_clusters_now ? work : max_clusters_now;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -951,10 +960,15 @@ template <int KEEP>
 static int tc_gemm_topk_inst(const CUtensorMap* maps, const TcParams& p, int grid, cudaStream_t stream) {
   constexpr int BN = 256;
   auto kern = tc_gemm_kernel<BN, false, false, float, KEEP>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes));
-    attr_set = true;
+  static std::mutex attr_mu;
+  static bool attr_done[kMaxDevices] = {};
+  {
+    std::lock_guard<std::mutex> lock(attr_mu);
+    bool& attr_set = attr_done[current_device()];
+    if (!attr_set) {
+      EGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes));
+      attr_set = true;
+    }
   }
   (void)launch_kernel(kern, grid, TC_THREADS_TOPK, TcCfg<BN>::kSmemBytes, stream, maps[0], maps[1], maps[2], maps[3], maps[4], maps[4], p);
   EGP_LAUNCH_CHECK();

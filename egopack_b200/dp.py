@@ -28,6 +28,7 @@ class _Bucket:
         self.pending = len(params)
         self.flat: Optional[torch.Tensor] = None
         self.work = None
+        self.ready = False
 
 
 class GradientAllReduce:
@@ -55,6 +56,9 @@ class GradientAllReduce:
         self._owner = {}
         self._handles = []
         self._avg = False
+        self._next = 0                                        # buckets launch in index order on EVERY rank
+        self._enabled = True
+        self._seen = set()                                    # parameters whose gradient arrived in this step
         if overlap and self.world > 1:
             for b in self.buckets:
                 for p in b.params:
@@ -70,19 +74,43 @@ class GradientAllReduce:
         b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
 
     def _on_grad(self, p):
+        if not self._enabled:                                 # inside no_sync(): gradients only accumulate locally
+            return
         b = self._owner[p]
+        if b.work is not None or p in self._seen:
+            raise RuntimeError("GradientAllReduce: a gradient arrived after its bucket was reduced -- more than one "
+                               "backward per finish(); wrap the earlier micro-batches in `with sync.no_sync():`")
+        self._seen.add(p)
         b.pending -= 1
         if b.pending == 0:
-            self._launch(b)
+            b.ready = True
+            # a bucket is launched only after every earlier bucket: the collective order is then the bucket order on
+            # all ranks, whatever order the hooks fire in (and whichever parameters a rank leaves unused)
+            while self._next < len(self.buckets) and self.buckets[self._next].ready:
+                self._launch(self.buckets[self._next])
+                self._next += 1
+
+    def no_sync(self):
+        """Context manager for gradient accumulation: backward passes inside it do not start the all-reduce; the first
+        backward outside it reduces the accumulated gradients."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            old, self._enabled = self._enabled, False
+            try:
+                yield
+            finally:
+                self._enabled = old
+        return ctx()
 
     def finish(self):
         """Wait for every bucket; afterwards every ``p.grad`` IS its slice of the averaged bucket (a view: no copy-back
         kernels; ``zero_grad(set_to_none=True)`` drops the views before the next backward)."""
         if self.world == 1:
             return
-        for b in self.buckets:
-            if b.work is None:                                # params without a hook firing (unused / no overlap)
-                self._launch(b)
+        for b in self.buckets[self._next:]:                   # not launched from a hook (unused params / no overlap):
+            self._launch(b)                                   # still in bucket order
         for b in self.buckets:
             b.work.wait()
             if not self._avg:
@@ -92,7 +120,9 @@ class GradientAllReduce:
                 n = p.numel()
                 p.grad = b.flat[off:off + n].view_as(p)
                 off += n
-            b.pending, b.flat, b.work = len(b.params), None, None
+            b.pending, b.flat, b.work, b.ready = len(b.params), None, None, False
+        self._next = 0
+        self._seen.clear()
 
     def remove(self):
         for h in self._handles:

@@ -57,4 +57,8 @@ class GraphedStep:
                     if k in ("x", "y", "pos"):
                         cur.copy_(src, non_blocking=True)
         self.graph.replay()
+        # the replayed optimizer kernels changed the parameters on the device, but no Python version counter moved:
+        # invalidate every cache derived from them (bf16 weight copies, normalised prototype banks) for eager code
+        # that runs between replays (periodic validation)
+        ops.bump_param_generation()
         return self.loss

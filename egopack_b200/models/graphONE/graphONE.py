@@ -76,7 +76,7 @@ class GraphONE(nn.Module):
     def _bank(self, task: str):
         w = self.embeddings[task].weight
         cd = config.compute_dtype()
-        key = (w.data_ptr(), w._version, cd)
+        key = (w.data_ptr(), w._version, ops.param_generation(), cd)
         hit = self._bank_cache.get(task)
         if hit is None or hit[0] != key:
             wd = w.detach()

@@ -53,13 +53,22 @@ def _c(t: Optional[Tensor]) -> Optional[Tensor]:
     return None if t is None else (t if t.is_contiguous() else t.contiguous())
 
 
+def _i64(t: Tensor, name: str) -> Tensor:
+    """Index tensors cross the C ABI as raw ``int64_t*`` (the reference's layout for pos / batch / ptr / edge_index /
+    labels): anything else would be reinterpreted, so it is refused here instead of read out of bounds there."""
+    if t.dtype != torch.int64:
+        raise TypeError(f"{name} must be int64 (torch.long), got {t.dtype}; convert with .long() "
+                        "(float positions as in plain PyG are not accepted by the band kernels)")
+    return _c(t)
+
+
 # =====================================================================================================
 # graph structure
 # =====================================================================================================
 def band_edge_index(pos: Tensor, batch: Tensor, ptr: Tensor, r: float, max_num_neighbors: int = 32,
                     monotone: Optional[bool] = None) -> Tensor:
     """``RadiusGraph(r, loop=False)`` over a batch of graphs: int64 [2,E], dst-major, src ascending."""
-    pos, batch, ptr = _c(pos.view(-1)), _c(batch), _c(ptr)
+    pos, batch, ptr = _i64(pos.view(-1), "pos"), _i64(batch, "batch"), _i64(ptr, "ptr")
     n = pos.numel()
     if n == 0:
         return torch.empty((2, 0), dtype=torch.int64, device=pos.device)
@@ -79,7 +88,7 @@ def band_edge_index(pos: Tensor, batch: Tensor, ptr: Tensor, r: float, max_num_n
 
 def lta_edge_index(pos: Tensor, y: Tensor, batch: Tensor, ptr: Tensor, r: float, max_num_neighbors: int = 32) -> Tensor:
     """``LTATemporalConnectivity(r)`` applied per graph of a batch: int64 [2,E] sorted by (src,dst)."""
-    pos, y, batch, ptr = _c(pos.view(-1)), _c(y), _c(batch), _c(ptr)
+    pos, y, batch, ptr = _i64(pos.view(-1), "pos"), _i64(y, "y"), _i64(batch, "batch"), _i64(ptr, "ptr")
     n = pos.numel()
     if n == 0:
         return torch.empty((2, 0), dtype=torch.int64, device=pos.device)
@@ -116,12 +125,15 @@ def band_structure(batch: Tensor, ptr: Tensor, k: int) -> GraphStructure:
     lo = torch.empty(n, dtype=torch.int32, device=dev)
     hi = torch.empty(n, dtype=torch.int32, device=dev)
     inv = torch.empty(n, dtype=torch.float32, device=dev)
-    L.call("egp_band_windows", L.ptr(_c(batch)), L.ptr(_c(ptr)), n, int(k), L.ptr(lo), L.ptr(hi), L.ptr(inv), L.stream())
+    L.call("egp_band_windows", L.ptr(_i64(batch, "batch")), L.ptr(_i64(ptr, "ptr")), n, int(k), L.ptr(lo), L.ptr(hi),
+           L.ptr(inv), L.stream())
     return GraphStructure(n=n, band_k=int(k), win_lo=lo, win_hi=hi, inv_deg=inv)
 
 
 def csr_structure(edge_index: Tensor, n: int) -> GraphStructure:
-    edge_index = _c(edge_index)
+    edge_index = _i64(edge_index, "edge_index")
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise ValueError(f"edge_index must be [2, E], got {tuple(edge_index.shape)}")
     e = edge_index.shape[1]
     dev = edge_index.device
     out = GraphStructure(n=n)
@@ -308,8 +320,24 @@ def _dropout_stream() -> Tuple[int, int]:
     return int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF, _dropout_calls
 
 
+# Bumped whenever parameters may have changed WITHOUT their Python version counters moving: a CUDA-graph replay
+# runs the captured optimizer kernels on the device only (egopack_b200.graphs.GraphedStep.__call__).  Every cache of
+# values derived from parameters (bf16 weight copies here, normalised prototype banks in GraphONE) keys on it.
+_param_generation = 0
+
+
+def param_generation() -> int:
+    return _param_generation
+
+
+def bump_param_generation() -> None:
+    global _param_generation
+    _param_generation += 1
+
+
 class _WeightCache:
-    """bf16 copies of fp32 parameters, refreshed when the parameter is updated in place (optimizer step).
+    """bf16 copies of fp32 parameters, refreshed when the parameter is updated in place (optimizer step: the tensor's
+    version counter moves) or by a CUDA-graph replay (``param_generation`` moves).
 
     Entries are keyed by storage address but validated through a weak reference to the source tensor, so a new
     parameter that happens to reuse a freed address can never pick up a stale copy."""
@@ -326,14 +354,14 @@ class _WeightCache:
         hit = self._store.get(key)
         if hit is not None:
             src = hit[0]()
-            if src is not None and src.data_ptr() == w.data_ptr() and hit[1] == w._version:
+            if src is not None and src.data_ptr() == w.data_ptr() and hit[1] == (w._version, _param_generation):
                 return hit[2]
         c = cast(w.detach(), dtype)
         if pad_rows:
             c = torch.cat([c, c.new_zeros((pad_rows - w.shape[0], w.shape[1]))], 0)
         if len(self._store) > 4096:
             self._store = {k: v for k, v in self._store.items() if v[0]() is not None}
-        self._store[key] = (weakref.ref(w), w._version, c)
+        self._store[key] = (weakref.ref(w), (w._version, _param_generation), c)
         return c
 
 
@@ -449,9 +477,12 @@ class RowLayerNorm(torch.autograd.Function):
         mean = torch.empty(n, dtype=torch.float32, device=x.device)
         rstd = torch.empty(n, dtype=torch.float32, device=x.device)
         seed, offset = _dropout_stream() if dropout_p > 0 else (0, 0)
+        rng = RNG_STATE if dropout_p > 0 else None
+        # eager: the full 64-bit call counter (never repeats); under CUDA-graph capture the per-step part comes from the
+        # device-side state (added as step << 20), so only the call-site index inside a step is passed here
+        offset = (offset & 0xFFFFF) if rng is not None else (offset & 0xFFFFFFFFFFFFFFFF)
         L.call("egp_row_layernorm_fwd", L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(mean), L.ptr(rstd), n, c,
-               float(eps), act, float(dropout_p), seed, offset & 0xFFFFF, L.ptr(RNG_STATE) if dropout_p > 0 else None,
-               _code(x), L.stream())
+               float(eps), act, float(dropout_p), seed, offset, L.ptr(rng), _code(x), L.stream())
         need_y = act == ACT_RELU or dropout_p > 0
         ctx.save_for_backward(x, y if need_y else None, w, mean, rstd)
         ctx.act, ctx.out_scale = act, (1.0 / (1.0 - dropout_p) if dropout_p > 0 else 1.0)
@@ -516,7 +547,8 @@ class PosEncAdd(torch.autograd.Function):
         x = _c(x)
         n, c = x.shape
         out = torch.empty_like(x)
-        L.call("egp_posenc_add", L.ptr(x), L.ptr(_c(pos.view(-1))), L.ptr(_c(freq)), L.ptr(out), n, c, _code(x), L.stream())
+        L.call("egp_posenc_add", L.ptr(x), L.ptr(_i64(pos.view(-1), "pos")), L.ptr(_c(freq)), L.ptr(out), n, c, _code(x),
+               L.stream())
         return out
 
     @staticmethod
@@ -587,8 +619,9 @@ class SegmentMaxPool(torch.autograd.Function):
         g, c = ptr.numel() - 1, x.shape[1]
         out = torch.empty((g, c), dtype=x.dtype, device=x.device)
         arg = torch.empty((g, c), dtype=torch.int32, device=x.device)
-        L.call("egp_segment_max_pool_fwd", L.ptr(x), L.ptr(_c(ptr)), L.ptr(out), L.ptr(arg), g, c, _code(x), L.stream())
-        ctx.save_for_backward(arg, _c(batch))
+        L.call("egp_segment_max_pool_fwd", L.ptr(x), L.ptr(_i64(ptr, "ptr")), L.ptr(out), L.ptr(arg), g, c, _code(x),
+               L.stream())
+        ctx.save_for_backward(arg, _i64(batch, "batch"))
         ctx.n = x.shape[0]
         return out
 
@@ -646,14 +679,14 @@ class ProtoMaxCombine(torch.autograd.Function):
         dbank = None
         if ctx.needs_input_grad[1]:
             dbank = torch.zeros(ctx.bank_shape, dtype=torch.float32, device=f.device)
-            L.call("egp_proto_max_scatter_bwd", L.ptr(da), L.ptr(f), L.ptr(bank_cd), L.ptr(_c(idx)), L.ptr(dbank),
+            L.call("egp_proto_max_scatter_bwd", L.ptr(da), L.ptr(f), L.ptr(bank_cd), L.ptr(_i64(idx, "idx")), L.ptr(dbank),
                    f.shape[0], idx.shape[1], f.shape[1], _code(f), L.stream())
         return df, dbank, None, None
 
 
 def class_sum_f64(x: Tensor, labels: Tensor, num_classes: int, out: Optional[Tensor] = None) -> Tensor:
     """out[label[i]] += x[i] in fp64 (rows with label < 0 are skipped)."""
-    x, labels = _c(x), _c(labels)
+    x, labels = _c(x), _i64(labels, "labels")
     if out is None:
         out = torch.zeros((num_classes, x.shape[1]), dtype=torch.float64, device=x.device)
     L.call("egp_class_sum_f64", L.ptr(x), L.ptr(labels), L.ptr(out), x.shape[0], x.shape[1], num_classes, _code(x), L.stream())
@@ -680,7 +713,7 @@ def label_rank(logits: Tensor, labels: Tensor, ignore_index: int = -1) -> Tensor
 
 def segment_argmax(values: Tensor, ptr: Tensor, apply_sigmoid: bool = False) -> Tensor:
     """int64 [G]: first arg-max of (sigmoid of) values inside every graph [ptr[g], ptr[g+1]), relative to ptr[g]."""
-    values, ptr = _c(values.detach().float()), _c(ptr)
+    values, ptr = _c(values.detach().float()), _i64(ptr, "ptr")
     out = torch.empty(ptr.shape[0] - 1, dtype=torch.int64, device=values.device)
     if out.shape[0]:
         L.call("egp_segment_argmax", L.ptr(values), L.ptr(ptr), out.shape[0], int(apply_sigmoid), L.ptr(out), L.stream())
@@ -720,7 +753,7 @@ def cos_topk(fn: Tensor, pn: Tensor, k: int, fn16: Optional[Tensor] = None, pn16
 
 
 def proto_max_gather(bank: Tensor, idx: Tensor) -> Tensor:
-    bank, idx = _c(bank), _c(idx)
+    bank, idx = _c(bank), _i64(idx, "idx")
     b, k = idx.shape
     c = bank.shape[1]
     m = torch.empty((b, c), dtype=bank.dtype, device=bank.device)

@@ -74,3 +74,46 @@ def test_graphed_step_matches_eager():
         assert torch.allclose(p, q, atol=1e-2, rtol=2e-2)
     moved = sum(float((p - q0).abs().max()) for p, q0 in zip(params, _build(0)[2]))
     assert moved > 1e-3, "replays must apply optimizer updates"
+
+
+def test_eager_eval_between_replays_sees_updated_weights():
+    """a CUDA-graph replay updates the parameters on the device without moving their Python version
+    counters, so the bf16 weight cache must be invalidated by the replay itself -- otherwise a periodic validation
+    forward keeps running on the weights of the FIRST validation."""
+    egopack_b200.set_precision("bf16")
+    model, tasks, params, opt = _build(0)
+    opt = torch.optim.Adam(params, lr=5e-2, capturable=True)           # large steps: stale weights are unmistakable
+
+    def step(b):
+        opt.zero_grad(set_to_none=True)
+        loss, _ = steps.mtl_losses(model, tasks, b)
+        loss.backward()
+        opt.step()
+        return loss
+
+    runner = GraphedStep(step, _batches(1), warmup=2)
+    probe = _batches(7)["ar"]
+
+    def eager_eval():
+        model.eval()
+        with torch.no_grad():
+            out = model(probe).float()
+        model.train()
+        return out
+
+    def fp32_eval():                                                  # same forward, weights read fresh in fp32
+        with egopack_b200.precision("fp32"):
+            return eager_eval()
+
+    for seed in (2, 3):
+        for _ in range(3):
+            runner(_batches(seed))
+        got, want = eager_eval(), fp32_eval()
+        err = float((got - want).abs().max() / want.abs().max())
+        assert err <= 3e-2, (seed, err)
+    # and the two validations really saw different weights
+    a = eager_eval()
+    for _ in range(3):
+        runner(_batches(5))
+    b = eager_eval()
+    assert float((a - b).abs().max()) > 1e-3

@@ -109,3 +109,28 @@ def test_device_feeder_preserves_order_structure_and_errors():
         raise ValueError("loader failed")
     with pytest.raises(ValueError, match="loader failed"):
         list(DeviceFeeder(broken(), "cpu"))
+
+
+def test_index_dtype_is_validated_before_the_c_abi():
+    """index tensors cross the C ABI as raw int64_t*; any other dtype must be refused on the host
+    (a float32 pos or an int32 batch would otherwise be read out of bounds on the device)."""
+    import pytest
+    from egopack_b200 import ops
+    pos = torch.arange(6, dtype=torch.float32)
+    batch = torch.zeros(6, dtype=torch.int64)
+    ptr = torch.tensor([0, 6])
+    with pytest.raises(TypeError):
+        ops.band_edge_index(pos, batch, ptr, 1.5)
+    with pytest.raises(TypeError):
+        ops.band_structure(batch.int(), ptr, 1)
+    with pytest.raises(TypeError):
+        ops.csr_structure(torch.zeros((2, 3), dtype=torch.int32), 6)
+    with pytest.raises(TypeError):
+        ops.lta_edge_index(pos.long(), torch.zeros((6, 2), dtype=torch.int32), batch, ptr, 1.5)
+
+
+def test_weight_cache_keys_on_param_generation():
+    from egopack_b200 import ops
+    g0 = ops.param_generation()
+    ops.bump_param_generation()
+    assert ops.param_generation() == g0 + 1
