@@ -28,9 +28,13 @@ SIGNATURES: Dict[str, tuple] = {
     "egp_lta_edge_count": (I, [P, P, I64, P, P, I64, F, I, P, P]),
     "egp_lta_edge_fill": (I, [P, P, I64, P, P, I64, F, I, P, I64, P, P]),
     "egp_band_windows": (I, [P, P, I64, I, P, P, P, P]),
+    "egp_lta_star_counts": (I, [P, I64, P, I64, F, P, P]),
+    "egp_band_star_windows": (I, [P, P, I64, I64, I, P, I64, I64, P, P, P, P, P, P, P, P]),
     "egp_csr_build": (I, [P, I64, I64, I, P, P, P, P]),
     "egp_csr_inv_degree": (I, [P, I64, P, P]),
     "egp_sage_mean_band": (I, [P, P, I64, I64, I64, I64, I, P, P, P, P, I, P]),
+    "egp_sage_mean_band_star_workspace": (SZ, [I64, I64, I64]),
+    "egp_sage_mean_band_star": (I, [P, P, I64, I64, I64, I64, I, P, P, P, P, P, P, P, P, I64, I, P, SZ, P]),
     "egp_sage_mean_csr": (I, [P, P, I64, I64, I64, I64, P, P, P, P, I, P]),
     "egp_graph_layernorm_workspace": (SZ, [I64, I64]),
     "egp_graph_layernorm_fwd": (I, [P, P, P, P, P, I64, I64, F, I, F, I, P, SZ, P]),
@@ -63,6 +67,11 @@ SIGNATURES: Dict[str, tuple] = {
     "egp_max_combine_bwd": (I, [P, P, P, P, I64, I, P]),
     "egp_segment_max_pool_fwd": (I, [P, P, P, P, I64, I64, I, P]),
     "egp_segment_max_pool_bwd": (I, [P, P, P, P, I64, I64, I, P]),
+    "egp_ce_loss_fwd": (I, [P, I64, P, I64, I64, I64, I64, F, P, I, P, P]),
+    "egp_ce_loss_bwd": (I, [P, I64, P, P, I64, P, I64, I64, I64, I64, F, P, I64, I, P]),
+    "egp_bce_logits_fwd": (I, [P, P, P, I64, P]),
+    "egp_bce_logits_bwd": (I, [P, P, P, I64, P, I64, P]),
+    "egp_weighted_mean": (I, [P, I64, F, P, I, P]),
     "egp_label_rank": (I, [P, I64, P, I64, I64, I64, I64, P, P]),
     "egp_segment_argmax": (I, [P, P, I64, I, P, P]),
     "egp_edit_distance_min": (I, [P, P, I64, I64, I64, P, P]),
@@ -122,12 +131,14 @@ CALL_COUNTS: Dict[str, int] = {}
 KERNELS_PER_CALL = {
     "egp_band_edge_count": 1, "egp_band_edge_fill": 1, "egp_exclusive_scan_i32": 1, "egp_lta_edge_count": 1,
     "egp_lta_edge_fill": 1, "egp_band_windows": 1, "egp_csr_build": 4, "egp_csr_inv_degree": 1,
-    "egp_sage_mean_band": 1, "egp_sage_mean_csr": 1, "egp_graph_layernorm_fwd": 2, "egp_graph_layernorm_bwd": 4,
+    "egp_sage_mean_band": 1, "egp_sage_mean_csr": 1, "egp_lta_star_counts": 1, "egp_band_star_windows": 1,
+    "egp_sage_mean_band_star": 1,   # +1 fix-up launch in the backward direction (counted in ops._aggregate_launch) "egp_graph_layernorm_fwd": 2, "egp_graph_layernorm_bwd": 4,
     "egp_row_layernorm_fwd": 1, "egp_row_layernorm_bwd": 2, "egp_posenc_add": 1, "egp_cast": 1, "egp_add": 1,
     "egp_axpby": 1, "egp_act_bwd": 1, "egp_act_bwd_colsum": 2, "egp_colsum": 2, "egp_mask_scale": 1, "egp_gemm": 1, "egp_row_normalize": 1,
     "egp_row_inv_norm": 1, "egp_cos_topk": 3, "egp_proto_max_gather": 1, "egp_max_combine_fwd": 1,
     "egp_max_combine_bwd": 1, "egp_segment_max_pool_fwd": 1, "egp_segment_max_pool_bwd": 1,
     "egp_label_rank": 1, "egp_segment_argmax": 1, "egp_edit_distance_min": 1,
+    "egp_ce_loss_fwd": 1, "egp_ce_loss_bwd": 1, "egp_bce_logits_fwd": 1, "egp_bce_logits_bwd": 1, "egp_weighted_mean": 1,
 }
 
 

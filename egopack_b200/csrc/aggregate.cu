@@ -25,15 +25,41 @@ constexpr int kAggThreads = 128;
 // consecutive rows; every row is loaded exactly once (U independent loads in flight per thread), unpacked,
 // optionally pre-scaled, and then reused by the 2K neighbouring outputs straight from registers.  All window
 // indices are compile-time constants (the loops are fully unrolled), so nothing spills to local memory.
-template <typename T, int K, int U>
-__global__ void __launch_bounds__(kAggThreads, 8)
+//
+// MODE selects the star extension used by LTA graphs (band + "last input clips -> every forecast clip", see
+// band_star_windows_kernel in edges.cu):
+//   kBandPlain : pure band.
+//   kBandExt   : forward direction.  A star target also sums the few source rows outside its band, [ext_lo, ext_hi)
+//                (at most K rows, the same ones for every target of a graph: L1/L2 hits).
+//   kBandHub   : backward direction.  A star source receives from ~every row of its graph; instead of a 125-row gather
+//                in one thread, every thread adds the (scaled) rows it streams anyway to a per-graph hub sum when they
+//                are star targets, and flushes that partial once per (strip, graph) to hub_part[strip + graph]
+//                (a unique, monotone index).  sage_hub_fixup_kernel then rewrites the <= K source rows of each graph
+//                from the partials in a fixed order -- deterministic, and the tensor is still read exactly once.
+enum { kBandPlain = 0, kBandExt = 1, kBandHub = 2 };
+
+template <typename T, int K, int U, int MODE>
+__global__ void __launch_bounds__(kAggThreads, MODE == kBandHub ? 6 : 8)
 sage_mean_band_reg_kernel(const T* __restrict__ x, T* __restrict__ out, int n, int64_t channels, int64_t ldx,
                           int64_t ldo, int rows_per_cta, const int32_t* __restrict__ win_lo,
                           const int32_t* __restrict__ win_hi, const float* __restrict__ scale_out,
-                          const float* __restrict__ scale_in) {
+                          const float* __restrict__ scale_in, const int32_t* __restrict__ ext_lo,
+                          const int32_t* __restrict__ ext_hi, const int32_t* __restrict__ hub_slot,
+                          float* __restrict__ hub_part) {
   pdl_enter();
   constexpr int VN = Vec<T>::N;
   constexpr int W = 2 * K + U;
+  float hub[MODE == kBandHub ? VN : 1];
+  int cur_slot = -1;
+  auto hub_flush = [&](int64_t col_) {
+    if constexpr (MODE == kBandHub) {
+      if (cur_slot >= 0) {
+        float* hp = hub_part + ((int64_t)blockIdx.x + cur_slot) * channels + col_;
+#pragma unroll
+        for (int c = 0; c < VN; c += 4) *reinterpret_cast<float4*>(hp + c) = make_float4(hub[c], hub[c + 1], hub[c + 2], hub[c + 3]);
+      }
+    }
+  };
   const int64_t col = ((int64_t)blockIdx.y * kAggThreads + threadIdx.x) * VN;
   if (col >= channels) return;
   const int r0 = blockIdx.x * rows_per_cta;
@@ -72,6 +98,30 @@ sage_mean_band_reg_kernel(const T* __restrict__ x, T* __restrict__ out, int n, i
             for (int c = 0; c < VN; ++c) acc.v[c] += s * v.v[c];
           }
         }
+        if constexpr (MODE == kBandExt) {
+          const int el = ext_lo[i], eh = ext_hi[i];
+          for (int j = el; j < eh; ++j) {
+            const Vec<T> v = Vec<T>::load(xc + (int64_t)j * ldx);
+            const float s = scale_in ? scale_in[j] : 1.f;
+#pragma unroll
+            for (int c = 0; c < VN; ++c) acc.v[c] += s * v.v[c];
+          }
+        }
+        if constexpr (MODE == kBandHub) {
+          const int slot = hub_slot[i];
+          if (slot != cur_slot) {
+            hub_flush(col);
+            cur_slot = slot;
+#pragma unroll
+            for (int c = 0; c < VN; ++c) hub[c] = 0.f;
+          }
+          if (slot >= 0) {
+            const Vec<T> v = w[u + K].unpack();   // the row itself
+            const float s = scale_in ? scale_in[i] : 1.f;
+#pragma unroll
+            for (int c = 0; c < VN; ++c) hub[c] += s * v.v[c];
+          }
+        }
         const float so = scale_out ? scale_out[i] : 1.f;
 #pragma unroll
         for (int c = 0; c < VN; ++c) acc.v[c] *= so;
@@ -80,6 +130,53 @@ sage_mean_band_reg_kernel(const T* __restrict__ x, T* __restrict__ out, int n, i
     }
 #pragma unroll
     for (int d = 0; d < 2 * K; ++d) w[d] = w[d + U];
+  }
+  hub_flush(col);
+}
+
+// Rewrites the star-source rows of every graph after a kBandHub pass: out[s] = s_out(s) * (sum of the band neighbours
+// of s that are NOT star targets + the graph's hub sum).  grid (graphs, column chunks).
+template <typename T>
+__global__ void __launch_bounds__(kAggThreads)
+sage_hub_fixup_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t channels, int64_t ldx, int64_t ldo,
+                      int rows_per_cta, const int32_t* __restrict__ win_lo, const int32_t* __restrict__ win_hi,
+                      const float* __restrict__ scale_out, const float* __restrict__ scale_in,
+                      const int32_t* __restrict__ graph_meta, const float* __restrict__ hub_part) {
+  pdl_enter();
+  constexpr int VN = Vec<T>::N;
+  const int64_t col = ((int64_t)blockIdx.y * kAggThreads + threadIdx.x) * VN;
+  if (col >= channels) return;
+  const int g = blockIdx.x;
+  const int src_lo = graph_meta[4 * g], src_hi = graph_meta[4 * g + 1];
+  const int tgt_lo = graph_meta[4 * g + 2], tgt_hi = graph_meta[4 * g + 3];
+  if (src_lo >= src_hi || tgt_lo >= tgt_hi) return;
+  float h[VN];
+#pragma unroll
+  for (int c = 0; c < VN; ++c) h[c] = 0.f;
+  for (int strip = tgt_lo / rows_per_cta; strip <= (tgt_hi - 1) / rows_per_cta; ++strip) {   // fixed order
+    const float* hp = hub_part + ((int64_t)strip + g) * channels + col;
+#pragma unroll
+    for (int c = 0; c < VN; c += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(hp + c);
+      h[c] += t.x; h[c + 1] += t.y; h[c + 2] += t.z; h[c + 3] += t.w;
+    }
+  }
+  for (int s = src_lo; s < src_hi; ++s) {
+    Vec<T> acc;
+#pragma unroll
+    for (int c = 0; c < VN; ++c) acc.v[c] = 0.f;
+    const int lo = win_lo[s], hi = win_hi[s];
+    for (int j = lo; j <= hi; ++j) {
+      if (j == s || (j >= tgt_lo && j < tgt_hi)) continue;
+      const Vec<T> v = Vec<T>::load(x + (int64_t)j * ldx + col);
+      const float sj = scale_in ? scale_in[j] : 1.f;
+#pragma unroll
+      for (int c = 0; c < VN; ++c) acc.v[c] += sj * v.v[c];
+    }
+    const float so = scale_out ? scale_out[s] : 1.f;
+#pragma unroll
+    for (int c = 0; c < VN; ++c) acc.v[c] = (acc.v[c] + h[c]) * so;
+    acc.store(out + (int64_t)s * ldo + col);
   }
 }
 
@@ -238,18 +335,43 @@ sage_mean_csr_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n, in
   }
 }
 
+static int64_t band_reg_rows(int64_t n, int64_t gy, int U) {
+  int64_t rows = (n * gy) / ((int64_t)sm_count() * 16);      // ~2 waves of 8 CTAs per SM
+  rows = rows < 4 * U ? 4 * U : (rows > 512 ? 512 : rows);   // halo re-read <= 2K/(4U)
+  return (rows + U - 1) / U * U;
+}
+
+struct StarArgs {                 // all null for a plain band
+  const int32_t* ext_lo = nullptr;
+  const int32_t* ext_hi = nullptr;
+  const int32_t* hub_slot = nullptr;
+  const int32_t* graph_meta = nullptr;
+  int64_t num_graphs = 0;
+  float* hub_part = nullptr;      // [strips + num_graphs, channels]
+};
+
 template <typename T, int K, int U>
 static int launch_band_reg(const void* x, void* out, int64_t n, int64_t channels, int64_t ldx, int64_t ldo,
                            const int32_t* win_lo, const int32_t* win_hi, const float* scale_out, const float* scale_in,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, const StarArgs& st = StarArgs()) {
   constexpr int VN = Vec<T>::N;
   const unsigned gy = (unsigned)ceil_div(channels, (int64_t)kAggThreads * VN);
-  int64_t rows = (n * gy) / ((int64_t)sm_count() * 16);      // ~2 waves of 8 CTAs per SM
-  rows = rows < 4 * U ? 4 * U : (rows > 512 ? 512 : rows);   // halo re-read <= 2K/(4U)
-  rows = (rows + U - 1) / U * U;
+  const int64_t rows = band_reg_rows(n, gy, U);
   dim3 grid((unsigned)ceil_div(n, rows), gy);
-  (void)launch_kernel(sage_mean_band_reg_kernel<T, K, U>, grid, kAggThreads, 0, stream, (const T*)x, (T*)out, (int)n, channels, ldx, ldo,
-                                                                       (int)rows, win_lo, win_hi, scale_out, scale_in);
+#define EGP_BAND_ARGS (const T*)x, (T*)out, (int)n, channels, ldx, ldo, (int)rows, win_lo, win_hi, scale_out, scale_in, \
+                      st.ext_lo, st.ext_hi, st.hub_slot, st.hub_part
+  if (st.hub_slot) {
+    (void)launch_kernel(sage_mean_band_reg_kernel<T, K, U, kBandHub>, grid, kAggThreads, 0, stream, EGP_BAND_ARGS);
+    EGP_LAUNCH_CHECK();
+    (void)launch_kernel(sage_hub_fixup_kernel<T>, dim3((unsigned)st.num_graphs, gy), kAggThreads, 0, stream, (const T*)x, (T*)out,
+                        channels, ldx, ldo, (int)rows, win_lo, win_hi, scale_out, scale_in, st.graph_meta,
+                        (const float*)st.hub_part);
+  } else if (st.ext_lo) {
+    (void)launch_kernel(sage_mean_band_reg_kernel<T, K, U, kBandExt>, grid, kAggThreads, 0, stream, EGP_BAND_ARGS);
+  } else {
+    (void)launch_kernel(sage_mean_band_reg_kernel<T, K, U, kBandPlain>, grid, kAggThreads, 0, stream, EGP_BAND_ARGS);
+  }
+#undef EGP_BAND_ARGS
   EGP_LAUNCH_CHECK();
   return EGP_OK;
 }
@@ -300,6 +422,43 @@ int egp_sage_mean_band(const void* x, void* out, int64_t n, int64_t channels, in
     if (k == 3) return launch_band_reg<T, 3, 4>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
     if (k == 4) return launch_band_reg<T, 4, 4>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s);
     return launch_band_run<T>(x, out, n, channels, ldx, ldo, k, win_lo, win_hi, scale_out, scale_in, s);
+  });
+  return EGP_OK;
+}
+
+size_t egp_sage_mean_band_star_workspace(int64_t n, int64_t channels, int64_t num_graphs) {
+  // hub partials: one fp32 row per (strip, graph) pair; strips are at least 16 rows long
+  return sizeof(float) * (size_t)(ceil_div(n, 16) + num_graphs + 1) * (size_t)channels + 128;
+}
+
+int egp_sage_mean_band_star(const void* x, void* out, int64_t n, int64_t channels, int64_t ldx, int64_t ldo, int k,
+                            const int32_t* win_lo, const int32_t* win_hi, const float* scale_out,
+                            const float* scale_in, const int32_t* ext_lo, const int32_t* ext_hi,
+                            const int32_t* hub_slot, const int32_t* graph_meta, int64_t num_graphs, int dtype,
+                            void* workspace, size_t ws_bytes, void* stream) {
+  EGP_REQUIRE(x && out && win_lo && win_hi, "sage_mean_band_star: null pointer");
+  EGP_REQUIRE(k >= 0 && k <= 4, "sage_mean_band_star: radius %d out of range [0,4] (wider stars use the CSR path)", k);
+  EGP_REQUIRE((ext_lo && ext_hi && !hub_slot) || (hub_slot && graph_meta && !ext_lo && !ext_hi),
+              "sage_mean_band_star: pass either the forward extension (ext_lo/ext_hi) or the backward hub (hub_slot/graph_meta)");
+  const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(channels % vn == 0 && ldx % vn == 0 && ldo % vn == 0 && aligned16(x) && aligned16(out),
+              "sage_mean_band_star: channels/strides must keep rows 16-byte aligned");
+  if (n == 0 || channels == 0) return EGP_OK;
+  StarArgs st;
+  st.ext_lo = ext_lo; st.ext_hi = ext_hi; st.hub_slot = hub_slot; st.graph_meta = graph_meta; st.num_graphs = num_graphs;
+  if (hub_slot) {
+    if (!workspace || ws_bytes < egp_sage_mean_band_star_workspace(n, channels, num_graphs)) {
+      set_error("sage_mean_band_star: workspace too small");
+      return EGP_ERR_WORKSPACE;
+    }
+    st.hub_part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 15) & ~(uintptr_t)15);
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    if (k <= 1) return launch_band_reg<T, 1, 8>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s, st);
+    if (k == 2) return launch_band_reg<T, 2, 8>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s, st);
+    if (k == 3) return launch_band_reg<T, 3, 4>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s, st);
+    return launch_band_reg<T, 4, 4>(x, out, n, channels, ldx, ldo, win_lo, win_hi, scale_out, scale_in, s, st);
   });
   return EGP_OK;
 }

@@ -189,6 +189,92 @@ __global__ void band_windows_kernel(const int64_t* __restrict__ batch, const int
   inv_deg[i] = 1.0f / (float)(d > 1 ? d : 1);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// band + star structure (LTA graphs without materialising edge_index)
+// ---------------------------------------------------------------------------------------------------------
+// one warp per graph: n_in = #(y[:,0] == -1), n_fc = #(y[:,0] > 0), first_src = max(ceil(n_in - r), 0)
+// (lta_temp_connectivity.py:48-52; the `> 0` -- verb label 0 is not counted -- is the reference's)
+__global__ void lta_star_counts_kernel(const int64_t* __restrict__ y, int64_t y_cols, const int64_t* __restrict__ ptr,
+                                       int64_t num_graphs, float r, int32_t* __restrict__ star) {
+  pdl_enter();
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= num_graphs) return;
+  const int64_t lo = ptr[g], hi = ptr[g + 1];
+  int n_in = 0, n_fc = 0;
+  for (int64_t t = lo + lane; t < hi; t += 32) {
+    const int64_t v = y[t * y_cols];
+    n_in += (v == -1);
+    n_fc += (v > 0);
+  }
+  n_in = warp_sum(n_in);
+  n_fc = warp_sum(n_fc);
+  if (lane == 0) {
+    int first = (int)ceilf((float)n_in - r);
+    if (first < 0) first = 0;
+    star[3 * g + 0] = n_in;
+    star[3 * g + 1] = n_fc;
+    star[3 * g + 2] = first;
+  }
+}
+
+// Per node: band window [lo,hi] clipped to the graph, the forward extension (for a star TARGET t: the star sources that
+// are not already inside its band, a contiguous range [ext_lo, ext_hi)), the backward hub slot (for a star target of a
+// graph that has at least one source: the graph's global index; -1 otherwise) and 1/max(in-degree, 1).
+// Per graph: graph_meta = {src_lo, src_hi, tgt_lo, tgt_hi} (absolute rows; empty ranges without a star).
+// All row / graph indices written are GLOBAL (row_offset / graph_offset added) so that several task batches can be
+// laid out back to back in one structure (Graph.forward_many).
+__global__ void band_star_windows_kernel(const int64_t* __restrict__ batch, const int64_t* __restrict__ ptr, int64_t n,
+                                         int k, const int32_t* __restrict__ star, int64_t row_offset,
+                                         int64_t graph_offset, int32_t* __restrict__ win_lo,
+                                         int32_t* __restrict__ win_hi, float* __restrict__ inv_deg,
+                                         int32_t* __restrict__ ext_lo, int32_t* __restrict__ ext_hi,
+                                         int32_t* __restrict__ hub_slot, int32_t* __restrict__ graph_meta) {
+  pdl_enter();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t g = batch[i];
+  const int64_t g_lo = ptr[g], g_hi = ptr[g + 1];
+  const int64_t lo = max(i - k, g_lo);
+  const int64_t hi = min(i + k, g_hi - 1);
+  int deg = (int)(hi - lo);
+  int64_t src_lo = 0, src_hi = 0, tgt_lo = 0, tgt_hi = 0;
+  if (star) {
+    const int64_t n_in = star[3 * g], n_fc = star[3 * g + 1], first = star[3 * g + 2];
+    if (n_fc > 0 && n_in > first) {
+      src_lo = g_lo + first;
+      src_hi = g_lo + n_in;
+      tgt_lo = g_lo + n_in;
+      tgt_hi = min(g_lo + n_in + n_fc, g_hi);
+    }
+  }
+  int64_t el = 0, eh = 0;
+  int slot = -1;
+  if (i >= tgt_lo && i < tgt_hi) {          // star target: sources outside its band
+    el = src_lo;
+    eh = min(src_hi, i - k);
+    if (eh < el) eh = el;
+    deg += (int)(eh - el);
+    slot = (int)(g + graph_offset);
+  }
+  win_lo[i] = (int32_t)(lo + row_offset);
+  win_hi[i] = (int32_t)(hi + row_offset);
+  inv_deg[i] = 1.0f / (float)(deg > 1 ? deg : 1);
+  if (ext_lo) {
+    ext_lo[i] = (int32_t)(el + row_offset);
+    ext_hi[i] = (int32_t)(eh + row_offset);
+    hub_slot[i] = slot;
+    if (i == g_lo) {
+      int32_t* m = graph_meta + 4 * g;
+      m[0] = (int32_t)(src_lo + row_offset);
+      m[1] = (int32_t)(src_hi + row_offset);
+      m[2] = (int32_t)(tgt_lo + row_offset);
+      m[3] = (int32_t)(tgt_hi + row_offset);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // CSR build
 // ---------------------------------------------------------------------------------------------------------
@@ -310,6 +396,33 @@ int egp_band_windows(const int64_t* batch, const int64_t* ptr, int64_t n, int k,
   if (n == 0) return EGP_OK;
   (void)launch_kernel(band_windows_kernel, (unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream, batch, ptr, n, k, win_lo,
                                                                                     win_hi, inv_deg);
+  EGP_LAUNCH_CHECK();
+  return EGP_OK;
+}
+
+int egp_lta_star_counts(const int64_t* y, int64_t y_cols, const int64_t* ptr, int64_t num_graphs, float r,
+                        int32_t* star, void* stream) {
+  EGP_REQUIRE(y && ptr && star, "lta_star_counts: null pointer");
+  EGP_REQUIRE(y_cols >= 1 && r > 0.f, "lta_star_counts: bad arguments");
+  if (num_graphs == 0) return EGP_OK;
+  (void)launch_kernel(lta_star_counts_kernel, (unsigned)ceil_div(num_graphs * 32, 128), 128, 0, (cudaStream_t)stream, y, y_cols, ptr,
+                      num_graphs, r, star);
+  EGP_LAUNCH_CHECK();
+  return EGP_OK;
+}
+
+int egp_band_star_windows(const int64_t* batch, const int64_t* ptr, int64_t n, int64_t num_graphs, int k,
+                          const int32_t* star, int64_t row_offset, int64_t graph_offset, int32_t* win_lo,
+                          int32_t* win_hi, float* inv_deg, int32_t* ext_lo, int32_t* ext_hi, int32_t* hub_slot,
+                          int32_t* graph_meta, void* stream) {
+  EGP_REQUIRE(batch && ptr && win_lo && win_hi && inv_deg, "band_star_windows: null pointer");
+  EGP_REQUIRE((ext_lo && ext_hi && hub_slot && graph_meta) || (!ext_lo && !ext_hi && !hub_slot && !graph_meta && !star),
+              "band_star_windows: the star outputs come together (and are needed when a star descriptor is given)");
+  EGP_REQUIRE(k >= 0 && n + row_offset < (int64_t)INT32_MAX && num_graphs + graph_offset < (int64_t)INT32_MAX,
+              "band_star_windows: bad k or too many nodes");
+  if (n == 0) return EGP_OK;
+  (void)launch_kernel(band_star_windows_kernel, (unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream, batch, ptr, n, k, star,
+                      row_offset, graph_offset, win_lo, win_hi, inv_deg, ext_lo, ext_hi, hub_slot, graph_meta);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
 }

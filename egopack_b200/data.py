@@ -15,6 +15,7 @@ import torch
 class Data:
     def __init__(self, x=None, edge_index=None, edge_attr=None, y=None, pos=None, **kwargs):
         object.__setattr__(self, "_fields", {})
+        object.__setattr__(self, "_lazy", {})
         for k, v in dict(x=x, edge_index=edge_index, edge_attr=edge_attr, y=y, pos=pos, **kwargs).items():
             if v is not None:
                 self._fields[k] = v
@@ -24,19 +25,39 @@ class Data:
     def __getattr__(self, key: str) -> Any:
         if key.startswith("__"):
             raise AttributeError(key)
-        return object.__getattribute__(self, "_fields").get(key)
+        fields = object.__getattribute__(self, "_fields")
+        if key in fields:
+            return fields[key]
+        lazy = object.__getattribute__(self, "_lazy")
+        if key in lazy:                                      # materialise on first read, then it is a plain field
+            value = lazy.pop(key)(self)
+            if value is not None:
+                fields[key] = value
+            return value
+        return None
 
     def __setattr__(self, key: str, value: Any) -> None:
+        self._lazy.pop(key, None)
         if value is None:
             self._fields.pop(key, None)
         else:
             self._fields[key] = value
 
-    def __contains__(self, key: str) -> bool:
+    def set_lazy(self, key: str, producer) -> None:
+        """Register ``producer(data) -> value`` for an attribute that is expensive (or needs a host round trip) to build
+        and that the kernels do not read: our transforms use it for ``edge_index`` when the graph is a band (+ star) --
+        the aggregation kernels work from ``band_k`` / ``star``, so the int64 edge list is only built if someone asks."""
+        self._fields.pop(key, None)
+        self._lazy[key] = producer
+
+    def is_materialized(self, key: str) -> bool:
         return key in self._fields
 
+    def __contains__(self, key: str) -> bool:
+        return key in self._fields or key in self._lazy
+
     def keys(self) -> List[str]:
-        return list(self._fields)
+        return list(self._fields) + list(self._lazy)
 
     @property
     def num_nodes(self) -> int:
@@ -51,6 +72,17 @@ class Data:
             if torch.is_tensor(v):
                 self._fields[k] = v.to(device, non_blocking=non_blocking)
         self._fields.pop("_egp_structure", None)            # device-specific cache
+        return self
+
+    def to_feature_dtype(self, dtype: torch.dtype = torch.bfloat16) -> "Data":
+        """Store the node features ``x`` in ``dtype`` (what a loader does once per sample, on the host).  With bf16 the
+        batch is half the bytes over PCIe and the result is bit-identical: in the bf16 compute mode ``Graph.forward``
+        rounds fp32 features to bf16 (round-to-nearest-even, like this conversion) before the first GEMM anyway."""
+        x = self._fields.get("x")
+        if x is not None and x.dtype != dtype:
+            pinned = x.device.type == "cpu" and x.is_pinned()
+            x = x.to(dtype)
+            self._fields["x"] = x.pin_memory() if pinned else x
         return self
 
     def pin_memory(self) -> "Data":

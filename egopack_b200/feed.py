@@ -1,17 +1,21 @@
-"""Batch feed: multi-task loader interleaving and the pinned, double-buffered host -> device hand-over
+"""Batch feed: multi-task loader interleaving and the pinned, pipelined host -> device hand-over
 (utils/dataloading.py:8-70 and the per-sample transforms of main_temporal.py:168-169).
 
 The reference builds ``edge_index`` on the CPU inside DataLoader workers (torch_cluster KD-tree per sample), collates
 int64 edges, and ships everything with ``batch.to(device, non_blocking=True)`` on the compute stream.  Here the host
-side only moves ``x, pos, y, batch, ptr``; a ``DeviceFeeder`` uploads batch i+1 on a copy stream while step i computes,
-and runs the graph transforms (``RadiusGraph`` / ``LTATemporalConnectivity``: count + scan + fill kernels) on the device
-right behind the copy.  At 18.4 KB of fp32 features per node the feed is PCIe-bound, so hiding it behind the step is
-what matters; the edges never cross the bus.
+side only moves ``x, pos, y, batch, ptr``; a ``DeviceFeeder`` enqueues the copies of batch i+1 on a copy stream BEFORE
+it hands batch i to the training loop, and runs the graph transforms (``RadiusGraph`` / ``LTATemporalConnectivity``) on
+the device right behind them -- as structural hints (``band_k``, ``star``) with a lazy ``edge_index``, so nothing in the
+hand-over waits on the GPU.  The feed is PCIe-bound: 18.4 KB of fp32 features per node, 9.2 KB when the loader stores
+them as bf16 (``Batch.to_feature_dtype`` -- bit-identical to the cast the first GEMM's operand goes through anyway);
+``bind_host_memory_to_gpu`` keeps the pinned buffers on the GPU's own NUMA node, which is what an 8-GPU box needs to
+run eight such feeds at once.
 """
 from __future__ import annotations
 
 from typing import Iterable, Iterator, Mapping, Optional, Sequence, Tuple, Union
 
+import os
 import queue
 import threading
 
@@ -19,7 +23,7 @@ import torch
 
 from .data import Batch, Data
 
-__all__ = ["multiloader", "DeviceFeeder"]
+__all__ = ["multiloader", "DeviceFeeder", "bind_host_memory_to_gpu", "unit_spaced_host"]
 
 
 class multiloader:
@@ -57,22 +61,82 @@ _DONE = object()
 BatchLike = Union[Data, Sequence[Optional[Data]], Mapping[str, Optional[Data]]]
 
 
+def _parse_cpulist(text: str):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.extend(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_host_memory_to_gpu(device_index: int) -> dict:
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off, so that pinned host buffers allocated
+    afterwards (first touch) live in that node's memory and the H2D copies do not cross the socket interconnect.
+
+    On a 2-socket 8-GPU box every rank otherwise allocates wherever the launcher happened to run (round 1: all eight
+    feeds came out of NUMA node 0 and shared 184 GB/s).  Returns what was done -- ``{"numa_node": n, "cpus": k}`` or
+    ``{"skipped": reason}``; never raises (containers often hide /sys or forbid sched_setaffinity)."""
+    try:
+        import torch.cuda as tc
+        props = tc.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+    except Exception as ex:  # noqa: BLE001
+        return {"skipped": f"no PCI id: {ex}"}
+    try:
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return {"skipped": f"{bus}: numa_node=-1 (single node or hidden)", "pci": bus}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = _parse_cpulist(fh.read())
+        allowed = os.sched_getaffinity(0)
+        use = sorted(set(cpus) & allowed) or None
+        if not use:
+            return {"skipped": f"node {node} has no CPU this process may use", "pci": bus, "numa_node": node}
+        os.sched_setaffinity(0, use)
+        return {"pci": bus, "numa_node": node, "cpus": len(use)}
+    except Exception as ex:  # noqa: BLE001
+        return {"skipped": f"{type(ex).__name__}: {ex}", "pci": bus}
+
+
+def unit_spaced_host(pos: torch.Tensor, batch: Optional[torch.Tensor]) -> bool:
+    """Host-side version of the transforms' band test (pos increases by exactly 1 inside every graph), evaluated on the
+    CPU copy BEFORE the upload so that the device-side transforms need no read-back."""
+    pos = pos.view(-1)
+    if pos.numel() < 2:
+        return True
+    d = pos[1:] - pos[:-1]
+    ok = d == 1
+    if batch is not None:
+        ok = ok | (batch[1:] != batch[:-1])
+    return bool(ok.all())
+
+
 class DeviceFeeder:
     """Iterates a host loader and yields the same structure with every batch resident on ``device`` and its graph
-    structure built there.
+    structure described there.
 
     * ``transforms``: one callable for every batch, or a dict / sequence matching the loader's items
       (e.g. ``{"ar": RadiusGraph(1.5), "lta": LTATemporalConnectivity(1.5)}``); applied ON THE DEVICE after the copy.
-    * a worker thread copies item i+1 (and builds its edges) on a private stream while the consumer runs step i; the
-      consumer's stream waits on the copy's event, and the tensors are ``record_stream``-ed so the caching allocator
-      does not recycle them while the step still reads them.  Up to three batches are alive at a time (one being
-      consumed, one landed, one in flight).
+      They are sync-free: the band test is answered on the host copy (``pos_unit_spaced``), the LTA star is counted by a
+      kernel, and ``edge_index`` stays lazy.
+    * pipelining: the copies (and transform kernels) of item i+1 are enqueued on a private copy stream before item i is
+      yielded, so they overlap step i whatever the consumer does with it (including ``loss.item()``); the consumer's
+      stream waits on the copy's event and the tensors are ``record_stream``-ed so the caching allocator does not
+      recycle them while the step still reads them.  All CUDA calls are made by the consuming thread; with
+      ``prefetch_thread=True`` a helper thread only drives the HOST loader (collation, pinning) one item ahead.
     * host tensors that are not pinned yet are pinned once per batch (``pin=True``); pass loaders built with
       ``pin_memory=True`` (utils/dataloading.py:64) to skip that.
+    * ``feature_dtype``: convert ``x`` on the host before the copy (a loader that stores bf16 features should do this
+      once per sample instead: ``Batch.to_feature_dtype``).
     """
 
-    def __init__(self, loader: Iterable, device, transforms=None, pin: bool = True):
+    def __init__(self, loader: Iterable, device, transforms=None, pin: bool = True, prefetch_thread: bool = False,
+                 feature_dtype: Optional[torch.dtype] = None):
         self.loader, self.device, self.transforms, self.pin = loader, torch.device(device), transforms, pin
+        self.prefetch_thread, self.feature_dtype = prefetch_thread, feature_dtype
         self._cuda = self.device.type == "cuda"
         if self._cuda and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -88,27 +152,46 @@ class DeviceFeeder:
             return t.get(key)
         return t[key]
 
+    def _prepare_host(self, b):
+        """Host-side work of one batch (may run in the helper thread): feature dtype, pinning, the band hint."""
+        if b is None or not isinstance(b, Data):
+            return b
+        if self.feature_dtype is not None and b.x is not None and b.x.dtype != self.feature_dtype and b.x.device.type == "cpu":
+            b.x = b.x.to(self.feature_dtype)
+        if b.pos is not None and b.pos.device.type == "cpu" and getattr(b, "pos_unit_spaced", None) is None \
+                and not b.pos.is_floating_point():
+            b.pos_unit_spaced = unit_spaced_host(b.pos, b.batch)
+        if self._cuda and self.pin:
+            for k in list(b._fields):
+                v = b._fields[k]
+                if torch.is_tensor(v) and v.device.type == "cpu" and not v.is_pinned():
+                    b._fields[k] = v.pin_memory()
+        return b
+
+    def _prepare_item(self, item):
+        if item is None or isinstance(item, Data) or hasattr(item, "edge_index") or hasattr(item, "x"):
+            return self._prepare_host(item)
+        if isinstance(item, Mapping):
+            return {k: self._prepare_host(v) for k, v in item.items()}
+        return tuple(self._prepare_host(v) for v in item)
+
     def _copy_one(self, b: Optional[Data]) -> Optional[Data]:
         if b is None:
             return None
         if not isinstance(b, Data):                             # a real PyG batch: its own .to keeps every attribute
             return b.to(self.device, non_blocking=True)
         out = Batch()
-        for k in b.keys():
+        for k, v in b._fields.items():                          # lazy attributes of the host batch are not forced
             if k.startswith("_"):
                 continue
-            v = getattr(b, k)
             if torch.is_tensor(v):
-                if self._cuda and self.pin and not v.is_pinned() and v.device.type == "cpu":
-                    v = v.pin_memory()
                 self.h2d_bytes += v.numel() * v.element_size() if v.device != self.device else 0
                 v = v.to(self.device, non_blocking=True)
             setattr(out, k, v)
         return out
 
     def _move(self, item: BatchLike):
-        """All copies of the item are enqueued first; only then the transforms run (they read edge counts back, and a
-        host wait between two copies would leave the bus idle)."""
+        """All copies of the item are enqueued first, then the transforms' kernels."""
         tf = self._transform_for
         if item is None or isinstance(item, Data) or hasattr(item, "edge_index") or hasattr(item, "x"):
             out = self._copy_one(item)
@@ -134,26 +217,26 @@ class DeviceFeeder:
         for b in items:
             if b is None:
                 continue
-            for k in (b.keys() if hasattr(b, "keys") else ()):
-                v = getattr(b, k)
+            fields = getattr(b, "_fields", None)
+            for v in (fields.values() if fields is not None else ()):
                 if torch.is_tensor(v):
                     yield v
 
-    def __iter__(self) -> Iterator:
-        # A worker thread drives the loader and the copy stream: the transforms size their outputs on the host (edge
-        # counts are read back), and those waits must not hold up the consumer, which is enqueueing the current step.
-        # The queue holds one landed item, so at most: one being consumed, one landed, one in flight.
-        q: "queue.Queue" = queue.Queue(maxsize=1)
+    def _host_items(self) -> Iterator:
+        """The host loader, prepared; optionally one item ahead in a helper thread (host work only -- no CUDA calls)."""
+        if not self.prefetch_thread:
+            for item in self.loader:
+                yield self._prepare_item(item)
+            return
+        q: "queue.Queue" = queue.Queue(maxsize=2)
         stop = threading.Event()
 
         def work():
             try:
-                if self._cuda:
-                    torch.cuda.set_device(self.device)
                 for item in self.loader:
                     if stop.is_set():
                         return
-                    q.put(self._upload(item))
+                    q.put(self._prepare_item(item))
                 q.put(_DONE)
             except BaseException as ex:  # noqa: BLE001 -- re-raised in the consumer
                 q.put(ex)
@@ -167,13 +250,7 @@ class DeviceFeeder:
                     return
                 if isinstance(got, BaseException):
                     raise got
-                moved, done = got
-                if done is not None:
-                    cur = torch.cuda.current_stream(self.device)
-                    cur.wait_event(done)
-                    for v in self._tensors(moved):
-                        v.record_stream(cur)
-                yield moved
+                yield got
         finally:
             stop.set()
             while worker.is_alive():     # unblock a producer waiting on the full queue
@@ -182,3 +259,25 @@ class DeviceFeeder:
                 except queue.Empty:
                     pass
                 worker.join(timeout=0.05)
+
+    def __iter__(self) -> Iterator:
+        host = self._host_items()
+        try:
+            pending = None
+            first = next(host, _DONE)
+            if first is not _DONE:
+                pending = self._upload(first)
+            while pending is not None:
+                moved, done = pending
+                nxt = next(host, _DONE)
+                pending = self._upload(nxt) if nxt is not _DONE else None      # item i+1 is on the bus before i is used
+                if done is not None:
+                    cur = torch.cuda.current_stream(self.device)
+                    cur.wait_event(done)
+                    for v in self._tensors(moved):
+                        v.record_stream(cur)
+                yield moved
+        finally:
+            close = getattr(host, "close", None)
+            if close is not None:
+                close()

@@ -23,6 +23,11 @@ from . import ops
 _TENSOR_FIELDS = ("x", "pos", "y", "batch", "ptr", "edge_index")
 
 
+def _materialized(b, key: str) -> bool:
+    probe = getattr(b, "is_materialized", None)
+    return probe(key) if callable(probe) else getattr(b, key, None) is not None
+
+
 class GraphedStep:
     def __init__(self, step_fn: Callable[[Dict[str, object]], torch.Tensor], static_inputs: Dict[str, object],
                  warmup: int = 3):
@@ -48,11 +53,15 @@ class GraphedStep:
         if inputs is not None and inputs is not self.static:
             for t, b in inputs.items():
                 dst = self.static[t]
-                for k in _TENSOR_FIELDS:
+                if getattr(b, "band_k", None) != getattr(dst, "band_k", None):
+                    raise ValueError(f"GraphedStep: 'band_k' of task '{t}' changed; capture a new graph")
+                for k in _TENSOR_FIELDS + ("star",):
+                    if k == "edge_index" and not (_materialized(b, k) and _materialized(dst, k)):
+                        continue                              # band(+star) batches: band_k / star describe the structure
                     src, cur = getattr(b, k, None), getattr(dst, k, None)
                     if src is None or cur is None:
                         continue
-                    if src.shape != cur.shape or (k in ("edge_index", "ptr", "batch") and not torch.equal(src.to(cur.device), cur)):
+                    if src.shape != cur.shape or (k in ("edge_index", "ptr", "batch", "star") and not torch.equal(src.to(cur.device), cur)):
                         raise ValueError(f"GraphedStep: '{k}' of task '{t}' changed shape/structure; capture a new graph")
                     if k in ("x", "y", "pos"):
                         cur.copy_(src, non_blocking=True)

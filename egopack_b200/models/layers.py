@@ -13,11 +13,21 @@ from .. import ops
 from ..ops import ACT_NONE, ACT_RELU, GraphStructure
 
 
+def _batch_ptr(data, n: int, dev):
+    batch = data.batch if getattr(data, "batch", None) is not None else torch.zeros(n, dtype=torch.long, device=dev)
+    ptr = getattr(data, "ptr", None)
+    if ptr is None:
+        counts = torch.bincount(batch)
+        ptr = torch.cat([counts.new_zeros(1), counts.cumsum(0)])
+    return batch, ptr
+
+
 def structure_for(data, n: int) -> GraphStructure:
     """Aggregation structure of a batch, cached on the batch object.
 
-    ``band_k`` (set by our RadiusGraph when positions are unit spaced) selects the sliding-window kernel;
-    any other ``edge_index`` -- LTA star edges, graphs built by real PyG -- goes through a deterministic CSR.
+    ``band_k`` (set by our RadiusGraph / LTATemporalConnectivity when positions are unit spaced) selects the
+    sliding-window kernels -- with ``star`` (LTA) their band+star variants; any other ``edge_index`` (graphs built by
+    real PyG, stars wider than radius 4) goes through a deterministic CSR.
     """
     cached = getattr(data, "_egp_structure", None)
     dev = data.pos.device if getattr(data, "pos", None) is not None else data.x.device
@@ -25,12 +35,8 @@ def structure_for(data, n: int) -> GraphStructure:
         return cached
     band_k = getattr(data, "band_k", None)
     if band_k is not None:
-        batch = data.batch if getattr(data, "batch", None) is not None else torch.zeros(n, dtype=torch.long, device=dev)
-        ptr = getattr(data, "ptr", None)
-        if ptr is None:
-            counts = torch.bincount(batch)
-            ptr = torch.cat([counts.new_zeros(1), counts.cumsum(0)])
-        gs = ops.band_structure(batch, ptr, int(band_k))
+        batch, ptr = _batch_ptr(data, n, dev)
+        gs = ops.band_structure(batch, ptr, int(band_k), getattr(data, "star", None))
     else:
         gs = ops.csr_structure(data.edge_index, n)
     try:
@@ -38,6 +44,23 @@ def structure_for(data, n: int) -> GraphStructure:
     except Exception:  # foreign batch types may refuse new attributes; rebuilding per call is still correct
         pass
     return gs
+
+
+def structure_for_many(batches, sizes) -> GraphStructure:
+    """One band(+star) structure over several batches laid out back to back (``Graph.forward_many``).  Requires every
+    batch to carry the same ``band_k`` hint; returns None otherwise (the caller then runs the batches one by one)."""
+    ks = {getattr(b, "band_k", None) for b in batches}
+    if len(ks) != 1 or None in ks:
+        return None
+    k = int(ks.pop())
+    if k > 4 and any(getattr(b, "star", None) is not None for b in batches):
+        return None
+    parts = []
+    for b, n in zip(batches, sizes):
+        dev = b.pos.device if getattr(b, "pos", None) is not None else b.x.device
+        batch, ptr = _batch_ptr(b, n, dev)
+        parts.append((batch, ptr, getattr(b, "star", None)))
+    return ops.band_structure_many(parts, k)
 
 
 class PositionalEncoding(nn.Module):

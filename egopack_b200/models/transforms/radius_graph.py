@@ -26,36 +26,64 @@ def _ptr_of(data, n: int, device):
 
 
 def unit_spaced(pos: torch.Tensor, batch: torch.Tensor) -> bool:
-    """True when pos increases by exactly 1 inside every graph (then the radius graph is an index band)."""
+    """True when pos increases by exactly 1 inside every graph (then the radius graph is an index band).
+    On a CUDA tensor this reads one flag back (a host sync); the feeder records the answer on the HOST copy before the
+    upload (``data.pos_unit_spaced``) so the device-side transforms never have to."""
     if pos.numel() < 2:
         return True
     d = pos[1:] - pos[:-1]
     return bool(((d == 1) | (batch[1:] != batch[:-1])).all().item())
 
 
+def unit_spaced_hint(data, pos: torch.Tensor, batch: torch.Tensor) -> bool:
+    hint = getattr(data, "pos_unit_spaced", None)
+    if hint is not None:
+        return bool(hint)
+    return unit_spaced(pos, batch)
+
+
+def _supports_lazy(data) -> bool:
+    return callable(getattr(data, "set_lazy", None))
+
+
 class RadiusGraph:
+    """``lazy=True`` (default): when the batch lives on the GPU and its positions are unit spaced, only the structural
+    hint ``band_k`` is recorded and ``edge_index`` is registered as a lazy attribute -- it is built (count + scan + fill,
+    one host read of the edge count) the first time somebody reads it.  The aggregation kernels never do."""
+
     def __init__(self, r: float, loop: bool = False, max_num_neighbors: int = 32, flow: str = "source_to_target",
-                 num_workers: int = 1, device=None):
+                 num_workers: int = 1, device=None, lazy: bool = True):
         if loop:
             raise NotImplementedError("the reference only builds loop-free radius graphs")
         if flow != "source_to_target":
             raise NotImplementedError("only flow='source_to_target' is used by the reference")
         self.r, self.loop, self.max_num_neighbors, self.flow = r, loop, max_num_neighbors, flow
-        self.device = device
+        self.device, self.lazy = device, lazy
+
+    def _edges(self, data):
+        pos = data.pos.view(-1)
+        home = pos.device
+        dev = torch.device(self.device) if self.device is not None else (home if home.type == "cuda" else torch.device("cuda"))
+        batch, ptr = _ptr_of(data, pos.numel(), home)
+        return ops.band_edge_index(pos.to(dev), batch.to(dev), ptr.to(dev), self.r, self.max_num_neighbors).to(home)
 
     def __call__(self, data):
         data.edge_attr = None
         pos = data.pos.view(-1)
         home = pos.device
-        dev = torch.device(self.device) if self.device is not None else (home if home.type == "cuda" else torch.device("cuda"))
-        n = pos.numel()
-        batch, ptr = _ptr_of(data, n, home)
-        pos_d, batch_d, ptr_d = pos.to(dev), batch.to(dev), ptr.to(dev)
-        edge_index = ops.band_edge_index(pos_d, batch_d, ptr_d, self.r, self.max_num_neighbors)
-        data.edge_index = edge_index.to(home)
         k = int(math.floor(self.r))
-        if unit_spaced(pos_d, batch_d) and 2 * k + 1 <= self.max_num_neighbors + 1 and self.r > k:
-            data.band_k = k                                          # hint consumed by Graph.forward
+        band_shape = 2 * k + 1 <= self.max_num_neighbors + 1 and self.r > k
+        if self.lazy and band_shape and home.type == "cuda" and _supports_lazy(data):
+            batch, _ = _ptr_of(data, pos.numel(), home)
+            if unit_spaced_hint(data, pos, batch):
+                data.band_k = k                                      # hint consumed by Graph.forward
+                data.set_lazy("edge_index", self._edges)
+                return data
+        data.edge_index = self._edges(data)
+        if band_shape:
+            batch, _ = _ptr_of(data, pos.numel(), home)
+            if unit_spaced_hint(data, pos, batch):                   # checked where the data lives
+                data.band_k = k
         return data
 
     def __repr__(self):

@@ -113,21 +113,61 @@ class GraphStructure:
     win_lo: Optional[Tensor] = None
     win_hi: Optional[Tensor] = None
     inv_deg: Optional[Tensor] = None          # 1/max(in-degree,1)
+    # band + star (LTATemporalConnectivity without an edge list; see egp_band_star_windows)
+    ext_lo: Optional[Tensor] = None
+    ext_hi: Optional[Tensor] = None
+    hub_slot: Optional[Tensor] = None
+    graph_meta: Optional[Tensor] = None
+    num_graphs: int = 0
     rowptr_in: Optional[Tensor] = None        # CSR grouped by dst (forward)
     col_in: Optional[Tensor] = None
     rowptr_out: Optional[Tensor] = None       # CSR grouped by src (backward)
     col_out: Optional[Tensor] = None
 
 
-def band_structure(batch: Tensor, ptr: Tensor, k: int) -> GraphStructure:
-    n = batch.numel()
-    dev = batch.device
+def lta_star_counts(y: Tensor, ptr: Tensor, r: float) -> Tensor:
+    """int32 [G,3] = (n_in, n_fc, first_src) per graph (lta_temp_connectivity.py:48-52), computed on the device."""
+    y, ptr = _i64(y, "y"), _i64(ptr, "ptr")
+    g = ptr.numel() - 1
+    ycols = y.shape[1] if y.dim() > 1 else 1
+    star = torch.empty((g, 3), dtype=torch.int32, device=y.device)
+    L.call("egp_lta_star_counts", L.ptr(y), ycols, L.ptr(ptr), g, float(r), L.ptr(star), L.stream())
+    return star
+
+
+def band_structure(batch: Tensor, ptr: Tensor, k: int, star: Optional[Tensor] = None) -> GraphStructure:
+    """Band (radius k, unit-spaced positions) of ONE collated batch, optionally with the LTA star of every graph."""
+    return band_structure_many([(batch, ptr, star)], k)
+
+
+def band_structure_many(parts, k: int) -> GraphStructure:
+    """One structure over several collated batches laid out back to back (``Graph.forward_many``): ``parts`` is a list
+    of ``(batch, ptr, star_or_None)``; rows / graphs of part p are offset by the sizes of the parts before it."""
+    dev = parts[0][0].device
+    n = sum(b.numel() for b, _, _ in parts)
+    g = sum(p.numel() - 1 for _, p, _ in parts)
+    with_star = any(st is not None for _, _, st in parts)
     lo = torch.empty(n, dtype=torch.int32, device=dev)
     hi = torch.empty(n, dtype=torch.int32, device=dev)
     inv = torch.empty(n, dtype=torch.float32, device=dev)
-    L.call("egp_band_windows", L.ptr(_i64(batch, "batch")), L.ptr(_i64(ptr, "ptr")), n, int(k), L.ptr(lo), L.ptr(hi),
-           L.ptr(inv), L.stream())
-    return GraphStructure(n=n, band_k=int(k), win_lo=lo, win_hi=hi, inv_deg=inv)
+    elo = ehi = slot = meta = None
+    if with_star:
+        elo = torch.empty(n, dtype=torch.int32, device=dev)
+        ehi = torch.empty(n, dtype=torch.int32, device=dev)
+        slot = torch.empty(n, dtype=torch.int32, device=dev)
+        meta = torch.zeros((g, 4), dtype=torch.int32, device=dev)
+    ro = go = 0
+    for batch, ptr, star in parts:
+        nn, gg = batch.numel(), ptr.numel() - 1
+        sl = slice(ro, ro + nn)
+        L.call("egp_band_star_windows", L.ptr(_i64(batch, "batch")), L.ptr(_i64(ptr, "ptr")), nn, gg, int(k),
+               L.ptr(_c(star)), ro, go, L.ptr(lo[sl]), L.ptr(hi[sl]), L.ptr(inv[sl]),
+               L.ptr(elo[sl]) if with_star else None, L.ptr(ehi[sl]) if with_star else None,
+               L.ptr(slot[sl]) if with_star else None, L.ptr(meta[go:go + gg]) if with_star else None, L.stream())
+        ro += nn
+        go += gg
+    return GraphStructure(n=n, band_k=int(k), win_lo=lo, win_hi=hi, inv_deg=inv, ext_lo=elo, ext_hi=ehi, hub_slot=slot,
+                          graph_meta=meta, num_graphs=g)
 
 
 def csr_structure(edge_index: Tensor, n: int) -> GraphStructure:
@@ -156,16 +196,29 @@ def _aggregate(x: Tensor, gs: GraphStructure, backward: bool) -> Tensor:
     n, c = x.shape
     out = torch.empty_like(x)
     so, si = (None, gs.inv_deg) if backward else (gs.inv_deg, None)
-    with _Traced("sage_mean_band" if gs.band_k is not None else "sage_mean_csr", 2.0 * n * c * x.element_size(), "B"):
+    kind = "sage_mean_csr" if gs.band_k is None else ("sage_mean_band_star" if gs.ext_lo is not None else "sage_mean_band")
+    with _Traced(kind, 2.0 * n * c * x.element_size(), "B", f"k={gs.band_k}" if gs.band_k is not None else ""):
         _aggregate_launch(x, out, gs, backward, so, si, n, c)
     return out
 
 
 def _aggregate_launch(x, out, gs, backward, so, si, n, c):
-    if gs.band_k is not None:
+    if gs.band_k is not None and gs.ext_lo is not None and gs.band_k <= 4:
+        nb, ws = 0, None
+        if backward:
+            nb = L.size("egp_sage_mean_band_star_workspace", n, c, gs.num_graphs)
+            ws = L.workspace(nb, x.device, "hub")
+            L.CALL_COUNTS["egp_sage_hub_fixup(kernel)"] = L.CALL_COUNTS.get("egp_sage_hub_fixup(kernel)", 0) + 1
+        L.call("egp_sage_mean_band_star", L.ptr(x), L.ptr(out), n, c, c, c, gs.band_k, L.ptr(gs.win_lo), L.ptr(gs.win_hi),
+               L.ptr(so), L.ptr(si), None if backward else L.ptr(gs.ext_lo), None if backward else L.ptr(gs.ext_hi),
+               L.ptr(gs.hub_slot) if backward else None, L.ptr(gs.graph_meta) if backward else None, gs.num_graphs,
+               _code(x), L.ptr(ws), nb, L.stream())
+    elif gs.band_k is not None and gs.ext_lo is None:
         L.call("egp_sage_mean_band", L.ptr(x), L.ptr(out), n, c, c, c, gs.band_k, L.ptr(gs.win_lo), L.ptr(gs.win_hi),
                L.ptr(so), L.ptr(si), _code(x), L.stream())
     else:
+        if gs.rowptr_in is None:
+            raise RuntimeError("this graph structure needs a CSR (star with radius > 4): build it with csr_structure")
         rp, col = (gs.rowptr_out, gs.col_out) if backward else (gs.rowptr_in, gs.col_in)
         L.call("egp_sage_mean_csr", L.ptr(x), L.ptr(out), n, c, c, c, L.ptr(rp), L.ptr(col), L.ptr(so), L.ptr(si),
                _code(x), L.stream())

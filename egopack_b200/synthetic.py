@@ -22,7 +22,8 @@ def generator(seed: int, config_id: int = 0, rank: int = 0) -> torch.Generator:
 
 def make_batch(task: str, num_graphs: int, nodes_per_graph: int, gen: torch.Generator, *, feature_dim: int = FEATURE_DIM,
                num_segments: int = NUM_SEGMENTS, band_k: Optional[int] = 1, unlabeled: float = 0.0,
-               n_verbs: int = N_VERBS, n_nouns: int = N_NOUNS, lta_inputs: int = 2, pin: bool = False) -> Batch:
+               n_verbs: int = N_VERBS, n_nouns: int = N_NOUNS, lta_inputs: int = 2, pin: bool = False,
+               feature_dtype: Optional[torch.dtype] = None) -> Batch:
     """One collated task batch WITHOUT ``edge_index`` (the transform adds it; ``band_k`` is the structural hint
     our RadiusGraph would record).  task in {'ar','lta','oscc','pnr'}."""
     n = num_graphs * nodes_per_graph
@@ -52,6 +53,8 @@ def make_batch(task: str, num_graphs: int, nodes_per_graph: int, gen: torch.Gene
         raise ValueError(task)
     if band_k is not None and task != "lta":
         b.band_k = band_k
+    if feature_dtype is not None:                            # a loader that stores bf16 features (Batch.to_feature_dtype)
+        b.to_feature_dtype(feature_dtype)
     if pin:
         b.pin_memory()
     return b

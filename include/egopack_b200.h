@@ -75,6 +75,22 @@ int egp_lta_edge_fill(const int64_t* pos, const int64_t* y, int64_t y_cols, cons
  * inv_deg[i] = 1/max(win_hi-win_lo, 1).                                                                      */
 int egp_band_windows(const int64_t* batch, const int64_t* ptr, int64_t num_nodes, int k,
                      int32_t* win_lo, int32_t* win_hi, float* inv_deg, void* stream);
+/* LTA star descriptor per graph (lta_temp_connectivity.py:48-53), no host round trip:
+ * star[3g] = n_in = #(y[:,0]==-1), star[3g+1] = n_fc = #(y[:,0]>0), star[3g+2] = first_src = max(ceil(n_in-r),0).
+ * The star edges are {s -> t : s in [first_src, n_in), t in [n_in, n_in+n_fc)} (graph-local indices).            */
+int egp_lta_star_counts(const int64_t* y, int64_t y_cols, const int64_t* ptr, int64_t num_graphs, float r,
+                        int32_t* star, void* stream);
+/* band windows + the star extension of egp_sage_mean_band_star for one collated batch, written with GLOBAL row / graph
+ * indices (row_offset / graph_offset added) so several task batches can share one structure (Graph.forward_many).
+ *   win_lo/win_hi/inv_deg [n]  as egp_band_windows, inv_deg counting the star in-edges too
+ *   ext_lo/ext_hi [n]          forward: for a star target, the star sources outside its band (a contiguous range)
+ *   hub_slot [n]               backward: global graph index for star targets of a graph with >= 1 source, else -1
+ *   graph_meta [num_graphs,4]  {src_lo, src_hi, tgt_lo, tgt_hi} absolute rows (caller-zeroed; empty without a star)
+ * star == NULL (then the four star outputs may be NULL too) gives the plain band.                                  */
+int egp_band_star_windows(const int64_t* batch, const int64_t* ptr, int64_t num_nodes, int64_t num_graphs, int k,
+                          const int32_t* star, int64_t row_offset, int64_t graph_offset, int32_t* win_lo,
+                          int32_t* win_hi, float* inv_deg, int32_t* ext_lo, int32_t* ext_hi, int32_t* hub_slot,
+                          int32_t* graph_meta, void* stream);
 /* CSR from an arbitrary int64 edge_index [2,E]: group_by = 1 groups by dst (rows = dst, cols = src; forward),
  * 0 groups by src (rows = src, cols = dst; backward).  Columns inside a row are sorted ascending
  * (deterministic).  rowptr int32 [N+1], col int32 [E]; `cursor` is int32 [N] scratch.                       */
@@ -92,6 +108,17 @@ int egp_csr_inv_degree(const int32_t* rowptr, int64_t num_nodes, float* inv_deg,
 int egp_sage_mean_band(const void* x, void* out, int64_t num_nodes, int64_t channels, int64_t ldx,
                        int64_t ldo, int k, const int32_t* win_lo, const int32_t* win_hi,
                        const float* scale_out, const float* scale_in, int dtype, void* stream);
+/* band + star (LTATemporalConnectivity graphs, k <= 4) without an edge list and with the tensor read once:
+ *   forward  (ext_lo/ext_hi given, hub_slot NULL): a star target also sums its out-of-band source rows;
+ *   backward (hub_slot/graph_meta given, ext NULL): star targets are accumulated into per-graph hub sums inside the
+ *            band pass (per-(strip, graph) partials in `workspace`, combined in a fixed order -> deterministic) and a
+ *            second small kernel rewrites the star-source rows.  scale_in / scale_out as in egp_sage_mean_band.      */
+size_t egp_sage_mean_band_star_workspace(int64_t num_nodes, int64_t channels, int64_t num_graphs);
+int egp_sage_mean_band_star(const void* x, void* out, int64_t num_nodes, int64_t channels, int64_t ldx, int64_t ldo,
+                            int k, const int32_t* win_lo, const int32_t* win_hi, const float* scale_out,
+                            const float* scale_in, const int32_t* ext_lo, const int32_t* ext_hi,
+                            const int32_t* hub_slot, const int32_t* graph_meta, int64_t num_graphs, int dtype,
+                            void* workspace, size_t ws_bytes, void* stream);
 int egp_sage_mean_csr(const void* x, void* out, int64_t num_nodes, int64_t channels, int64_t ldx,
                       int64_t ldo, const int32_t* rowptr, const int32_t* col, const float* scale_out,
                       const float* scale_in, int dtype, void* stream);
@@ -168,6 +195,31 @@ int egp_gemm(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb
              const float* bias, const void* residual, int64_t ldr, void* C, int64_t ldc,
              int64_t M, int64_t N, int64_t K, int act, float slope, int in_dtype, int out_dtype,
              int accumulate, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a11: losses (fp32 logits) ---------------------------------------------------------------------------------
+ * Cross entropy, reduction='none', with ignore_index and label smoothing -- nn.CrossEntropyLoss(ignore_index=-1,
+ * reduction='none') per label head, summed over heads (models/tasks/recognition.py:21,61-69; lta.py:21,73-74;
+ * criterion/wrapper.py:80-82; main_temporal.py:285,291) and F.cross_entropy(label_smoothing=0.1) for OSCC (oscc.py:88-96):
+ *   loss[i] = (1-eps) * (lse_i - z[i,t_i]) + eps * (lse_i - mean_c z[i,c]);   0 when t_i == ignore_index (or outside
+ *   [0, classes)).  labels int64, read at labels[i*label_stride] (a column of y [N,2]).
+ *   fwd: accumulate != 0 ADDS to loss (the sum over heads); lse float [n] is saved for the backward.
+ *   bwd: dlogits[i,c] = dloss[i*dloss_stride] * (softmax(z_i)[c] - (1-eps)[c==t_i] - eps/classes) (dloss_stride 0
+ *        broadcasts a scalar); out_dtype EGP_F32 writes [n, ldd]; EGP_BF16 writes bf16 and zero-fills columns
+ *        classes..ldd-1 (a 16-byte-pitch operand for the classifier's dgrad / wgrad GEMMs).                        */
+int egp_ce_loss_fwd(const float* logits, int64_t ld, const int64_t* labels, int64_t label_stride, int64_t n,
+                    int64_t classes, int64_t ignore_index, float label_smoothing, float* loss, int accumulate,
+                    float* lse, void* stream);
+int egp_ce_loss_bwd(const float* logits, int64_t ld, const float* lse, const int64_t* labels, int64_t label_stride,
+                    const float* dloss, int64_t dloss_stride, int64_t n, int64_t classes, int64_t ignore_index,
+                    float label_smoothing, void* dlogits, int64_t ldd, int out_dtype, void* stream);
+/* nn.BCEWithLogitsLoss(reduction='none') (models/tasks/pnr.py:38,82-83): loss = max(z,0) - z*t + log1p(exp(-|z|));
+ * dz = dloss * (sigmoid(z) - t).  z, target, loss float [n]. */
+int egp_bce_logits_fwd(const float* z, const float* target, float* loss, int64_t n, void* stream);
+int egp_bce_logits_bwd(const float* z, const float* target, const float* dloss, int64_t dloss_stride, float* dz,
+                       int64_t n, void* stream);
+/* out[0] (+)= weight * mean(x[0..n)) -- `w * loss.mean()` summed over tasks (main_temporal.py:99-128); one block, fixed
+ * summation order (fp64 partials). */
+int egp_weighted_mean(const float* x, int64_t n, float weight, float* out, int accumulate, void* stream);
 
 /* ---- a14: cosine k-NN of nodes against a prototype bank (GraphONE.__compute_edges, graphONE.py:119-141) ---
  * d = 1 - (F/|F|)(P/|P|)^T ; idx[i,:] = the k smallest d, ascending, ties -> lower prototype index.

@@ -140,3 +140,31 @@ def test_device_feeder_uploads_and_builds_edges_on_device():
         assert canon_edges(db["lta"].edge_index) == canon_edges(torch.cat(want_lta, 1))
     assert n == 3 and feeder.h2d_bytes == 3 * sum(v.numel() * v.element_size() for b in host[0].values()
                                                  for v in (b.x, b.pos, b.y, b.batch, b.ptr))
+
+
+def test_transforms_are_lazy_and_sync_free_on_device_batches():
+    """On a GPU-resident batch the transforms only record the structural hints (band_k, star); edge_index is built on
+    first read and equals the eager construction.  A host-side hint (pos_unit_spaced) removes the last read-back."""
+    g = torch.Generator().manual_seed(4)
+    graphs = []
+    for _ in range(6):
+        n_in, n_fc = int(torch.randint(1, 4, (1,), generator=g)), int(torch.randint(1, 12, (1,), generator=g))
+        y = torch.full((n_in + n_fc, 2), -1, dtype=torch.long)
+        y[n_in:] = torch.randint(0, 5, (n_fc, 2), generator=g)
+        graphs.append(Data(x=torch.zeros(n_in + n_fc, 1), y=y, pos=torch.arange(n_in + n_fc)))
+    host = Batch.from_data_list(graphs)
+    eager = LTATemporalConnectivity(r=1.5)(Batch.from_data_list(graphs))           # host batch: eager, returned on the host
+    assert eager.is_materialized("edge_index") and eager.edge_index.device.type == "cpu"
+    dev = Batch.from_data_list(graphs).to(DEV)
+    dev.pos_unit_spaced = True
+    dev = LTATemporalConnectivity(r=1.5)(dev)
+    assert dev.band_k == 1 and dev.star is not None and not dev.is_materialized("edge_index")
+    assert "edge_index" in dev
+    assert torch.equal(dev.edge_index.cpu(), eager.edge_index) and dev.is_materialized("edge_index")
+    dev2 = RadiusGraph(r=2.5)(Batch.from_data_list(graphs).to(DEV))
+    assert dev2.band_k == 2 and not dev2.is_materialized("edge_index")
+    assert canon_edges(dev2.edge_index) == canon_edges(pyg.radius_graph(host.pos, 2.5, host.batch))
+    # not unit spaced: no hint, eager edges, generic CSR path
+    odd = Batch.from_data_list([Data(x=torch.zeros(4, 1), pos=torch.tensor([0, 2, 4, 6]))]).to(DEV)
+    odd = RadiusGraph(r=2.5)(odd)
+    assert odd.band_k is None and odd.is_materialized("edge_index")

@@ -45,6 +45,83 @@ def test_sage_mean_band_and_csr_forward_backward(dtype, tol, k):
         assert rel_max(y, want) < 2e-7
 
 
+def _lta_batch(gen, num_graphs, k, sizes=None):
+    """Random LTA-shaped graphs: n_in inputs (verb -1) then forecasts whose verb may be 0 (the `> 0` quirk) and, for
+    some graphs, trailing unlabeled-but-not-input nodes; also graphs without inputs / without forecasts."""
+    ys, pos, lens = [], [], []
+    for g in range(num_graphs):
+        n_in = int(torch.randint(0, k + 3, (1,), generator=gen))
+        n_fc = int(torch.randint(0, 24, (1,), generator=gen)) if sizes is None else sizes - n_in
+        y = torch.full((n_in + n_fc, 2), -1, dtype=torch.long)
+        y[n_in:, 0] = torch.randint(0, 4, (n_fc,), generator=gen)
+        y[n_in:, 1] = torch.randint(0, 4, (n_fc,), generator=gen)
+        if n_in + n_fc == 0:
+            y = torch.full((1, 2), 3, dtype=torch.long)
+        ys.append(y)
+        pos.append(torch.arange(y.shape[0]))
+        lens.append(y.shape[0])
+    batch, ptr = graph_sizes_to_index(lens)
+    return torch.cat(ys), torch.cat(pos), batch, ptr
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+def test_sage_mean_band_star_matches_edge_list(dtype, tol, k):
+    """LTA graphs (band + star) aggregated WITHOUT an edge list (egp_band_star_windows + egp_sage_mean_band_star:
+    forward extension rows, backward fused hub sums + fix-up) == scatter-mean over the reference's edge list
+    (egp_lta_edge_* is held to the reference's own transform by tests/test_gpu_edges.py)."""
+    gen = torch.Generator().manual_seed(10 + k)
+    y, pos, batch, ptr = _lta_batch(gen, 37, k)
+    n, c = batch.numel(), 264
+    r = k + 0.5
+    ei = ops.lta_edge_index(pos.to(DEV), y.to(DEV), batch.to(DEV), ptr.to(DEV), r).cpu()
+    x = torch.randn(n, c, generator=gen).to(dtype)
+    w = torch.randn(n, c, generator=gen).to(dtype)
+    xr = x.float().clone().requires_grad_(True)
+    want = pyg.scatter(xr.index_select(0, ei[0]), ei[1], 0, n, "mean")
+    want.backward(w.float())
+    star = ops.lta_star_counts(y.to(DEV), ptr.to(DEV), r)
+    n_in = torch.stack([(y[ptr[g]:ptr[g + 1], 0] == -1).sum() for g in range(ptr.numel() - 1)])
+    n_fc = torch.stack([(y[ptr[g]:ptr[g + 1], 0] > 0).sum() for g in range(ptr.numel() - 1)])
+    assert torch.equal(star[:, 0].cpu().long(), n_in) and torch.equal(star[:, 1].cpu().long(), n_fc)
+    gs = ops.band_structure(batch.to(DEV), ptr.to(DEV), k, star)
+    deg = torch.bincount(ei[1], minlength=n).clamp(min=1).float()
+    assert torch.equal(gs.inv_deg.cpu(), 1.0 / deg)
+    xd = x.detach().to(DEV).requires_grad_(True)
+    out = ops.SageMean.apply(xd, gs)
+    out.backward(w.to(DEV))
+    assert rel_max(out, want) < tol and rel_max(xd.grad, xr.grad) < tol
+    # deterministic: the hub sums are combined in a fixed order
+    xd2 = x.detach().to(DEV).requires_grad_(True)
+    ops.SageMean.apply(xd2, gs).backward(w.to(DEV))
+    assert torch.equal(xd.grad, xd2.grad)
+
+
+def test_band_star_structure_of_several_batches_back_to_back():
+    """Graph.forward_many lays several task batches out in one structure (global row / graph indices)."""
+    gen = torch.Generator().manual_seed(5)
+    y, pos, batch, ptr = _lta_batch(gen, 9, 1)
+    batch2, ptr2 = graph_sizes_to_index([7, 1, 30])
+    n1, n2 = batch.numel(), batch2.numel()
+    star = ops.lta_star_counts(y.to(DEV), ptr.to(DEV), 1.5)
+    parts = [(batch2.to(DEV), ptr2.to(DEV), None), (batch.to(DEV), ptr.to(DEV), star), (batch2.to(DEV), ptr2.to(DEV), None)]
+    gs = ops.band_structure_many(parts, 1)
+    x = torch.randn(n2 + n1 + n2, 64, generator=gen)
+    w = torch.randn(n2 + n1 + n2, 64, generator=gen)
+    xd = x.to(DEV).requires_grad_(True)
+    ops.SageMean.apply(xd, gs).backward(w.to(DEV))
+    singles = [ops.band_structure(batch2.to(DEV), ptr2.to(DEV), 1), ops.band_structure(batch.to(DEV), ptr.to(DEV), 1, star),
+               ops.band_structure(batch2.to(DEV), ptr2.to(DEV), 1)]
+    off = 0
+    for g1, nn in zip(singles, (n2, n1, n2)):
+        xs = x[off:off + nn].to(DEV).requires_grad_(True)
+        o = ops.SageMean.apply(xs, g1)
+        o.backward(w[off:off + nn].to(DEV))
+        assert torch.equal(ops.SageMean.apply(xd.detach(), gs)[off:off + nn], o.detach())
+        assert torch.allclose(xd.grad[off:off + nn], xs.grad, atol=1e-6, rtol=1e-6)
+        off += nn
+
+
 def test_sage_mean_isolated_nodes_and_directed_star():
     # node 3 has no in-edges (mean of nothing = 0); star edges are directed (LTA connectivity)
     ei = torch.tensor([[0, 1, 0, 1, 2], [1, 0, 4, 4, 4]])
