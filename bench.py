@@ -9,11 +9,19 @@ Workload (BASELINE.json configs[1], "c2"): multi-task AR+LTA+PNR training step o
 all-reduce (N>1) + Adam step -- i.e. the body of main_temporal.py:76-130; nothing is skipped.  Per GPU every
 task batch holds ``--videos`` graphs of ``--nodes`` segments (weak scaling: per-GPU work is fixed as N grows).
 
-One JSON line on rank 0.  ``value`` = nodes/s with inputs resident in HBM; ``e2e`` = the same step fed from pinned
-HOST memory every step (H2D of features/labels/structure inside the timed region, D2H of the loss);
+One JSON line on rank 0.  ``value`` = nodes/s with inputs resident in HBM; ``e2e`` = the same step fed through the
+package's public feed (``egopack_b200.feed.DeviceFeeder``) from pinned HOST memory every step (H2D of features /
+labels / structure inside the timed region, device-side graph transforms, D2H of the loss);
 ``roofline`` = the dominant kernel family (tcgen05 GEMMs) traced per launch with CUDA events on the launching
-stream; ``cpu_baseline`` = the oracle (CPU restatement of the reference) on a bounded sample of the same workload.
-``--impl reference`` times that CPU oracle alone (the reference's own torch_geometric stack is not installable).
+stream, ``roofline_hbm`` = every memory-bound kernel of the step the same way; ``cpu_baseline`` = the oracle (CPU
+restatement of the reference) on a bounded sample of the same workload; ``extra`` (N=1) = the other BASELINE
+configurations (c3 EgoPack backpack, c4 long video) measured device-resident in the same run.
+``--impl reference`` times the CPU oracle alone (the reference's own torch_geometric stack is not installable, and
+/root/reference does not exist on the GPU box).
+
+Features: the loader stores the Omnivore features as bf16 (``Batch.to_feature_dtype``; ``--feature-dtype fp32`` keeps
+the reference's fp32 storage).  In the bf16 compute mode that is bit-identical to feeding fp32 features (the first
+GEMM's operand is the same round-to-nearest-even either way, tests/test_gpu_models.py) and halves the PCIe bytes.
 """
 from __future__ import annotations
 
@@ -48,7 +56,13 @@ def parse():
     ap.add_argument("--videos", type=int, default=256, help="graphs per task batch per GPU")
     ap.add_argument("--nodes", type=int, default=128, help="segments (nodes) per graph")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-videos", type=int, default=16, help="graphs per task batch of the CPU sample")
+    ap.add_argument("--cpu-videos", type=int, default=64, help="graphs per task batch of the CPU sample (bounded sample)")
+    ap.add_argument("--feature-dtype", default="auto", choices=["auto", "bf16", "fp32"],
+                    help="host storage of the features: auto = bf16 in the bf16 compute mode, fp32 in the fp32 parity mode")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --videos graphs per task PER GPU; strong: --videos graphs per task in TOTAL, split over the ranks")
+    ap.add_argument("--no-extra", action="store_true", help="skip the c3 / c4 sub-lines of the N=1 run")
+    ap.add_argument("--cpu-sweep", action="store_true", help="(--impl reference) also time 16 / 64 / 256 graphs per task, one step each")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
                     help="c2 = MTL AR+LTA+PNR (the BASELINE metric's config); c3 = EgoPack OSCC + AR/LTA/PNR prototype backpack; "
@@ -178,24 +192,60 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------------------
-def native_run(args, rank: int, world: int, local_rank: int):
+WORKLOAD_TEXT = {
+    "c2": "c2: MTL AR+LTA+PNR shared temporal GNN (experiments/mtl.yaml: k=1, hidden 1024, depth 3, TRN hidden 1024, "
+          "dropout 0.5), full train step = zero_grad+fwd+loss+bwd+grad-allreduce+Adam",
+    "c3": "c3: EgoPack OSCC primary + frozen AR/LTA/PNR prototype backpack (k=4, depth 3, residual, {protos} "
+          "prototypes/bank, late fusion), Graph trainable, full train step",
+    "c4": "c4: long-video stress (BASELINE configs[3]): AR over 2048-segment graphs, temporal radius 16 (33-wide band), "
+          "4 GNN layers, hidden 1024, full train step",
+}
+# algorithmic HBM bytes are attached to the traced launches in egopack_b200/ops.py (2*C*b per node for the
+# aggregation, 3*C*b / 5*C*b graph-LN fwd / bwd, 2*C*b / 3-4*C*b row-LN fwd / bwd, 2*C*b posenc, C*b pooling)
+HBM_KERNELS = ("sage_mean_band", "sage_mean_band_star", "sage_mean_csr", "graph_layernorm_fwd", "graph_layernorm_bwd",
+               "row_layernorm_fwd", "row_layernorm_bwd", "posenc_add", "act_bwd_colsum", "colsum", "cast",
+               "segment_max_pool_fwd", "proto_max_gather", "max_combine_fwd")
+
+
+def load_traffic():
+    """DRAM bytes per launch measured under `ncu --set full` for the kernels that ship in THIS tree (profiles/r2_*)."""
+    for name in ("r2_ncu_traffic.json",):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            return {k: v for k, v in json.load(open(path)).items() if isinstance(v, dict)}
+    return {}
+
+
+def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2", full: bool = True):
+    """One workload on this rank's GPU.  `full` adds the e2e, small-batch and roofline sections (the main line);
+    the c3 / c4 sub-lines of an N=1 run only take the device-resident timing plus the kernel trace."""
+    import gc
+
     import egopack_b200
     from egopack_b200 import _lib, ops, steps
     from egopack_b200 import synthetic as syn
     from egopack_b200.dp import GradientAllReduce
+    from egopack_b200.feed import DeviceFeeder, bind_host_memory_to_gpu
     from egopack_b200.models.graph import Graph
     from egopack_b200.models.graphONE.graphONE import GraphONE
     from egopack_b200.models.tasks import LTATask, OSCCTask, PNRTask, RecognitionTask
-    from egopack_b200.models.transforms import LTATemporalConnectivity
+    from egopack_b200.models.transforms import LTATemporalConnectivity, RadiusGraph
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = bind_host_memory_to_gpu(local_rank) if full else None   # before any pinned allocation
     egopack_b200.set_precision(args.precision)
     torch.manual_seed(SEED)                                   # identical replicas on every rank
-    c3, c4 = args.workload == "c3", args.workload == "c4"
+    c3, c4 = workload == "c3", workload == "c4"
     k_radius, depth = (16, 4) if c4 else (K_RADIUS, DEPTH)
-    if c4 and (args.videos, args.nodes) == (256, 128):        # BASELINE configs[3]: 256 videos x 2048 segments
-        args.nodes = 2048
+    videos, nodes = args.videos, args.nodes
+    if c4:                                                    # BASELINE configs[3]: 256 videos x 2048 segments
+        videos, nodes = (256, 2048) if (args.videos, args.nodes) == (256, 128) else (args.videos, args.nodes)
+    if args.scaling == "strong":
+        from egopack_b200.dp import shard_graphs
+        videos = len(shard_graphs(videos, rank, world))
+    feat_dtype = {"auto": torch.bfloat16 if args.precision == "bf16" else torch.float32,
+                  "bf16": torch.bfloat16, "fp32": torch.float32}[args.feature_dtype]
     model = Graph(syn.FEATURE_DIM, HIDDEN, depth, temporal_pooling={"hidden_size": TRN_HIDDEN, "dropout": DROPOUT},
                   num_segments=syn.NUM_SEGMENTS).to(dev)
     heads = (syn.N_VERBS, syn.N_NOUNS)
@@ -226,37 +276,34 @@ def native_run(args, rank: int, world: int, local_rank: int):
         params += [p for p in graphone.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5, fused=True)
     sync = GradientAllReduce(params) if world > 1 else None
-    lta_edges = LTATemporalConnectivity(r=k_radius + 0.5)
+    feed_tf = {t: (LTATemporalConnectivity(r=k_radius + 0.5) if t == "lta" else RadiusGraph(r=k_radius + 0.5))
+               for t in task_names}
 
     gen = syn.generator(SEED, 2, rank)                        # every rank draws its own shard of graphs
-    host = {t: syn.make_batch(t, args.videos, args.nodes, gen, band_k=k_radius, pin=True) for t in task_names}
-    n_nodes = args.videos * args.nodes * len(task_names)
-    h2d_bytes = sum(v.numel() * v.element_size() for b in host.values() for v in (b.x, b.pos, b.y, b.batch, b.ptr))
+    n_nodes = videos * nodes * len(task_names)
+    on_device = not full                                      # sub-lines: synthetic features drawn on the device
+    if on_device:
+        host = None
+        dgen = torch.Generator(device=dev).manual_seed(SEED + 1000 * 2 + rank)
+        resident = {}
+        for t in task_names:
+            hb = syn.make_batch(t, videos, nodes, gen, feature_dim=1, num_segments=1, band_k=k_radius)   # labels / structure
+            d = egopack_b200.Batch()
+            d.x = torch.randn(videos * nodes, syn.NUM_SEGMENTS, syn.FEATURE_DIM, generator=dgen, device=dev,
+                              dtype=torch.float32).to(feat_dtype)
+            for k in ("pos", "y", "batch", "ptr"):
+                setattr(d, k, getattr(hb, k).to(dev))
+            d.pos_unit_spaced = True
+            resident[t] = feed_tf[t](d)
+        h2d_bytes = 0
+    else:
+        host = {t: syn.make_batch(t, videos, nodes, gen, band_k=k_radius, pin=True, feature_dtype=feat_dtype)
+                for t in task_names}
+        h2d_bytes = sum(v.numel() * v.element_size() for b in host.values() for v in (b.x, b.pos, b.y, b.batch, b.ptr))
 
-    def upload_copies(stream=None):
-        """Phase 1 of the feed: enqueue the pinned H2D copies of one step's inputs (no host waits)."""
-        out = {}
-        with torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
-            for t, hb in host.items():
-                d = egopack_b200.Batch()
-                for k in ("x", "pos", "y", "batch", "ptr"):
-                    setattr(d, k, getattr(hb, k).to(dev, non_blocking=True))
-                out[t] = d
-        return out
-
-    def upload_structure(out, stream=None):
-        """Phase 2: device-side edge / structure construction behind the copies (reads edge counts back: host waits)."""
-        with torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
-            for t, d in out.items():
-                if t == "lta":
-                    lta_edges(d)                               # band + star edges, on the device
-                else:
-                    d.band_k = k_radius                        # unit-spaced pos: the band needs no edge_index
-        return out
-
-    def upload(stream=None):
-        """H2D of one step's inputs + device-side edge/structure construction (what a DataLoader hands over)."""
-        return upload_structure(upload_copies(stream), stream)
+    def host_loader(n):
+        for _ in range(n):
+            yield host
 
     def step(batches):
         opt.zero_grad(set_to_none=True)
@@ -284,7 +331,8 @@ def native_run(args, rank: int, world: int, local_rank: int):
         return float(t.item())
 
     # ---- device-resident timing ------------------------------------------------------------------------
-    resident = upload()
+    if not on_device:
+        resident = next(iter(DeviceFeeder(host_loader(1), dev, feed_tf)))
     clocks = ClockSampler(local_rank)
     clocks.start()
     for _ in range(args.warmup):
@@ -304,6 +352,7 @@ def native_run(args, rank: int, world: int, local_rank: int):
     launches = _lib.kernel_launches()
     ms_per_step = ms_total / args.steps
     value = world * n_nodes / (ms_per_step / 1e3)
+    last = float(loss.item())
 
     if args.quick and args.gap_profile and rank == 0:
         from torch.profiler import ProfilerActivity, profile
@@ -324,88 +373,63 @@ def native_run(args, rank: int, world: int, local_rank: int):
         hist = {"<1us": 0, "1-2us": 0, "2-5us": 0, "5-20us": 0, ">20us": 0}
         for g, _ in gaps:
             hist["<1us" if g < 1 else "1-2us" if g < 2 else "2-5us" if g < 5 else "5-20us" if g < 20 else ">20us"] += 1
+        by_name = {}
+        for a, b, nme in ks:
+            r = by_name.setdefault(nme[:90], [0, 0.0])
+            r[0] += 1
+            r[1] += b - a
         os.makedirs(os.path.dirname(os.path.abspath(args.gap_profile)), exist_ok=True)
         json.dump({"steps": 2, "kernels": len(ks), "span_us": span, "busy_us": busy, "idle_us": span - busy,
                    "idle_frac": (span - busy) / span, "gap_hist": hist,
-                   "largest_gaps_us_before": [(round(g, 1), n[:80]) for g, n in gaps[:25]]},
+                   "largest_gaps_us_before": [(round(g, 1), n[:80]) for g, n in gaps[:25]],
+                   "kernel_time_us": {k: [v[0], round(v[1], 1)] for k, v in sorted(by_name.items(), key=lambda kv: -kv[1][1])[:60]}},
                   open(args.gap_profile, "w"), indent=1)
     if args.quick:
         return {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "gpu_launches": int(launches), "quick": True}
 
-    # ---- end-to-end timing: pinned host -> device every step, loss read back every step -------------------
-    # step i+1's inputs are uploaded on a copy stream (and its edges built on the device) while step i computes
-    from egopack_b200.feed import DeviceFeeder
-    from egopack_b200.models.transforms import RadiusGraph
-    feed_tf = {t: (lta_edges if t == "lta" else RadiusGraph(r=k_radius + 0.5)) for t in task_names}
-
-    def host_loader(n):
-        for _ in range(n):
-            yield host
-
-    for b in DeviceFeeder(host_loader(2), dev, feed_tf):
-        float(step(b).item())
-    barrier()
-    feeder = DeviceFeeder(host_loader(args.steps), dev, feed_tf)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if os.environ.get("EGP_BENCH_E2E") != "feeder":
-        # default: single-thread ordering -- enqueue the copies of step i+1, then step i, then i+1's edge construction
-        # (which waits on the host for edge counts), then read the loss.
-        # EGP_BENCH_E2E=feeder runs the same loop through the threaded DeviceFeeder instead; at this batch size its
-        # worker loses ~10 ms/step to GIL hand-offs around the edge-count read-backs (A/B on one box: 48 vs 39 ms)
-        copy_stream = torch.cuda.Stream()
-        e0.record()
-        nxt = upload(copy_stream)
-        for i in range(args.steps):
-            torch.cuda.current_stream().wait_stream(copy_stream)
-            cur = nxt
-            for d in cur.values():
-                for k in ("x", "pos", "y", "batch", "ptr"):
-                    getattr(d, k).record_stream(torch.cuda.current_stream())
-            more = i + 1 < args.steps
-            if more:
-                nxt = upload_copies(copy_stream)               # the bus starts on step i+1 before step i is enqueued,
-            loss = step(cur)                                   # so host waits inside the step cannot delay the copy
-            if more:
-                upload_structure(nxt, copy_stream)             # its edges are built (host waits) behind the step's launches
-            last = float(loss.item())
-        e1.record()
-        feeder.h2d_bytes = h2d_bytes * args.steps
-    else:
+    # ---- end-to-end timing: the public feed (DeviceFeeder) from pinned host memory every step, loss read back ------
+    # the feeder enqueues the copies of step i+1 (and its device-side transforms) on its copy stream before it hands
+    # out step i, so they overlap the step; nothing in the hand-over waits on the GPU
+    e2e = None
+    if full:
+        for b in DeviceFeeder(host_loader(2), dev, feed_tf):
+            float(step(b).item())
+        barrier()
+        feeder = DeviceFeeder(host_loader(args.steps), dev, feed_tf)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for b in feeder:
             loss = step(b)
             last = float(loss.item())                          # D2H of the loss every step
         e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    e2e_value = world * n_nodes / (e2e_ms / 1e3)
-    assert feeder.h2d_bytes == h2d_bytes * args.steps, (feeder.h2d_bytes, h2d_bytes)
+        barrier()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        assert feeder.h2d_bytes == h2d_bytes * args.steps, (feeder.h2d_bytes, h2d_bytes)
+        e2e = {"value": round(world * n_nodes / (e2e_ms / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+               "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3),
+               "h2d_gbps_per_gpu": round(h2d_bytes / (e2e_ms / 1e3) / 1e9, 1),
+               "note": "egopack_b200.feed.DeviceFeeder: pinned host -> device copy of every step's inputs on a copy stream "
+                       "(enqueued before the previous step is handed out), device-side graph transforms (band_k / star hints, "
+                       "lazy edge_index), loss.item() per step"}
+        b = None
 
     # ---- launch-bound regime: the reference's own batch size (16 graphs/task), eager vs one CUDA graph per step ------
     small = None
-    if world == 1 and not c3 and not c4:
+    if full and world == 1 and workload == "c2":
         try:
-            import gc
             from egopack_b200.graphs import GraphedStep
             # AccumulateGrad nodes created on the default stream by the eager steps above must not survive into the
             # capture stream: drop every reference to the old autograd graphs first
             loss = None
-            nxt = cur = None
             gc.collect()
             sv, sn = 16, 16
             sgen = syn.generator(SEED, 9, rank)
-            shost = {t: syn.make_batch(t, sv, sn, sgen, band_k=k_radius) for t in task_names}
             sdev = {}
-            for t, hb in shost.items():
-                d = egopack_b200.Batch()
-                for k in ("x", "pos", "y", "batch", "ptr"):
-                    setattr(d, k, getattr(hb, k).to(dev))
-                if t == "lta":
-                    lta_edges(d)
-                else:
-                    d.band_k = k_radius
-                sdev[t] = d
+            for t in task_names:
+                d = syn.make_batch(t, sv, sn, sgen, band_k=k_radius, feature_dtype=feat_dtype).to(dev)
+                d.pos_unit_spaced = True
+                sdev[t] = feed_tf[t](d)
             opt2 = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5, fused=True, capturable=True)
 
             def small_step(b):
@@ -440,7 +464,7 @@ def native_run(args, rank: int, world: int, local_rank: int):
         except Exception as ex:  # noqa: BLE001 -- a probe; never let it take the bench line down
             small = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
-    # ---- per-launch trace for the roofline (separate, untimed steps) ---------------------------------------
+    # ---- per-launch trace for the rooflines (separate, untimed steps) ---------------------------------------
     pk = peaks()
     ops.TRACE = []
     for _ in range(2):
@@ -451,6 +475,9 @@ def native_run(args, rank: int, world: int, local_rank: int):
     shapes = {}
     for name, work, unit, a, b, detail in trace:
         ms = a.elapsed_time(b)
+        if name.startswith("sage_mean") and detail:            # the aggregation kernels differ by radius: keep them apart
+            name = f"{name} {detail}"
+            detail = ""
         r = agg.setdefault(name, {"work": 0.0, "ms": 0.0, "n": 0, "unit": unit})
         r["work"] += work
         r["ms"] += ms
@@ -460,15 +487,13 @@ def native_run(args, rank: int, world: int, local_rank: int):
             d["work"] += work
             d["ms"] += ms
             d["n"] += 1
-    roof, roof_hbm = None, None
-    traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")     # measured once under ncu, per launch
-    if os.path.exists(tpath):
-        traffic = {k: v for k, v in json.load(open(tpath)).items() if isinstance(v, dict)}
+    traffic = load_traffic()
 
     def traffic_of(kernel):
         t = traffic.get(kernel)
         return (int(t["bytes"]), f"ncu dram bytes of one launch: {t['launch']} ({t['source']})") if t else (None, None)
+
+    roof, roof_hbm = None, []
     if "gemm_tcgen05" in agg or "gemm_ffma" in agg:
         g = agg.get("gemm_tcgen05") or agg["gemm_ffma"]
         ach = g["work"] / (g["ms"] / 1e3) / 1e12
@@ -478,17 +503,15 @@ def native_run(args, rank: int, world: int, local_rank: int):
                 "traffic": traffic_of("tc_gemm_kernel")[0], "traffic_note": traffic_of("tc_gemm_kernel")[1],
                 "launches_per_step": g["n"] // 2, "ms_per_step": round(g["ms"] / 2, 3),
                 "share_of_step": round(g["ms"] / 2 / ms_per_step, 3), "peak_source": f"{pk['source']} (sustained bf16 GEMM)"}
-    for nme in ("sage_mean_band", "sage_mean_csr"):
-        if nme in agg:
-            a = agg[nme]
-            ach = a["work"] / (a["ms"] / 1e3) / 1e9
-            r = {"bound": "hbm", "kernel": nme, "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
-                 "frac": round(ach / pk["hbm"], 4), "traffic": traffic_of(nme)[0], "traffic_note": traffic_of(nme)[1],
-                 "launches_per_step": a["n"] // 2,
-                 "ms_per_step": round(a["ms"] / 2, 3), "peak_source": pk["source"]}
-            roof_hbm = roof_hbm or []
-            roof_hbm.append(r)
-    if args.trace_out and rank == 0:
+    for nme, a in agg.items():
+        if nme.split(" ")[0] not in HBM_KERNELS:
+            continue
+        ach = a["work"] / (a["ms"] / 1e3) / 1e9
+        roof_hbm.append({"bound": "hbm", "kernel": nme, "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": round(ach / pk["hbm"], 4), "traffic": traffic_of(nme)[0], "traffic_note": traffic_of(nme)[1],
+                         "launches_per_step": a["n"] // 2, "ms_per_step": round(a["ms"] / 2, 3), "peak_source": pk["source"]})
+    roof_hbm.sort(key=lambda r: -r["ms_per_step"])
+    if args.trace_out and rank == 0 and full:
         os.makedirs(os.path.dirname(os.path.abspath(args.trace_out)), exist_ok=True)
         summary = {k: {**v, "ms_per_step": v["ms"] / 2} for k, v in agg.items()}
         summary["gemm_shapes"] = {k: {"launches_per_step": v["n"] // 2, "ms_per_step": round(v["ms"] / 2, 4),
@@ -496,33 +519,32 @@ def native_run(args, rank: int, world: int, local_rank: int):
                                   for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])}
         json.dump(summary, open(args.trace_out, "w"), indent=1)
 
+    feat_name = "bf16" if feat_dtype == torch.bfloat16 else "fp32"
+    config = {"workload": WORKLOAD_TEXT[workload].format(protos=args.protos),
+              "graphs_per_task_per_gpu": videos, "nodes_per_graph": nodes,
+              "nodes_per_step_per_gpu": n_nodes,
+              "features": f"[N,3,1536] {feat_name} N(0,1)" + (" (stored by the loader as bf16: Batch.to_feature_dtype; bit-identical "
+                                                             "to fp32 features in the bf16 compute mode)" if feat_name == "bf16" else ""),
+              "parallelism": f"dp{world}",
+              "l2": (f"inputs larger than L2 ({h2d_bytes / 2**20:.0f} MiB of features per step)" if not on_device else
+                     f"inputs larger than L2 ({n_nodes * 4608 * 2 / 2**20:.0f} MiB of features per step, drawn on the device)"),
+              "final_loss": round(last, 4)}
+    if numa is not None:
+        config["host_memory_binding"] = numa
     out = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": ("c3: EgoPack OSCC primary + frozen AR/LTA/PNR prototype backpack (k=4, depth 3, residual, "
-                                f"{args.protos} prototypes/bank, late fusion), Graph trainable, full train step"
-                                if c3 else
-                                "c4: long-video stress (BASELINE configs[3]): AR over 2048-segment graphs, temporal radius 16 "
-                                "(33-wide band), 4 GNN layers, hidden 1024, full train step"
-                                if c4 else
-                                "c2: MTL AR+LTA+PNR shared temporal GNN (experiments/mtl.yaml: k=1, hidden 1024, depth 3, "
-                                "TRN hidden 1024, dropout 0.5), full train step = zero_grad+fwd+loss+bwd+grad-allreduce+Adam"),
-                   "graphs_per_task_per_gpu": args.videos, "nodes_per_graph": args.nodes,
-                   "nodes_per_step_per_gpu": n_nodes, "features": "[N,3,1536] fp32 N(0,1)", "parallelism": f"dp{world}",
-                   "l2": f"inputs larger than L2 ({h2d_bytes / 2**20:.0f} MiB of features per step)",
-                   "final_loss": round(last, 4)},
-        "clocks": clock_info,
-        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
-                "ms_per_step": round(e2e_ms, 3), "note": "pinned host -> device copy of every step's inputs on a copy stream "
-                                                          "(overlapping the previous step), device-side edge construction, loss.item() per step"},
-        "gpu_launches": int(launches),
-        "roofline": roof,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": config, "clocks": clock_info,
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
     }
     if roof_hbm:
         out["roofline_hbm"] = roof_hbm
     if small is not None:
         out["small_batch"] = small
+    # release this workload's memory before the next one
+    del model, tasks, opt, params, resident
+    gc.collect()
+    torch.cuda.empty_cache()
     return out
 
 
@@ -541,16 +563,22 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_oracle_run(args.cpu_videos, args.nodes, max(args.steps, 1), min(args.warmup, 2))
-        print(json.dumps({
+        r = cpu_oracle_run(args.cpu_videos, args.nodes, max(args.steps, 1), max(args.warmup, 0))
+        line = {
             "impl": "reference", "metric": METRIC, "value": round(r["value"], 1), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": round(r["ms_per_step"], 1),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "c2: MTL AR+LTA+PNR shared temporal GNN, full train step (CPU oracle, bounded sample)",
-                       "graphs_per_task": args.cpu_videos, "nodes_per_graph": args.nodes},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 1),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            # the arm's own config; every CPU step is a bounded sample of it (cpu_baseline.sample says which)
+            "config": {"workload": WORKLOAD_TEXT["c2"], "graphs_per_task_per_gpu": args.videos,
+                       "nodes_per_graph": args.nodes, "nodes_per_step_per_gpu": args.videos * args.nodes * len(TASKS),
+                       "features": "[N,3,1536] fp32 N(0,1)", "parallelism": "cpu",
+                       "sample_graphs_per_task": args.cpu_videos},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": round(r["value"], 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }), file=result_out, flush=True)
+        }
+        if args.cpu_sweep:
+            line["sweep_nodes_per_s"] = {str(v): round(cpu_oracle_run(v, args.nodes, 1, 1)["value"], 1) for v in (16, 64, 256)}
+        print(json.dumps(line), file=result_out, flush=True)
         return
 
     if not torch.cuda.is_available():
@@ -559,7 +587,20 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    out = native_run(args, rank, world, local_rank)
+    out = native_run(args, rank, world, local_rank, args.workload, full=True)
+    if world == 1 and not args.quick and not args.no_extra and args.workload == "c2":
+        # the other BASELINE configurations, device-resident, in the same run (configs[2] and configs[3])
+        extra = {}
+        sub = argparse.Namespace(**vars(args))
+        sub.steps, sub.warmup, sub.trace_out = min(args.steps, 5), 3, None
+        for wl in ("c3", "c4"):
+            try:
+                r = native_run(sub, rank, world, local_rank, wl, full=False)
+                extra[wl] = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "clocks",
+                                               "gpu_launches", "roofline", "roofline_hbm") if k in r}
+            except Exception as ex:  # noqa: BLE001 -- never let a sub-line take the main line down
+                extra[wl] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+        out["extra"] = extra
     if rank == 0:
         if not args.no_cpu_baseline and world == 1 and not args.quick:
             r = cpu_oracle_run(args.cpu_videos, args.nodes, 3, 1)

@@ -47,14 +47,24 @@ def _compile(src: str, verbose: bool) -> str:
     return obj
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, refresh=()) -> str:
+    """Compile + link.  With an unchanged source digest nothing is rebuilt, except the translation units named in
+    ``refresh`` (``__graft_entry__.build()`` always recompiles a few, so "does it build" is answered by the compiler
+    and not by a stamp file that travelled with the tree)."""
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "digest.txt")
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+    fresh = os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig
+    if not force and fresh and not refresh:
         return LIB
+    todo = sources() if (force or not fresh) else [s for s in sources() if s in set(refresh)]
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        objs = list(ex.map(lambda s: _compile(s, verbose), sources()))
+        list(ex.map(lambda s: _compile(s, verbose), todo))
+    objs = [os.path.join(OBJ, s[:-3] + ".o") for s in sources()]
+    missing = [o for o in objs if not os.path.exists(o)]
+    if missing:                                              # objects do not travel in git: build whatever is absent
+        with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            list(ex.map(lambda o: _compile(os.path.basename(o)[:-2] + ".cu", verbose), missing))
     cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

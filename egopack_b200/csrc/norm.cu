@@ -21,20 +21,33 @@ constexpr int kNormThreads = 256;
 // ---------------------------------------------------------------------------------------------------------
 // graph LayerNorm forward
 // ---------------------------------------------------------------------------------------------------------
+// Segments: the statistics of gnn.LayerNorm(batch=None) span ONE forward call.  Graph.forward_many runs several task
+// batches through the shared weights as one tensor, so the rows are split into up to kMaxGlnSegs consecutive
+// segments (one per original forward call), each with its own mu / sigma; dweight / dbias sum over all of them.
+constexpr int kMaxGlnSegs = 8;
+struct GlnSegs {
+  int count;
+  int64_t row[kMaxGlnSegs + 1];  // segment s = rows [row[s], row[s+1])
+};
+
 struct GlnWorkspace {            // layout of the caller-provided workspace
-  unsigned int ticket;           // last-block election
-  unsigned int pad[3];
-  double scal[4];                // backward: S1 = sum(g_hat), S2 = sum(g_hat * (x-mu))
-};                               // followed by: double partial[2*G]; float colpart[G][2][C]
+  unsigned int ticket[kMaxGlnSegs];   // last-block election, per segment
+  double scal[2 * kMaxGlnSegs];  // backward, per segment: S1 = sum(g_hat), S2 = sum(g_hat * (x-mu))
+};                               // followed by: double partial[2*G*S]; float colpart[G*S][2][C]
 
 template <typename T>
 __global__ void __launch_bounds__(kNormThreads)
-gln_stats_kernel(const T* __restrict__ x, int64_t nvec, double inv_count, double* __restrict__ partial,
+gln_stats_kernel(const T* __restrict__ x, GlnSegs segs, int64_t channels, double* __restrict__ partial,
                  unsigned int* __restrict__ ticket, double* __restrict__ stats) {
   pdl_enter();
   constexpr int VN = Vec<T>::N;
   __shared__ double red[32];
   __shared__ bool is_last;
+  const int seg = blockIdx.y;
+  const int64_t rows = segs.row[seg + 1] - segs.row[seg];
+  const int64_t nvec = rows * channels / VN;
+  x += segs.row[seg] * channels;
+  partial += (size_t)seg * 2 * gridDim.x;
   double s = 0.0, q = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,7 +79,7 @@ gln_stats_kernel(const T* __restrict__ x, int64_t nvec, double inv_count, double
     partial[2 * blockIdx.x] = s;
     partial[2 * blockIdx.x + 1] = q;
     __threadfence();
-    const unsigned int t = atomicAdd(ticket, 1u);
+    const unsigned int t = atomicAdd(ticket + seg, 1u);
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
@@ -80,12 +93,13 @@ gln_stats_kernel(const T* __restrict__ x, int64_t nvec, double inv_count, double
     ts = block_sum(ts, red);
     tq = block_sum(tq, red);
     if (threadIdx.x == 0) {
+      const double inv_count = rows > 0 ? 1.0 / ((double)rows * (double)channels) : 0.0;
       const double mu = ts * inv_count;
       double var = tq * inv_count - mu * mu;
       var = var > 0.0 ? var : 0.0;
-      stats[0] = mu;
-      stats[1] = sqrt(var);
-      *ticket = 0u;
+      stats[2 * seg] = mu;
+      stats[2 * seg + 1] = sqrt(var);
+      ticket[seg] = 0u;
     }
   }
 }
@@ -95,12 +109,16 @@ gln_stats_kernel(const T* __restrict__ x, int64_t nvec, double inv_count, double
 template <typename T, bool FIXED>
 __global__ void __launch_bounds__(kNormThreads)
 gln_apply_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                 T* __restrict__ y, const double* __restrict__ stats, int64_t nvec, int64_t channels, float eps,
+                 T* __restrict__ y, const double* __restrict__ stats, GlnSegs segs, int64_t channels, float eps,
                  int act, float slope) {
   pdl_enter();
   constexpr int VN = Vec<T>::N;
-  const float mu = (float)stats[0];
-  const float rs = (float)(1.0 / (stats[1] + (double)eps));
+  const int seg = blockIdx.y;
+  const int64_t nvec = (segs.row[seg + 1] - segs.row[seg]) * channels / VN;
+  x += segs.row[seg] * channels;
+  y += segs.row[seg] * channels;
+  const float mu = (float)stats[2 * seg];
+  const float rs = (float)(1.0 / (stats[2 * seg + 1] + (double)eps));
   const int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float wv[VN], bv[VN];
   if (FIXED) {
@@ -145,16 +163,17 @@ __device__ __forceinline__ float act_grad(float pre, int act, float slope) {
 template <typename T>
 __global__ void __launch_bounds__(kNormThreads)
 gln_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ w,
-                      const float* __restrict__ b, const double* __restrict__ stats, int64_t n, int64_t channels,
+                      const float* __restrict__ b, const double* __restrict__ stats, GlnSegs segs, int64_t channels,
                       int rows_per_cta, float eps, int act, float slope, float* __restrict__ colpart,
                       double* __restrict__ scalpart) {
   pdl_enter();
   constexpr int VN = Vec<T>::N;
   __shared__ double red[32];
+  const int seg = blockIdx.z;
   const int64_t col = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * VN;
   const bool live = col < channels;
-  const float mu = (float)stats[0];
-  const float rs = (float)(1.0 / (stats[1] + (double)eps));
+  const float mu = (float)stats[2 * seg];
+  const float rs = (float)(1.0 / (stats[2 * seg + 1] + (double)eps));
   float wv[VN], bv[VN], dw[VN], db[VN];
 #pragma unroll
   for (int c = 0; c < VN; ++c) {
@@ -164,7 +183,8 @@ gln_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const f
     db[c] = 0.f;
   }
   double s1 = 0.0, s2 = 0.0;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(r0 + rows_per_cta, n);
+  const int64_t r0 = min(segs.row[seg] + (int64_t)blockIdx.x * rows_per_cta, segs.row[seg + 1]);
+  const int64_t r1 = min(r0 + rows_per_cta, segs.row[seg + 1]);
   if (live) {
     auto row_update = [&](const Vec<T>& g, const Vec<T>& a) {
       float l1 = 0.f, l2 = 0.f;
@@ -194,7 +214,7 @@ gln_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const f
       for (int u = 0; u < 4; ++u) row_update(gr[u].unpack(), ar[u].unpack());
     }
     for (; i < r1; ++i) row_update(Vec<T>::load(dy + i * channels + col), Vec<T>::load(x + i * channels + col));
-    float* cp = colpart + (size_t)blockIdx.x * 2 * channels;
+    float* cp = colpart + ((size_t)seg * gridDim.x + blockIdx.x) * 2 * channels;
 #pragma unroll
     for (int c = 0; c < VN; ++c) {
       cp[col + c] = dw[c];
@@ -204,7 +224,7 @@ gln_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const f
   s1 = block_sum(s1, red);
   s2 = block_sum(s2, red);
   if (threadIdx.x == 0) {
-    const size_t p = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2;
+    const size_t p = (((size_t)seg * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 2;
     scalpart[p] = s1;
     scalpart[p + 1] = s2;
   }
@@ -214,7 +234,8 @@ gln_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const f
 // columns and splits the part rows over 1024 / kFinCols groups (few serial iterations per thread, ~128 CTAs for 1024
 // channels: the kernel is pure latency), then combines the groups in a fixed order: shuffles inside a warp, shared
 // memory across warps.  out_k[c] = sum_g colpart[g][k][c].
-// The extra block `colblocks` (if scal != null) reduces the scalar pairs: scal[0..1] = sum scalpart.
+// Blocks colblocks.. (one per graph-LN segment, if scal != null) reduce the scalar pairs: scal[2s..2s+1] = sum over
+// that segment's scal_parts entries of scalpart.
 constexpr int kFinThreads = 1024;
 constexpr int kFinCols = 8;                       // columns per block: 32-byte segments of a partial row
 constexpr int kFinGroups = kFinThreads / kFinCols;
@@ -268,7 +289,9 @@ col_finalize_kernel(const float* __restrict__ colpart, int parts, int64_t channe
       float* o = warp == 0 ? out0 : (warp == 1 ? out1 : out2);
       if (lane < kFinCols && cc < channels && o) o[cc] = t;
     }
-  } else {
+  } else {  // one extra block per segment reduces that segment's scalar pairs
+    const int seg = (int)blockIdx.x - colblocks;
+    scalpart += (size_t)seg * 2 * scal_parts;
     double s1 = 0.0, s2 = 0.0;
     for (int p = threadIdx.x; p < scal_parts; p += blockDim.x) {
       s1 += scalpart[2 * p];
@@ -276,7 +299,7 @@ col_finalize_kernel(const float* __restrict__ colpart, int parts, int64_t channe
     }
     s1 = block_sum(s1, red);
     s2 = block_sum(s2, red);
-    if (threadIdx.x == 0) { scal[0] = s1; scal[1] = s2; }
+    if (threadIdx.x == 0) { scal[2 * seg] = s1; scal[2 * seg + 1] = s2; }
   }
 }
 
@@ -284,20 +307,27 @@ template <typename T, bool FIXED>
 __global__ void __launch_bounds__(kNormThreads)
 gln_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ b, const double* __restrict__ stats, const double* __restrict__ scal,
-                     T* __restrict__ dx, int64_t nvec, int64_t channels, double inv_count, float eps, int act,
-                     float slope, float* __restrict__ dxpart /* [gridDim.x, C] or null; FIXED only */) {
+                     T* __restrict__ dx, GlnSegs segs, int64_t channels, float eps, int act,
+                     float slope, float* __restrict__ dxpart /* [gridDim.y * gridDim.x, C] or null; FIXED only */) {
   pdl_enter();
   constexpr int VN = Vec<T>::N;
   __shared__ float csum[kNormThreads * VN];
   float dsum[VN];
 #pragma unroll
   for (int c = 0; c < VN; ++c) dsum[c] = 0.f;
-  const double sigma = stats[1];
-  const float mu = (float)stats[0];
+  const int seg = blockIdx.y;
+  const int64_t seg_rows = segs.row[seg + 1] - segs.row[seg];
+  const int64_t nvec = seg_rows * channels / VN;
+  dy += segs.row[seg] * channels;
+  x += segs.row[seg] * channels;
+  dx += segs.row[seg] * channels;
+  const double inv_count = seg_rows > 0 ? 1.0 / ((double)seg_rows * (double)channels) : 0.0;
+  const double sigma = stats[2 * seg + 1];
+  const float mu = (float)stats[2 * seg];
   const float rs = (float)(1.0 / (sigma + (double)eps));
-  const float m1 = (float)(scal[0] * inv_count);  // mean(g_hat)
+  const float m1 = (float)(scal[2 * seg] * inv_count);  // mean(g_hat)
   const double den = sigma * (sigma + (double)eps) * (sigma + (double)eps);
-  const float k2 = den > 0.0 ? (float)(scal[1] * inv_count / den) : 0.f;
+  const float k2 = den > 0.0 ? (float)(scal[2 * seg + 1] * inv_count / den) : 0.f;
   const int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float wv[VN], bv[VN];
   auto load_params = [&](int64_t c0) {
@@ -326,7 +356,7 @@ gln_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
     a.store(dx + v * VN);
   }
   if (FIXED && dxpart)
-    block_column_partial<VN>(dsum, (int)(channels / VN), dxpart + (size_t)blockIdx.x * channels, csum);
+    block_column_partial<VN>(dsum, (int)(channels / VN), dxpart + ((size_t)seg * gridDim.x + blockIdx.x) * channels, csum);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -721,69 +751,125 @@ using namespace egp;
 
 extern "C" {
 
-size_t egp_graph_layernorm_workspace(int64_t n, int64_t channels) {
+static size_t gln_workspace_bytes(int64_t n, int64_t channels, int nseg) {
   const int parts = gln_parts(n);
   const int64_t gy = ceil_div(channels, (int64_t)kNormThreads * 4);
   const int g_stats = sm_count() * 4;
   size_t bytes = sizeof(GlnWorkspace);
-  const size_t np = (size_t)(parts * gy > g_stats ? parts * gy : g_stats);
+  const size_t np = (size_t)(parts * gy > g_stats ? parts * gy : g_stats) * (size_t)nseg;
   bytes += sizeof(double) * 2 * np;
-  bytes += sizeof(float) * 2 * (size_t)parts * (size_t)channels;            // dweight/dbias partials
-  bytes += sizeof(float) * (size_t)(sm_count() * 8) * (size_t)channels;     // dx column-sum partials
-  const size_t cs = colsum_workspace_bytes(n, channels);                    // fallback column sum of dx
+  bytes += sizeof(float) * 2 * (size_t)parts * (size_t)nseg * (size_t)channels;      // dweight/dbias partials
+  bytes += sizeof(float) * (size_t)(sm_count() * 8) * (size_t)nseg * (size_t)channels;  // dx column-sum partials
+  const size_t cs = colsum_workspace_bytes(n, channels);                              // fallback column sum of dx
   return bytes + cs + 128;
 }
 
-int egp_graph_layernorm_fwd(const void* x, const float* weight, const float* bias, void* y, double* stats,
-                            int64_t n, int64_t channels, float eps, int act, float slope, int dtype,
-                            void* workspace, size_t ws_bytes, void* stream) {
+static int gln_segments(int64_t n, int nseg, const int64_t* seg_rows, GlnSegs* out, const char* who) {
+  if (nseg < 1 || nseg > kMaxGlnSegs) {
+    set_error("%s: %d segments (1..%d supported)", who, nseg, kMaxGlnSegs);
+    return EGP_ERR_INVALID;
+  }
+  out->count = nseg;
+  if (!seg_rows) {
+    if (nseg != 1) { set_error("%s: seg_rows is required for more than one segment", who); return EGP_ERR_INVALID; }
+    out->row[0] = 0;
+    out->row[1] = n;
+    return EGP_OK;
+  }
+  for (int i = 0; i <= nseg; ++i) out->row[i] = seg_rows[i];
+  for (int i = 0; i < nseg; ++i)
+    if (out->row[i + 1] < out->row[i]) { set_error("%s: seg_rows must be non-decreasing", who); return EGP_ERR_INVALID; }
+  if (out->row[0] != 0 || out->row[nseg] != n) {
+    set_error("%s: seg_rows must run from 0 to num_nodes", who);
+    return EGP_ERR_INVALID;
+  }
+  return EGP_OK;
+}
+
+static int64_t gln_max_seg_rows(const GlnSegs& sg) {
+  int64_t m = 0;
+  for (int i = 0; i < sg.count; ++i) m = m > sg.row[i + 1] - sg.row[i] ? m : sg.row[i + 1] - sg.row[i];
+  return m;
+}
+
+size_t egp_graph_layernorm_workspace(int64_t n, int64_t channels) { return gln_workspace_bytes(n, channels, 1); }
+size_t egp_graph_layernorm_seg_workspace(int64_t n, int64_t channels, int nseg) {
+  return gln_workspace_bytes(n, channels, nseg < 1 ? 1 : (nseg > kMaxGlnSegs ? kMaxGlnSegs : nseg));
+}
+
+int egp_graph_layernorm_seg_fwd(const void* x, const float* weight, const float* bias, void* y, double* stats,
+                                int64_t n, int64_t channels, int nseg, const int64_t* seg_rows, float eps, int act,
+                                float slope, int dtype, void* workspace, size_t ws_bytes, void* stream) {
   EGP_REQUIRE(x && weight && bias && y && stats && workspace, "graph_layernorm_fwd: null pointer");
   const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
   EGP_REQUIRE(channels % vn == 0 && aligned16(x) && aligned16(y), "graph_layernorm_fwd: channels %% %d != 0 or unaligned", (int)vn);
-  if (ws_bytes < egp_graph_layernorm_workspace(n, channels)) {
-    set_error("graph_layernorm_fwd: workspace %zu < %zu", ws_bytes, egp_graph_layernorm_workspace(n, channels));
+  GlnSegs sg;
+  int rc = gln_segments(n, nseg, seg_rows, &sg, "graph_layernorm_fwd");
+  if (rc != EGP_OK) return rc;
+  if (ws_bytes < gln_workspace_bytes(n, channels, nseg)) {
+    set_error("graph_layernorm_fwd: workspace %zu < %zu", ws_bytes, gln_workspace_bytes(n, channels, nseg));
     return EGP_ERR_WORKSPACE;
   }
   if (n == 0) return EGP_OK;
   cudaStream_t s = (cudaStream_t)stream;
   GlnWorkspace* ws = (GlnWorkspace*)workspace;
   double* partial = (double*)(ws + 1);
-  EGP_CUDA(cudaMemsetAsync(&ws->ticket, 0, sizeof(unsigned int), s));
+  EGP_CUDA(cudaMemsetAsync(ws->ticket, 0, sizeof(ws->ticket), s));
   EGP_DISPATCH_DTYPE(dtype, T, {
-    const int64_t nvec = n * channels / Vec<T>::N;
-    const int g1 = norm_grid(nvec, kNormThreads * 4);
-    (void)launch_kernel(gln_stats_kernel<T>, g1, kNormThreads, 0, s, (const T*)x, nvec, 1.0 / ((double)n * (double)channels), partial,
-                                                     &ws->ticket, stats);
+    const int64_t nvec = gln_max_seg_rows(sg) * channels / Vec<T>::N;     // grid sized for the largest segment
+    int g1 = norm_grid(nvec, kNormThreads * 4);
+    if (nseg > 1) {                                           // keep the chip-wide CTA count of a one-segment launch
+      const int cap = sm_count() * 4 / nseg;
+      g1 = g1 > cap ? (cap > 1 ? cap : 1) : g1;
+    }
+    (void)launch_kernel(gln_stats_kernel<T>, dim3(g1, nseg), kNormThreads, 0, s, (const T*)x, sg, channels, partial, ws->ticket, stats);
     EGP_LAUNCH_CHECK();
     const int g2 = norm_grid(nvec, kNormThreads * 2) * 2;
     const bool fixed = ((int64_t)g2 * kNormThreads) % (channels / Vec<T>::N) == 0;
-    if (fixed) (void)launch_kernel(gln_apply_kernel<T, true>, g2, kNormThreads, 0, s, (const T*)x, weight, bias, (T*)y, stats, nvec, channels, eps, act, slope);
-    else (void)launch_kernel(gln_apply_kernel<T, false>, g2, kNormThreads, 0, s, (const T*)x, weight, bias, (T*)y, stats, nvec, channels, eps, act, slope);
+    if (fixed) (void)launch_kernel(gln_apply_kernel<T, true>, dim3(g2, nseg), kNormThreads, 0, s, (const T*)x, weight, bias, (T*)y, stats, sg, channels, eps, act, slope);
+    else (void)launch_kernel(gln_apply_kernel<T, false>, dim3(g2, nseg), kNormThreads, 0, s, (const T*)x, weight, bias, (T*)y, stats, sg, channels, eps, act, slope);
     EGP_LAUNCH_CHECK();
   });
   return EGP_OK;
 }
 
-int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, const float* bias,
-                            const double* stats, void* dx, float* dweight, float* dbias, float* dx_colsum, int64_t n,
-                            int64_t channels, float eps, int act, float slope, int dtype, void* workspace,
-                            size_t ws_bytes, void* stream) {
+int egp_graph_layernorm_fwd(const void* x, const float* weight, const float* bias, void* y, double* stats,
+                            int64_t n, int64_t channels, float eps, int act, float slope, int dtype,
+                            void* workspace, size_t ws_bytes, void* stream) {
+  return egp_graph_layernorm_seg_fwd(x, weight, bias, y, stats, n, channels, 1, nullptr, eps, act, slope, dtype, workspace,
+                                     ws_bytes, stream);
+}
+
+int egp_graph_layernorm_seg_bwd(const void* dy, const void* x, const float* weight, const float* bias,
+                                const double* stats, void* dx, float* dweight, float* dbias, float* dx_colsum, int64_t n,
+                                int64_t channels, int nseg, const int64_t* seg_rows, float eps, int act, float slope,
+                                int dtype, void* workspace, size_t ws_bytes, void* stream) {
   EGP_REQUIRE(dy && x && weight && bias && stats && dx && workspace, "graph_layernorm_bwd: null pointer");
   const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
   EGP_REQUIRE(channels % vn == 0 && aligned16(x) && aligned16(dy) && aligned16(dx),
               "graph_layernorm_bwd: channels %% %d != 0 or unaligned", (int)vn);
-  if (ws_bytes < egp_graph_layernorm_workspace(n, channels)) {
+  GlnSegs sg;
+  int rcs = gln_segments(n, nseg, seg_rows, &sg, "graph_layernorm_bwd");
+  if (rcs != EGP_OK) return rcs;
+  if (ws_bytes < gln_workspace_bytes(n, channels, nseg)) {
     set_error("graph_layernorm_bwd: workspace too small");
     return EGP_ERR_WORKSPACE;
   }
   cudaStream_t s = (cudaStream_t)stream;
   if (n == 0) {
     if (dx_colsum) EGP_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * channels, s));
+    if (dweight) EGP_CUDA(cudaMemsetAsync(dweight, 0, sizeof(float) * channels, s));
+    if (dbias) EGP_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * channels, s));
     return EGP_OK;
   }
   GlnWorkspace* ws = (GlnWorkspace*)workspace;
-  const int parts = gln_parts(n);
-  const int rows_per = (int)ceil_div(n, parts);
+  const int64_t max_rows = gln_max_seg_rows(sg);
+  int parts = gln_parts(max_rows);
+  if (nseg > 1) {                                             // keep the chip-wide CTA count of the one-segment launch
+    const int cap = gln_parts(n) / nseg > 1 ? gln_parts(n) / nseg : 1;
+    if (parts > cap) parts = cap;
+  }
+  const int rows_per = (int)ceil_div(max_rows, parts);
   EGP_DISPATCH_DTYPE(dtype, T, {
     constexpr int VN = Vec<T>::N;
     const int64_t nvec_row = channels / VN;
@@ -791,34 +877,34 @@ int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, 
     const int gy = (int)ceil_div(nvec_row, (int64_t)rthreads);
     const int gy_ws = (int)ceil_div(channels, (int64_t)kNormThreads * 4);
     const int g_stats = sm_count() * 4;
-    const size_t np = (size_t)(parts * gy_ws > g_stats ? parts * gy_ws : g_stats);
+    const int parts_ws = gln_parts(n);
+    const size_t np = (size_t)(parts_ws * gy_ws > g_stats ? parts_ws * gy_ws : g_stats) * (size_t)nseg;
     double* scalpart = (double*)(ws + 1);
     float* colpart = (float*)(scalpart + 2 * np);
-    float* dxpart = colpart + 2 * (size_t)parts * channels;
-    void* cs_ws = dxpart + (size_t)(sm_count() * 8) * channels;
-    EGP_REQUIRE((size_t)parts * gy <= np, "graph_layernorm_bwd: internal partial sizing");
-    (void)launch_kernel(gln_bwd_reduce_kernel<T>, dim3(parts, gy), rthreads, 0, s, 
-        (const T*)dy, (const T*)x, weight, bias, stats, n, channels, rows_per, eps, act, slope, colpart, scalpart);
+    float* dxpart = colpart + 2 * (size_t)parts_ws * nseg * channels;
+    void* cs_ws = dxpart + (size_t)(sm_count() * 8) * nseg * channels;
+    EGP_REQUIRE((size_t)parts * gy * nseg <= np && parts <= parts_ws, "graph_layernorm_bwd: internal partial sizing");
+    (void)launch_kernel(gln_bwd_reduce_kernel<T>, dim3(parts, gy, nseg), rthreads, 0, s,
+        (const T*)dy, (const T*)x, weight, bias, stats, sg, channels, rows_per, eps, act, slope, colpart, scalpart);
     EGP_LAUNCH_CHECK();
     const int colblocks = (int)ceil_div(channels, kFinCols);
-    (void)launch_kernel(col_finalize_kernel, colblocks + 1, kFinThreads, 0, s, colpart, parts, channels, 2, dweight, dbias, nullptr,
+    (void)launch_kernel(col_finalize_kernel, colblocks + nseg, kFinThreads, 0, s, colpart, parts * nseg, channels, 2, dweight, dbias, nullptr,
                                                               scalpart, parts * gy, ws->scal, colblocks);
     EGP_LAUNCH_CHECK();
-    const int64_t nvec = n * channels / VN;
-    const int g2 = norm_grid(nvec, kNormThreads * 2) * 2;
+    const int64_t nvec = max_rows * channels / VN;
+    const int g2 = norm_grid(nvec, kNormThreads * 2) * 2;     // <= 8 per SM: dxpart holds that many rows per segment
     const bool fixed = ((int64_t)g2 * kNormThreads) % nvec_row == 0;
     const bool fuse = dx_colsum && fixed && nvec_row <= kNormThreads && kNormThreads % nvec_row == 0;
-    const double inv_count = 1.0 / ((double)n * (double)channels);
     if (fixed)
-      (void)launch_kernel(gln_bwd_apply_kernel<T, true>, g2, kNormThreads, 0, s, (const T*)dy, (const T*)x, weight, bias, stats, ws->scal,
-                                                                (T*)dx, nvec, channels, inv_count, eps, act, slope,
+      (void)launch_kernel(gln_bwd_apply_kernel<T, true>, dim3(g2, nseg), kNormThreads, 0, s, (const T*)dy, (const T*)x, weight, bias, stats, ws->scal,
+                                                                (T*)dx, sg, channels, eps, act, slope,
                                                                 fuse ? dxpart : nullptr);
     else
-      (void)launch_kernel(gln_bwd_apply_kernel<T, false>, g2, kNormThreads, 0, s, (const T*)dy, (const T*)x, weight, bias, stats, ws->scal,
-                                                                 (T*)dx, nvec, channels, inv_count, eps, act, slope, nullptr);
+      (void)launch_kernel(gln_bwd_apply_kernel<T, false>, dim3(g2, nseg), kNormThreads, 0, s, (const T*)dy, (const T*)x, weight, bias, stats, ws->scal,
+                                                                 (T*)dx, sg, channels, eps, act, slope, nullptr);
     EGP_LAUNCH_CHECK();
     if (fuse) {
-      (void)launch_kernel(col_finalize_kernel, colblocks, kFinThreads, 0, s, dxpart, g2, channels, 1, dx_colsum, nullptr, nullptr, nullptr, 0,
+      (void)launch_kernel(col_finalize_kernel, colblocks, kFinThreads, 0, s, dxpart, g2 * nseg, channels, 1, dx_colsum, nullptr, nullptr, nullptr, 0,
                                                             nullptr, colblocks);
       EGP_LAUNCH_CHECK();
     } else if (dx_colsum) {
@@ -827,6 +913,14 @@ int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, 
     }
   });
   return EGP_OK;
+}
+
+int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, const float* bias,
+                            const double* stats, void* dx, float* dweight, float* dbias, float* dx_colsum, int64_t n,
+                            int64_t channels, float eps, int act, float slope, int dtype, void* workspace,
+                            size_t ws_bytes, void* stream) {
+  return egp_graph_layernorm_seg_bwd(dy, x, weight, bias, stats, dx, dweight, dbias, dx_colsum, n, channels, 1, nullptr, eps,
+                                     act, slope, dtype, workspace, ws_bytes, stream);
 }
 
 size_t egp_row_layernorm_workspace(int64_t n, int64_t channels) {

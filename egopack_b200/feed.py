@@ -131,12 +131,15 @@ class DeviceFeeder:
       ``pin_memory=True`` (utils/dataloading.py:64) to skip that.
     * ``feature_dtype``: convert ``x`` on the host before the copy (a loader that stores bf16 features should do this
       once per sample instead: ``Batch.to_feature_dtype``).
+    * ``fuse_features``: the ``x`` tensors of the task batches of one step land in ONE device allocation, back to back
+      (each batch still sees its own rows), so ``Graph.forward_many`` can feed them to the first Linear as a single
+      GEMM operand.
     """
 
     def __init__(self, loader: Iterable, device, transforms=None, pin: bool = True, prefetch_thread: bool = False,
-                 feature_dtype: Optional[torch.dtype] = None):
+                 feature_dtype: Optional[torch.dtype] = None, fuse_features: bool = True):
         self.loader, self.device, self.transforms, self.pin = loader, torch.device(device), transforms, pin
-        self.prefetch_thread, self.feature_dtype = prefetch_thread, feature_dtype
+        self.prefetch_thread, self.feature_dtype, self.fuse_features = prefetch_thread, feature_dtype, fuse_features
         self._cuda = self.device.type == "cuda"
         if self._cuda and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -175,7 +178,7 @@ class DeviceFeeder:
             return {k: self._prepare_host(v) for k, v in item.items()}
         return tuple(self._prepare_host(v) for v in item)
 
-    def _copy_one(self, b: Optional[Data]) -> Optional[Data]:
+    def _copy_one(self, b: Optional[Data], x_slot: Optional[torch.Tensor] = None) -> Optional[Data]:
         if b is None:
             return None
         if not isinstance(b, Data):                             # a real PyG batch: its own .to keeps every attribute
@@ -186,9 +189,31 @@ class DeviceFeeder:
                 continue
             if torch.is_tensor(v):
                 self.h2d_bytes += v.numel() * v.element_size() if v.device != self.device else 0
-                v = v.to(self.device, non_blocking=True)
+                if k == "x" and x_slot is not None:
+                    x_slot.copy_(v, non_blocking=True)
+                    v = x_slot
+                else:
+                    v = v.to(self.device, non_blocking=True)
             setattr(out, k, v)
         return out
+
+    def _feature_slots(self, batches):
+        """One device allocation for the ``x`` of all batches of an item (rows back to back), or None per batch when
+        they cannot share one (different trailing shape / dtype, foreign batch types, already on the device)."""
+        xs = [getattr(b, "x", None) if isinstance(b, Data) else None for b in batches]
+        live = [x for x in xs if x is not None]
+        if not self.fuse_features or not self._cuda or len(live) < 2 or any(x.device.type != "cpu" for x in live) \
+                or len({(tuple(x.shape[1:]), x.dtype) for x in live}) != 1:
+            return [None] * len(batches)
+        buf = torch.empty((sum(x.shape[0] for x in live), *live[0].shape[1:]), dtype=live[0].dtype, device=self.device)
+        slots, off = [], 0
+        for x in xs:
+            if x is None:
+                slots.append(None)
+            else:
+                slots.append(buf[off:off + x.shape[0]])
+                off += x.shape[0]
+        return slots
 
     def _move(self, item: BatchLike):
         """All copies of the item are enqueued first, then the transforms' kernels."""
@@ -197,9 +222,11 @@ class DeviceFeeder:
             out = self._copy_one(item)
             return tf(0)(out) if out is not None and tf(0) is not None else out
         if isinstance(item, Mapping):
-            moved = {k: self._copy_one(v) for k, v in item.items()}
+            slots = self._feature_slots(list(item.values()))
+            moved = {k: self._copy_one(v, sl) for (k, v), sl in zip(item.items(), slots)}
             return {k: (tf(k)(v) if v is not None and tf(k) is not None else v) for k, v in moved.items()}
-        moved = [self._copy_one(v) for v in item]
+        slots = self._feature_slots(list(item))
+        moved = [self._copy_one(v, sl) for v, sl in zip(item, slots)]
         return tuple(tf(i)(v) if v is not None and tf(i) is not None else v for i, v in enumerate(moved))
 
     def _upload(self, item):

@@ -16,13 +16,14 @@ fixed sequence of sm_100a kernels:
 from __future__ import annotations
 
 import importlib
-from typing import Any
+from typing import Any, List, Sequence
 
+import torch
 import torch.nn as nn
 
 from .. import config, ops
 from ..ops import ACT_LEAKY
-from .layers import GraphLayerNorm, PositionalEncoding, SAGEConv, structure_for
+from .layers import GraphLayerNorm, PositionalEncoding, SAGEConv, structure_for, structure_for_many
 
 
 def _instantiate(spec: Any, *args):
@@ -55,12 +56,12 @@ class TemporalNet(nn.Module):
             setattr(self, f"module_{3 * d + 2}", nn.LeakyReLU(negative_slope=0.2))
         setattr(self, f"module_{3 * depth}", nn.Linear(hidden_size, hidden_size))
 
-    def forward(self, z, gs, residual=None):
+    def forward(self, z, gs, residual=None, seg_rows=None):
         for d in range(self.depth):
             conv = getattr(self, f"module_{3 * d}")
             norm = getattr(self, f"module_{3 * d + 1}")
             slope = getattr(self, f"module_{3 * d + 2}").negative_slope
-            z = norm(conv(z, gs), act=ACT_LEAKY, slope=slope)
+            z = norm(conv(z, gs), act=ACT_LEAKY, slope=slope, seg_rows=seg_rows)
         last = getattr(self, f"module_{3 * self.depth}")
         return ops.linear(z, last.weight, last.bias, residual=residual)
 
@@ -95,3 +96,43 @@ class Graph(nn.Module):
             z = self.positional_encoding.add_to(x, data.pos)
             x = self.net(z, gs, residual=x)
         return x
+
+    def forward_many(self, batches: Sequence) -> List[torch.Tensor]:
+        """``[self(b) for b in batches]`` as ONE pass over the stacked rows (main_temporal.py:87-90 runs the shared
+        ``Graph`` once per task batch): every weight-shared Linear becomes a single GEMM over all task batches (and
+        yields one weight gradient instead of one per batch to be summed), the aggregation runs over one band(+star)
+        structure with global row indices, and graph-mode LayerNorm keeps its per-call statistics through row
+        segments -- so the result equals the per-batch forwards up to summation order.  Falls back to per-batch
+        forwards when the batches cannot share a structure (different radii, CSR graphs) or features need a gradient."""
+        batches = list(batches)
+        if len(batches) <= 1:
+            return [self.forward(b) for b in batches]
+        xs = [b.x for b in batches]
+        if any(not x.is_cuda for x in xs):
+            raise RuntimeError("egopack_b200.Graph runs on CUDA only (no CPU fallback); move the batch to the GPU")
+        sizes = [int(x.shape[0]) for x in xs]
+        gs = None
+        if hasattr(self, "net"):
+            gs = structure_for_many(batches, sizes)
+        stackable = (not hasattr(self, "net") or gs is not None) and not any(x.requires_grad for x in xs) \
+            and len({x.dim() for x in xs}) == 1 and len(batches) <= 8
+        if not stackable:
+            return [self.forward(b) for b in batches]
+        cd = config.compute_dtype()
+        xs = [ops.dropout(ops.Cast.apply(x, cd), self.pre_dropout.p, self.training) for x in xs]
+        if self.temporal_pooling is not None and hasattr(self.temporal_pooling, "forward_many"):
+            x = self.temporal_pooling.forward_many(xs)
+        elif self.temporal_pooling is not None:
+            x = torch.cat([self.temporal_pooling(xi, b.batch, b.pos) for xi, b in zip(xs, batches)], 0)
+        else:
+            if xs[0].dim() != 2:
+                raise ValueError("without temporal pooling the node features must be [N, hidden]")
+            x = torch.cat(xs, 0)
+        if hasattr(self, "net"):
+            seg_rows = [0]
+            for n in sizes:
+                seg_rows.append(seg_rows[-1] + n)
+            pos = torch.cat([b.pos.view(-1) for b in batches], 0)
+            z = self.positional_encoding.add_to(x, pos)
+            x = self.net(z, gs, residual=x, seg_rows=tuple(seg_rows))
+        return list(ops.SplitRows.apply(x, *sizes))

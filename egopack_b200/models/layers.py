@@ -109,8 +109,8 @@ class GraphLayerNorm(nn.Module):
         self.weight = nn.Parameter(torch.ones(in_channels))
         self.bias = nn.Parameter(torch.zeros(in_channels))
 
-    def forward(self, x: Tensor, act: int = ACT_NONE, slope: float = 0.0) -> Tensor:
-        return ops.GraphLayerNorm.apply(x, self.weight, self.bias, self.eps, act, slope)
+    def forward(self, x: Tensor, act: int = ACT_NONE, slope: float = 0.0, seg_rows=None) -> Tensor:
+        return ops.GraphLayerNorm.apply(x, self.weight, self.bias, self.eps, act, slope, seg_rows)
 
 
 def row_layernorm(ln: nn.LayerNorm, x: Tensor, act: int = ACT_NONE, dropout_p: float = 0.0) -> Tensor:

@@ -65,7 +65,7 @@ class OSCCTask(ProjectionTask):
 
     def compute_loss(self, logits, targets):
         if self.loss_func == "ce":
-            return F.cross_entropy(logits, targets, ignore_index=-1, reduction="none", label_smoothing=0.1)
+            return ops.cross_entropy(logits, targets, ignore_index=-1, label_smoothing=0.1)
         if self.loss_func == "bce":
-            return F.binary_cross_entropy_with_logits(logits, F.one_hot(targets, 2).float(), reduction="none")
+            return ops.bce_with_logits(logits, F.one_hot(targets, 2).float())
         raise NotImplementedError("the focal OSCC loss (torchvision) is not configured by any reference experiment")

@@ -7,6 +7,7 @@ from typing import Dict, Mapping, Optional, Tuple
 import torch
 import torch.nn as nn
 
+from ... import ops
 from .task import ProjectionTask, TaskLiteral
 
 logger = logging.getLogger(__name__)
@@ -47,4 +48,4 @@ class PNRTask(ProjectionTask):
         return self._head(self.aux_classifiers[t], features)
 
     def compute_loss(self, logits: torch.Tensor, targets: torch.Tensor):
-        return self.loss_fn(logits, targets.float())
+        return ops.bce_with_logits(logits, targets)

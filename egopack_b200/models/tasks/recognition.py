@@ -8,6 +8,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.nn import ModuleDict, ModuleList
 
+from ... import ops
 from .task import ProjectionTask, TaskLiteral
 
 
@@ -42,11 +43,12 @@ class _MultiHeadTask(ProjectionTask):
         return tuple(self._head(c, features) for c in self.aux_classifiers[t])
 
     def compute_loss(self, logits: Tuple[torch.Tensor], targets: torch.Tensor, return_separate_losses: bool = False):
-        losses = torch.stack([self.loss_fn(l, t) for l, t in zip(logits, targets.unbind(1))])
-        total = losses.sum(0)
         if return_separate_losses:
-            return total, losses.unbind(0)
-        return total
+            losses = [ops.cross_entropy(l, t, ignore_index=self.loss_fn.ignore_index)
+                      for l, t in zip(logits, targets.unbind(1))]
+            return torch.stack(losses).sum(0), tuple(losses)        # logging path (validate.py), not the training step
+        # sum over the label heads inside the loss kernel (criterion/wrapper.py:80-82 semantics)
+        return ops.cross_entropy(tuple(logits), targets, ignore_index=self.loss_fn.ignore_index)
 
 
 class RecognitionTask(_MultiHeadTask):

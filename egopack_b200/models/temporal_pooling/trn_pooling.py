@@ -34,13 +34,24 @@ class TRNPooling(TemporalPooling):
             nn.Linear(hidden_size, output_size),
         )
 
-    def forward(self, x, *_):
-        n = x.shape[0]
+    def _flat(self, x):
         if x.dim() == 3 and (x.shape[1] != self.num_segments or x.shape[2] != self.input_size):
             raise ValueError(f"expected [N, {self.num_segments}, {self.input_size}] features, got {tuple(x.shape)}")
-        h = x.reshape(n, self.num_segments * self.input_size)
+        return x.reshape(x.shape[0], self.num_segments * self.input_size)
+
+    def _tail(self, h):
+        """Everything after the first Linear: LN+ReLU+Dropout, Linear, LN+ReLU+Dropout, Linear."""
         p = self.proj
-        for lin, ln, drop in ((p[0], p[1], p[3]), (p[4], p[5], p[7])):
-            h = ops.linear(h, lin.weight, lin.bias)
-            h = row_layernorm(ln, h, act=ACT_RELU, dropout_p=drop.p if self.training else 0.0)   # LN+ReLU+Dropout fused
+        h = row_layernorm(p[1], h, act=ACT_RELU, dropout_p=p[3].p if self.training else 0.0)   # LN+ReLU+Dropout fused
+        h = ops.linear(h, p[4].weight, p[4].bias)
+        h = row_layernorm(p[5], h, act=ACT_RELU, dropout_p=p[7].p if self.training else 0.0)
         return ops.linear(h, p[8].weight, p[8].bias)
+
+    def forward(self, x, *_):
+        p = self.proj
+        return self._tail(ops.linear(self._flat(x), p[0].weight, p[0].bias))
+
+    def forward_many(self, xs):
+        """Several feature tensors through the shared weights as ONE stacked pass ([sum N_t, output_size])."""
+        p = self.proj
+        return self._tail(ops.LinearCat.apply(p[0].weight, p[0].bias, *[self._flat(x) for x in xs]))

@@ -279,7 +279,8 @@ def colsum(x: Tensor) -> Tensor:
     out = torch.empty(cols, dtype=torch.float32, device=x.device)
     nb = L.size("egp_colsum_workspace", rows, cols)
     ws = L.workspace(nb, x.device)
-    L.call("egp_colsum", L.ptr(x), L.ptr(out), rows, cols, x.stride(0), _code(x), L.ptr(ws), nb, L.stream())
+    with _Traced("colsum", 1.0 * rows * cols * x.element_size(), "B"):
+        L.call("egp_colsum", L.ptr(x), L.ptr(out), rows, cols, x.stride(0), _code(x), L.ptr(ws), nb, L.stream())
     return out
 
 
@@ -288,7 +289,8 @@ def cast(x: Tensor, dtype: torch.dtype) -> Tensor:
         return x
     x = _c(x)
     out = torch.empty(x.shape, dtype=dtype, device=x.device)
-    L.call("egp_cast", L.ptr(x), L.ptr(out), x.numel(), _code(x), L.DTYPE_CODE[dtype], L.stream())
+    with _Traced("cast", 1.0 * x.numel() * (x.element_size() + out.element_size()), "B"):
+        L.call("egp_cast", L.ptr(x), L.ptr(out), x.numel(), _code(x), L.DTYPE_CODE[dtype], L.stream())
     return out
 
 
@@ -355,8 +357,9 @@ def act_bwd_colsum(dy: Tensor, y: Tensor, act: int, slope: float) -> Tuple[Tenso
     cs = torch.empty(cols, dtype=torch.float32, device=dy.device)
     nb = L.size("egp_act_bwd_colsum_workspace", rows, cols)
     ws = L.workspace(nb, dy.device)
-    L.call("egp_act_bwd_colsum", L.ptr(dy), L.ptr(y), L.ptr(dx), L.ptr(cs), rows, cols, act, float(slope), _code(dy),
-           L.ptr(ws), nb, L.stream())
+    with _Traced("act_bwd_colsum", 3.0 * rows * cols * dy.element_size(), "B"):
+        L.call("egp_act_bwd_colsum", L.ptr(dy), L.ptr(y), L.ptr(dx), L.ptr(cs), rows, cols, act, float(slope), _code(dy),
+               L.ptr(ws), nb, L.stream())
     return dx, cs
 
 
@@ -509,6 +512,90 @@ class Linear(torch.autograd.Function):
         return dx, dw, db, dx2, dw2, dres, None, None, None
 
 
+class LinearCat(torch.autograd.Function):
+    """``cat([x_1, ..., x_T]) W^T + b`` without materialising the concatenation: every part's GEMM writes its rows of
+    ONE output tensor (a single GEMM when the parts already sit back to back in memory).  Used by
+    ``Graph.forward_many`` for the first TRN Linear (K = S*D = 4608): the task batches arrive as separate feature
+    tensors, everything after this layer runs on the stacked rows.  The inputs are data (no input gradient); the weight
+    gradient is accumulated part by part into one fp32 buffer."""
+
+    @staticmethod
+    def forward(ctx, w, b, *xs):
+        cd = xs[0].dtype
+        n_out, k = w.shape
+        rows = [x.shape[0] for x in xs]
+        xs = [_c(x) for x in xs]
+        wc = weight_cache.get(w, cd)
+        out = torch.empty((sum(rows), n_out), dtype=cd, device=xs[0].device)
+        esz = xs[0].element_size()
+        # parts that are consecutive views of ONE allocation (DeviceFeeder(fuse_features=True)) are a single operand
+        adjacent = all(a.untyped_storage().data_ptr() == b_.untyped_storage().data_ptr()
+                       and a.data_ptr() + a.numel() * esz == b_.data_ptr() for a, b_ in zip(xs, xs[1:]))
+        if adjacent:
+            whole = torch.as_strided(xs[0], (sum(rows), k), (k, 1))
+            gemm(whole, False, wc, False, sum(rows), n_out, k, bias=b, out=out)
+        else:
+            off = 0
+            for x, m in zip(xs, rows):
+                if m:
+                    gemm(x, False, wc, False, m, n_out, k, bias=b, out=out[off:off + m])
+                off += m
+        ctx.save_for_backward(w, *xs)
+        ctx.rows, ctx.has_bias, ctx.adjacent = rows, b is not None, adjacent
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        w, *xs = ctx.saved_tensors
+        cd = xs[0].dtype
+        n_out, k = w.shape
+        dy = _c(dy)
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            db = _take_colsum(dy)
+            if db is None:
+                db = colsum(dy)
+        dw = None
+        if ctx.needs_input_grad[0]:
+            gc = cast(dy, cd)
+            dw = torch.empty((n_out, k), dtype=torch.float32, device=dy.device)
+            if ctx.adjacent:
+                total = sum(ctx.rows)
+                whole = torch.as_strided(xs[0], (total, k), (k, 1))
+                gemm(gc, True, whole, True, n_out, k, total, out_dtype=torch.float32, out=dw)
+            else:
+                off, first = 0, True
+                for x, m in zip(xs, ctx.rows):
+                    if m:
+                        gemm(gc[off:off + m], True, x, True, n_out, k, m, out_dtype=torch.float32, out=dw, accumulate=not first)
+                        first = False
+                    off += m
+                if first:
+                    dw.zero_()
+        return (dw, db, *([None] * len(xs)))
+
+
+class SplitRows(torch.autograd.Function):
+    """Row blocks of a stacked activation as separate tensors (the per-task features coming out of
+    ``Graph.forward_many``); the backward stacks the blocks' gradients again (missing ones are zero)."""
+
+    @staticmethod
+    def forward(ctx, x, *rows):
+        ctx.rows = rows
+        ctx.meta = (x.shape[1:], x.dtype, x.device)
+        outs, off = [], 0
+        for m in rows:
+            outs.append(x[off:off + m])
+            off += m
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        tail, dtype, dev = ctx.meta
+        parts = [g if g is not None else torch.zeros((m, *tail), dtype=dtype, device=dev) for g, m in zip(grads, ctx.rows)]
+        return (torch.cat(parts, 0), *([None] * len(ctx.rows)))
+
+
 def linear(x, w, b=None, *, x2=None, w2=None, residual=None, act=ACT_NONE, slope=0.0, out_dtype=None):
     return Linear.apply(x, w, b, x2, w2, residual, act, slope, out_dtype)
 
@@ -534,8 +621,9 @@ class RowLayerNorm(torch.autograd.Function):
         # eager: the full 64-bit call counter (never repeats); under CUDA-graph capture the per-step part comes from the
         # device-side state (added as step << 20), so only the call-site index inside a step is passed here
         offset = (offset & 0xFFFFF) if rng is not None else (offset & 0xFFFFFFFFFFFFFFFF)
-        L.call("egp_row_layernorm_fwd", L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(mean), L.ptr(rstd), n, c,
-               float(eps), act, float(dropout_p), seed, offset, L.ptr(rng), _code(x), L.stream())
+        with _Traced("row_layernorm_fwd", 2.0 * n * c * x.element_size(), "B"):
+            L.call("egp_row_layernorm_fwd", L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(mean), L.ptr(rstd), n, c,
+                   float(eps), act, float(dropout_p), seed, offset, L.ptr(rng), _code(x), L.stream())
         need_y = act == ACT_RELU or dropout_p > 0
         ctx.save_for_backward(x, y if need_y else None, w, mean, rstd)
         ctx.act, ctx.out_scale = act, (1.0 / (1.0 - dropout_p) if dropout_p > 0 else 1.0)
@@ -552,44 +640,59 @@ class RowLayerNorm(torch.autograd.Function):
         dxs = torch.empty(c, dtype=torch.float32, device=x.device)
         nb = L.size("egp_row_layernorm_workspace", n, c)
         ws = L.workspace(nb, x.device)
-        L.call("egp_row_layernorm_bwd", L.ptr(dy), L.ptr(x), L.ptr(y), L.ptr(w), L.ptr(mean), L.ptr(rstd), L.ptr(dx),
-               L.ptr(dw), L.ptr(db), L.ptr(dxs), n, c, ctx.act, float(ctx.out_scale), _code(x), L.ptr(ws), nb, L.stream())
+        # dy, x (and y when a ReLU / dropout mask is read back) in, dx out
+        with _Traced("row_layernorm_bwd", (4.0 if y is not None else 3.0) * n * c * x.element_size(), "B"):
+            L.call("egp_row_layernorm_bwd", L.ptr(dy), L.ptr(x), L.ptr(y), L.ptr(w), L.ptr(mean), L.ptr(rstd), L.ptr(dx),
+                   L.ptr(dw), L.ptr(db), L.ptr(dxs), n, c, ctx.act, float(ctx.out_scale), _code(x), L.ptr(ws), nb, L.stream())
         return _attach_colsum(dx, dxs), dw, db, None, None, None
 
 
 class GraphLayerNorm(torch.autograd.Function):
     """gnn.LayerNorm in graph mode WITHOUT a batch vector (models/graph.py:43): statistics over the whole
-    [N,C] tensor, ``x / (std + eps)``, per-channel affine; fused with LeakyReLU (models/graph.py:44)."""
+    [N,C] tensor, ``x / (std + eps)``, per-channel affine; fused with LeakyReLU (models/graph.py:44).
+
+    ``seg_rows`` (a tuple of cumulative row offsets ``(0, n1, n1+n2, ..., N)``) splits the rows into consecutive
+    segments that are normalised independently -- one per original forward call when ``Graph.forward_many`` runs
+    several task batches through the shared weights at once (the statistics of the reference are per call)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, eps: float, act: int, slope: float):
+    def forward(ctx, x, w, b, eps: float, act: int, slope: float, seg_rows=None):
+        import ctypes
         x = _c(x)
         n, c = x.shape
+        segs = tuple(int(v) for v in seg_rows) if seg_rows is not None else (0, n)
+        nseg = len(segs) - 1
+        seg_arr = (ctypes.c_int64 * (nseg + 1))(*segs)
         y = torch.empty_like(x)
-        stats = torch.empty(2, dtype=torch.float64, device=x.device)
-        nb = L.size("egp_graph_layernorm_workspace", n, c)
+        stats = torch.empty(2 * nseg, dtype=torch.float64, device=x.device)
+        nb = L.size("egp_graph_layernorm_seg_workspace", n, c, nseg)
         ws = L.workspace(nb, x.device)
-        L.call("egp_graph_layernorm_fwd", L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(stats), n, c, float(eps), act,
-               float(slope), _code(x), L.ptr(ws), nb, L.stream())
+        with _Traced("graph_layernorm_fwd", 3.0 * n * c * x.element_size(), "B"):      # stats pass + apply pass
+            L.call("egp_graph_layernorm_seg_fwd", L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(stats), n, c, nseg, seg_arr,
+                   float(eps), act, float(slope), _code(x), L.ptr(ws), nb, L.stream())
         ctx.save_for_backward(x, w, b, stats)
-        ctx.cfg = (float(eps), act, float(slope))
+        ctx.cfg = (float(eps), act, float(slope), segs)
         return y
 
     @staticmethod
     def backward(ctx, dy):
+        import ctypes
         x, w, b, stats = ctx.saved_tensors
-        eps, act, slope = ctx.cfg
+        eps, act, slope, segs = ctx.cfg
+        nseg = len(segs) - 1
+        seg_arr = (ctypes.c_int64 * (nseg + 1))(*segs)
         dy = _c(dy)
         n, c = x.shape
         dx = torch.empty_like(x)
         dw = torch.empty(c, dtype=torch.float32, device=x.device)
         db = torch.empty(c, dtype=torch.float32, device=x.device)
-        nb = L.size("egp_graph_layernorm_workspace", n, c)
+        nb = L.size("egp_graph_layernorm_seg_workspace", n, c, nseg)
         ws = L.workspace(nb, x.device)
         dxs = torch.empty(c, dtype=torch.float32, device=x.device)
-        L.call("egp_graph_layernorm_bwd", L.ptr(dy), L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(stats), L.ptr(dx), L.ptr(dw),
-               L.ptr(db), L.ptr(dxs), n, c, eps, act, slope, _code(x), L.ptr(ws), nb, L.stream())
-        return _attach_colsum(dx, dxs), dw, db, None, None, None
+        with _Traced("graph_layernorm_bwd", 5.0 * n * c * x.element_size(), "B"):      # reduce (dy,x) + apply (dy,x -> dx)
+            L.call("egp_graph_layernorm_seg_bwd", L.ptr(dy), L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(stats), L.ptr(dx), L.ptr(dw),
+                   L.ptr(db), L.ptr(dxs), n, c, nseg, seg_arr, eps, act, slope, _code(x), L.ptr(ws), nb, L.stream())
+        return _attach_colsum(dx, dxs), dw, db, None, None, None, None
 
 
 class PosEncAdd(torch.autograd.Function):
@@ -600,8 +703,9 @@ class PosEncAdd(torch.autograd.Function):
         x = _c(x)
         n, c = x.shape
         out = torch.empty_like(x)
-        L.call("egp_posenc_add", L.ptr(x), L.ptr(_i64(pos.view(-1), "pos")), L.ptr(_c(freq)), L.ptr(out), n, c, _code(x),
-               L.stream())
+        with _Traced("posenc_add", 2.0 * n * c * x.element_size(), "B"):
+            L.call("egp_posenc_add", L.ptr(x), L.ptr(_i64(pos.view(-1), "pos")), L.ptr(_c(freq)), L.ptr(out), n, c, _code(x),
+                   L.stream())
         return out
 
     @staticmethod
@@ -661,6 +765,135 @@ def dropout(x: Tensor, p: float, training: bool) -> Tensor:
 
 
 # =====================================================================================================
+# losses (a11)
+# =====================================================================================================
+def _logits_2d(l: Tensor) -> Tensor:
+    if l.dtype != torch.float32:
+        raise TypeError(f"loss kernels take fp32 logits (the classifier heads emit fp32), got {l.dtype}")
+    if l.dim() != 2 or l.stride(1) != 1:
+        l = l.reshape(l.shape[0], -1).contiguous()
+    return l
+
+
+class MultiHeadCrossEntropy(torch.autograd.Function):
+    """sum_h CrossEntropy(logits_h, targets[:, h], ignore_index, label_smoothing, reduction='none') -> [N]
+    (criterion/wrapper.py:80-82 around nn.CrossEntropyLoss, models/tasks/recognition.py:61-69, lta.py:73-74; one head
+    with smoothing 0.1 is OSCC's loss, oscc.py:88-96).  ``targets`` is int64 [N, H] (or [N] for one head)."""
+
+    @staticmethod
+    def forward(ctx, targets, ignore_index: int, label_smoothing: float, *logits):
+        targets = _i64(targets, "targets")
+        n = logits[0].shape[0]
+        heads = len(logits)
+        tcols = targets.shape[1] if targets.dim() > 1 else 1
+        if tcols < heads or targets.shape[0] != n:
+            raise ValueError(f"targets {tuple(targets.shape)} do not match {heads} heads of {n} rows")
+        dev = logits[0].device
+        loss = torch.empty(n, dtype=torch.float32, device=dev)
+        lses = torch.empty((heads, n), dtype=torch.float32, device=dev)
+        ls = [_logits_2d(l) for l in logits]
+        for h, l in enumerate(ls):
+            L.call("egp_ce_loss_fwd", L.ptr(l), l.stride(0), L.ptr(targets) + 8 * h, tcols, n, l.shape[1], int(ignore_index),
+                   float(label_smoothing), L.ptr(loss), int(h > 0), L.ptr(lses[h]), L.stream())
+        ctx.save_for_backward(targets, lses, *ls)
+        ctx.cfg = (int(ignore_index), float(label_smoothing), tcols)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        targets, lses, *ls = ctx.saved_tensors
+        ignore_index, smoothing, tcols = ctx.cfg
+        n = ls[0].shape[0]
+        if dloss.dtype != torch.float32:
+            dloss = dloss.float()
+        gstride = dloss.stride(0) if dloss.dim() else 0        # an expanded scalar (stride 0) is read in place
+        grads = []
+        for h, l in enumerate(ls):
+            c = l.shape[1]
+            d = torch.empty((n, c), dtype=torch.float32, device=l.device)
+            L.call("egp_ce_loss_bwd", L.ptr(l), l.stride(0), L.ptr(lses[h]), L.ptr(targets) + 8 * h, tcols, L.ptr(dloss),
+                   gstride, n, c, ignore_index, smoothing, L.ptr(d), d.stride(0), F32, L.stream())
+            grads.append(d)
+        return (None, None, None, *grads)
+
+
+def cross_entropy(logits, targets: Tensor, ignore_index: int = -100, label_smoothing: float = 0.0) -> Tensor:
+    """Per-sample cross entropy (reduction='none'); ``logits`` is one fp32 [N,C] tensor or a tuple of heads."""
+    if torch.is_tensor(logits):
+        logits = (logits,)
+    return MultiHeadCrossEntropy.apply(targets, ignore_index, label_smoothing, *logits)
+
+
+class BCEWithLogits(torch.autograd.Function):
+    """nn.BCEWithLogitsLoss(reduction='none') (models/tasks/pnr.py:38,82-83)."""
+
+    @staticmethod
+    def forward(ctx, z, target):
+        if z.dtype != torch.float32:
+            raise TypeError(f"loss kernels take fp32 logits, got {z.dtype}")
+        z, target = _c(z), _c(target if target.dtype == torch.float32 else target.float())
+        if z.shape != target.shape:
+            raise ValueError(f"BCE: logits {tuple(z.shape)} vs targets {tuple(target.shape)}")
+        loss = torch.empty_like(z)
+        L.call("egp_bce_logits_fwd", L.ptr(z), L.ptr(target), L.ptr(loss), z.numel(), L.stream())
+        ctx.save_for_backward(z, target)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        z, target = ctx.saved_tensors
+        dz = torch.empty_like(z)
+        flat_stride = 0 if (dloss.dim() == 0 or all(s == 0 for s in dloss.stride())) else 1
+        g = dloss if flat_stride == 0 else _c(dloss)
+        L.call("egp_bce_logits_bwd", L.ptr(z), L.ptr(target), L.ptr(g), flat_stride, L.ptr(dz), z.numel(), L.stream())
+        return dz, None
+
+
+def bce_with_logits(z: Tensor, target: Tensor) -> Tensor:
+    return BCEWithLogits.apply(z, target)
+
+
+class WeightedMeanSum(torch.autograd.Function):
+    """total = sum_t w_t * mean(loss_t) (main_temporal.py:99-128: ``losses.append(w * loss.mean())`` ...
+    ``torch.stack(losses).sum()``) as one accumulation chain; the backward hands every loss_t an EXPANDED scalar
+    (stride 0), which the loss kernels read in place -- no [N] gradient is materialised."""
+
+    @staticmethod
+    def forward(ctx, weights, *losses):
+        dev = losses[0].device
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        flat = []
+        for i, (w, l) in enumerate(zip(weights, losses)):
+            if l.dtype != torch.float32:
+                raise TypeError(f"per-sample losses are fp32, got {l.dtype}")
+            l = _c(l).view(-1)
+            flat.append(l.shape[0])
+            L.call("egp_weighted_mean", L.ptr(l), l.shape[0], float(w), L.ptr(out), int(i > 0), L.stream())
+        ctx.cfg = (tuple(float(w) for w in weights), tuple(flat), tuple(l.shape for l in losses))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        weights, counts, shapes = ctx.cfg
+        outs = []
+        for w, n, shp in zip(weights, counts, shapes):
+            outs.append(axpby_scalar(g, w / max(n, 1)).expand(shp))
+        return (None, *outs)
+
+
+def axpby_scalar(g: Tensor, alpha: float) -> Tensor:
+    """alpha * g for a 0-dim fp32 tensor (one tiny kernel; the result is expanded, never materialised per row)."""
+    out = torch.empty((), dtype=torch.float32, device=g.device)
+    gg = g if g.dtype == torch.float32 else g.float()
+    L.call("egp_weighted_mean", L.ptr(gg), 1, float(alpha), L.ptr(out), 0, L.stream())
+    return out
+
+
+def weighted_mean_sum(losses, weights) -> Tensor:
+    return WeightedMeanSum.apply(tuple(weights), *losses)
+
+
+# =====================================================================================================
 # pooling / GraphONE pieces
 # =====================================================================================================
 class SegmentMaxPool(torch.autograd.Function):
@@ -672,8 +905,9 @@ class SegmentMaxPool(torch.autograd.Function):
         g, c = ptr.numel() - 1, x.shape[1]
         out = torch.empty((g, c), dtype=x.dtype, device=x.device)
         arg = torch.empty((g, c), dtype=torch.int32, device=x.device)
-        L.call("egp_segment_max_pool_fwd", L.ptr(x), L.ptr(_i64(ptr, "ptr")), L.ptr(out), L.ptr(arg), g, c, _code(x),
-               L.stream())
+        with _Traced("segment_max_pool_fwd", 1.0 * x.shape[0] * c * x.element_size(), "B"):
+            L.call("egp_segment_max_pool_fwd", L.ptr(x), L.ptr(_i64(ptr, "ptr")), L.ptr(out), L.ptr(arg), g, c, _code(x),
+                   L.stream())
         ctx.save_for_backward(arg, _i64(batch, "batch"))
         ctx.n = x.shape[0]
         return out
@@ -696,7 +930,8 @@ class MaxCombine(torch.autograd.Function):
     def forward(ctx, f, m):
         f, m = _c(f), _c(m)
         a = torch.empty_like(f)
-        L.call("egp_max_combine_fwd", L.ptr(f), L.ptr(m), L.ptr(a), f.numel(), _code(f), L.stream())
+        with _Traced("max_combine_fwd", 3.0 * f.numel() * f.element_size(), "B"):
+            L.call("egp_max_combine_fwd", L.ptr(f), L.ptr(m), L.ptr(a), f.numel(), _code(f), L.stream())
         ctx.save_for_backward(f, m)
         return a
 
@@ -800,8 +1035,9 @@ def cos_topk(fn: Tensor, pn: Tensor, k: int, fn16: Optional[Tensor] = None, pn16
     idx = torch.empty((b, k), dtype=torch.int64, device=fn.device)
     nb = L.size("egp_cos_topk_workspace", b, kp, k)
     ws = L.workspace(nb, fn.device, "topk")
-    L.call("egp_cos_topk", L.ptr(fn), L.ptr(pn), L.ptr(_c(fn16)), L.ptr(_c(pn16)), b, kp, c, int(k), L.ptr(idx),
-           L.ptr(ws), nb, L.stream())
+    with _Traced("cos_topk", 2.0 * b * kp * c, "FLOP", f"{b}x{kp}x{c} k={k}"):
+        L.call("egp_cos_topk", L.ptr(fn), L.ptr(pn), L.ptr(_c(fn16)), L.ptr(_c(pn16)), b, kp, c, int(k), L.ptr(idx),
+               L.ptr(ws), nb, L.stream())
     return idx
 
 
@@ -810,5 +1046,6 @@ def proto_max_gather(bank: Tensor, idx: Tensor) -> Tensor:
     b, k = idx.shape
     c = bank.shape[1]
     m = torch.empty((b, c), dtype=bank.dtype, device=bank.device)
-    L.call("egp_proto_max_gather", L.ptr(bank), L.ptr(idx), L.ptr(m), b, k, c, _code(bank), _code(bank), L.stream())
+    with _Traced("proto_max_gather", 1.0 * b * c * bank.element_size() + 8.0 * b * k, "B"):   # write m, read idx (bank: L2)
+        L.call("egp_proto_max_gather", L.ptr(bank), L.ptr(idx), L.ptr(m), b, k, c, _code(bank), _code(bank), L.stream())
     return m

@@ -8,22 +8,32 @@ from __future__ import annotations
 from typing import Dict, Optional, Sequence
 
 import torch
-import torch.nn.functional as F
+
+from . import ops
 
 TASK_ORDER = ("ar", "lta", "oscc", "pnr")           # main_temporal.py:93-126 order of the loss terms
 
 
+def _graph_features(model, batches: Dict[str, object]) -> Dict[str, torch.Tensor]:
+    """``feat_t = model(data_t)`` for every task batch (main_temporal.py:87-90, main_egopack.py:113-117).  The native
+    ``Graph`` runs them as one stacked pass over its shared weights (``forward_many``); any other module is called per
+    batch exactly as the reference does."""
+    many = getattr(model, "forward_many", None)
+    if callable(many) and len(batches) > 1:
+        return dict(zip(batches.keys(), many(list(batches.values()))))
+    return {t: model(b) for t, b in batches.items()}
+
+
 def multi_head_ce(logits, targets):
     """criterion/wrapper.py:80-82 around CrossEntropyLoss(ignore_index=-1, reduction='none') (main_temporal.py:285)."""
-    return torch.stack([F.cross_entropy(l, t, ignore_index=-1, reduction="none")
-                        for l, t in zip(logits, targets.unbind(1))]).sum(0)
+    return ops.cross_entropy(tuple(logits), targets, ignore_index=-1)
 
 
 def mtl_losses(model, tasks: Dict[str, torch.nn.Module], batches: Dict[str, object],
                weights: Optional[Dict[str, float]] = None):
     """Forward + loss of one MTL step (main_temporal.py:87-126).  Returns (total, {task: per-sample loss})."""
     weights = weights or {}
-    feats = {t: model(b) for t, b in batches.items()}
+    feats = _graph_features(model, batches)
     terms, per_task = [], {}
     for t in TASK_ORDER:
         if t not in batches:
@@ -31,15 +41,15 @@ def mtl_losses(model, tasks: Dict[str, torch.nn.Module], batches: Dict[str, obje
         task, data = tasks[t], batches[t]
         f = task.forward_features(feats[t])
         if t == "oscc":
-            loss = F.cross_entropy(task.forward_logits(f, data.batch, ptr=getattr(data, "ptr", None)), data.y,
-                                   reduction="none")                       # main_temporal.py:291
+            loss = ops.cross_entropy(task.forward_logits(f, data.batch, ptr=getattr(data, "ptr", None)), data.y,
+                                     ignore_index=-100)                    # plain nn.CrossEntropyLoss, main_temporal.py:291
         elif t == "pnr":
-            loss = F.binary_cross_entropy_with_logits(task.forward_logits(f), data.y.float(), reduction="none")
+            loss = ops.bce_with_logits(task.forward_logits(f), data.y)
         else:
             loss = multi_head_ce(task.forward_logits(f), data.y)
         per_task[t] = loss
-        terms.append(weights.get(t, 1.0) * loss.mean())
-    return torch.stack(terms).sum(), per_task
+        terms.append(weights.get(t, 1.0))
+    return ops.weighted_mean_sum(list(per_task.values()), terms), per_task
 
 
 def egopack_task_loss(feat, batch, y, primary, others: Sequence[torch.nn.Module], graphone, late_fusion: bool = True,
@@ -61,7 +71,7 @@ def egopack_losses(model, tasks: Dict[str, torch.nn.Module], batches: Dict[str, 
     """One EgoPack step (main_egopack.py:113-152) over whichever task batches are present."""
     weights = weights or {}
     with torch.set_grad_enabled(backprop_temporal_graph):
-        feats = {t: model(b) for t, b in batches.items()}
+        feats = _graph_features(model, batches)
     terms, per_task = [], {}
     for t in ("ar", "oscc", "lta", "pnr"):                                   # main_egopack.py:121-149 order
         if t not in batches:
@@ -71,5 +81,5 @@ def egopack_losses(model, tasks: Dict[str, torch.nn.Module], batches: Dict[str, 
         loss = egopack_task_loss(feats[t], data.batch, data.y, tasks[t], others, graphone, late_fusion,
                                  ptr=getattr(data, "ptr", None))
         per_task[t] = loss
-        terms.append(weights.get(t, 1.0) * loss.mean())
-    return torch.stack(terms).sum(), per_task
+        terms.append(weights.get(t, 1.0))
+    return ops.weighted_mean_sum(list(per_task.values()), terms), per_task

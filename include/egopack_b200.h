@@ -138,6 +138,19 @@ int egp_graph_layernorm_bwd(const void* dy, const void* x, const float* weight, 
                             int64_t num_nodes, int64_t channels, float eps, int act, float slope, int dtype,
                             void* workspace, size_t ws_bytes, void* stream);
 
+/* Segmented form: rows are split into `nseg` (<= 8) consecutive segments [seg_rows[s], seg_rows[s+1]) -- HOST array of
+ * nseg+1 offsets, seg_rows[0] = 0, seg_rows[nseg] = num_nodes -- each normalised with its OWN global statistics
+ * (stats: double[2*nseg]); dweight / dbias / dx_colsum sum over all segments.  One segment per original forward call
+ * when several task batches share the weights in one pass (Graph.forward_many): the reference normalises per call. */
+size_t egp_graph_layernorm_seg_workspace(int64_t num_nodes, int64_t channels, int nseg);
+int egp_graph_layernorm_seg_fwd(const void* x, const float* weight, const float* bias, void* y, double* stats,
+                                int64_t num_nodes, int64_t channels, int nseg, const int64_t* seg_rows, float eps,
+                                int act, float slope, int dtype, void* workspace, size_t ws_bytes, void* stream);
+int egp_graph_layernorm_seg_bwd(const void* dy, const void* x, const float* weight, const float* bias,
+                                const double* stats, void* dx, float* dweight, float* dbias, float* dx_colsum,
+                                int64_t num_nodes, int64_t channels, int nseg, const int64_t* seg_rows, float eps,
+                                int act, float slope, int dtype, void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- row LayerNorm (+ReLU) (+Dropout) (nn.LayerNorm -> ReLU -> Dropout in TRNPooling trn_pooling.py:30-37; tasks
  *      task.py:20; GraphONE graphONE.py:61); mean/rstd float [N] are saved for the backward ---------------------
  * fwd: y = dropout_p(act(LN(x))); the keep decisions come from Philox4x32-10(seed; element-vector index, offset), so

@@ -339,3 +339,55 @@ def test_colsum_byproducts_feed_bias_gradients(dtype, tol):
     btol = 1e-4 if dtype == torch.float32 else 6e-2
     assert rel_max(bd.grad, br.grad) < btol, rel_max(bd.grad, br.grad)
     assert rel_max(wd.grad, wr.grad) < btol
+
+
+@pytest.mark.parametrize("classes", [(115, 478), (2,), (5, 1000, 33)])
+@pytest.mark.parametrize("smoothing", [0.0, 0.1])
+def test_cross_entropy_kernels_match_torch(classes, smoothing):
+    """a11: multi-head CE (ignore_index, label smoothing, reduction none) fwd + bwd == F.cross_entropy summed over heads
+    (recognition.py:61-69, wrapper.py:80-82, oscc.py:88-96); per-task mean and weighted total (main_temporal.py:99-128)."""
+    g = torch.Generator().manual_seed(len(classes))
+    n = 1000
+    logits = [torch.randn(n, c, generator=g) * 3 for c in classes]
+    y = torch.stack([torch.randint(0, c, (n,), generator=g) for c in classes], 1)
+    y[torch.rand(n, generator=g) < 0.3] = -1
+    ref_in = [l.clone().requires_grad_(True) for l in logits]
+    want = torch.stack([F.cross_entropy(l, t, ignore_index=-1, reduction="none", label_smoothing=smoothing)
+                        for l, t in zip(ref_in, y.unbind(1))]).sum(0)
+    (0.7 * want.mean()).backward()
+    got_in = [l.to(DEV).requires_grad_(True) for l in logits]
+    got = ops.cross_entropy(tuple(got_in), y.to(DEV), ignore_index=-1, label_smoothing=smoothing)
+    total = ops.weighted_mean_sum([got], [0.7])
+    total.backward()
+    assert rel_max(got, want) < 1e-5
+    assert abs(float(total) - 0.7 * float(want.mean())) < 1e-5 * abs(float(want.mean()))
+    for a, b in zip(got_in, ref_in):
+        assert rel_max(a.grad, b.grad) < 1e-5
+        assert float(a.grad[y[:, 0] == -1].abs().max()) == 0.0                     # ignored rows get no gradient
+    # a non-broadcast upstream gradient as well
+    w = torch.rand(n, generator=g)
+    got_in2 = [l.to(DEV).requires_grad_(True) for l in logits]
+    ops.cross_entropy(tuple(got_in2), y.to(DEV), ignore_index=-1, label_smoothing=smoothing).backward(w.to(DEV))
+    ref_in2 = [l.clone().requires_grad_(True) for l in logits]
+    torch.stack([F.cross_entropy(l, t, ignore_index=-1, reduction="none", label_smoothing=smoothing)
+                 for l, t in zip(ref_in2, y.unbind(1))]).sum(0).backward(w)
+    for a, b in zip(got_in2, ref_in2):
+        assert rel_max(a.grad, b.grad) < 1e-5
+
+
+def test_bce_and_weighted_total_match_torch():
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(777, generator=g) * 4
+    t = (torch.rand(777, generator=g) < 0.1).float()
+    other = torch.rand(50, generator=g)
+    zr, orf = z.clone().requires_grad_(True), other.clone().requires_grad_(True)
+    want = F.binary_cross_entropy_with_logits(zr, t, reduction="none")
+    torch.stack([1.0 * want.mean(), 0.25 * orf.mean()]).sum().backward()
+    zd, od = z.to(DEV).requires_grad_(True), other.to(DEV).requires_grad_(True)
+    got = ops.bce_with_logits(zd, t.to(DEV))
+    total = ops.weighted_mean_sum([got, od], [1.0, 0.25])
+    total.backward()
+    assert rel_max(got, want) < 1e-5 and rel_max(zd.grad, zr.grad) < 1e-5 and rel_max(od.grad, orf.grad) < 1e-6
+    assert abs(float(total) - float(want.mean() + 0.25 * other.mean())) < 1e-5
+    with pytest.raises(TypeError):
+        ops.cross_entropy(torch.zeros(4, 3, device=DEV, dtype=torch.bfloat16), torch.zeros(4, dtype=torch.long, device=DEV))

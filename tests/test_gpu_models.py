@@ -408,3 +408,72 @@ def test_lta_metric_unchanged_fp32():
     got = eo.metric_lta_edit_distance(preds[0].view(V, n, 5)[:, 2:], target)
     want = eo.metric_lta_edit_distance(rpreds[0].view(V, n, 5)[:, 2:], target)
     assert got == want
+
+
+def _three_task_batches(gen, D, S, V, n, heads=(7, 11)):
+    out = {}
+    for t in ("ar", "lta", "pnr"):
+        b = syn.make_batch(t, V, n, gen, feature_dim=D, num_segments=S, band_k=1, n_verbs=heads[0], n_nouns=heads[1]).to(DEV)
+        out[t] = LTATemporalConnectivity(1.5)(b) if t == "lta" else RadiusGraph(1.5)(b)
+    return out
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("bf16", 1e-2)])
+def test_forward_many_equals_per_batch_forwards(mode, tol):
+    """Graph.forward_many (one stacked pass: shared-weight GEMMs over all task batches, one band+star structure,
+    segmented graph-LayerNorm statistics) == [Graph(b) for b in batches] (main_temporal.py:87-90), outputs and
+    every parameter gradient; only summation order differs."""
+    egopack_b200.set_precision(mode)
+    gen = torch.Generator().manual_seed(21)
+    D, S, H, HT, V, n = 48, 3, 128, 96, 6, 40
+    torch.manual_seed(3)
+    model = Graph(D, H, 3, temporal_pooling=dict(TP, hidden_size=HT), num_segments=S).to(DEV)
+    batches = _three_task_batches(gen, D, S, V, n)
+    ws = [torch.randn(V * n, H, generator=gen).to(DEV) for _ in batches]
+    singles = [model(b) for b in batches.values()]
+    sum((o.float() * w).sum() for o, w in zip(singles, ws)).backward()
+    want = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    many = model.forward_many(list(batches.values()))
+    assert len(many) == 3 and all(m.shape == s.shape for m, s in zip(many, singles))
+    sum((o.float() * w).sum() for o, w in zip(many, ws)).backward()
+    for m, s in zip(many, singles):
+        assert rel_max(m, s) < tol
+    for k, p in model.named_parameters():
+        err = rel_l2(p.grad, want[k]) if mode == "bf16" else rel_max(p.grad, want[k])
+        assert err < (2e-2 if mode == "bf16" else tol), (k, err)
+    # unused outputs (a task without a loss term) get a zero gradient block, not an error
+    model.zero_grad(set_to_none=True)
+    many = model.forward_many(list(batches.values()))
+    many[1].float().sum().backward()
+    assert all(p.grad is not None for p in model.parameters())
+    # the features of one step may live in ONE allocation (DeviceFeeder(fuse_features=True)): single-GEMM first layer
+    buf = torch.cat([b.x for b in batches.values()], 0)
+    off = 0
+    for b in batches.values():
+        b.x = buf[off:off + V * n]
+        off += V * n
+    fused = model.forward_many(list(batches.values()))
+    for m, s in zip(fused, singles):
+        assert rel_max(m, s) < tol
+
+
+def test_bf16_stored_features_are_bit_identical_to_fp32_features():
+    """A loader that stores the Omnivore features as bf16 (Batch.to_feature_dtype: half the H2D bytes) gets exactly the
+    forward of fp32 features in the bf16 compute mode -- the first GEMM's operand is the same rounding either way."""
+    egopack_b200.set_precision("bf16")
+    gen = torch.Generator().manual_seed(22)
+    D, S, H, HT, V, n = 64, 3, 128, 128, 4, 33
+    torch.manual_seed(4)
+    model = Graph(D, H, 2, temporal_pooling=dict(TP, hidden_size=HT), num_segments=S).to(DEV).eval()
+    h32 = syn.make_batch("ar", V, n, torch.Generator().manual_seed(22), feature_dim=D, num_segments=S, band_k=1)
+    h16 = syn.make_batch("ar", V, n, torch.Generator().manual_seed(22), feature_dim=D, num_segments=S, band_k=1,
+                         feature_dtype=torch.bfloat16)
+    assert h16.x.dtype == torch.bfloat16 and h32.x.dtype == torch.float32
+    assert torch.equal(h16.x, h32.x.bfloat16())
+    b32, b16 = RadiusGraph(1.5)(h32.to(DEV)), RadiusGraph(1.5)(h16.to(DEV))
+    with torch.no_grad():
+        assert torch.equal(model(b32), model(b16))
+    # and the fp32 parity mode still accepts them (cast up)
+    with egopack_b200.precision("fp32"), torch.no_grad():
+        assert model(b16).dtype == torch.float32
