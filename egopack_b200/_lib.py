@@ -59,10 +59,10 @@ SIGNATURES: Dict[str, tuple] = {
     "egp_gemm_workspace": (SZ, [I64, I64, I64]),
     "egp_gemm": (I, [P, I64, I, P, I64, I, P, I64, P, I64, I64, P, P, I64, P, I64, I64, I64, I64, I, F, I, I, I, P,
                      SZ, P]),
-    "egp_row_normalize": (I, [P, P, I64, I64, I, I, P]),
+    "egp_row_normalize": (I, [P, P, I64, I64, I, I, P, P]),
     "egp_row_inv_norm": (I, [P, P, I64, I64, I64, I, P]),
     "egp_cos_topk_workspace": (SZ, [I64, I64, I64]),
-    "egp_cos_topk": (I, [P, P, P, P, I64, I64, I64, I, P, P, SZ, P]),
+    "egp_cos_topk": (I, [P, P, P, P, I64, I64, I64, I, P, P, F, P, P, P, SZ, P]),
     "egp_proto_max_gather": (I, [P, P, P, I64, I64, I64, I, I, P]),
     "egp_proto_max_scatter_bwd": (I, [P, P, P, P, P, I64, I64, I64, I, P]),
     "egp_class_sum_f64": (I, [P, P, P, I64, I64, I64, I, P]),

@@ -43,7 +43,7 @@ bool pdl_enabled() {
 
 extern "C" {
 
-int egp_version(void) { return 1; }
+int egp_version(void) { return 2; }
 
 int egp_last_error(char* buf, size_t len) {
   if (!buf || len == 0) return EGP_ERR_INVALID;

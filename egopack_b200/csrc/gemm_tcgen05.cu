@@ -260,6 +260,8 @@ struct TcParams {
   int tma_store;       // epilogue stages 32x128B boxes in smem and stores them with TMA (coalesced, clipped)
   int topk;            // TOPK kernels: candidates kept per row (8 or 16); 0 otherwise
   int32_t* cand;       // TOPK kernels: [M, TOPK] column indices of the largest entries of each row (unordered)
+  float* cand_thr;     // TOPK kernels (optional): [M, kTopkGroups] smallest score each group KEPT -- every column of the
+                       // group that is not a candidate scored at most this (the k-NN miss detector's threshold)
   int debug;           // EGP_TC_DEBUG (timing experiments) bit 0: skip the stores, bit 1: skip the TMEM loads too, bit 2: all CTAs load tile (0,0), bit 3: skip the B loads of odd k-blocks
   uint32_t idesc;
 };
@@ -509,6 +511,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (n_blk == p.n_tiles - 1 && row_ok) {
 #pragma unroll
           for (int q = 0; q < KK; ++q) p.cand[(m * kTopkGroups + group) * KK + q] = ti[q];
+          if (p.cand_thr) p.cand_thr[m * kTopkGroups + group] = tmin;
         }
         continue;
       }
@@ -886,7 +889,7 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
   p.m_tiles = m_tiles; p.n_tiles = n_tiles;
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.C = C; p.ldc = ldc;
   p.act = act; p.slope = slope; p.accumulate = accumulate;
-  p.topk = 0; p.cand = nullptr;
+  p.topk = 0; p.cand = nullptr; p.cand_thr = nullptr;
   static const int tc_debug = [] { const char* e = getenv("EGP_TC_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = tc_debug;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_trans ? 1 : 0) << 15) |
@@ -978,7 +981,7 @@ static int tc_gemm_topk_inst(const CUtensorMap* maps, const TcParams& p, int gri
 int tc_topk_groups() { return kTopkGroups; }
 
 int tc_gemm_topk_launch(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K, int keep,
-                        int32_t* cand, cudaStream_t stream) {
+                        int32_t* cand, float* cand_thr, cudaStream_t stream) {
   if (M == 0) return EGP_OK;
   if (keep != 8 && keep != 16) {
     set_error("tc_gemm_topk: keep must be 8 or 16");
@@ -997,6 +1000,7 @@ int tc_gemm_topk_launch(const void* A, int64_t lda, const void* B, int64_t ldb, 
   p.act = EGP_ACT_NONE;
   p.topk = keep;
   p.cand = cand;
+  p.cand_thr = cand_thr;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
   CUtensorMap maps[5];
   int rc;

@@ -24,7 +24,7 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
                    int64_t ldr, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int act, float slope,
                    int out_dtype, int accumulate, cudaStream_t stream);
 int tc_gemm_topk_launch(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K, int keep,
-                        int32_t* cand, cudaStream_t stream);
+                        int32_t* cand, float* cand_thr, cudaStream_t stream);
 int tc_topk_groups();
 bool tc_gemm_supported(const void* A, int64_t lda, const void* B, int64_t ldb, const void* A2, int64_t lda2,
                        const void* B2, int64_t ldb2);
@@ -84,11 +84,21 @@ row_topk_kernel(const float* __restrict__ S, int64_t rows, int64_t cols, int nou
   }
 }
 
-// exact fp32 re-score of KK candidates per row, then the k smallest d = 1 - <f, p>
+// exact fp32 re-score of KK candidates per row, then the k smallest d = 1 - <f, p>.
+//
+// Miss detector (thr != null).  The candidates were chosen by their bf16 tensor-core score s16; every column j that is
+// NOT a candidate scored s16_j <= thr_g (the smallest score its column group kept).  Its exact score obeys
+//   s_j = s16_j - (df.p16_j + f.dp_j)  =>  s_j <= thr_g + |df| + |dp_j| + |df||dp_j|      (Cauchy-Schwarz, |f| = |p| = 1)
+// with df / dp the bf16 rounding errors of the normalised rows: |df| is measured per row by egp_row_normalize
+// (f_err), max_j |dp_j| once per bank (p_err).  If the k-th best exact candidate score clears that bound for every
+// group, no column outside the candidate set can belong to the top-k; otherwise the row is FLAGGED (appended to
+// flagged_rows) and the host re-runs it through the exact fp32 path.
 template <int KK>
 __global__ void __launch_bounds__(kTopkThreads)
 rerank_kernel(const float* __restrict__ fn, const float* __restrict__ pn, const int32_t* __restrict__ cand,
-              int64_t rows, int64_t protos, int64_t channels, int k, int64_t* __restrict__ idx) {
+              int64_t rows, int64_t protos, int64_t channels, int k, int64_t* __restrict__ idx,
+              const float* __restrict__ thr, int groups, const float* __restrict__ f_err, float p_err,
+              int64_t row_base, int32_t* __restrict__ flagged_rows, int32_t* __restrict__ flagged_count) {
   pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -117,6 +127,7 @@ rerank_kernel(const float* __restrict__ fn, const float* __restrict__ pn, const 
     }
   }
   if (lane == 0) {
+    float kth = FLT_MAX;
     for (int o = 0; o < k; ++o) {  // selection of the k best of KK (KK <= 32)
       int best = 0;
 #pragma unroll
@@ -128,15 +139,29 @@ rerank_kernel(const float* __restrict__ fn, const float* __restrict__ pn, const 
 #pragma unroll
       for (int c = 0; c < KK; ++c)
         if (c == best) { bd = d[c]; bi = id[c]; d[c] = FLT_MAX; id[c] = INT_MAX; }
-      (void)bd;
+      kth = bd;
       idx[row * k + o] = (int64_t)bi;
+    }
+    if (thr) {
+      float t = -FLT_MAX;
+      for (int g = 0; g < groups; ++g) t = fmaxf(t, thr[row * groups + g]);
+      const float fe = f_err ? f_err[row_base + row] : 0.00390625f;   // 2^-8: the unit roundoff of bf16
+      // fp32 slack: the tensor-core accumulation of s16 and the fmaf chain of the exact score (C terms of <= 1 ulp(1)
+      // each, even if every rounding went the same way), and the rounding of d = 1 - s
+      const float bound = fe + p_err + fe * p_err + 1e-4f;
+      const float s_k = 1.0f - kth;   // k-th best exact similarity among the candidates
+      if (!(s_k - t > bound)) {       // also true for NaN scores
+        const int slot = atomicAdd(flagged_count, 1);
+        flagged_rows[slot] = (int32_t)(row_base + row);
+      }
     }
   }
 }
 
 template <typename T, typename O>
 __global__ void __launch_bounds__(kTopkThreads)
-row_normalize_kernel(const T* __restrict__ x, O* __restrict__ out, int64_t rows, int64_t cols) {
+row_normalize_kernel(const T* __restrict__ x, O* __restrict__ out, int64_t rows, int64_t cols,
+                     float* __restrict__ round_err) {
   pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -145,7 +170,18 @@ row_normalize_kernel(const T* __restrict__ x, O* __restrict__ out, int64_t rows,
   float q = 0.f;
   for (int64_t c = lane; c < cols; c += 32) { const float v = to_float<T>(xr[c]); q += v * v; }
   const float nrm = sqrtf(warp_sum(q));
-  for (int64_t c = lane; c < cols; c += 32) out[row * cols + c] = from_float<O>(to_float<T>(xr[c]) / nrm);
+  float e = 0.f;
+  for (int64_t c = lane; c < cols; c += 32) {
+    const float v = to_float<T>(xr[c]) / nrm;
+    const O o = from_float<O>(v);
+    out[row * cols + c] = o;
+    const float dlt = to_float<O>(o) - v;
+    e += dlt * dlt;
+  }
+  if (round_err) {   // |stored row - exact normalised row|_2, rounded up: the k-NN miss detector's per-row error
+    e = warp_sum(e);
+    if (lane == 0) round_err[row] = sqrtf(e) * 1.0001f + 1e-7f;
+  }
 }
 
 }  // namespace egp
@@ -154,19 +190,20 @@ using namespace egp;
 
 extern "C" {
 
-int egp_row_normalize(const void* x, void* out, int64_t rows, int64_t cols, int in_dtype, int out_dtype, void* stream) {
+int egp_row_normalize(const void* x, void* out, int64_t rows, int64_t cols, int in_dtype, int out_dtype, float* round_err,
+                      void* stream) {
   EGP_REQUIRE(x && out, "row_normalize: null pointer");
   if (rows == 0) return EGP_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned grid = (unsigned)ceil_div(rows, kTopkThreads / 32);
   if (in_dtype == EGP_F32 && out_dtype == EGP_F32)
-    (void)launch_kernel(row_normalize_kernel<float, float>, grid, kTopkThreads, 0, s, (const float*)x, (float*)out, rows, cols);
+    (void)launch_kernel(row_normalize_kernel<float, float>, grid, kTopkThreads, 0, s, (const float*)x, (float*)out, rows, cols, round_err);
   else if (in_dtype == EGP_F32 && out_dtype == EGP_BF16)
-    (void)launch_kernel(row_normalize_kernel<float, __nv_bfloat16>, grid, kTopkThreads, 0, s, (const float*)x, (__nv_bfloat16*)out, rows, cols);
+    (void)launch_kernel(row_normalize_kernel<float, __nv_bfloat16>, grid, kTopkThreads, 0, s, (const float*)x, (__nv_bfloat16*)out, rows, cols, round_err);
   else if (in_dtype == EGP_BF16 && out_dtype == EGP_F32)
-    (void)launch_kernel(row_normalize_kernel<__nv_bfloat16, float>, grid, kTopkThreads, 0, s, (const __nv_bfloat16*)x, (float*)out, rows, cols);
+    (void)launch_kernel(row_normalize_kernel<__nv_bfloat16, float>, grid, kTopkThreads, 0, s, (const __nv_bfloat16*)x, (float*)out, rows, cols, round_err);
   else if (in_dtype == EGP_BF16 && out_dtype == EGP_BF16)
-    (void)launch_kernel(row_normalize_kernel<__nv_bfloat16, __nv_bfloat16>, grid, kTopkThreads, 0, s, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, rows, cols);
+    (void)launch_kernel(row_normalize_kernel<__nv_bfloat16, __nv_bfloat16>, grid, kTopkThreads, 0, s, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, rows, cols, round_err);
   else {
     set_error("row_normalize: bad dtype pair %d -> %d", in_dtype, out_dtype);
     return EGP_ERR_INVALID;
@@ -179,27 +216,35 @@ static int topk_kk(int k) { return k + 8 <= 16 ? 16 : (k + 8 <= 32 ? 32 : 0); }
 
 size_t egp_cos_topk_workspace(int64_t num_nodes, int64_t num_protos, int64_t k) {
   const int64_t rows = num_nodes < kTopkChunkRows ? num_nodes : kTopkChunkRows;
-  return (size_t)rows * (size_t)num_protos * sizeof(float) + (size_t)rows * 32 * sizeof(int32_t) + 512;
+  return (size_t)rows * (size_t)num_protos * sizeof(float) + (size_t)rows * 32 * sizeof(int32_t) +
+         (size_t)rows * 4 * sizeof(float) + 1024;   // similarities (unfused paths), candidates, group thresholds
 }
 
 int egp_cos_topk(const float* fn, const float* pn, const void* fn16, const void* pn16, int64_t num_nodes,
-                 int64_t num_protos, int64_t channels, int k, int64_t* idx, void* workspace, size_t ws_bytes,
+                 int64_t num_protos, int64_t channels, int k, int64_t* idx, const float* f_round_err,
+                 float p_round_err, int32_t* flagged_rows, int32_t* flagged_count, void* workspace, size_t ws_bytes,
                  void* stream) {
   EGP_REQUIRE(fn && pn && idx && workspace, "cos_topk: null pointer");
+  EGP_REQUIRE((flagged_rows == nullptr) == (flagged_count == nullptr), "cos_topk: flagged_rows and flagged_count come together");
+  const bool guard = flagged_rows != nullptr;
   EGP_REQUIRE(k >= 1 && k <= 32 && k <= num_protos, "cos_topk: k=%d must be in [1, min(32, num_protos)]", k);
   EGP_REQUIRE(channels % 4 == 0 && aligned16(fn) && aligned16(pn), "cos_topk: channels must be a multiple of 4");
   if (ws_bytes < egp_cos_topk_workspace(num_nodes, num_protos, k)) {
     set_error("cos_topk: workspace %zu < %zu", ws_bytes, egp_cos_topk_workspace(num_nodes, num_protos, k));
     return EGP_ERR_WORKSPACE;
   }
-  if (num_nodes == 0) return EGP_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  if (guard) EGP_CUDA(cudaMemsetAsync(flagged_count, 0, sizeof(int32_t), s));
+  if (num_nodes == 0) return EGP_OK;
   const int kk = topk_kk(k);
-  const bool tensor = fn16 && pn16 && kk > 0 && kk <= num_protos &&
+  // the miss detector lives in the fused path (kk == 16, i.e. k <= 8): a guarded call with a larger k is exact fp32
+  const bool tensor = fn16 && pn16 && kk > 0 && kk <= num_protos && (!guard || kk == 16) &&
                       tc_gemm_supported(fn16, channels, pn16, channels, nullptr, 0, nullptr, 0);
   const int64_t chunk = num_nodes < kTopkChunkRows ? num_nodes : kTopkChunkRows;
   float* S = (float*)workspace;
   int32_t* cand = (int32_t*)((char*)workspace + (((size_t)chunk * num_protos * sizeof(float) + 255) & ~(size_t)255));
+  float* thr = (float*)((char*)cand + (((size_t)chunk * 32 * sizeof(int32_t) + 255) & ~(size_t)255));
+  const int groups = tc_topk_groups();
   for (int64_t r0 = 0; r0 < num_nodes; r0 += chunk) {
     const int64_t rows = (num_nodes - r0) < chunk ? (num_nodes - r0) : chunk;
     const unsigned grid = (unsigned)ceil_div(rows, kTopkThreads / 32);
@@ -212,12 +257,14 @@ int egp_cos_topk(const float* fn, const float* pn, const void* fn16, const void*
       // every column group keeps its own set: keep 8 per group when k+4 <= 8 (k+4 covered the true top-k on every
       // row in SURVEY app. B), else 16; the re-rank sees groups*keep candidates (unused slots hold INT_MAX)
       const int keep = (k + 4 <= 8) ? 8 : 16;
-      rc = tc_gemm_topk_launch(a, channels, pn16, channels, rows, num_protos, channels, keep, cand, s);
+      rc = tc_gemm_topk_launch(a, channels, pn16, channels, rows, num_protos, channels, keep, cand, guard ? thr : nullptr, s);
       if (rc != EGP_OK) return rc;
-      if (keep * tc_topk_groups() == 16)
-        (void)launch_kernel(rerank_kernel<16>, grid, kTopkThreads, 0, s, fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k);
+      if (keep * groups == 16)
+        (void)launch_kernel(rerank_kernel<16>, grid, kTopkThreads, 0, s, fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k,
+                            guard ? (const float*)thr : nullptr, groups, f_round_err, p_round_err, r0, flagged_rows, flagged_count);
       else
-        (void)launch_kernel(rerank_kernel<32>, grid, kTopkThreads, 0, s, fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k);
+        (void)launch_kernel(rerank_kernel<32>, grid, kTopkThreads, 0, s, fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k,
+                            guard ? (const float*)thr : nullptr, groups, f_round_err, p_round_err, r0, flagged_rows, flagged_count);
     } else if (tensor) {
       const __nv_bfloat16* a = (const __nv_bfloat16*)fn16 + r0 * channels;
       rc = tc_gemm_launch(a, channels, 0, pn16, channels, 0, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, 0, S,
@@ -225,10 +272,12 @@ int egp_cos_topk(const float* fn, const float* pn, const void* fn16, const void*
       if (rc != EGP_OK) return rc;
       if (kk == 16) {
         (void)launch_kernel(row_topk_kernel<16, false, int32_t>, grid, kTopkThreads, 0, s, S, rows, num_protos, 16, cand);
-        (void)launch_kernel(rerank_kernel<16>, grid, kTopkThreads, 0, s, fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k);
+        (void)launch_kernel(rerank_kernel<16>, grid, kTopkThreads, 0, s, fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k,
+                            (const float*)nullptr, 0, (const float*)nullptr, 0.f, r0, (int32_t*)nullptr, (int32_t*)nullptr);
       } else {
         (void)launch_kernel(row_topk_kernel<32, false, int32_t>, grid, kTopkThreads, 0, s, S, rows, num_protos, 32, cand);
-        (void)launch_kernel(rerank_kernel<32>, grid, kTopkThreads, 0, s, fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k);
+        (void)launch_kernel(rerank_kernel<32>, grid, kTopkThreads, 0, s, fn + r0 * channels, pn, cand, rows, num_protos, channels, k, idx + r0 * k,
+                            (const float*)nullptr, 0, (const float*)nullptr, 0.f, r0, (int32_t*)nullptr, (int32_t*)nullptr);
       }
     } else {
       rc = sgemm_launch(fn + r0 * channels, channels, 0, pn, channels, 0, nullptr, 0, nullptr, 0, 0, nullptr, nullptr,

@@ -71,6 +71,9 @@ class GraphONE(nn.Module):
             task: nn.ModuleList([_Stage(features_size, hidden_size) for _ in range(depth)])
             for task in self.task_labels})
         self._bank_cache: Dict[str, tuple] = {}
+        # miss detector of the tensor-core k-NN (one host read of the flagged-row count per bank and forward);
+        # pass knn_guard=False (swallowed by the reference's **kwargs) to trade the guarantee for a sync-free forward
+        self.knn_guard = bool(kwargs.get("knn_guard", True))
 
     # normalised fp32 / bf16 copies of a bank, recomputed only when the embedding changes
     def _bank(self, task: str):
@@ -81,18 +84,26 @@ class GraphONE(nn.Module):
         if hit is None or hit[0] != key:
             wd = w.detach()
             pn = ops.row_normalize(wd, torch.float32)
-            pn16 = ops.row_normalize(wd, torch.bfloat16) if cd == torch.bfloat16 else None
-            hit = (key, pn, pn16, ops.cast(wd, cd))
+            pn16 = p_err = None
+            if cd == torch.bfloat16:
+                pn16, perr_rows = ops.row_normalize(wd, torch.bfloat16, with_round_err=True)
+                # largest bf16 rounding error of a prototype row: one host read per bank version (frozen banks: once)
+                p_err = float(perr_rows.max().item()) if not torch.cuda.is_current_stream_capturing() else 2.0 ** -8
+            hit = (key, pn, pn16, ops.cast(wd, cd), p_err)
             self._bank_cache[task] = hit
-        return hit[1], hit[2], hit[3]
+        return hit[1], hit[2], hit[3], hit[4]
 
     @torch.no_grad()
     def nearest_prototypes(self, task: str, features: torch.Tensor) -> torch.Tensor:
-        """[B, k] indices of the k nearest prototypes (cosine), nearest first -- graphONE.py:119-141."""
-        pn, pn16, _ = self._bank(task)
+        """[B, k] indices of the k nearest prototypes (cosine), nearest first -- graphONE.py:119-141.  In the bf16 mode
+        the similarity runs on the tensor cores; rows where bf16 rounding could have hidden a true neighbour are
+        detected from the measured rounding errors and re-ranked exactly (``knn_guard``)."""
+        pn, pn16, _, p_err = self._bank(task)
         fn = ops.row_normalize(features.detach(), torch.float32)
-        fn16 = ops.row_normalize(features.detach(), torch.bfloat16) if pn16 is not None else None
-        return ops.cos_topk(fn, pn, self.k, fn16, pn16)
+        fn16 = f_err = None
+        if pn16 is not None:
+            fn16, f_err = ops.row_normalize(features.detach(), torch.bfloat16, with_round_err=True)
+        return ops.cos_topk(fn, pn, self.k, fn16, pn16, f_err=f_err, p_err=p_err, guard=self.knn_guard)
 
     def interact(self, features: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch.Tensor], Dict[str, List[torch.Tensor]]]:
         output: Dict[str, torch.Tensor] = {}
@@ -106,7 +117,7 @@ class GraphONE(nn.Module):
             raise RuntimeError("egopack_b200.GraphONE runs on CUDA only (no CPU fallback)")
         f = ops.Cast.apply(features, config.compute_dtype())
         idx = self.nearest_prototypes(task, f)                # constant across stages: matched on the inputs
-        _, _, bank = self._bank(task)
+        _, _, bank, _ = self._bank(task)
         weight = self.embeddings[task].weight
         if weight.requires_grad and torch.is_grad_enabled():  # freeze=False: gradients reach the arg-max prototypes
             m = lambda cur: ops.ProtoMaxCombine.apply(cur, weight, bank, idx)

@@ -1019,15 +1019,32 @@ def edit_distance_min(preds: Tensor, labels: Tensor) -> Tensor:
     return out
 
 
-def row_normalize(x: Tensor, out_dtype: torch.dtype = torch.float32) -> Tensor:
+def row_normalize(x: Tensor, out_dtype: torch.dtype = torch.float32, with_round_err: bool = False):
+    """x / ||x||_2 per row.  ``with_round_err`` also returns float [rows]: the L2 distance between the stored (rounded)
+    row and the exact normalised row -- what the k-NN miss detector adds to its bound for a bf16 operand."""
     x = _c(x)
     out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
-    L.call("egp_row_normalize", L.ptr(x), L.ptr(out), x.shape[0], x.shape[1], _code(x), L.DTYPE_CODE[out_dtype], L.stream())
-    return out
+    err = torch.empty(x.shape[0], dtype=torch.float32, device=x.device) if with_round_err else None
+    L.call("egp_row_normalize", L.ptr(x), L.ptr(out), x.shape[0], x.shape[1], _code(x), L.DTYPE_CODE[out_dtype], L.ptr(err),
+           L.stream())
+    return (out, err) if with_round_err else out
 
 
-def cos_topk(fn: Tensor, pn: Tensor, k: int, fn16: Optional[Tensor] = None, pn16: Optional[Tensor] = None) -> Tensor:
-    """k nearest prototypes by cosine dissimilarity for every row of the NORMALISED fp32 features ``fn``."""
+# k-NN guard statistics (cumulative): rows scored through the tensor-core path / rows the miss detector sent to the
+# exact fp32 path.  bench.py and the tests report them.
+KNN_STATS = {"rows": 0, "flagged": 0, "calls": 0}
+
+
+def cos_topk(fn: Tensor, pn: Tensor, k: int, fn16: Optional[Tensor] = None, pn16: Optional[Tensor] = None,
+             f_err: Optional[Tensor] = None, p_err: Optional[float] = None, guard: bool = True) -> Tensor:
+    """k nearest prototypes by cosine dissimilarity for every row of the NORMALISED fp32 features ``fn``
+    (GraphONE.__compute_edges, graphONE.py:119-141): exact fp32 ranking, ties -> lower prototype index.
+
+    With bf16 copies the similarity runs on the tensor cores and only the candidates kept in the GEMM epilogue are
+    re-scored in fp32.  ``guard`` makes that safe: rows where bf16 rounding could have kept a true neighbour out of the
+    candidate set (bound from the measured rounding errors ``f_err`` [B] and ``p_err`` = max over the bank) are
+    re-run through the exact fp32 path.  Reading the flagged count is one host round trip per call; ``guard=False``
+    (or CUDA-graph capture) skips it."""
     fn, pn = _c(fn), _c(pn)
     assert fn.dtype == torch.float32 and pn.dtype == torch.float32
     b, c = fn.shape
@@ -1035,9 +1052,30 @@ def cos_topk(fn: Tensor, pn: Tensor, k: int, fn16: Optional[Tensor] = None, pn16
     idx = torch.empty((b, k), dtype=torch.int64, device=fn.device)
     nb = L.size("egp_cos_topk_workspace", b, kp, k)
     ws = L.workspace(nb, fn.device, "topk")
+    tensor_path = fn16 is not None and pn16 is not None
+    guard = guard and tensor_path and b > 0 and not torch.cuda.is_current_stream_capturing()
+    rows = count = None
+    if guard:
+        rows = torch.empty(b, dtype=torch.int32, device=fn.device)
+        count = torch.empty(1, dtype=torch.int32, device=fn.device)
     with _Traced("cos_topk", 2.0 * b * kp * c, "FLOP", f"{b}x{kp}x{c} k={k}"):
         L.call("egp_cos_topk", L.ptr(fn), L.ptr(pn), L.ptr(_c(fn16)), L.ptr(_c(pn16)), b, kp, c, int(k), L.ptr(idx),
+               L.ptr(_c(f_err)), float(p_err if p_err is not None else 2.0 ** -8), L.ptr(rows), L.ptr(count),
                L.ptr(ws), nb, L.stream())
+    if guard:
+        n_flag = int(count.item())
+        KNN_STATS["rows"] += b
+        KNN_STATS["flagged"] += n_flag
+        KNN_STATS["calls"] += 1
+        if n_flag:
+            sel = rows[:n_flag].long()
+            sub = fn.index_select(0, sel)
+            nb2 = L.size("egp_cos_topk_workspace", n_flag, kp, k)
+            ws2 = L.workspace(nb2, fn.device, "topk")
+            exact = torch.empty((n_flag, k), dtype=torch.int64, device=fn.device)
+            L.call("egp_cos_topk", L.ptr(sub), L.ptr(pn), None, None, n_flag, kp, c, int(k), L.ptr(exact), None, 0.0, None,
+                   None, L.ptr(ws2), nb2, L.stream())
+            idx.index_copy_(0, sel, exact)
     return idx
 
 

@@ -37,7 +37,7 @@ enum { EGP_F32 = 0, EGP_BF16 = 1 };
 enum { EGP_ACT_NONE = 0, EGP_ACT_RELU = 1, EGP_ACT_LEAKY_RELU = 2 };
 
 /* ---- library ------------------------------------------------------------------------------------------ */
-int egp_version(void);                               /* ABI version, bumped on any signature change */
+int egp_version(void);                               /* ABI version (2), bumped on any signature change */
 int egp_last_error(char* buf, size_t len);           /* copies the calling thread's last error message */
 int egp_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -236,16 +236,27 @@ int egp_weighted_mean(const float* x, int64_t n, float weight, float* out, int a
 
 /* ---- a14: cosine k-NN of nodes against a prototype bank (GraphONE.__compute_edges, graphONE.py:119-141) ---
  * d = 1 - (F/|F|)(P/|P|)^T ; idx[i,:] = the k smallest d, ascending, ties -> lower prototype index.
- *   egp_row_normalize: out = x / ||x||_2 per row (fp32 math, no epsilon -- cos_dissimilarity, graphONE.py:148-151)
+ *   egp_row_normalize: out = x / ||x||_2 per row (fp32 math, no epsilon -- cos_dissimilarity, graphONE.py:148-151);
+ *                      round_err (optional, float [rows]) receives |stored row - exact normalised row|_2, i.e. the
+ *                      rounding error of a bf16 output row (the miss detector's per-row error bound).
  *   egp_cos_topk     : fn/pn = fp32 NORMALISED rows [B,C] / [Kp,C].  With fn16/pn16 == NULL the similarity is an
- *                      fp32 GEMM.  With bf16 normalised copies the similarity runs on the tensor cores, the top
- *                      candidates (k+8 rounded up to 16/32) are re-scored exactly in fp32 from fn/pn.
+ *                      fp32 GEMM and the selection is exact.  With bf16 normalised copies the similarity runs on the
+ *                      tensor cores with the best candidates kept in the GEMM epilogue, and the candidates are
+ *                      re-scored exactly in fp32 from fn/pn.
+ *                      Miss detector (flagged_rows/flagged_count != NULL): a row whose k-th exact candidate score does
+ *                      not clear [largest bf16 score outside the candidate set] + f_round_err[row] + p_round_err (+
+ *                      their product + fp32 slack) -- i.e. a row where bf16 rounding COULD have hidden a true
+ *                      neighbour -- is appended to flagged_rows (int32 [B], unordered) and counted in flagged_count
+ *                      (int32 [1], zeroed by the call); the caller re-runs those rows with fn16 == NULL.
+ *                      f_round_err NULL assumes the worst case 2^-8 per row; p_round_err = max over prototypes.
  *   workspace        : egp_cos_topk_workspace(B, Kp, k) bytes (row-chunked [<=32768, Kp] fp32 similarities).    */
-int egp_row_normalize(const void* x, void* out, int64_t rows, int64_t cols, int in_dtype, int out_dtype, void* stream);
+int egp_row_normalize(const void* x, void* out, int64_t rows, int64_t cols, int in_dtype, int out_dtype,
+                      float* round_err, void* stream);
 int egp_row_inv_norm(const void* x, float* out, int64_t rows, int64_t cols, int64_t ldx, int dtype, void* stream);
 size_t egp_cos_topk_workspace(int64_t num_nodes, int64_t num_protos, int64_t k);
 int egp_cos_topk(const float* fn, const float* pn, const void* fn16, const void* pn16, int64_t num_nodes,
-                 int64_t num_protos, int64_t channels, int k, int64_t* idx, void* workspace, size_t ws_bytes,
+                 int64_t num_protos, int64_t channels, int k, int64_t* idx, const float* f_round_err,
+                 float p_round_err, int32_t* flagged_rows, int32_t* flagged_count, void* workspace, size_t ws_bytes,
                  void* stream);
 
 /* ---- a15: prototype max-gather and max-combine (reduced GraphONE stage) ------------

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol_and_prototypes_match():
     for name, nargs in fns.items():
         assert hasattr(lib, name), f"{name} not exported"
         assert len(_lib.SIGNATURES[name][1]) == nargs, name
-    assert lib.egp_version() == 1
+    assert lib.egp_version() == 2
 
 
 def test_ops_refuse_host_tensors():
