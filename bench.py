@@ -494,8 +494,8 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
         return (int(t["bytes"]), f"ncu dram bytes of one launch: {t['launch']} ({t['source']})") if t else (None, None)
 
     roof, roof_hbm = None, []
-    if "gemm_tcgen05" in agg or "gemm_ffma" in agg:
-        g = agg.get("gemm_tcgen05") or agg["gemm_ffma"]
+    if "gemm_tcgen05" in agg or "gemm_fp32" in agg:
+        g = agg.get("gemm_tcgen05") or agg["gemm_fp32"]
         ach = g["work"] / (g["ms"] / 1e3) / 1e12
         peak = pk["tensor_sustained"]
         roof = {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05/TMEM/TMA)" if "gemm_tcgen05" in agg else "sgemm_kernel",

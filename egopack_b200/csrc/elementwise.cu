@@ -351,6 +351,51 @@ int colsum_launch(const void* x, float* out, int64_t rows, int64_t cols, int64_t
   return EGP_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 operand -> bf16 split terms for the fp32-on-tensor-cores GEMM (bf16x3 / bf16x6)
+// x = x1 + x2 + x3 (+ <= 2^-24 |x|) with x1 = bf16(x), x2 = bf16(x - x1), x3 = bf16(x - x1 - x2): three bf16 numbers
+// carry the 24-bit significand of an fp32 value.  The GEMM  sum_k a_k b_k  is then evaluated as the sum of bf16 x bf16
+// products (a_i, b_j) on the tcgen05 pipe with fp32 accumulation -- the products are concatenated along K, so ONE launch
+// of the ordinary bf16 kernel (same epilogue: bias, activation, residual) computes it.
+// Output: T blocks; block t holds term sel[t] of every element, element (r, c) of block t at
+//   dst[t * block_stride + r * ldd + c];  rows R..Rp-1 and columns C..Cp-1 of every block are zero-filled.
+// ---------------------------------------------------------------------------------------------------------
+struct SplitSel { int t[6]; };
+
+__global__ void __launch_bounds__(kEwThreads)
+split_bf16_kernel(const float* __restrict__ src, int64_t lds, int64_t R, int64_t C, int64_t Rp, int64_t Cp,
+                  __nv_bfloat16* __restrict__ dst, int64_t block_stride, int64_t ldd, int T, SplitSel sel) {
+  pdl_enter();
+  const int64_t cvec = Cp / 4;                      // Cp is a multiple of 8
+  const int64_t total = Rp * cvec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cvec, c0 = (i - r * cvec) * 4;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (r < R && c0 + j < C) ? src[r * lds + c0 + j] : 0.f;
+    __nv_bfloat16 term[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat16 x1 = __float2bfloat16_rn(v[j]);
+      const float r1 = v[j] - __bfloat162float(x1);
+      const __nv_bfloat16 x2 = __float2bfloat16_rn(r1);
+      const float r2 = r1 - __bfloat162float(x2);
+      term[0][j] = x1; term[1][j] = x2; term[2][j] = __float2bfloat16_rn(r2);
+    }
+    for (int t = 0; t < T; ++t) {
+      const int w = sel.t[t];
+      __nv_bfloat16* d = dst + (int64_t)t * block_stride + r * ldd + c0;
+      // 8-byte store: c0 % 4 == 0, ldd % 8 == 0, block_stride % 8 == 0, dst 16-byte aligned
+      uint2 pk;
+      const __nv_bfloat16* tw = w == 0 ? term[0] : (w == 1 ? term[1] : term[2]);
+      pk.x = (uint32_t)__bfloat16_as_ushort(tw[0]) | ((uint32_t)__bfloat16_as_ushort(tw[1]) << 16);
+      pk.y = (uint32_t)__bfloat16_as_ushort(tw[2]) | ((uint32_t)__bfloat16_as_ushort(tw[3]) << 16);
+      *reinterpret_cast<uint2*>(d) = pk;
+    }
+  }
+}
+
 }  // namespace egp
 
 using namespace egp;
@@ -418,6 +463,24 @@ int egp_cast_pad(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t r
     set_error("cast_pad: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
     return EGP_ERR_INVALID;
   }
+  EGP_LAUNCH_CHECK();
+  return EGP_OK;
+}
+
+int egp_split_bf16(const float* src, int64_t lds, int64_t rows, int64_t cols, int64_t rows_padded, int64_t cols_padded,
+                   void* dst, int64_t block_stride, int64_t ldd, int num_blocks, const int* term_of_block, void* stream) {
+  EGP_REQUIRE(src && dst && term_of_block, "split_bf16: null pointer");
+  EGP_REQUIRE(num_blocks >= 1 && num_blocks <= 6, "split_bf16: 1..6 blocks");
+  EGP_REQUIRE(rows_padded >= rows && cols_padded >= cols && cols_padded % 8 == 0 && ldd % 8 == 0 && block_stride % 8 == 0 &&
+              aligned16(dst) && lds >= cols, "split_bf16: padded sizes / pitches must keep 16-byte bf16 rows");
+  SplitSel sel;
+  for (int t = 0; t < 6; ++t) {
+    sel.t[t] = t < num_blocks ? term_of_block[t] : 0;
+    EGP_REQUIRE(sel.t[t] >= 0 && sel.t[t] <= 2, "split_bf16: terms are 0, 1, 2");
+  }
+  if (rows_padded == 0 || cols_padded == 0) return EGP_OK;
+  (void)launch_kernel(split_bf16_kernel, ew_grid(rows_padded * (cols_padded / 4)), kEwThreads, 0, (cudaStream_t)stream, src, lds, rows,
+                      cols, rows_padded, cols_padded, (__nv_bfloat16*)dst, block_stride, ldd, num_blocks, sel);
   EGP_LAUNCH_CHECK();
   return EGP_OK;
 }

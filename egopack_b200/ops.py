@@ -254,7 +254,7 @@ def gemm(a: Tensor, a_trans: bool, b: Tensor, b_trans: bool, m: int, n: int, k: 
         assert bias.dtype == torch.float32
     if residual is not None:
         assert residual.dtype == out.dtype and residual.shape == out.shape
-    name = "gemm_tcgen05" if a.dtype == torch.bfloat16 else "gemm_ffma"
+    name = "gemm_tcgen05" if a.dtype == torch.bfloat16 else "gemm_fp32"
     detail = ""
     if TRACE is not None:
         detail = (f"{m}x{n}x{k}" + (f"+{k2}" if k2 else "") + f" {'T' if a_trans else 'N'}{'T' if b_trans else 'N'}"
@@ -266,10 +266,58 @@ def gemm(a: Tensor, a_trans: bool, b: Tensor, b_trans: bool, m: int, n: int, k: 
 
 
 def _gemm_launch(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate):
+    if a.dtype == torch.float32:
+        from . import config
+        kind = config.get_fp32_gemm()
+        if kind != "ffma" and m > 0 and n > 0 and k > 0:
+            return _gemm_fp32_tensor(kind, a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope,
+                                     accumulate)
     L.call("egp_gemm", L.ptr(a), a.stride(0), int(a_trans), L.ptr(b), b.stride(0), int(b_trans),
            L.ptr(a2), a2.stride(0) if a2 is not None else 0, L.ptr(b2), b2.stride(0) if b2 is not None else 0, int(k2),
            L.ptr(_c(bias)), L.ptr(residual), residual.stride(0) if residual is not None else 0,
            L.ptr(out), out.stride(0), m, n, k, int(act), float(slope), _code(a), L.DTYPE_CODE[out.dtype],
+           int(accumulate), None, 0, L.stream())
+
+
+# term products (A term, B term) of the split GEMM, smallest first so the fp32 accumulator adds them in increasing
+# magnitude: bf16x3 keeps the products down to 2^-16 |a||b|, bf16x6 down to 2^-24
+_SPLIT_PRODUCTS = {"bf16x3": ((1, 0), (0, 1), (0, 0)),
+                   "bf16x6": ((1, 1), (2, 0), (0, 2), (1, 0), (0, 1), (0, 0))}
+
+
+def _split_operand(x: Tensor, rows: int, k: int, trans: bool, terms) -> Tuple[Tensor, int]:
+    """bf16 operand [rows, T*Kseg] (K-major) or [T*Kseg, rows_padded] (MN-major) holding the chosen split terms of the
+    fp32 operand ``x`` side by side along K.  Returns (tensor, K') with K' = T * Kseg, Kseg = K rounded up to 8."""
+    import ctypes
+    T = len(terms)
+    kseg = (k + 7) // 8 * 8
+    sel = (ctypes.c_int * T)(*terms)
+    if not trans:                                     # x is [rows, k]
+        out = torch.empty((rows, T * kseg), dtype=torch.bfloat16, device=x.device)
+        L.call("egp_split_bf16", L.ptr(x), x.stride(0), rows, k, rows, kseg, L.ptr(out), kseg, T * kseg, T, sel, L.stream())
+    else:                                             # x is [k, rows]
+        rp = (rows + 7) // 8 * 8
+        out = torch.empty((T * kseg, rp), dtype=torch.bfloat16, device=x.device)
+        L.call("egp_split_bf16", L.ptr(x), x.stride(0), k, rows, kseg, rp, L.ptr(out), kseg * rp, rp, T, sel, L.stream())
+    return out, T * kseg
+
+
+def _gemm_fp32_tensor(kind, a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate):
+    """fp32 GEMM on the tcgen05 pipe: both operands are split into bf16 terms and the term products are laid out along
+    K, so the ordinary bf16 kernel (TMA, TMEM fp32 accumulation, fused epilogue) computes the fp32 result in one launch."""
+    prods = _SPLIT_PRODUCTS[kind]
+    ta, tb = [p[0] for p in prods], [p[1] for p in prods]
+    a_s, kk = _split_operand(a, m, k, a_trans, ta)
+    b_s, _ = _split_operand(b, n, k, b_trans, tb)
+    a2_s = b2_s = None
+    kk2 = 0
+    if a2 is not None and k2 > 0:
+        a2_s, kk2 = _split_operand(a2, m, k2, a_trans, ta)
+        b2_s, _ = _split_operand(b2, n, k2, b_trans, tb)
+    L.call("egp_gemm", L.ptr(a_s), a_s.stride(0), int(a_trans), L.ptr(b_s), b_s.stride(0), int(b_trans),
+           L.ptr(a2_s), a2_s.stride(0) if a2_s is not None else 0, L.ptr(b2_s), b2_s.stride(0) if b2_s is not None else 0,
+           int(kk2), L.ptr(_c(bias)), L.ptr(residual), residual.stride(0) if residual is not None else 0,
+           L.ptr(out), out.stride(0), m, n, kk, int(act), float(slope), BF16, L.DTYPE_CODE[out.dtype],
            int(accumulate), None, 0, L.stream())
 
 

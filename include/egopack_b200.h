@@ -175,6 +175,15 @@ int egp_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype
 /* dst[rows, ldd] = cast(src[rows, cols] with pitch lds), columns cols..ldd-1 zero-filled (16-byte pitch for TMA) */
 int egp_cast_pad(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols, int src_dtype,
                  int dst_dtype, void* stream);
+/* fp32 -> bf16 split terms for the fp32-on-tensor-cores GEMM: x = x0 + x1 + x2 with x0 = bf16(x), x1 = bf16(x - x0),
+ * x2 = bf16(x - x0 - x1) (24 significand bits).  src fp32 [rows, cols] (pitch lds); dst receives num_blocks (<= 6) bf16
+ * blocks, block t = term term_of_block[t] (HOST array, values 0..2) of every element, element (r,c) at
+ * dst[t*block_stride + r*ldd + c]; rows rows..rows_padded-1 and columns cols..cols_padded-1 of each block are zeroed.
+ * Blocks side by side (block_stride = cols_padded, ldd = num_blocks*cols_padded) extend a K-major GEMM operand along K;
+ * blocks stacked (block_stride = rows_padded*ldd) extend an MN-major one.  The fp32 Linear of the parity mode
+ * (nn.Linear in fp32, models/graph.py:46 and every other Linear of the path) is ONE egp_gemm over such operands. */
+int egp_split_bf16(const float* src, int64_t lds, int64_t rows, int64_t cols, int64_t rows_padded, int64_t cols_padded,
+                   void* dst, int64_t block_stride, int64_t ldd, int num_blocks, const int* term_of_block, void* stream);
 /* out = a + b (same dtype) */
 int egp_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
 /* out = alpha*a + beta*b (b may be NULL: out = alpha*a) */

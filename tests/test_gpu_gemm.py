@@ -94,7 +94,53 @@ def test_tc_cta_pair_tiles(kw):
                                 dict(m=64, n=200, k=300, a_trans=True, b_trans=True),
                                 dict(m=256, n=128, k=96, k2=64, bias=True, residual=True), dict(m=1024, n=1024, k=1024)])
 def test_ffma_fp32(kw):
-    run_case(F32, **kw)
+    from egopack_b200 import config
+    old = config.get_fp32_gemm()
+    try:
+        config.set_fp32_gemm("ffma")
+        run_case(F32, **kw)
+    finally:
+        config.set_fp32_gemm(old)
+
+
+FP32_TC = [dict(m=100, n=70, k=50), dict(m=300, n=130, k=77, b_trans=True, bias=True, act=1),
+           dict(m=64, n=200, k=300, a_trans=True, b_trans=True), dict(m=257, n=115, k=192, bias=True),
+           dict(m=256, n=128, k=96, k2=64, bias=True, residual=True), dict(m=1024, n=1024, k=1024),
+           dict(m=333, n=1024, k=115, b_trans=True), dict(m=115, n=1024, k=4728, a_trans=True, b_trans=True),
+           dict(m=4728, n=1000, k=320, k2=192, bias=True, act=2), dict(m=2048, n=1024, k=4608, bias=True)]
+
+
+@pytest.mark.parametrize("kw", FP32_TC)
+@pytest.mark.parametrize("kind,tol", [("bf16x6", 2e-5), ("bf16x3", 3e-4)])
+def test_fp32_gemm_on_tensor_cores(kw, kind, tol):
+    """precision('fp32') Linears on the tcgen05 pipe: fp32 operands split into bf16 terms, the term products laid out
+    along K (egp_split_bf16 + ONE bf16 egp_gemm).  bf16x6 keeps fp32-level accuracy (every layout, ragged K / N, dual
+    operands, epilogues); bf16x3 trades it for 2x the speed."""
+    from egopack_b200 import config
+    old = config.get_fp32_gemm()
+    try:
+        config.set_fp32_gemm(kind)
+        g = torch.Generator().manual_seed(1)
+        m, n, k = kw["m"], kw["n"], kw["k"]
+        a_trans, b_trans, k2 = kw.get("a_trans", False), kw.get("b_trans", False), kw.get("k2", 0)
+        A = torch.randn((k, m) if a_trans else (m, k), generator=g)
+        B = torch.randn((k, n) if b_trans else (n, k), generator=g)
+        A2 = torch.randn((k2, m) if a_trans else (m, k2), generator=g) if k2 else None
+        B2 = torch.randn((k2, n) if b_trans else (n, k2), generator=g) if k2 else None
+        bi = torch.randn(n, generator=g) if kw.get("bias") else None
+        R = torch.randn(m, n, generator=g) if kw.get("residual") else None
+        mm = lambda a, b: (a.double().t() if a_trans else a.double()) @ (b.double() if b_trans else b.double().t())
+        ref = mm(A, B) + (mm(A2, B2) if k2 else 0)
+        ref = ref + bi.double() if bi is not None else ref
+        act = kw.get("act", 0)
+        ref = ref.relu() if act == 1 else (torch.where(ref > 0, ref, 0.2 * ref) if act == 2 else ref)
+        ref = ref + R.double() if R is not None else ref
+        d = lambda t: None if t is None else t.to(DEV)
+        out = ops.gemm(d(A), a_trans, d(B), b_trans, m, n, k, a2=d(A2), b2=d(B2), k2=k2, bias=d(bi), residual=d(R), act=act,
+                       slope=0.2)
+        assert out.dtype == F32 and rel_max(out, ref) < tol * (1 if k + k2 <= 8192 else 4), (kind, rel_max(out, ref))
+    finally:
+        config.set_fp32_gemm(old)
 
 
 def test_ffma_serves_bf16_operands_tma_cannot_address():

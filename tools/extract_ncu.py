@@ -1,6 +1,6 @@
 """Extract the judged metrics of one kernel from an `ncu --set full` report into a small CSV (not a pytest file).
 
-    python tests/extract_ncu.py report.ncu-rep > profiles/rN_ncu_<kernel>.csv
+    python tools/extract_ncu.py report.ncu-rep > profiles/rN_ncu_<kernel>.csv
 """
 import csv
 import subprocess

@@ -1,6 +1,6 @@
 """Per-kernel microbenchmark at the bench workload's shapes (not a pytest file).
 
-    python tests/kernel_bench.py [filter] [--reps 10]
+    python tools/kernel_bench.py [filter] [--reps 10]
 
 Times each C-ABI op in isolation with CUDA events on the launching stream, flushing L2 between repetitions, and
 prints achieved TFLOP/s (GEMMs) or GB/s of ALGORITHMIC bytes (memory-bound kernels) against MEASURED_PEAKS.json.
@@ -197,6 +197,105 @@ def main():
         f16, p16 = ops.row_normalize(f, BF), ops.row_normalize(p, BF)
         return lambda: ops.cos_topk(fn, pn, 4, f16, p16)
     cases.append(("cos_topk_k4_kp4096 (GEMM flops)", build_topk, 2.0 * N * 4096 * H, "TFLOP/s"))
+
+    # ---- round 2 additions: LTA band+star, pooling / GraphONE pieces, losses, fused dropout, fp32 GEMM on tensor cores
+    def lta_structure(n_nodes):
+        v = n_nodes // 128
+        batch = torch.arange(v, device=DEV).repeat_interleave(128)
+        ptr = torch.arange(v + 1, device=DEV) * 128
+        y = torch.randint(1, 100, (n_nodes, 2), device=DEV)
+        y.view(v, 128, 2)[:, :2] = -1                                    # 2 input clips, 126 forecast clips per graph
+        star = ops.lta_star_counts(y, ptr, 1.5)
+        return ops.band_structure(batch, ptr, 1, star)
+
+    for nn in (N, 3 * N):
+        def build_star(backward, nn=nn):
+            gs, x = lta_structure(nn), rnd(nn, H)
+            return lambda: ops._aggregate(x, gs, backward)
+        mem_case(f"sage_mean_band_star_k1_fwd_bf16_n{nn}", lambda nn=nn: build_star(False, nn), 2 * nn * H * 2)
+        mem_case(f"sage_mean_band_star_k1_bwd_bf16_n{nn}", lambda nn=nn: build_star(True, nn), 2 * nn * H * 2)
+
+    def build_band_bwd():
+        gs, x = band(1), rnd(N, H)
+        return lambda: ops._aggregate(x, gs, True)
+    mem_case("sage_mean_band_k1_bwd_bf16", build_band_bwd, 2 * N * H * 2)
+
+    def build_rln_drop():
+        x, w, b = rnd(N, H), rnd(H, dt=torch.float32), rnd(H, dt=torch.float32)
+        return lambda: ops.RowLayerNorm.apply(x, w, b, 1e-5, ACT_RELU, 0.5)
+    mem_case("row_ln_relu_dropout_fwd_bf16", build_rln_drop, 2 * N * H * 2)
+
+    def build_pool(backward):
+        v = N // 128
+        x = rnd(N, H).requires_grad_(True)
+        batch = torch.arange(v, device=DEV).repeat_interleave(128)
+        ptr = torch.arange(v + 1, device=DEV) * 128
+        if not backward:
+            return lambda: ops.SegmentMaxPool.apply(x.detach(), ptr, batch)
+        y = ops.SegmentMaxPool.apply(x, ptr, batch)
+        dy = rnd(v, H)
+        return lambda: torch.autograd.grad(y, x, dy, retain_graph=True)
+    mem_case("segment_max_pool_fwd_bf16 (read x)", lambda: build_pool(False), N * H * 2)
+    mem_case("segment_max_pool_bwd_bf16 (write dx)", lambda: build_pool(True), N * H * 2)
+
+    def build_proto_gather():
+        bank = rnd(4096, H)
+        idx = torch.randint(0, 4096, (N, 4), device=DEV)
+        return lambda: ops.proto_max_gather(bank, idx)
+    mem_case("proto_max_gather_k4_bf16 (write m + idx; bank in L2)", build_proto_gather, N * H * 2 + N * 4 * 8)
+
+    def build_maxc(backward):
+        f, m = rnd(N, H).requires_grad_(True), rnd(N, H)
+        if not backward:
+            return lambda: ops.MaxCombine.apply(f.detach(), m)
+        a = ops.MaxCombine.apply(f, m)
+        da = rnd(N, H)
+        return lambda: torch.autograd.grad(a, f, da, retain_graph=True)
+    mem_case("max_combine_fwd_bf16", lambda: build_maxc(False), 3 * N * H * 2)
+    mem_case("max_combine_bwd_bf16", lambda: build_maxc(True), 4 * N * H * 2)
+
+    def build_class_sum():
+        x = rnd(N, H)
+        labels = torch.randint(0, 115 * 478, (N,), device=DEV)
+        out = torch.zeros(115 * 478, H, dtype=torch.float64, device=DEV)
+        return lambda: ops.class_sum_f64(x, labels, 115 * 478, out)
+    mem_case("class_sum_f64_bf16 (read x + fp64 atomics on 8 B/elt)", build_class_sum, N * H * 2 + N * H * 8)
+
+    def build_ce(backward):
+        lv, ln = rnd(N, 115, dt=torch.float32).requires_grad_(True), rnd(N, 478, dt=torch.float32).requires_grad_(True)
+        y = torch.stack([torch.randint(0, 115, (N,), device=DEV), torch.randint(0, 478, (N,), device=DEV)], 1)
+        if not backward:
+            return lambda: ops.cross_entropy((lv.detach(), ln.detach()), y, ignore_index=-1)
+        loss = ops.cross_entropy((lv, ln), y, ignore_index=-1)
+        g_ = torch.ones((), device=DEV).expand(N)
+        return lambda: torch.autograd.grad(loss, (lv, ln), g_, retain_graph=True)
+    mem_case("ce_2heads_fwd (read logits)", lambda: build_ce(False), N * (115 + 478) * 4)
+    mem_case("ce_2heads_bwd (read logits, write dlogits)", lambda: build_ce(True), 2 * N * (115 + 478) * 4)
+
+    from egopack_b200 import config as _cfg
+
+    def fp32_case(kind, name, m, n, k, **kw):
+        def build():
+            A = rnd(k, m, dt=torch.float32) if kw.get("a_trans") else rnd(m, k, dt=torch.float32)
+            B = rnd(k, n, dt=torch.float32) if kw.get("b_trans") else rnd(n, k, dt=torch.float32)
+            bi = rnd(n, dt=torch.float32)
+            out = torch.empty(m, n, dtype=torch.float32, device=DEV)
+
+            def run():
+                old = _cfg.get_fp32_gemm()
+                _cfg.set_fp32_gemm(kind)
+                try:
+                    ops.gemm(A, bool(kw.get("a_trans")), B, bool(kw.get("b_trans")), m, n, k, bias=bi, out=out)
+                finally:
+                    _cfg.set_fp32_gemm(old)
+            return run
+        cases.append((name, build, 2.0 * m * n * k, "TFLOP/s"))
+
+    for kind in ("bf16x6", "bf16x3", "ffma"):
+        fp32_case(kind, f"gemm_fp32_{kind}_fwd_k1024 (fp32-equivalent flops, split kernels included)", N, H, H)
+    fp32_case("bf16x6", "gemm_fp32_bf16x6_fwd_k4608 (fp32-equivalent flops, split kernels included)", N, H, K0)
+    fp32_case("bf16x6", "gemm_fp32_bf16x6_wgrad_1024x1024 (fp32-equivalent flops, split kernels included)", H, H, N,
+              a_trans=True, b_trans=True)
 
     print(f"{'kernel':40s} {'ms':>9s} {'achieved':>12s} {'of peak':>8s}")
     out = {}

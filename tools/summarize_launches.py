@@ -1,6 +1,6 @@
 """Aggregate an ncu launch list (``--metrics gpu__time_duration.sum --csv``) per kernel (not a pytest file).
 
-    python tests/summarize_launches.py launches.csv [steps] > summary.csv
+    python tools/summarize_launches.py launches.csv [steps] > summary.csv
 
 `steps` = how many steps the profiled command ran (default 2: one warm-up + one timed); the per-step columns divide
 by it.  ncu serialises kernels and starts each from a cold cache, so the SHARE of a kernel is what carries over to
