@@ -61,6 +61,9 @@ def parse():
                     help="host storage of the features: auto = bf16 in the bf16 compute mode, fp32 in the fp32 parity mode")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --videos graphs per task PER GPU; strong: --videos graphs per task in TOTAL, split over the ranks")
+    ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
+                    help="flat = egopack_b200.optim.FlatAdam (one kernel over flat buffers, writes the bf16 weight copies); "
+                         "torch = torch.optim.Adam(fused=True)")
     ap.add_argument("--no-extra", action="store_true", help="skip the c3 / c4 sub-lines of the N=1 run")
     ap.add_argument("--cpu-sweep", action="store_true", help="(--impl reference) also time 16 / 64 / 256 graphs per task, one step each")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -274,7 +277,11 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
     params = list(model.parameters()) + [p for t in tasks.values() for p in t.parameters()]
     if graphone is not None:
         params += [p for p in graphone.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5, fused=True)
+    if args.optimizer == "flat":
+        from egopack_b200.optim import FlatAdam
+        opt = FlatAdam(params, lr=1e-5, weight_decay=1e-5)
+    else:
+        opt = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5, fused=True)
     sync = GradientAllReduce(params) if world > 1 else None
     feed_tf = {t: (LTATemporalConnectivity(r=k_radius + 0.5) if t == "lta" else RadiusGraph(r=k_radius + 0.5))
                for t in task_names}
@@ -430,7 +437,9 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
                 d = syn.make_batch(t, sv, sn, sgen, band_k=k_radius, feature_dtype=feat_dtype).to(dev)
                 d.pos_unit_spaced = True
                 sdev[t] = feed_tf[t](d)
-            opt2 = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5, fused=True, capturable=True)
+            # FlatAdam reads its step counter and learning rate from device memory: capturable as is
+            opt2 = opt if args.optimizer == "flat" else torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5, fused=True,
+                                                                         capturable=True)
 
             def small_step(b):
                 opt2.zero_grad(set_to_none=True)
@@ -525,7 +534,7 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
               "nodes_per_step_per_gpu": n_nodes,
               "features": f"[N,3,1536] {feat_name} N(0,1)" + (" (stored by the loader as bf16: Batch.to_feature_dtype; bit-identical "
                                                              "to fp32 features in the bf16 compute mode)" if feat_name == "bf16" else ""),
-              "parallelism": f"dp{world}",
+              "parallelism": f"dp{world}", "optimizer": "FlatAdam (egp_adam_step)" if args.optimizer == "flat" else "torch fused Adam",
               "l2": (f"inputs larger than L2 ({h2d_bytes / 2**20:.0f} MiB of features per step)" if not on_device else
                      f"inputs larger than L2 ({n_nodes * 4608 * 2 / 2**20:.0f} MiB of features per step, drawn on the device)"),
               "final_loss": round(last, 4)}

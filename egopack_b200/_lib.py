@@ -70,6 +70,7 @@ SIGNATURES: Dict[str, tuple] = {
     "egp_max_combine_bwd": (I, [P, P, P, P, I64, I, P]),
     "egp_segment_max_pool_fwd": (I, [P, P, P, P, I64, I64, I, P]),
     "egp_segment_max_pool_bwd": (I, [P, P, P, P, I64, I64, I, P]),
+    "egp_adam_step": (I, [P, P, P, P, P, P, P, P, I64, P, I, P, P, F, F, F, F, P]),
     "egp_split_bf16": (I, [P, I64, I64, I64, I64, I64, P, I64, I64, I, P, P]),
     "egp_ce_loss_fwd": (I, [P, I64, P, I64, I64, I64, I64, F, P, I, P, P]),
     "egp_ce_loss_bwd": (I, [P, I64, P, P, I64, P, I64, I64, I64, I64, F, P, I64, I, P]),
@@ -144,7 +145,7 @@ KERNELS_PER_CALL = {
     "egp_row_inv_norm": 1, "egp_cos_topk": 3, "egp_proto_max_gather": 1, "egp_max_combine_fwd": 1,
     "egp_max_combine_bwd": 1, "egp_segment_max_pool_fwd": 1, "egp_segment_max_pool_bwd": 1,
     "egp_label_rank": 1, "egp_segment_argmax": 1, "egp_edit_distance_min": 1,
-    "egp_split_bf16": 1, "egp_ce_loss_fwd": 1, "egp_ce_loss_bwd": 1, "egp_bce_logits_fwd": 1, "egp_bce_logits_bwd": 1, "egp_weighted_mean": 1,
+    "egp_adam_step": 2, "egp_split_bf16": 1, "egp_ce_loss_fwd": 1, "egp_ce_loss_bwd": 1, "egp_bce_logits_fwd": 1, "egp_bce_logits_bwd": 1, "egp_weighted_mean": 1,
 }
 
 

@@ -374,6 +374,7 @@ rln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float
   // CUDA-graph replays cannot change kernel arguments, so the per-step part of the Philox stream may come from device
   // memory: rng_state = {seed, step}; the call-site index stays in `offset`
   if (rng_state) { seed = rng_state[0]; offset += rng_state[1] << 20; }
+  const uint32_t drop_key = drop_thr16 ? dropout_key(seed, offset) : 0u;   // once per thread, not per vector
   constexpr int VN = Vec<T>::N;
   constexpr int Q = VN / 4;  // float4 pieces per 16-byte vector of T
   __shared__ float4 sw[NVL * Q * 32], sb[NVL * Q * 32];
@@ -440,7 +441,7 @@ rln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float
           o.v[4 * h + 3] = apply_act((a.v[4 * h + 3] - mu) * rs * w4.w + b4.w, act, 0.f);
         }
         if (drop_thr16) {  // fused inverted dropout (nn.Dropout after the ReLU, trn_pooling.py:31,36)
-          const uint32_t keep = dropout_keep_bits((uint64_t)row * nvec + v, seed, offset, drop_thr16);
+          const uint32_t keep = dropout_keep_bits_keyed((uint64_t)row * nvec + v, drop_key, drop_thr16);
 #pragma unroll
           for (int c = 0; c < VN; ++c) o.v[c] = ((keep >> c) & 1u) ? o.v[c] * keep_scale : 0.f;
         }
@@ -640,6 +641,7 @@ rln_fwd_wide_kernel(const T* __restrict__ x, const float* __restrict__ w, const 
                     uint64_t offset, const uint64_t* __restrict__ rng_state) {
   pdl_enter();
   if (rng_state) { seed = rng_state[0]; offset += rng_state[1] << 20; }
+  const uint32_t drop_key = drop_thr16 ? dropout_key(seed, offset) : 0u;
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const int nvec = (int)(channels / VN);
@@ -666,7 +668,7 @@ rln_fwd_wide_kernel(const T* __restrict__ x, const float* __restrict__ w, const 
 #pragma unroll
       for (int c = 0; c < VN; ++c) a.v[c] = apply_act((a.v[c] - mu) * rs * w[v * VN + c] + b[v * VN + c], act, 0.f);
       if (drop_thr16) {
-        const uint32_t keep = dropout_keep_bits((uint64_t)row * nvec + v, seed, offset, drop_thr16);
+        const uint32_t keep = dropout_keep_bits_keyed((uint64_t)row * nvec + v, drop_key, drop_thr16);
 #pragma unroll
         for (int c = 0; c < VN; ++c) a.v[c] = ((keep >> c) & 1u) ? a.v[c] * keep_scale : 0.f;
       }

@@ -23,12 +23,20 @@ segment_max_fwd_kernel(const T* __restrict__ x, const int64_t* __restrict__ ptr,
   int32_t bi[VN];
 #pragma unroll
   for (int c = 0; c < VN; ++c) { best[c] = -FLT_MAX; bi[c] = -1; }
-  for (int64_t i = r0; i < r1; ++i) {
-    const Vec<T> a = Vec<T>::load(x + i * channels + col);
+  auto take = [&](const Vec<T>& a, int64_t i) {
 #pragma unroll
     for (int c = 0; c < VN; ++c)
       if (a.v[c] > best[c] || bi[c] < 0) { best[c] = a.v[c]; bi[c] = (int32_t)i; }
+  };
+  int64_t i = r0;
+  for (; i + 8 <= r1; i += 8) {  // eight independent 16-byte loads in flight per thread (one CTA per graph: latency bound)
+    Raw<T> a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = Raw<T>::load(x + (i + u) * channels + col);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) take(a[u].unpack(), i + u);
   }
+  for (; i < r1; ++i) take(Vec<T>::load(x + i * channels + col), i);
   Vec<T> o;
 #pragma unroll
   for (int c = 0; c < VN; ++c) {
@@ -44,15 +52,38 @@ segment_max_bwd_kernel(const T* __restrict__ dout, const int32_t* __restrict__ a
                        const int64_t* __restrict__ batch, T* __restrict__ dx, int64_t nvec, int64_t channels) {
   pdl_enter();
   constexpr int VN = Vec<T>::N;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e0 = v * VN;
-    const int64_t row = e0 / channels, c0 = e0 % channels;
-    const int64_t g = batch[row];
-    const Vec<T> d = Vec<T>::load(dout + g * channels + c0);
-    Vec<T> o;
+  constexpr int U = 4;  // vectors per thread per iteration: U dependent chains (batch -> dout / arg) in flight
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += U * stride) {
+    int64_t row[U], c0[U], g[U];
 #pragma unroll
-    for (int c = 0; c < VN; ++c) o.v[c] = (arg[g * channels + c0 + c] == (int32_t)row) ? d.v[c] : 0.f;
-    o.store(dx + e0);
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      const int64_t e0 = (v < nvec ? v : v0) * VN;
+      row[u] = e0 / channels;
+      c0[u] = e0 % channels;
+      g[u] = batch[row[u]];
+    }
+    Raw<T> d[U];
+    int4 a0[U], a1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      d[u] = Raw<T>::load(dout + g[u] * channels + c0[u]);
+      const int4* ap = reinterpret_cast<const int4*>(arg + g[u] * channels + c0[u]);
+      a0[u] = ap[0];
+      if (VN == 8) a1[u] = ap[1];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v >= nvec) continue;
+      const Vec<T> dv = d[u].unpack();
+      const int32_t am[8] = {a0[u].x, a0[u].y, a0[u].z, a0[u].w, a1[u].x, a1[u].y, a1[u].z, a1[u].w};
+      Vec<T> o;
+#pragma unroll
+      for (int c = 0; c < VN; ++c) o.v[c] = (am[c] == (int32_t)row[u]) ? dv.v[c] : 0.f;
+      o.store(dx + v * VN);
+    }
   }
 }
 
@@ -62,16 +93,55 @@ proto_max_gather_kernel(const T* __restrict__ protos, const int64_t* __restrict_
                         int64_t nvec, int64_t k, int64_t channels) {
   pdl_enter();
   constexpr int VN = Vec<T>::N;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e0 = v * VN;
-    const int64_t row = e0 / channels, c0 = e0 % channels;
-    Vec<T> best = Vec<T>::load(protos + idx[row * k] * channels + c0);
-    for (int64_t j = 1; j < k; ++j) {
-      const Vec<T> a = Vec<T>::load(protos + idx[row * k + j] * channels + c0);
+  constexpr int U = 4;  // output vectors per thread per iteration: U * k gathers in flight behind U index loads
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += U * stride) {
+    int64_t row[U], c0[U];
 #pragma unroll
-      for (int c = 0; c < VN; ++c) best.v[c] = fmaxf(best.v[c], a.v[c]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      const int64_t e0 = (v < nvec ? v : v0) * VN;
+      row[u] = e0 / channels;
+      c0[u] = e0 % channels;
     }
-    best.store(m + e0);
+    if (k == 4) {  // the configured neighbour count (experiments/egopack/*.yaml): everything unrolled
+      int64_t j[U][4];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) j[u][q] = idx[row[u] * 4 + q];
+      Raw<T> a[U][4];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[u][q] = Raw<T>::load(protos + j[u][q] * channels + c0[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t v = v0 + u * stride;
+        if (v >= nvec) continue;
+        Vec<T> best = a[u][0].unpack();
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+          const Vec<T> t = a[u][q].unpack();
+#pragma unroll
+          for (int c = 0; c < VN; ++c) best.v[c] = fmaxf(best.v[c], t.v[c]);
+        }
+        best.store(m + v * VN);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t v = v0 + u * stride;
+        if (v >= nvec) continue;
+        Vec<T> best = Vec<T>::load(protos + idx[row[u] * k] * channels + c0[u]);
+        for (int64_t q = 1; q < k; ++q) {
+          const Vec<T> t = Vec<T>::load(protos + idx[row[u] * k + q] * channels + c0[u]);
+#pragma unroll
+          for (int c = 0; c < VN; ++c) best.v[c] = fmaxf(best.v[c], t.v[c]);
+        }
+        best.store(m + v * VN);
+      }
+    }
   }
 }
 

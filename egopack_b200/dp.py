@@ -67,7 +67,12 @@ class GradientAllReduce:
 
     def _launch(self, b: _Bucket):
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in b.params]
-        b.flat = torch.cat([g.reshape(-1) for g in grads])
+        pieces = []
+        for g in grads:                                       # every gradient starts on a 16-byte boundary of the bucket,
+            pieces.append(g.reshape(-1))                      # so the optimizer kernel can read the views vectorised
+            if g.numel() % 4:
+                pieces.append(g.new_zeros(4 - g.numel() % 4))
+        b.flat = torch.cat(pieces)
         # NCCL averages inside the collective; gloo (CPU tests) has no AVG, so it sums and finish() divides
         self._avg = b.flat.is_cuda
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
@@ -119,7 +124,7 @@ class GradientAllReduce:
             for p in b.params:
                 n = p.numel()
                 p.grad = b.flat[off:off + n].view_as(p)
-                off += n
+                off += (n + 3) // 4 * 4
             b.pending, b.flat, b.work, b.ready = len(b.params), None, None, False
         self._next = 0
         self._seen.clear()

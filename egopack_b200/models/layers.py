@@ -95,6 +95,9 @@ class SAGEConv(nn.Module):
     def forward(self, x: Tensor, gs: GraphStructure) -> Tensor:
         if self.aggr != "mean":
             raise NotImplementedError("max aggregation is implemented by GraphONE's reduced stage")
+        if self.project and self.in_channels % 8 == 0 and self.out_channels % 8 == 0:
+            return ops.SageLayer.apply(x, self.lin.weight, self.lin.bias, self.lin_l.weight, self.lin_l.bias,
+                                       self.lin_r.weight, gs)
         xs = ops.linear(x, self.lin.weight, self.lin.bias, act=ACT_RELU) if self.project else x
         agg = ops.SageMean.apply(xs, gs)
         return ops.linear(agg, self.lin_l.weight, self.lin_l.bias, x2=x, w2=self.lin_r.weight)

@@ -448,12 +448,30 @@ class _WeightCache:
 
     def __init__(self):
         self._store = {}
+        self._shadow = {}                # id(param) -> [weakref(param), bf16 view kept current by FlatAdam, version]
+
+    def register_shadow(self, w: Tensor, view: Tensor) -> None:
+        """``view`` is a low-precision copy of ``w`` that an optimizer rewrites in the same kernel that updates ``w``
+        (egopack_b200.optim.FlatAdam).  It is handed out instead of a cast while ``w`` has not been modified by
+        anything else since the optimizer last synced it (version counter)."""
+        self._shadow[id(w)] = [weakref.ref(w), view, w._version]
+
+    def shadows_synced(self, params) -> None:
+        for w in params:
+            ent = self._shadow.get(id(w))
+            if ent is not None and ent[0]() is w:
+                ent[2] = w._version
 
     def get(self, w: Tensor, dtype: torch.dtype, pad_rows: int = 0) -> Tensor:
         """`pad_rows` > rows appends zero rows (dgrad of a classifier whose gradient had its class dim padded)."""
         pad_rows = pad_rows if pad_rows > w.shape[0] else 0
         if w.dtype == dtype and not pad_rows:
             return w
+        if not pad_rows:
+            ent = self._shadow.get(id(w))
+            if ent is not None and ent[0]() is w and ent[1].dtype == dtype and ent[2] == w._version \
+                    and ent[1].shape == w.shape:
+                return ent[1]
         key = (w.data_ptr(), tuple(w.shape), dtype, pad_rows)
         hit = self._store.get(key)
         if hit is not None:
@@ -558,6 +576,53 @@ class Linear(torch.autograd.Function):
         if dres is not None and dres.dtype != ctx.res_dtype:
             dres = cast(dres, ctx.res_dtype)
         return dx, dw, db, dx2, dw2, dres, None, None, None
+
+
+class SageLayer(torch.autograd.Function):
+    """u = lin_l(mean_{j -> i} relu(lin(z))_j) + lin_r(z): gnn.SAGEConv(H, H, project=True, aggr='mean') as ONE autograd
+    node (models/graph.py:42).  Forward: ReLU-epilogue GEMM -> band / band+star / CSR mean -> dual-operand GEMM.
+    Backward: the two gradient contributions of the layer input -- through the projection and through lin_r -- come
+    out of ONE dual-operand dgrad GEMM, ``dz = g Wp + du Wr`` accumulated in the same TMEM tile, instead of two GEMMs
+    and an elementwise add of two [N, H] tensors by autograd."""
+
+    @staticmethod
+    def forward(ctx, z, wp, bp, wl, bl, wr, gs):
+        z = _c(z)
+        cd = z.dtype
+        m, h = z.shape
+        ho = wl.shape[0]
+        wpc, wlc, wrc = weight_cache.get(wp, cd), weight_cache.get(wl, cd), weight_cache.get(wr, cd)
+        xs = gemm(z, False, wpc, False, m, h, h, bias=bp, act=ACT_RELU)
+        agg = _aggregate(xs, gs, backward=False)
+        u = gemm(agg, False, wlc, False, m, ho, h, a2=z, b2=wrc, k2=h, bias=bl)
+        ctx.save_for_backward(z, xs, agg, wp, wl, wr)
+        ctx.gs, ctx.has_bl = gs, bl is not None
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        z, xs, agg, wp, wl, wr = ctx.saved_tensors
+        cd = z.dtype
+        m, h = z.shape
+        ho = wl.shape[0]
+        du = _c(du)
+        dbl = None
+        if ctx.has_bl and ctx.needs_input_grad[4]:
+            dbl = _take_colsum(du)                                        # by-product of the graph-LN backward upstream
+            if dbl is None:
+                dbl = colsum(du)
+        duc = cast(du, cd)
+        wpc, wlc, wrc = weight_cache.get(wp, cd), weight_cache.get(wl, cd), weight_cache.get(wr, cd)
+        dagg = gemm(duc, False, wlc, True, m, h, ho)                      # through lin_l
+        dxs = _aggregate(dagg, ctx.gs, backward=True)                     # transposed mean aggregation
+        g, dbp = act_bwd_colsum(dxs, xs, ACT_RELU, 0.0)                   # through the projection's ReLU (+ its bias grad)
+        dz = None
+        if ctx.needs_input_grad[0]:
+            dz = gemm(g, False, wpc, True, m, h, h, a2=duc, b2=wrc, k2=ho)    # g Wp + du Wr in one TMEM tile
+        dwp = gemm(g, True, z, True, h, h, m, out_dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        dwl = gemm(duc, True, agg, True, ho, h, m, out_dtype=torch.float32) if ctx.needs_input_grad[3] else None
+        dwr = gemm(duc, True, z, True, ho, h, m, out_dtype=torch.float32) if ctx.needs_input_grad[5] else None
+        return dz, dwp, dbp if ctx.needs_input_grad[2] else None, dwl, dbl, dwr, None
 
 
 class LinearCat(torch.autograd.Function):

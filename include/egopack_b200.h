@@ -153,7 +153,7 @@ int egp_graph_layernorm_seg_bwd(const void* dy, const void* x, const float* weig
 
 /* ---- row LayerNorm (+ReLU) (+Dropout) (nn.LayerNorm -> ReLU -> Dropout in TRNPooling trn_pooling.py:30-37; tasks
  *      task.py:20; GraphONE graphONE.py:61); mean/rstd float [N] are saved for the backward ---------------------
- * fwd: y = dropout_p(act(LN(x))); the keep decisions come from Philox4x32-10(seed; element-vector index, offset), so
+ * fwd: y = dropout_p(act(LN(x))); the keep decisions are a pure function of (seed, offset, element-vector index) -- Philox4x32-10 folds seed/offset into a key, a 32-bit multiply-xorshift hash draws the bits per vector -- so
  *      no mask is stored; rng_state (optional, device uint64[2] = {seed, step}) overrides the seed and adds step<<20 to
  *      the offset so that CUDA-graph replays draw fresh masks.  bwd: a zero in the saved output y means "ReLU inactive or dropped"; the incoming gradient
  *      is scaled by out_scale = 1/(1-p).  dx_colsum (optional) as in egp_graph_layernorm_bwd. */
@@ -242,6 +242,21 @@ int egp_bce_logits_bwd(const float* z, const float* target, const float* dloss, 
 /* out[0] (+)= weight * mean(x[0..n)) -- `w * loss.mean()` summed over tasks (main_temporal.py:99-128); one block, fixed
  * summation order (fp64 partials). */
 int egp_weighted_mean(const float* x, int64_t n, float weight, float* out, int accumulate, void* stream);
+
+/* ---- (f)-2: optimiser step (torch.optim.Adam(lr, weight_decay) of main_temporal.py:265-271 / main_egopack.py:317-324,
+ *      stepped at main_temporal.py:130) over FLAT buffers, one pass -----------------------------------------------------
+ * g' = g + weight_decay*p; m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ *   p, m, v      float [total]: parameters / exp_avg / exp_avg_sq of all tensors back to back (starts padded to 8 elements)
+ *   shadow       bf16 [total] or NULL: receives bf16(p) of every updated element (the bf16 GEMM operands)
+ *   seg_off      int64 device [num_tensors+1]: element offset of every tensor in the flat buffers
+ *   chunk_*      device work table, num_chunks entries: tensor index / flat start / length (<= 4096, inside one tensor)
+ *   grads        HOST array of num_tensors DEVICE pointers (float, contiguous); NULL = tensor without gradient: skipped
+ *   step         device int64[1]: completed steps; the call uses t = step+1 and then increments it
+ *   lr           device float[1] (LR schedulers and CUDA-graph replays share one code path)                           */
+int egp_adam_step(float* p, float* m, float* v, void* shadow, const int64_t* seg_off, const int32_t* chunk_tensor,
+                  const int64_t* chunk_start, const int32_t* chunk_len, int64_t num_chunks, const float* const* grads,
+                  int num_tensors, int64_t* step, const float* lr, float beta1, float beta2, float eps,
+                  float weight_decay, void* stream);
 
 /* ---- a14: cosine k-NN of nodes against a prototype bank (GraphONE.__compute_edges, graphONE.py:119-141) ---
  * d = 1 - (F/|F|)(P/|P|)^T ; idx[i,:] = the k smallest d, ascending, ties -> lower prototype index.

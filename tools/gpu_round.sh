@@ -22,13 +22,13 @@ fi
 if want ncu; then
   cap() {  # name regex extra-args... : one full capture of the first launch matching the regex
     local name=$1 re=$2; shift 2
-    ncu --set full --clock-control none --import-source on -k "regex:$re" -c 1 -f -o gpurun_out/r2_$name "$@" > gpurun_out/r2_ncu_$name.log 2>&1
+    ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$re" -c 1 -f -o gpurun_out/r2_$name "$@" > gpurun_out/r2_ncu_$name.log 2>&1
     python tools/extract_ncu.py gpurun_out/r2_$name.ncu-rep > gpurun_out/r2_ncu_$name.csv 2>/dev/null
     rm -f gpurun_out/r2_$name.ncu-rep
   }
   B="python bench.py --steps 1 --warmup 1 --quick --no-cpu-baseline"
-  cap sage_mean_band_star_fwd 'sage_mean_band_reg_kernel.*1, *8, *1' $B
-  cap sage_mean_band_star_bwd 'sage_mean_band_reg_kernel.*1, *8, *2' $B
+  cap sage_mean_band_star_fwd 'sage_mean_band_reg_kernel<[^>]*8, \(int\)1>' $B
+  cap sage_mean_band_star_bwd 'sage_mean_band_reg_kernel<[^>]*8, \(int\)2>' $B
   cap sage_hub_fixup 'sage_hub_fixup' $B
   cap rln_bwd_block 'rln_bwd_block_kernel' $B
   cap rln_fwd 'rln_fwd_kernel' $B
@@ -36,11 +36,12 @@ if want ncu; then
   cap gln_bwd_apply 'gln_bwd_apply_kernel' $B
   cap gln_stats 'gln_stats_kernel' $B
   cap gln_apply 'gln_apply_kernel' $B
-  cap colsum 'colsum_kernel' $B
-  cap gemm_fwd 'tc_gemm_kernel' -s 1 $B
-  cap sage_mean_band_k1 'sage_mean_band_reg_kernel.*1, *8, *0' python tools/kernel_bench.py sage_mean_band_k1_bf16 --reps 1
+  cap colsum 'colsum_partial_kernel' $B
+  cap act_bwd_colsum 'act_bwd_colsum_kernel' $B
+  cap gemm_fwd 'tc_gemm_kernel' $B
+  cap sage_mean_band_k1 'sage_mean_band_reg_kernel<[^>]*8, \(int\)0>' python tools/kernel_bench.py sage_mean_band_k1_bf16 --reps 1
   cap sage_mean_band_run_c4 'sage_mean_band_run_kernel' python tools/probe_band_wide.py
-  cap segment_max_pool 'segment_max_pool_fwd' python tools/kernel_bench.py segment_max_pool_fwd --reps 1
+  cap segment_max_pool 'segment_max_fwd_kernel' python tools/kernel_bench.py segment_max_pool_fwd --reps 1
   cap proto_max_gather 'proto_max_gather' python tools/kernel_bench.py proto_max_gather --reps 1
   cap ce_loss_fwd 'ce_loss_fwd' python tools/kernel_bench.py ce_2heads_fwd --reps 1
   ls gpurun_out/r2_ncu_*.csv | head -30

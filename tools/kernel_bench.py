@@ -191,12 +191,15 @@ def main():
         return lambda: ops.PosEncAdd.apply(x, pos, freq)
     mem_case("posenc_add_bf16", build_posenc, 2 * N * H * 2)
 
-    def build_topk():
+    def build_topk(guard=True):
         f, p = rnd(N, H, dt=torch.float32), rnd(4096, H, dt=torch.float32)
         fn, pn = ops.row_normalize(f), ops.row_normalize(p)
-        f16, p16 = ops.row_normalize(f, BF), ops.row_normalize(p, BF)
-        return lambda: ops.cos_topk(fn, pn, 4, f16, p16)
-    cases.append(("cos_topk_k4_kp4096 (GEMM flops)", build_topk, 2.0 * N * 4096 * H, "TFLOP/s"))
+        f16, fe = ops.row_normalize(f, BF, with_round_err=True)
+        p16, pe = ops.row_normalize(p, BF, with_round_err=True)
+        pmax = float(pe.max())
+        return lambda: ops.cos_topk(fn, pn, 4, f16, p16, f_err=fe, p_err=pmax, guard=guard)
+    for guard in (True, False):
+        cases.append((f"cos_topk_k4_kp4096 guard={guard} (GEMM flops)", (lambda g_=guard: build_topk(g_)), 2.0 * N * 4096 * H, "TFLOP/s"))
 
     # ---- round 2 additions: LTA band+star, pooling / GraphONE pieces, losses, fused dropout, fp32 GEMM on tensor cores
     def lta_structure(n_nodes):
