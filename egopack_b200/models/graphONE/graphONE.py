@@ -94,7 +94,7 @@ class GraphONE(nn.Module):
         return hit[1], hit[2], hit[3], hit[4]
 
     @torch.no_grad()
-    def nearest_prototypes(self, task: str, features: torch.Tensor) -> torch.Tensor:
+    def nearest_prototypes(self, task: str, features: torch.Tensor, defer: bool = False):
         """[B, k] indices of the k nearest prototypes (cosine), nearest first -- graphONE.py:119-141.  In the bf16 mode
         the similarity runs on the tensor cores; rows where bf16 rounding could have hidden a true neighbour are
         detected from the measured rounding errors and re-ranked exactly (``knn_guard``)."""
@@ -103,20 +103,26 @@ class GraphONE(nn.Module):
         fn16 = f_err = None
         if pn16 is not None:
             fn16, f_err = ops.row_normalize(features.detach(), torch.bfloat16, with_round_err=True)
-        return ops.cos_topk(fn, pn, self.k, fn16, pn16, f_err=f_err, p_err=p_err, guard=self.knn_guard)
+        return ops.cos_topk(fn, pn, self.k, fn16, pn16, f_err=f_err, p_err=p_err, guard=self.knn_guard, defer=defer)
 
     def interact(self, features: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch.Tensor], Dict[str, List[torch.Tensor]]]:
         output: Dict[str, torch.Tensor] = {}
         closest_nodes: Dict[str, List[torch.Tensor]] = {}
+        # the k-NN of every task first (it only depends on the incoming features: graphONE.py:102 matches on the original
+        # features at every stage), so the miss detector's flagged-row counts come back in ONE host round trip
+        cast, idx, pending = {}, {}, []
         for task in features.keys():
-            output[task], closest_nodes[task] = self._task_interaction(task, features[task])
+            if not features[task].is_cuda:
+                raise RuntimeError("egopack_b200.GraphONE runs on CUDA only (no CPU fallback)")
+            cast[task] = ops.Cast.apply(features[task], config.compute_dtype())
+            idx[task], pend = self.nearest_prototypes(task, cast[task], defer=True)
+            pending.append(pend)
+        ops.PendingTopk.resolve_all(pending)
+        for task in features.keys():
+            output[task], closest_nodes[task] = self._task_interaction(task, cast[task], idx[task])
         return output, closest_nodes
 
-    def _task_interaction(self, task: str, features: torch.Tensor):
-        if not features.is_cuda:
-            raise RuntimeError("egopack_b200.GraphONE runs on CUDA only (no CPU fallback)")
-        f = ops.Cast.apply(features, config.compute_dtype())
-        idx = self.nearest_prototypes(task, f)                # constant across stages: matched on the inputs
+    def _task_interaction(self, task: str, f: torch.Tensor, idx: torch.Tensor):
         _, _, bank, _ = self._bank(task)
         weight = self.embeddings[task].weight
         if weight.requires_grad and torch.is_grad_enabled():  # freeze=False: gradients reach the arg-max prototypes

@@ -1148,16 +1148,49 @@ def row_normalize(x: Tensor, out_dtype: torch.dtype = torch.float32, with_round_
 KNN_STATS = {"rows": 0, "flagged": 0, "calls": 0}
 
 
+class PendingTopk:
+    """A guarded tensor-core k-NN whose flagged-row count has not been read back yet.  ``resolve_all`` reads the counts
+    of several pending calls with ONE host round trip (GraphONE.interact queries one bank per task) and re-ranks the
+    flagged rows exactly."""
+
+    def __init__(self, idx, fn, pn, k, rows, count):
+        self.idx, self.fn, self.pn, self.k, self.rows, self.count = idx, fn, pn, k, rows, count
+
+    @staticmethod
+    def resolve_all(pending) -> None:
+        live = [p for p in pending if p is not None and p.count is not None]
+        if not live:
+            return
+        counts = torch.cat([p.count for p in live]).tolist() if len(live) > 1 else [int(live[0].count.item())]
+        for p, n_flag in zip(live, counts):
+            b, c = p.fn.shape
+            kp = p.pn.shape[0]
+            KNN_STATS["rows"] += b
+            KNN_STATS["flagged"] += int(n_flag)
+            KNN_STATS["calls"] += 1
+            if n_flag:
+                sel = p.rows[:n_flag].long()
+                sub = p.fn.index_select(0, sel)
+                nb2 = L.size("egp_cos_topk_workspace", n_flag, kp, p.k)
+                ws2 = L.workspace(nb2, p.fn.device, "topk")
+                exact = torch.empty((n_flag, p.k), dtype=torch.int64, device=p.fn.device)
+                L.call("egp_cos_topk", L.ptr(sub), L.ptr(p.pn), None, None, n_flag, kp, c, int(p.k), L.ptr(exact), None, 0.0,
+                       None, None, L.ptr(ws2), nb2, L.stream())
+                p.idx.index_copy_(0, sel, exact)
+            p.count = None
+
+
 def cos_topk(fn: Tensor, pn: Tensor, k: int, fn16: Optional[Tensor] = None, pn16: Optional[Tensor] = None,
-             f_err: Optional[Tensor] = None, p_err: Optional[float] = None, guard: bool = True) -> Tensor:
+             f_err: Optional[Tensor] = None, p_err: Optional[float] = None, guard: bool = True, defer: bool = False):
     """k nearest prototypes by cosine dissimilarity for every row of the NORMALISED fp32 features ``fn``
     (GraphONE.__compute_edges, graphONE.py:119-141): exact fp32 ranking, ties -> lower prototype index.
 
     With bf16 copies the similarity runs on the tensor cores and only the candidates kept in the GEMM epilogue are
     re-scored in fp32.  ``guard`` makes that safe: rows where bf16 rounding could have kept a true neighbour out of the
     candidate set (bound from the measured rounding errors ``f_err`` [B] and ``p_err`` = max over the bank) are
-    re-run through the exact fp32 path.  Reading the flagged count is one host round trip per call; ``guard=False``
-    (or CUDA-graph capture) skips it."""
+    re-run through the exact fp32 path.  Reading the flagged count is one host round trip; ``defer=True`` returns
+    ``(idx, pending)`` instead so that several calls share it (``PendingTopk.resolve_all``); ``guard=False`` (or
+    CUDA-graph capture) skips the detector."""
     fn, pn = _c(fn), _c(pn)
     assert fn.dtype == torch.float32 and pn.dtype == torch.float32
     b, c = fn.shape
@@ -1175,20 +1208,10 @@ def cos_topk(fn: Tensor, pn: Tensor, k: int, fn16: Optional[Tensor] = None, pn16
         L.call("egp_cos_topk", L.ptr(fn), L.ptr(pn), L.ptr(_c(fn16)), L.ptr(_c(pn16)), b, kp, c, int(k), L.ptr(idx),
                L.ptr(_c(f_err)), float(p_err if p_err is not None else 2.0 ** -8), L.ptr(rows), L.ptr(count),
                L.ptr(ws), nb, L.stream())
-    if guard:
-        n_flag = int(count.item())
-        KNN_STATS["rows"] += b
-        KNN_STATS["flagged"] += n_flag
-        KNN_STATS["calls"] += 1
-        if n_flag:
-            sel = rows[:n_flag].long()
-            sub = fn.index_select(0, sel)
-            nb2 = L.size("egp_cos_topk_workspace", n_flag, kp, k)
-            ws2 = L.workspace(nb2, fn.device, "topk")
-            exact = torch.empty((n_flag, k), dtype=torch.int64, device=fn.device)
-            L.call("egp_cos_topk", L.ptr(sub), L.ptr(pn), None, None, n_flag, kp, c, int(k), L.ptr(exact), None, 0.0, None,
-                   None, L.ptr(ws2), nb2, L.stream())
-            idx.index_copy_(0, sel, exact)
+    pending = PendingTopk(idx, fn, pn, k, rows, count) if guard else None
+    if defer:
+        return idx, pending
+    PendingTopk.resolve_all([pending])
     return idx
 
 
