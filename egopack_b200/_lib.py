@@ -149,8 +149,21 @@ KERNELS_PER_CALL = {
 }
 
 
+# EGP_NVTX=1: every C-ABI call is wrapped in an NVTX range named after the entry point, so a timeline (nsys, or ncu's
+# --nvtx filters: `ncu --nvtx --nvtx-include "egp_sage_mean_band_star/"`) attributes kernels to the operator that
+# launched them.  Off by default: a push/pop pair costs ~1 us of host time per call.
+NVTX = os.environ.get("EGP_NVTX", "0") not in ("", "0")
+
+
 def call(name: str, *args):
-    rc = getattr(load(), name)(*args)
+    if NVTX:
+        torch.cuda.nvtx.range_push(name)
+        try:
+            rc = getattr(load(), name)(*args)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    else:
+        rc = getattr(load(), name)(*args)
     CALL_COUNTS[name] = CALL_COUNTS.get(name, 0) + 1
     check(rc, name)
 

@@ -30,15 +30,17 @@ adam_step_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict
                  int tensor_base, int tensor_count, AdamGrads grads, const int64_t* __restrict__ step,
                  const float* __restrict__ lr, float beta1, float beta2, float eps, float weight_decay) {
   pdl_enter();
-  const float t = (float)(step[0] + 1);
-  const float bc1 = 1.f - powf(beta1, t);
-  const float bc2_sqrt = sqrtf(1.f - powf(beta2, t));
-  const float step_size = lr[0] / bc1;
+  const float lr0 = lr[0];
   for (int c = blockIdx.x; c < num_chunks; c += gridDim.x) {
     const int ti = chunk_tensor[c] - tensor_base;
     if (ti < 0 || ti >= tensor_count) continue;
     const float* g = grads.g[ti];
     if (!g) continue;                                   // no gradient this step: the tensor is skipped (torch semantics)
+    // torch keeps one step counter PER PARAMETER: a tensor without gradient does not advance its bias correction
+    const float t = (float)(step[chunk_tensor[c]] + 1);
+    const float bc1 = 1.f - powf(beta1, t);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, t));
+    const float step_size = lr0 / bc1;
     const int64_t start = chunk_start[c];
     const int len = chunk_len[c];
     const float* gc = g + (start - seg_off[chunk_tensor[c]]);
@@ -91,9 +93,10 @@ adam_step_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict
   }
 }
 
-__global__ void adam_tick_kernel(int64_t* __restrict__ step) {
+__global__ void adam_tick_kernel(int64_t* __restrict__ step, int tensor_base, int tensor_count, AdamGrads grads) {
   pdl_enter();
-  if (threadIdx.x == 0 && blockIdx.x == 0) step[0] += 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < tensor_count && grads.g[i]) step[tensor_base + i] += 1;
 }
 
 }  // namespace egp
@@ -108,6 +111,7 @@ int egp_adam_step(float* p, float* m, float* v, void* shadow, const int64_t* seg
                   float weight_decay, void* stream) {
   EGP_REQUIRE(p && m && v && seg_off && chunk_tensor && chunk_start && chunk_len && grads && step && lr,
               "adam_step: null pointer");
+  static_assert(kAdamMaxTensors <= 1024, "the tick kernel runs one thread per tensor of a launch");
   EGP_REQUIRE(num_tensors >= 0 && num_chunks >= 0 && num_chunks < (int64_t)INT32_MAX, "adam_step: bad sizes");
   EGP_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "adam_step: bad hyper-parameters");
   EGP_REQUIRE(aligned16(p) && aligned16(m) && aligned16(v) && (!shadow || aligned16(shadow)), "adam_step: flat buffers must be 16-byte aligned");
@@ -129,10 +133,10 @@ int egp_adam_step(float* p, float* m, float* v, void* shadow, const int64_t* seg
                           chunk_start, chunk_len, (int)num_chunks, base, count, tab, (const int64_t*)step, lr, beta1, beta2, eps,
                           weight_decay);
       EGP_LAUNCH_CHECK();
+      (void)launch_kernel(adam_tick_kernel, 1, kAdamMaxTensors, 0, s, step, base, count, tab);
+      EGP_LAUNCH_CHECK();
     }
   }
-  (void)launch_kernel(adam_tick_kernel, 1, 32, 0, s, step);
-  EGP_LAUNCH_CHECK();
   return EGP_OK;
 }
 

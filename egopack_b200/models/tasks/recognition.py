@@ -42,6 +42,19 @@ class _MultiHeadTask(ProjectionTask):
     def forward_aux_logits(self, features: torch.Tensor, t="ar", *args, **kwargs):
         return tuple(self._head(c, features) for c in self.aux_classifiers[t])
 
+    def loss_from_features(self, features: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        """``compute_loss(forward_logits(features), targets)`` as one fused autograd node (``ops.LinearCrossEntropy``:
+        head GEMMs + loss kernels, with the loss gradient emitted as the GEMM operand).  Used by the training-step glue
+        (``steps.mtl_losses``); falls back to the two reference calls when head dropout is active."""
+        from ... import config
+        if any(c[0].p > 0 for c in self.classifiers) and self.training:
+            return self.compute_loss(self.forward_logits(features), targets)
+        f = ops.Cast.apply(features, config.compute_dtype())
+        wb = []
+        for c in self.classifiers:
+            wb += [c[1].weight, c[1].bias]
+        return ops.LinearCrossEntropy.apply(f, targets, self.loss_fn.ignore_index, 0.0, *wb)
+
     def compute_loss(self, logits: Tuple[torch.Tensor], targets: torch.Tensor, return_separate_losses: bool = False):
         if return_separate_losses:
             losses = [ops.cross_entropy(l, t, ignore_index=self.loss_fn.ignore_index)

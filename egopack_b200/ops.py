@@ -930,6 +930,78 @@ class MultiHeadCrossEntropy(torch.autograd.Function):
         return (None, None, None, *grads)
 
 
+class LinearCrossEntropy(torch.autograd.Function):
+    """sum_h CrossEntropy(f W_h^T + b_h, targets[:, h]) -> per-sample loss [N]: the classifier heads of a multi-head task
+    (recognition.py:28-37,39-49: ``Sequential(Dropout, Linear)`` per label head) fused with their loss
+    (recognition.py:61-69) into one autograd node, for the training step.
+
+    What the fusion buys in the backward: the loss kernel writes d(logits) directly as the zero-padded bf16 operand of
+    the head's dgrad / wgrad GEMMs (no fp32 gradient round trip, no cast+pad kernel), the bias gradient is a column sum
+    of that operand, and the heads' contributions to d(features) chain through the GEMM epilogue (the second head's
+    dgrad takes the first one's result as its residual) instead of an elementwise add.  Logits are still materialised
+    in fp32 (they are what the loss reads), so values equal the unfused path."""
+
+    @staticmethod
+    def forward(ctx, f, targets, ignore_index: int, label_smoothing: float, *wb):
+        f = _c(f)
+        cd = f.dtype
+        n, k = f.shape
+        ws, bs = wb[0::2], wb[1::2]
+        heads = len(ws)
+        targets = _i64(targets, "targets")
+        tcols = targets.shape[1] if targets.dim() > 1 else 1
+        if tcols < heads or targets.shape[0] != n:
+            raise ValueError(f"targets {tuple(targets.shape)} do not match {heads} heads of {n} rows")
+        loss = torch.empty(n, dtype=torch.float32, device=f.device)
+        lses = torch.empty((heads, n), dtype=torch.float32, device=f.device)
+        logits = []
+        for h, (w, b) in enumerate(zip(ws, bs)):
+            c = w.shape[0]
+            cp = (c + 3) // 4 * 4                                    # 16-byte fp32 row pitch: TMA-store epilogue
+            lg = torch.empty((n, cp), dtype=torch.float32, device=f.device)[:, :c]
+            gemm(f, False, weight_cache.get(w, cd), False, n, c, k, bias=b, out_dtype=torch.float32, out=lg)
+            L.call("egp_ce_loss_fwd", L.ptr(lg), lg.stride(0), L.ptr(targets) + 8 * h, tcols, n, c, int(ignore_index),
+                   float(label_smoothing), L.ptr(loss), int(h > 0), L.ptr(lses[h]), L.stream())
+            logits.append(lg)
+        ctx.save_for_backward(f, targets, lses, *ws, *logits)
+        ctx.cfg = (int(ignore_index), float(label_smoothing), tcols, heads, tuple(b is not None for b in bs))
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        ignore_index, smoothing, tcols, heads, has_b = ctx.cfg
+        f, targets, lses, *rest = ctx.saved_tensors
+        ws, logits = rest[:heads], rest[heads:]
+        cd = f.dtype
+        n, k = f.shape
+        if dloss.dtype != torch.float32:
+            dloss = dloss.float()
+        gstride = dloss.stride(0) if dloss.dim() else 0
+        df = None
+        grads = []
+        for h, (w, lg) in enumerate(zip(ws, logits)):
+            c = w.shape[0]
+            if cd == torch.bfloat16:
+                cp = (c + 7) // 8 * 8
+                g = torch.empty((n, cp), dtype=torch.bfloat16, device=f.device)
+                L.call("egp_ce_loss_bwd", L.ptr(lg), lg.stride(0), L.ptr(lses[h]), L.ptr(targets) + 8 * h, tcols, L.ptr(dloss),
+                       gstride, n, c, ignore_index, smoothing, L.ptr(g), cp, BF16, L.stream())
+            else:
+                cp = c
+                g = torch.empty((n, c), dtype=torch.float32, device=f.device)
+                L.call("egp_ce_loss_bwd", L.ptr(lg), lg.stride(0), L.ptr(lses[h]), L.ptr(targets) + 8 * h, tcols, L.ptr(dloss),
+                       gstride, n, c, ignore_index, smoothing, L.ptr(g), c, F32, L.stream())
+            db = None
+            if has_b[h] and ctx.needs_input_grad[5 + 2 * h]:
+                db = colsum(g)[:c]
+            if ctx.needs_input_grad[0]:
+                wc = weight_cache.get(w, cd, pad_rows=cp)
+                df = gemm(g, False, wc, True, n, k, cp, residual=df)       # heads chain through the epilogue residual
+            dw = gemm(g, True, f, True, c, k, n, out_dtype=torch.float32) if ctx.needs_input_grad[4 + 2 * h] else None
+            grads += [dw, db]
+        return (df, None, None, None, *grads)
+
+
 def cross_entropy(logits, targets: Tensor, ignore_index: int = -100, label_smoothing: float = 0.0) -> Tensor:
     """Per-sample cross entropy (reduction='none'); ``logits`` is one fp32 [N,C] tensor or a tuple of heads."""
     if torch.is_tensor(logits):

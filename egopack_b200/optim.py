@@ -49,7 +49,7 @@ class FlatAdam(torch.optim.Optimizer):
         flat = torch.zeros(max(total, _ALIGN), dtype=torch.float32, device=dev)
         m, v = torch.zeros_like(flat), torch.zeros_like(flat)
         shadow = torch.zeros(flat.shape, dtype=self.shadow_dtype, device=dev) if self.shadow_dtype is not None else None
-        step = torch.zeros(1, dtype=torch.int64, device=dev)
+        step = torch.zeros(max(len(ps), 1), dtype=torch.int64, device=dev)        # one counter per parameter, as torch keeps
         lr = torch.full((1,), float(group["lr"]), dtype=torch.float32, device=dev)
         ct, cs, cl = [], [], []
         with torch.no_grad():
@@ -62,7 +62,7 @@ class FlatAdam(torch.optim.Optimizer):
                     ct.append(i)
                     cs.append(o + c0)
                     cl.append(min(_CHUNK, n - c0))
-                self.state[p] = {"step": step, "exp_avg": m[o:o + n].view(p.shape), "exp_avg_sq": v[o:o + n].view(p.shape)}
+                self.state[p] = {"step": step[i], "exp_avg": m[o:o + n].view(p.shape), "exp_avg_sq": v[o:o + n].view(p.shape)}
             if shadow is not None:
                 shadow.copy_(flat)
         fl = dict(params=ps, flat=flat, m=m, v=v, shadow=shadow, step=step, lr=lr, lr_host=float(group["lr"]),
@@ -133,6 +133,6 @@ class FlatAdam(torch.optim.Optimizer):
                     mv, vv = fl["m"][o:o + n].view(p.shape), fl["v"][o:o + n].view(p.shape)
                     mv.copy_(st["exp_avg"])
                     vv.copy_(st["exp_avg_sq"])
-                    fl["step"].fill_(int(torch.as_tensor(st["step"]).reshape(-1)[0].item()))
-                    self.state[p] = {"step": fl["step"], "exp_avg": mv, "exp_avg_sq": vv}
+                    fl["step"][i] = int(torch.as_tensor(st["step"]).reshape(-1)[0].item())
+                    self.state[p] = {"step": fl["step"][i], "exp_avg": mv, "exp_avg_sq": vv}
                 fl["lr_host"] = None                            # force a refresh of the device learning rate

@@ -45,6 +45,8 @@ def mtl_losses(model, tasks: Dict[str, torch.nn.Module], batches: Dict[str, obje
                                      ignore_index=-100)                    # plain nn.CrossEntropyLoss, main_temporal.py:291
         elif t == "pnr":
             loss = ops.bce_with_logits(task.forward_logits(f), data.y)
+        elif callable(getattr(task, "loss_from_features", None)):
+            loss = task.loss_from_features(f, data.y)                      # heads + criterion as one fused node
         else:
             loss = multi_head_ce(task.forward_logits(f), data.y)
         per_task[t] = loss

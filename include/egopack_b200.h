@@ -251,7 +251,8 @@ int egp_weighted_mean(const float* x, int64_t n, float weight, float* out, int a
  *   seg_off      int64 device [num_tensors+1]: element offset of every tensor in the flat buffers
  *   chunk_*      device work table, num_chunks entries: tensor index / flat start / length (<= 4096, inside one tensor)
  *   grads        HOST array of num_tensors DEVICE pointers (float, contiguous); NULL = tensor without gradient: skipped
- *   step         device int64[1]: completed steps; the call uses t = step+1 and then increments it
+ *   step         device int64[num_tensors]: completed steps PER TENSOR (torch keeps one counter per parameter); a tensor
+ *                with a gradient uses t = step+1 for its bias corrections and has its counter incremented
  *   lr           device float[1] (LR schedulers and CUDA-graph replays share one code path)                           */
 int egp_adam_step(float* p, float* m, float* v, void* shadow, const int64_t* seg_off, const int32_t* chunk_tensor,
                   const int64_t* chunk_start, const int32_t* chunk_len, int64_t num_chunks, const float* const* grads,
