@@ -47,7 +47,7 @@ def test_flat_adam_matches_torch_adam(wd):
     for p, q in zip(ours, ref):
         assert rel_max(p, q) < 2e-6, p.shape
     st, rst = opt.state[ours[0]], ropt.state[ref[0]]
-    assert rel_max(st["exp_avg"], rst["exp_avg"]) < 1e-6 and rel_max(st["exp_avg_sq"], rst["exp_avg_sq"]) < 1e-6
+    assert rel_max(st["exp_avg"], rst["exp_avg"]) < 3e-6 and rel_max(st["exp_avg_sq"], rst["exp_avg_sq"]) < 3e-6
     assert int(st["step"]) == 8
 
 
