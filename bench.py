@@ -406,6 +406,21 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
         for b in DeviceFeeder(host_loader(2), dev, feed_tf):
             float(step(b).item())
         barrier()
+        # what the platform gives this rank for the feature copies ALONE (all ranks copying at once, GPU otherwise idle):
+        # the ceiling of any feed, reported next to the e2e rate
+        probe_dst = {t: torch.empty(hb.x.shape, dtype=hb.x.dtype, device=dev) for t, hb in host.items()}
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rep in range(4):
+            if rep == 1:
+                barrier()
+                pe0.record()
+            for t, hb in host.items():
+                probe_dst[t].copy_(hb.x, non_blocking=True)
+        pe1.record()
+        barrier()
+        probe_ms = max_over_ranks(pe0.elapsed_time(pe1)) / 3
+        h2d_alone = sum(hb.x.numel() * hb.x.element_size() for hb in host.values()) / (probe_ms / 1e3) / 1e9
+        del probe_dst
         feeder = DeviceFeeder(host_loader(args.steps), dev, feed_tf)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -419,6 +434,7 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
         e2e = {"value": round(world * n_nodes / (e2e_ms / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3),
                "h2d_gbps_per_gpu": round(h2d_bytes / (e2e_ms / 1e3) / 1e9, 1),
+               "h2d_alone_gbps_per_gpu": round(h2d_alone, 1),
                "note": "egopack_b200.feed.DeviceFeeder: pinned host -> device copy of every step's inputs on a copy stream "
                        "(enqueued before the previous step is handed out), device-side graph transforms (band_k / star hints, "
                        "lazy edge_index), loss.item() per step"}

@@ -60,10 +60,14 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dev = torch.device("cuda", rank)
     torch.cuda.set_device(dev)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=90))
     model, tasks, params = _build(dev)
     mine = _shard_batches(rank, dev)
     local = _local_grads(model, tasks, params, mine)          # this rank's shard, no collective
+    # rank 0 also computes the OTHER rank's shard on its own GPU: the single-GPU reference of the same two shards
+    # (before the all-reduce hooks exist: a backward on one rank only must not launch collectives)
+    other = _local_grads(model, tasks, params, _shard_batches(1, dev)) if rank == 0 else None
     sync = GradientAllReduce(params, bucket_bytes=256 << 10)  # several buckets, launched from the backward hooks
     assert len(sync.buckets) > 1
     for p in params:
@@ -77,10 +81,9 @@ def _worker(rank, world, port, out):
     want = torch.stack(gathered).mean(0)
     scale = float(want.abs().max())
     err_avg = float((averaged - want).abs().max()) / scale
-    # rank 0 also recomputes the OTHER rank's shard on its own GPU: the single-GPU reference of the same two shards
+    sync.remove()
     err_cross = 0.0
     if rank == 0:
-        other = _local_grads(model, tasks, params, _shard_batches(1, dev))
         err_cross = float((other - gathered[1]).abs().max()) / float(gathered[1].abs().max())
     out[rank] = (err_avg, err_cross, float(loss))
     dist.barrier()
