@@ -42,6 +42,9 @@ SIGNATURES: Dict[str, tuple] = {
     "egp_graph_layernorm_seg_workspace": (SZ, [I64, I64, I]),
     "egp_graph_layernorm_seg_fwd": (I, [P, P, P, P, P, I64, I64, I, P, F, I, F, I, P, SZ, P]),
     "egp_graph_layernorm_seg_bwd": (I, [P, P, P, P, P, P, P, P, P, I64, I64, I, P, F, I, F, I, P, SZ, P]),
+    "egp_graph_layernorm_seg_fwd_rowstats": (I, [P, P, P, P, P, I64, I64, I, P, P, F, I, F, I, P]),
+    "egp_gemm_rowstats_bytes": (SZ, [I64, I64]),
+    "egp_gemm_rowstats": (I, [P, I64, I, P, I64, I, P, I64, P, I64, I64, P, P, I64, P, I64, I64, I64, I64, I, F, I, P, P]),
     "egp_row_layernorm_workspace": (SZ, [I64, I64]),
     "egp_row_layernorm_fwd": (I, [P, P, P, P, P, P, I64, I64, F, I, F, C.c_uint64, C.c_uint64, P, I, P]),
     "egp_row_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I64, I64, I, F, I, P, SZ, P]),
@@ -139,7 +142,8 @@ KERNELS_PER_CALL = {
     "egp_sage_mean_band": 1, "egp_sage_mean_csr": 1, "egp_lta_star_counts": 1, "egp_band_star_windows": 1,
     "egp_sage_mean_band_star": 1,   # +1 fix-up launch in the backward direction (counted in ops._aggregate_launch)
     "egp_graph_layernorm_fwd": 2, "egp_graph_layernorm_bwd": 4,
-    "egp_graph_layernorm_seg_fwd": 2, "egp_graph_layernorm_seg_bwd": 4,
+    "egp_graph_layernorm_seg_fwd": 2, "egp_graph_layernorm_seg_bwd": 4, "egp_graph_layernorm_seg_fwd_rowstats": 2,
+    "egp_gemm_rowstats": 1,
     "egp_row_layernorm_fwd": 1, "egp_row_layernorm_bwd": 2, "egp_posenc_add": 1, "egp_cast": 1, "egp_add": 1,
     "egp_axpby": 1, "egp_act_bwd": 1, "egp_act_bwd_colsum": 2, "egp_colsum": 2, "egp_mask_scale": 1, "egp_gemm": 1, "egp_row_normalize": 1,
     "egp_row_inv_norm": 1, "egp_cos_topk": 3, "egp_proto_max_gather": 1, "egp_max_combine_fwd": 1,

@@ -13,7 +13,8 @@ int sgemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64_t
 int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, const void* A2,
                    int64_t lda2, const void* B2, int64_t ldb2, int64_t K2, const float* bias, const void* residual,
                    int64_t ldr, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int act, float slope,
-                   int out_dtype, int accumulate, cudaStream_t stream);
+                   int out_dtype, int accumulate, cudaStream_t stream, double* rowstats);
+int64_t tc_gemm_rowstats_slots(int64_t N);
 bool tc_gemm_supported(const void* A, int64_t lda, const void* B, int64_t ldb, const void* A2, int64_t lda2,
                        const void* B2, int64_t ldb2);
 }  // namespace egp
@@ -45,9 +46,31 @@ int egp_gemm(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb
   static const bool force_simt = [] { const char* e = getenv("EGP_FORCE_SIMT"); return e && e[0] == '1'; }();
   if (!force_simt && in_dtype == EGP_BF16 && tc_gemm_supported(A, lda, B, ldb, A2, lda2, B2, ldb2) && K > 0)
     return tc_gemm_launch(A, lda, a_trans, B, ldb, b_trans, A2, lda2, B2, ldb2, K2, bias, residual, ldr, C, ldc, M, N,
-                          K, act, slope, out_dtype, accumulate, s);
+                          K, act, slope, out_dtype, accumulate, s, nullptr);
   return sgemm_launch(A, lda, a_trans, B, ldb, b_trans, A2, lda2, B2, ldb2, K2, bias, residual, ldr, C, ldc, M, N, K,
                       act, slope, in_dtype, out_dtype, accumulate, s);
+}
+
+size_t egp_gemm_rowstats_bytes(int64_t M, int64_t N) {
+  return sizeof(double) * 2 * (size_t)ceil_div(M, 128) * 4 * (size_t)tc_gemm_rowstats_slots(N);
+}
+
+int egp_gemm_rowstats(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, const void* A2,
+                      int64_t lda2, const void* B2, int64_t ldb2, int64_t K2, const float* bias, const void* residual,
+                      int64_t ldr, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int act, float slope,
+                      int out_dtype, double* rowstats, void* stream) {
+  EGP_REQUIRE(A && B && C && rowstats, "gemm_rowstats: null pointer");
+  EGP_REQUIRE(M >= 0 && N >= 0 && K > 0 && K2 >= 0, "gemm_rowstats: bad size");
+  EGP_REQUIRE((A2 == nullptr) == (B2 == nullptr), "gemm_rowstats: A2 and B2 must be given together");
+  EGP_REQUIRE(out_dtype == EGP_F32 || out_dtype == EGP_BF16, "gemm_rowstats: bad out_dtype %d", out_dtype);
+  EGP_REQUIRE(act >= EGP_ACT_NONE && act <= EGP_ACT_LEAKY_RELU, "gemm_rowstats: bad activation %d", act);
+  if (!A2) { K2 = 0; lda2 = 0; ldb2 = 0; }
+  if (!tc_gemm_supported(A, lda, B, ldb, A2, lda2, B2, ldb2)) {
+    set_error("gemm_rowstats: operands must be 16-byte aligned bf16 with 16-byte row pitches (tensor-core path only)");
+    return EGP_ERR_UNSUPPORTED;
+  }
+  return tc_gemm_launch(A, lda, a_trans, B, ldb, b_trans, A2, lda2, B2, ldb2, K2, bias, residual, ldr, C, ldc, M, N, K, act,
+                        slope, out_dtype, 0, (cudaStream_t)stream, rowstats);
 }
 
 }  // extern "C"

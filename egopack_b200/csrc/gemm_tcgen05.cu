@@ -262,6 +262,8 @@ struct TcParams {
   int32_t* cand;       // TOPK kernels: [M, TOPK] column indices of the largest entries of each row (unordered)
   float* cand_thr;     // TOPK kernels (optional): [M, kTopkGroups] smallest score each group KEPT -- every column of the
                        // group that is not a candidate scored at most this (the k-NN miss detector's threshold)
+  double* rowstats;    // optional: per (128-row block, TMEM quarter, n tile) {sum, sum of squares} of the values stored
+  int stat_slots;      // n-tile slots per (row block, quarter) in rowstats
   int debug;           // EGP_TC_DEBUG (timing experiments) bit 0: skip the stores, bit 1: skip the TMEM loads too, bit 2: all CTAs load tile (0,0), bit 3: skip the B loads of odd k-blocks
   uint32_t idesc;
 };
@@ -544,6 +546,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               bias_w[j] = (split == 0 && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
             asm volatile("bar.sync 1, 128;" ::: "memory");
           }
+          float st_s = 0.f, st_q = 0.f;   // rowstats: this thread's row, all columns of the tile
 #pragma unroll 1
           for (int c = 0; c < BN / CHT; ++c) {
             const int64_t nb = n0 + c * CHT;
@@ -596,6 +599,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                 for (int e = 0; e < Vec<OutT>::N; ++e) v[q * Vec<OutT>::N + e] += rr.v[e];
               }
+              if (p.rowstats) {   // statistics of the values as computed (fp32, before the output rounding)
+#pragma unroll
+                for (int e = 0; e < Vec<OutT>::N; ++e) {
+                  const float t = v[q * Vec<OutT>::N + e];
+                  st_s += t;
+                  st_q = fmaf(t, t, st_q);
+                }
+              }
               uint4 pk;
               if constexpr (sizeof(OutT) == 2) {
                 __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
@@ -615,6 +626,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (lane == 0) {
               tma_store_2d(&mapC, stage_w, (int)nb, (int)(m0 + quarter * 32), atomic);
               bulk_commit();
+            }
+          }
+          if (p.rowstats) {
+            // rows past M hold bias-only garbage: excluded.  One {sum, sumsq} pair per (row block, quarter, n tile), written
+            // exactly once, so a later reduction in a fixed order is deterministic
+            double ds = row_ok ? (double)st_s : 0.0, dq = row_ok ? (double)st_q : 0.0;
+            ds = warp_sum(ds);
+            dq = warp_sum(dq);
+            if (lane == 0) {
+              double* sp = p.rowstats + (((int64_t)m_blk * 4 + quarter) * p.stat_slots + n_blk) * 2;
+              sp[0] = ds;
+              sp[1] = dq;
             }
           }
           tc_fence_before();
@@ -860,10 +883,12 @@ static int tc_launch_major(int a_trans, int b_trans, const CUtensorMap* maps, co
   return EGP_ERR_INVALID;
 }
 
+int64_t tc_gemm_rowstats_slots(int64_t N) { return ceil_div(N, 64); }
+
 int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, const void* A2,
                    int64_t lda2, const void* B2, int64_t ldb2, int64_t K2, const float* bias, const void* residual,
                    int64_t ldr, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int act, float slope,
-                   int out_dtype, int accumulate, cudaStream_t stream) {
+                   int out_dtype, int accumulate, cudaStream_t stream, double* rowstats) {
   if (M == 0 || N == 0) return EGP_OK;
   const int sms = sm_count();
   const int m_tiles = (int)ceil_div(M, TBM);
@@ -890,6 +915,7 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.C = C; p.ldc = ldc;
   p.act = act; p.slope = slope; p.accumulate = accumulate;
   p.topk = 0; p.cand = nullptr; p.cand_thr = nullptr;
+  p.rowstats = rowstats; p.stat_slots = (int)tc_gemm_rowstats_slots(N);
   static const int tc_debug = [] { const char* e = getenv("EGP_TC_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = tc_debug;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_trans ? 1 : 0) << 15) |
@@ -930,6 +956,14 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
   const int esz = out_dtype == EGP_F32 ? 4 : 2;
   p.tma_store = (aligned16(C) && (ldc * esz) % 16 == 0 && bn >= 128 / esz &&
                  (!residual || (aligned16(residual) && (ldr * esz) % 16 == 0))) ? 1 : 0;
+  if (rowstats) {
+    // the statistics ride on the TMA-store epilogue of an unsplit GEMM with tiles at least one slot (64 columns) wide
+    if (!p.tma_store || bn < 64 || N % 64 != 0 || splits != 1 || accumulate) {
+      set_error("tc_gemm: row statistics need an unsplit GEMM with N %% 64 == 0 and a 16-byte aligned, pitched output");
+      return EGP_ERR_UNSUPPORTED;
+    }
+    EGP_CUDA(cudaMemsetAsync(rowstats, 0, sizeof(double) * 2 * (size_t)m_tiles * 4 * (size_t)p.stat_slots, stream));
+  }
   maps[4] = maps[0];
   maps[5] = maps[0];
   if (p.tma_store) {

@@ -104,6 +104,35 @@ gln_stats_kernel(const T* __restrict__ x, GlnSegs segs, int64_t channels, double
   }
 }
 
+// Statistics of a segment from the {sum, sum of squares} pairs that the producing GEMM's epilogue left per (128-row
+// block, TMEM quarter, n tile) (egp_gemm_rowstats): one block per segment, fixed summation order (deterministic).
+// Replaces gln_stats_kernel -- a full read of the tensor -- when the input of the LayerNorm comes straight out of a GEMM.
+__global__ void __launch_bounds__(kNormThreads)
+gln_stats_from_rowstats_kernel(const double* __restrict__ rowstats, int pairs_per_rowblock, GlnSegs segs, int64_t channels,
+                               double* __restrict__ stats) {
+  pdl_enter();
+  __shared__ double red[32];
+  const int seg = blockIdx.x;
+  const int64_t rb0 = segs.row[seg] / 128, rb1 = (segs.row[seg + 1] + 127) / 128;
+  const int64_t first = rb0 * pairs_per_rowblock, count = (rb1 - rb0) * pairs_per_rowblock;
+  double s = 0.0, q = 0.0;
+  for (int64_t i = threadIdx.x; i < count; i += blockDim.x) {
+    s += rowstats[2 * (first + i)];
+    q += rowstats[2 * (first + i) + 1];
+  }
+  s = block_sum(s, red);
+  q = block_sum(q, red);
+  if (threadIdx.x == 0) {
+    const int64_t rows = segs.row[seg + 1] - segs.row[seg];
+    const double inv_count = rows > 0 ? 1.0 / ((double)rows * (double)channels) : 0.0;
+    const double mu = s * inv_count;
+    double var = q * inv_count - mu * mu;
+    var = var > 0.0 ? var : 0.0;
+    stats[2 * seg] = mu;
+    stats[2 * seg + 1] = sqrt(var);
+  }
+}
+
 // FIXED: the grid stride is a multiple of the row length, so a thread always lands on the same 16-byte column and
 // keeps that column's weight/bias in registers (otherwise they are re-read, vectorised, every iteration).
 template <typename T, bool FIXED>
@@ -830,6 +859,35 @@ int egp_graph_layernorm_seg_fwd(const void* x, const float* weight, const float*
     const bool fixed = ((int64_t)g2 * kNormThreads) % (channels / Vec<T>::N) == 0;
     if (fixed) (void)launch_kernel(gln_apply_kernel<T, true>, dim3(g2, nseg), kNormThreads, 0, s, (const T*)x, weight, bias, (T*)y, stats, sg, channels, eps, act, slope);
     else (void)launch_kernel(gln_apply_kernel<T, false>, dim3(g2, nseg), kNormThreads, 0, s, (const T*)x, weight, bias, (T*)y, stats, sg, channels, eps, act, slope);
+    EGP_LAUNCH_CHECK();
+  });
+  return EGP_OK;
+}
+
+int egp_graph_layernorm_seg_fwd_rowstats(const void* x, const float* weight, const float* bias, void* y, double* stats,
+                                         int64_t n, int64_t channels, int nseg, const int64_t* seg_rows,
+                                         const double* rowstats, float eps, int act, float slope, int dtype,
+                                         void* stream) {
+  EGP_REQUIRE(x && weight && bias && y && stats && rowstats, "graph_layernorm_fwd_rowstats: null pointer");
+  const int64_t vn = dtype == EGP_BF16 ? 8 : 4;
+  EGP_REQUIRE(channels % vn == 0 && channels % 64 == 0 && aligned16(x) && aligned16(y),
+              "graph_layernorm_fwd_rowstats: channels must be a multiple of 64 and the tensors 16-byte aligned");
+  GlnSegs sg;
+  int rc = gln_segments(n, nseg, seg_rows, &sg, "graph_layernorm_fwd_rowstats");
+  if (rc != EGP_OK) return rc;
+  for (int i = 1; i < nseg; ++i)
+    EGP_REQUIRE(sg.row[i] % 128 == 0, "graph_layernorm_fwd_rowstats: inner segment boundaries must be multiples of 128 rows");
+  if (n == 0) return EGP_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int pairs = 4 * (int)ceil_div(channels, 64);
+  (void)launch_kernel(gln_stats_from_rowstats_kernel, nseg, kNormThreads, 0, s, rowstats, pairs, sg, channels, stats);
+  EGP_LAUNCH_CHECK();
+  EGP_DISPATCH_DTYPE(dtype, T, {
+    const int64_t nvec = gln_max_seg_rows(sg) * channels / Vec<T>::N;
+    const int g2 = norm_grid(nvec, kNormThreads * 2) * 2;
+    const bool fixed = ((int64_t)g2 * kNormThreads) % (channels / Vec<T>::N) == 0;
+    if (fixed) (void)launch_kernel(gln_apply_kernel<T, true>, dim3(g2, nseg), kNormThreads, 0, s, (const T*)x, weight, bias, (T*)y, (const double*)stats, sg, channels, eps, act, slope);
+    else (void)launch_kernel(gln_apply_kernel<T, false>, dim3(g2, nseg), kNormThreads, 0, s, (const T*)x, weight, bias, (T*)y, (const double*)stats, sg, channels, eps, act, slope);
     EGP_LAUNCH_CHECK();
   });
   return EGP_OK;

@@ -18,6 +18,10 @@ ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 F32, BF16 = 0, 1
 
 
+# EGP_ROWSTATS=0 disables the GEMM-epilogue statistics (A/B switch: graph-LN then runs its own stats pass)
+import os as _os
+ROWSTATS = _os.environ.get("EGP_ROWSTATS", "1") not in ("", "0")
+
 # Optional per-launch tracing for bench.py's roofline numbers: when TRACE is a list, traced ops append
 # (name, work, unit, start_event, end_event, detail) with CUDA events recorded on the launching (current) stream.
 TRACE = None
@@ -243,8 +247,10 @@ class SageMean(torch.autograd.Function):
 def gemm(a: Tensor, a_trans: bool, b: Tensor, b_trans: bool, m: int, n: int, k: int, *, a2: Optional[Tensor] = None,
          b2: Optional[Tensor] = None, k2: int = 0, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None,
          act: int = ACT_NONE, slope: float = 0.0, out_dtype: Optional[torch.dtype] = None,
-         out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
-    """C[m,n] = act(A B^T + A2 B2^T + bias) + residual, see ``egp_gemm``.  Operands must be 2-D contiguous."""
+         out: Optional[Tensor] = None, accumulate: bool = False, rowstats: bool = False) -> Tensor:
+    """C[m,n] = act(A B^T + A2 B2^T + bias) + residual, see ``egp_gemm``.  Operands must be 2-D contiguous.
+    ``rowstats=True`` tags the result with the row-block {sum, sum of squares} pairs of ``egp_gemm_rowstats`` when the
+    shape allows it (``_take_rowstats``), for a whole-tensor statistic downstream without another pass."""
     assert a.dtype == b.dtype, (a.dtype, b.dtype)
     out_dtype = out_dtype or a.dtype
     if out is None:
@@ -260,18 +266,53 @@ def gemm(a: Tensor, a_trans: bool, b: Tensor, b_trans: bool, m: int, n: int, k: 
         detail = (f"{m}x{n}x{k}" + (f"+{k2}" if k2 else "") + f" {'T' if a_trans else 'N'}{'T' if b_trans else 'N'}"
                   f" -> {'f32' if out.dtype == torch.float32 else 'bf16'}" + (" +bias" if bias is not None else "")
                   + (f" act{act}" if act else "") + (" +res" if residual is not None else "") + (" acc" if accumulate else ""))
+    stats = None
+    if rowstats and not accumulate and n % 64 == 0 and m > 0 and out.is_contiguous() and (
+            a.dtype == torch.bfloat16 or _fp32_on_tensor_cores()):
+        stats = torch.empty(L.size("egp_gemm_rowstats_bytes", m, n) // 8, dtype=torch.float64, device=a.device)
     with _Traced(name, 2.0 * m * n * (k + k2), "FLOP", detail):
-        _gemm_launch(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate)
+        _gemm_launch(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate, stats)
+    if stats is not None:
+        out._egp_rowstats = (out._version, stats)
     return out
 
 
-def _gemm_launch(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate):
+def _fp32_on_tensor_cores() -> bool:
+    from . import config
+    return config.get_fp32_gemm() != "ffma"
+
+
+def _take_rowstats(x: Tensor) -> Optional[Tensor]:
+    tag = getattr(x, "_egp_rowstats", None)
+    if tag is not None and tag[0] == x._version:
+        return tag[1]
+    return None
+
+
+def _tc_call(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate, stats):
+    """bf16 operands -> egp_gemm, or egp_gemm_rowstats when the epilogue statistics are wanted."""
+    if stats is not None:
+        L.call("egp_gemm_rowstats", L.ptr(a), a.stride(0), int(a_trans), L.ptr(b), b.stride(0), int(b_trans),
+               L.ptr(a2), a2.stride(0) if a2 is not None else 0, L.ptr(b2), b2.stride(0) if b2 is not None else 0, int(k2),
+               L.ptr(_c(bias)), L.ptr(residual), residual.stride(0) if residual is not None else 0,
+               L.ptr(out), out.stride(0), m, n, k, int(act), float(slope), L.DTYPE_CODE[out.dtype], L.ptr(stats), L.stream())
+        return
+    L.call("egp_gemm", L.ptr(a), a.stride(0), int(a_trans), L.ptr(b), b.stride(0), int(b_trans),
+           L.ptr(a2), a2.stride(0) if a2 is not None else 0, L.ptr(b2), b2.stride(0) if b2 is not None else 0, int(k2),
+           L.ptr(_c(bias)), L.ptr(residual), residual.stride(0) if residual is not None else 0,
+           L.ptr(out), out.stride(0), m, n, k, int(act), float(slope), BF16, L.DTYPE_CODE[out.dtype],
+           int(accumulate), None, 0, L.stream())
+
+
+def _gemm_launch(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate, stats=None):
     if a.dtype == torch.float32:
         from . import config
         kind = config.get_fp32_gemm()
         if kind != "ffma" and m > 0 and n > 0 and k > 0:
             return _gemm_fp32_tensor(kind, a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope,
-                                     accumulate)
+                                     accumulate, stats)
+    elif stats is not None:
+        return _tc_call(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate, stats)
     L.call("egp_gemm", L.ptr(a), a.stride(0), int(a_trans), L.ptr(b), b.stride(0), int(b_trans),
            L.ptr(a2), a2.stride(0) if a2 is not None else 0, L.ptr(b2), b2.stride(0) if b2 is not None else 0, int(k2),
            L.ptr(_c(bias)), L.ptr(residual), residual.stride(0) if residual is not None else 0,
@@ -302,7 +343,8 @@ def _split_operand(x: Tensor, rows: int, k: int, trans: bool, terms) -> Tuple[Te
     return out, T * kseg
 
 
-def _gemm_fp32_tensor(kind, a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate):
+def _gemm_fp32_tensor(kind, a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate,
+                      stats=None):
     """fp32 GEMM on the tcgen05 pipe: both operands are split into bf16 terms and the term products are laid out along
     K, so the ordinary bf16 kernel (TMA, TMEM fp32 accumulation, fused epilogue) computes the fp32 result in one launch."""
     prods = _SPLIT_PRODUCTS[kind]
@@ -314,11 +356,7 @@ def _gemm_fp32_tensor(kind, a, a_trans, b, b_trans, a2, b2, k2, bias, residual, 
     if a2 is not None and k2 > 0:
         a2_s, kk2 = _split_operand(a2, m, k2, a_trans, ta)
         b2_s, _ = _split_operand(b2, n, k2, b_trans, tb)
-    L.call("egp_gemm", L.ptr(a_s), a_s.stride(0), int(a_trans), L.ptr(b_s), b_s.stride(0), int(b_trans),
-           L.ptr(a2_s), a2_s.stride(0) if a2_s is not None else 0, L.ptr(b2_s), b2_s.stride(0) if b2_s is not None else 0,
-           int(kk2), L.ptr(_c(bias)), L.ptr(residual), residual.stride(0) if residual is not None else 0,
-           L.ptr(out), out.stride(0), m, n, kk, int(act), float(slope), BF16, L.DTYPE_CODE[out.dtype],
-           int(accumulate), None, 0, L.stream())
+    _tc_call(a_s, a_trans, b_s, b_trans, a2_s, b2_s, kk2, bias, residual, out, m, n, kk, act, slope, accumulate, stats)
 
 
 def colsum(x: Tensor) -> Tensor:
@@ -594,7 +632,8 @@ class SageLayer(torch.autograd.Function):
         wpc, wlc, wrc = weight_cache.get(wp, cd), weight_cache.get(wl, cd), weight_cache.get(wr, cd)
         xs = gemm(z, False, wpc, False, m, h, h, bias=bp, act=ACT_RELU)
         agg = _aggregate(xs, gs, backward=False)
-        u = gemm(agg, False, wlc, False, m, ho, h, a2=z, b2=wrc, k2=h, bias=bl)
+        # the statistics of the graph-mode LayerNorm that follows (models/graph.py:43) ride on this GEMM's epilogue
+        u = gemm(agg, False, wlc, False, m, ho, h, a2=z, b2=wrc, k2=h, bias=bl, rowstats=True)
         ctx.save_for_backward(z, xs, agg, wp, wl, wr)
         ctx.gs, ctx.has_bl = gs, bl is not None
         return u
@@ -778,11 +817,18 @@ class GraphLayerNorm(torch.autograd.Function):
         seg_arr = (ctypes.c_int64 * (nseg + 1))(*segs)
         y = torch.empty_like(x)
         stats = torch.empty(2 * nseg, dtype=torch.float64, device=x.device)
-        nb = L.size("egp_graph_layernorm_seg_workspace", n, c, nseg)
-        ws = L.workspace(nb, x.device)
-        with _Traced("graph_layernorm_fwd", 3.0 * n * c * x.element_size(), "B"):      # stats pass + apply pass
-            L.call("egp_graph_layernorm_seg_fwd", L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(stats), n, c, nseg, seg_arr,
-                   float(eps), act, float(slope), _code(x), L.ptr(ws), nb, L.stream())
+        pre = _take_rowstats(x) if ROWSTATS else None
+        if pre is not None and c % 64 == 0 and all(v % 128 == 0 for v in segs[1:-1]):
+            # the producing GEMM left row-block {sum, sumsq} pairs: no stats pass over x
+            with _Traced("graph_layernorm_fwd", 2.0 * n * c * x.element_size(), "B", "stats from the GEMM epilogue"):
+                L.call("egp_graph_layernorm_seg_fwd_rowstats", L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(stats), n, c,
+                       nseg, seg_arr, L.ptr(pre), float(eps), act, float(slope), _code(x), L.stream())
+        else:
+            nb = L.size("egp_graph_layernorm_seg_workspace", n, c, nseg)
+            ws = L.workspace(nb, x.device)
+            with _Traced("graph_layernorm_fwd", 3.0 * n * c * x.element_size(), "B"):      # stats pass + apply pass
+                L.call("egp_graph_layernorm_seg_fwd", L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(stats), n, c, nseg,
+                       seg_arr, float(eps), act, float(slope), _code(x), L.ptr(ws), nb, L.stream())
         ctx.save_for_backward(x, w, b, stats)
         ctx.cfg = (float(eps), act, float(slope), segs)
         return y

@@ -151,6 +151,14 @@ int egp_graph_layernorm_seg_bwd(const void* dy, const void* x, const float* weig
                                 int64_t num_nodes, int64_t channels, int nseg, const int64_t* seg_rows, float eps,
                                 int act, float slope, int dtype, void* workspace, size_t ws_bytes, void* stream);
 
+/* Forward from the row-block statistics of the producing GEMM (egp_gemm_rowstats) instead of a stats pass over x:
+ * a one-block-per-segment reduction of the pairs + the normalise pass (2*C*b bytes per node instead of 3*C*b).
+ * Inner segment boundaries must be multiples of 128 rows; channels a multiple of 64. */
+int egp_graph_layernorm_seg_fwd_rowstats(const void* x, const float* weight, const float* bias, void* y, double* stats,
+                                         int64_t num_nodes, int64_t channels, int nseg, const int64_t* seg_rows,
+                                         const double* rowstats, float eps, int act, float slope, int dtype,
+                                         void* stream);
+
 /* ---- row LayerNorm (+ReLU) (+Dropout) (nn.LayerNorm -> ReLU -> Dropout in TRNPooling trn_pooling.py:30-37; tasks
  *      task.py:20; GraphONE graphONE.py:61); mean/rstd float [N] are saved for the backward ---------------------
  * fwd: y = dropout_p(act(LN(x))); the keep decisions are a pure function of (seed, offset, element-vector index) -- Philox4x32-10 folds seed/offset into a key, a 32-bit multiply-xorshift hash draws the bits per vector -- so
@@ -258,6 +266,18 @@ int egp_adam_step(float* p, float* m, float* v, void* shadow, const int64_t* seg
                   const int64_t* chunk_start, const int32_t* chunk_len, int64_t num_chunks, const float* const* grads,
                   int num_tensors, int64_t* step, const float* lr, float beta1, float beta2, float eps,
                   float weight_decay, void* stream);
+
+/* egp_gemm (bf16 operands, tensor-core path only) that ALSO leaves, per (128-row block, 32-row quarter, 64-column slot),
+ * the {sum, sum of squares} of the values it stores -- computed in the epilogue from the fp32 accumulators, so a
+ * whole-tensor statistic of C (graph-mode LayerNorm right after SAGEConv, models/graph.py:42-43) needs no extra pass.
+ * rowstats: double [ceil(M/128)][4][ceil(N/64)][2] (egp_gemm_rowstats_bytes), zeroed by the call; requires N % 64 == 0
+ * and a 16-byte aligned, 16-byte pitched C; EGP_ERR_UNSUPPORTED otherwise (callers fall back to egp_gemm + a stats pass). */
+size_t egp_gemm_rowstats_bytes(int64_t M, int64_t N);
+int egp_gemm_rowstats(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans,
+                      const void* A2, int64_t lda2, const void* B2, int64_t ldb2, int64_t K2,
+                      const float* bias, const void* residual, int64_t ldr, void* C, int64_t ldc,
+                      int64_t M, int64_t N, int64_t K, int act, float slope, int out_dtype, double* rowstats,
+                      void* stream);
 
 /* ---- a14: cosine k-NN of nodes against a prototype bank (GraphONE.__compute_edges, graphONE.py:119-141) ---
  * d = 1 - (F/|F|)(P/|P|)^T ; idx[i,:] = the k smallest d, ascending, ties -> lower prototype index.

@@ -166,3 +166,31 @@ def test_linear_autograd_matches_torch():
         assert rel_max(y, want) < tol and rel_max(xd.grad, xr.grad) < tol
         assert rel_max(wd.grad, gw_ref) < tol and rel_max(bd.grad, gb_ref) < tol
         assert wd.grad.dtype == F32
+
+
+@pytest.mark.parametrize("dtype", [BF, F32])
+@pytest.mark.parametrize("m,n,k,k2", [(4728, 1024, 320, 192), (256, 128, 64, 0), (1000, 64, 512, 0), (32768, 1024, 1024, 1024)])
+def test_gemm_epilogue_row_statistics(dtype, m, n, k, k2):
+    """egp_gemm_rowstats: the {sum, sum of squares} pairs left by the epilogue add up to the statistics of the stored
+    tensor (rows past M excluded, CTA-pair tiles, dual operands, bf16 and fp32-on-tensor-cores outputs)."""
+    g = torch.Generator().manual_seed(m + n)
+    A = torch.randn(m, k, generator=g).to(dtype).to(DEV)
+    B = (torch.randn(n, k, generator=g) / k ** 0.5).to(dtype).to(DEV)
+    A2 = torch.randn(m, k2, generator=g).to(dtype).to(DEV) if k2 else None
+    B2 = (torch.randn(n, k2, generator=g) / max(k2, 1) ** 0.5).to(dtype).to(DEV) if k2 else None
+    bias = torch.randn(n, generator=g).to(DEV)
+    out = ops.gemm(A, False, B, False, m, n, k, a2=A2, b2=B2, k2=k2, bias=bias, rowstats=True)
+    stats = ops._take_rowstats(out)
+    assert stats is not None and stats.dtype == torch.float64
+    plain = ops.gemm(A, False, B, False, m, n, k, a2=A2, b2=B2, k2=k2, bias=bias)
+    assert torch.equal(out, plain)                                     # the statistics do not change the result
+    pairs = stats.view(-1, 2).sum(0)
+    ref = (A.double() @ B.double().t()) + (A2.double() @ B2.double().t() if k2 else 0) + bias.double()
+    tol = 1e-5 if dtype == F32 else 1e-6                               # bf16: same fp32 accumulators, exact up to summation order
+    assert abs(float(pairs[0]) - float(ref.sum())) <= 2e-3 * float(ref.abs().sum()) ** 0.5 + tol * float(ref.abs().sum())
+    assert abs(float(pairs[1]) - float((ref * ref).sum())) <= 1e-4 * float((ref * ref).sum())
+    # per row block: block b covers rows [128 b, 128 b + 128)
+    blocks = stats.view(-1, 4 * ((n + 63) // 64), 2).sum(1)
+    rb = min(3, blocks.shape[0] - 1)
+    want = (ref[128 * rb:128 * rb + 128] ** 2).sum()
+    assert abs(float(blocks[rb, 1]) - float(want)) <= 1e-4 * float(want)

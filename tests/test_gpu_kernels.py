@@ -391,3 +391,42 @@ def test_bce_and_weighted_total_match_torch():
     assert abs(float(total) - float(want.mean() + 0.25 * other.mean())) < 1e-5
     with pytest.raises(TypeError):
         ops.cross_entropy(torch.zeros(4, 3, device=DEV, dtype=torch.bfloat16), torch.zeros(4, dtype=torch.long, device=DEV))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 1e-2)])
+def test_graph_layernorm_from_gemm_epilogue_statistics(dtype, tol):
+    """The statistics of the graph-mode LayerNorm after a SAGE layer (models/graph.py:42-43) come out of the dual GEMM's
+    epilogue (egp_gemm_rowstats + egp_graph_layernorm_seg_fwd_rowstats) instead of a pass over the tensor: same result
+    as the stats-kernel path, with row segments (forward_many) and with segment boundaries that force the fallback."""
+    import egopack_b200
+    from egopack_b200.models.layers import GraphLayerNorm, SAGEConv
+    egopack_b200.set_precision("fp32" if dtype == torch.float32 else "bf16")
+    try:
+        g = torch.Generator().manual_seed(4)
+        torch.manual_seed(4)
+        H = 128
+        conv, norm = SAGEConv(H, H, project=True).to(DEV), GraphLayerNorm(H).to(DEV)
+        with torch.no_grad():
+            norm.weight.copy_(torch.rand(H, generator=g) + 0.5)
+            norm.bias.copy_(torch.randn(H, generator=g) * 0.1)
+        for sizes, segs in (([40] * 16, None), ([128] * 7, (0, 256, 640, 896)), ([50] * 6, (0, 100, 300))):
+            batch, ptr = graph_sizes_to_index(sizes)
+            n = batch.numel()
+            gs = ops.band_structure(batch.to(DEV), ptr.to(DEV), 2)
+            z = torch.randn(n, H, generator=g).to(dtype).to(DEV)
+            w = torch.randn(n, H, generator=g).to(DEV)
+            outs = []
+            for flag in (True, False):
+                ops.ROWSTATS = flag
+                zz = z.clone().requires_grad_(True)
+                u = conv(zz, gs)
+                assert (ops._take_rowstats(u) is not None) == flag
+                y = norm(u, act=ACT_LEAKY, slope=0.2, seg_rows=segs)
+                (y.float() * w).sum().backward()
+                outs.append((y.detach(), zz.grad.detach(), norm.weight.grad.clone()))
+                norm.weight.grad = None
+            assert rel_max(outs[0][0], outs[1][0]) < tol
+            assert rel_max(outs[0][1], outs[1][1]) < max(tol, 1e-5) and rel_max(outs[0][2], outs[1][2]) < max(tol, 1e-5)
+    finally:
+        ops.ROWSTATS = True
+        egopack_b200.set_precision("bf16")
