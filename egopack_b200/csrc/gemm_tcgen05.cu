@@ -274,7 +274,9 @@ struct TcParams {
 // own TMEM; each CTA runs its own epilogue.  Barriers: `full` lives in the leader (both producers' TMA bytes land
 // on it), `empty` / `tfull` are signalled in both CTAs by a multicast tcgen05.commit, `tempty` lives in the leader
 // and collects the (remote) arrivals of both CTAs' epilogue warps.
-template <int BN, bool A_MN, bool B_MN, typename OutT, int TOPK = 0, int CG = 1>
+// STATS: the epilogue also accumulates {sum, sum of squares} of what it stores (a separate instantiation: the extra
+// registers and instructions cost every GEMM ~5 % when they were a run-time branch of the common kernel).
+template <int BN, bool A_MN, bool B_MN, typename OutT, int TOPK = 0, int CG = 1, bool STATS = false>
 __global__ void __launch_bounds__(TOPK > 0 ? TC_THREADS_TOPK : TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2,
@@ -546,7 +548,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               bias_w[j] = (split == 0 && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
             asm volatile("bar.sync 1, 128;" ::: "memory");
           }
-          float st_s = 0.f, st_q = 0.f;   // rowstats: this thread's row, all columns of the tile
+          [[maybe_unused]] float st_s = 0.f, st_q = 0.f;   // STATS: this thread's row, all columns of the tile
 #pragma unroll 1
           for (int c = 0; c < BN / CHT; ++c) {
             const int64_t nb = n0 + c * CHT;
@@ -599,7 +601,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                 for (int e = 0; e < Vec<OutT>::N; ++e) v[q * Vec<OutT>::N + e] += rr.v[e];
               }
-              if (p.rowstats) {   // statistics of the values as computed (fp32, before the output rounding)
+              if constexpr (STATS) {   // statistics of the values as computed (fp32, before the output rounding)
 #pragma unroll
                 for (int e = 0; e < Vec<OutT>::N; ++e) {
                   const float t = v[q * Vec<OutT>::N + e];
@@ -628,7 +630,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               bulk_commit();
             }
           }
-          if (p.rowstats) {
+          if constexpr (STATS) {
             // rows past M hold bias-only garbage: excluded.  One {sum, sumsq} pair per (row block, quarter, n tile), written
             // exactly once, so a later reduction in a fixed order is deterministic
             double ds = row_ok ? (double)st_s : 0.0, dq = row_ok ? (double)st_q : 0.0;
@@ -815,9 +817,9 @@ bool tc_gemm_supported(const void* A, int64_t lda, const void* B, int64_t ldb, c
 }
 
 // `work` = tiles (CG == 1) or pair tiles (CG == 2) to distribute; the grid is min(work, resident CTAs / clusters)
-template <int BN, bool A_MN, bool B_MN, typename OutT, int CG>
+template <int BN, bool A_MN, bool B_MN, typename OutT, int CG, bool STATS = false>
 static int tc_launch_inst(const CUtensorMap* maps, const TcParams& p, int work, cudaStream_t stream) {
-  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, OutT, 0, CG>;
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, OutT, 0, CG, STATS>;
   constexpr int kSmem = TcCfg<BN, CG>::kSmemBytes;
   // cudaFuncSetAttribute is per DEVICE: a process that drives several GPUs (or a feeder thread racing the training
   // thread) must set it once on each of them
@@ -924,7 +926,7 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
   int splits = 1;
   const int tiles = (cg == 2 ? (m_tiles + 1) / 2 : m_tiles) * n_tiles, kb_all = p.kb1 + p.kb2;
   const int slots = sms / cg;  // concurrently running tiles (CTAs, or CTA pairs)
-  if (can_split && tiles * 2 <= slots && kb_all >= 8) {
+  if (can_split && !rowstats && tiles * 2 <= slots && kb_all >= 8) {
     splits = slots / tiles;
     if (splits > kb_all / 4) splits = kb_all / 4;
     if (splits < 1) splits = 1;
@@ -957,9 +959,10 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
   p.tma_store = (aligned16(C) && (ldc * esz) % 16 == 0 && bn >= 128 / esz &&
                  (!residual || (aligned16(residual) && (ldr * esz) % 16 == 0))) ? 1 : 0;
   if (rowstats) {
-    // the statistics ride on the TMA-store epilogue of an unsplit GEMM with tiles at least one slot (64 columns) wide
-    if (!p.tma_store || bn < 64 || N % 64 != 0 || splits != 1 || accumulate) {
-      set_error("tc_gemm: row statistics need an unsplit GEMM with N %% 64 == 0 and a 16-byte aligned, pitched output");
+    // the statistics ride on the TMA-store epilogue of the CTA-pair kernel (256-wide tiles, K-major operands): the
+    // shape of the SAGE layer's dual GEMM.  Anything else: the caller runs the plain GEMM and a statistics pass.
+    if (!p.tma_store || cg != 2 || bn != 256 || a_trans || b_trans || N % 64 != 0 || splits != 1 || accumulate) {
+      set_error("tc_gemm: row statistics need K-major operands, 256-wide CTA-pair tiles, N %% 64 == 0, no split-K");
       return EGP_ERR_UNSUPPORTED;
     }
     EGP_CUDA(cudaMemsetAsync(rowstats, 0, sizeof(double) * 2 * (size_t)m_tiles * 4 * (size_t)p.stat_slots, stream));
@@ -971,6 +974,9 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
     if (residual && (rc = make_map(residual, N, M, ldr, 128 / esz, 32, esz, &maps[5])) != EGP_OK) return rc;
   }
   const int total = tiles * splits;
+  if (rowstats)
+    return out_dtype == EGP_F32 ? tc_launch_inst<256, false, false, float, 2, true>(maps, p, total, stream)
+                                : tc_launch_inst<256, false, false, __nv_bfloat16, 2, true>(maps, p, total, stream);
   if (cg == 2)
     return out_dtype == EGP_F32 ? tc_launch_major<256, float, 2>(a_trans, b_trans, maps, p, total, stream)
                                 : tc_launch_major<256, __nv_bfloat16, 2>(a_trans, b_trans, maps, p, total, stream);

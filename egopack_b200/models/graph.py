@@ -56,12 +56,26 @@ class TemporalNet(nn.Module):
             setattr(self, f"module_{3 * d + 2}", nn.LeakyReLU(negative_slope=0.2))
         setattr(self, f"module_{3 * depth}", nn.Linear(hidden_size, hidden_size))
 
-    def forward(self, z, gs, residual=None, seg_rows=None):
+    def forward(self, x, gs, pos, pe, seg_rows=None):
+        """``x + net(x + PE(pos))`` (models/graph.py:63).  The first SAGE layer owns the positional-encoding add and the
+        residual branch (ops.SageLayerPE), so the two gradient paths into x meet in its dgrad GEMM epilogue."""
+        residual = x
+        z = None
         for d in range(self.depth):
             conv = getattr(self, f"module_{3 * d}")
             norm = getattr(self, f"module_{3 * d + 1}")
             slope = getattr(self, f"module_{3 * d + 2}").negative_slope
-            z = norm(conv(z, gs), act=ACT_LEAKY, slope=slope, seg_rows=seg_rows)
+            if d == 0:
+                if conv.fusable:
+                    if pe.granularity != 1.0:
+                        raise NotImplementedError("the reference uses the default granularity of 1.0")
+                    u, residual = ops.SageLayerPE.apply(x, conv.lin.weight, conv.lin.bias, conv.lin_l.weight,
+                                                        conv.lin_l.bias, conv.lin_r.weight, gs, pos, pe.frequency)
+                else:
+                    u = conv(pe.add_to(x, pos), gs)
+            else:
+                u = conv(z, gs)
+            z = norm(u, act=ACT_LEAKY, slope=slope, seg_rows=seg_rows)
         last = getattr(self, f"module_{3 * self.depth}")
         return ops.linear(z, last.weight, last.bias, residual=residual)
 
@@ -93,8 +107,7 @@ class Graph(nn.Module):
             raise ValueError("without temporal pooling the node features must be [N, hidden]")
         if hasattr(self, "net"):
             gs = structure_for(data, x.shape[0])
-            z = self.positional_encoding.add_to(x, data.pos)
-            x = self.net(z, gs, residual=x)
+            x = self.net(x, gs, data.pos, self.positional_encoding)
         return x
 
     def forward_many(self, batches: Sequence) -> List[torch.Tensor]:
@@ -133,6 +146,5 @@ class Graph(nn.Module):
             for n in sizes:
                 seg_rows.append(seg_rows[-1] + n)
             pos = torch.cat([b.pos.view(-1) for b in batches], 0)
-            z = self.positional_encoding.add_to(x, pos)
-            x = self.net(z, gs, residual=x, seg_rows=tuple(seg_rows))
+            x = self.net(x, gs, pos, self.positional_encoding, seg_rows=tuple(seg_rows))
         return list(ops.SplitRows.apply(x, *sizes))

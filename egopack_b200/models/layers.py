@@ -92,10 +92,15 @@ class SAGEConv(nn.Module):
         self.lin_l = nn.Linear(in_channels, out_channels, bias=bias)
         self.lin_r = nn.Linear(in_channels, out_channels, bias=False)
 
+    @property
+    def fusable(self) -> bool:
+        """One autograd node for the whole layer (ops.SageLayer): mean aggregation with projection, 16-byte rows."""
+        return self.aggr == "mean" and self.project and self.in_channels % 8 == 0 and self.out_channels % 8 == 0
+
     def forward(self, x: Tensor, gs: GraphStructure) -> Tensor:
         if self.aggr != "mean":
             raise NotImplementedError("max aggregation is implemented by GraphONE's reduced stage")
-        if self.project and self.in_channels % 8 == 0 and self.out_channels % 8 == 0:
+        if self.fusable:
             return ops.SageLayer.apply(x, self.lin.weight, self.lin.bias, self.lin_l.weight, self.lin_l.bias,
                                        self.lin_r.weight, gs)
         xs = ops.linear(x, self.lin.weight, self.lin.bias, act=ACT_RELU) if self.project else x

@@ -267,11 +267,21 @@ def gemm(a: Tensor, a_trans: bool, b: Tensor, b_trans: bool, m: int, n: int, k: 
                   f" -> {'f32' if out.dtype == torch.float32 else 'bf16'}" + (" +bias" if bias is not None else "")
                   + (f" act{act}" if act else "") + (" +res" if residual is not None else "") + (" acc" if accumulate else ""))
     stats = None
-    if rowstats and not accumulate and n % 64 == 0 and m > 0 and out.is_contiguous() and (
+    if rowstats and ROWSTATS and not accumulate and not a_trans and not b_trans and n % 256 == 0 and m >= 128 * 148 \
+            and out.is_contiguous() and (
             a.dtype == torch.bfloat16 or _fp32_on_tensor_cores()):
         stats = torch.empty(L.size("egp_gemm_rowstats_bytes", m, n) // 8, dtype=torch.float64, device=a.device)
     with _Traced(name, 2.0 * m * n * (k + k2), "FLOP", detail):
-        _gemm_launch(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate, stats)
+        if stats is not None:
+            try:
+                _gemm_launch(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate, stats)
+            except RuntimeError as ex:       # shape without the statistics epilogue (status -3): plain GEMM, no tag
+                if "status -3" not in str(ex):
+                    raise
+                stats = None
+                _gemm_launch(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate)
+        else:
+            _gemm_launch(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate)
     if stats is not None:
         out._egp_rowstats = (out._version, stats)
     return out
@@ -616,6 +626,58 @@ class Linear(torch.autograd.Function):
         return dx, dw, db, dx2, dw2, dres, None, None, None
 
 
+def _posenc_add(x: Tensor, pos: Tensor, freq: Tensor) -> Tensor:
+    n, c = x.shape
+    out = torch.empty_like(x)
+    with _Traced("posenc_add", 2.0 * n * c * x.element_size(), "B"):
+        L.call("egp_posenc_add", L.ptr(x), L.ptr(_i64(pos.view(-1), "pos")), L.ptr(_c(freq)), L.ptr(out), n, c, _code(x),
+               L.stream())
+    return out
+
+
+def _sage_forward(ctx, z, wp, bp, wl, bl, wr, gs):
+    cd = z.dtype
+    m, h = z.shape
+    ho = wl.shape[0]
+    wpc, wlc, wrc = weight_cache.get(wp, cd), weight_cache.get(wl, cd), weight_cache.get(wr, cd)
+    xs = gemm(z, False, wpc, False, m, h, h, bias=bp, act=ACT_RELU)
+    agg = _aggregate(xs, gs, backward=False)
+    # the statistics of the graph-mode LayerNorm that follows (models/graph.py:43) ride on this GEMM's epilogue
+    u = gemm(agg, False, wlc, False, m, ho, h, a2=z, b2=wrc, k2=h, bias=bl, rowstats=True)
+    ctx.save_for_backward(z, xs, agg, wp, wl, wr)
+    ctx.gs, ctx.has_bl = gs, bl is not None
+    return u
+
+
+def _sage_backward(ctx, du, need, extra_dz=None):
+    """need = (dz, dwp, dbp, dwl, dbl, dwr) flags.  ``extra_dz`` is added to dz in the dgrad GEMM's epilogue."""
+    z, xs, agg, wp, wl, wr = ctx.saved_tensors
+    cd = z.dtype
+    m, h = z.shape
+    ho = wl.shape[0]
+    du = _c(du)
+    dbl = None
+    if ctx.has_bl and need[4]:
+        dbl = _take_colsum(du)                                        # by-product of the graph-LN backward upstream
+        if dbl is None:
+            dbl = colsum(du)
+    duc = cast(du, cd)
+    wpc, wlc, wrc = weight_cache.get(wp, cd), weight_cache.get(wl, cd), weight_cache.get(wr, cd)
+    dagg = gemm(duc, False, wlc, True, m, h, ho)                      # through lin_l
+    dxs = _aggregate(dagg, ctx.gs, backward=True)                     # transposed mean aggregation
+    g, dbp = act_bwd_colsum(dxs, xs, ACT_RELU, 0.0)                   # through the projection's ReLU (+ its bias grad)
+    dz = None
+    if need[0]:
+        if extra_dz is not None and extra_dz.dtype != cd:
+            extra_dz = cast(_c(extra_dz), cd)
+        # g Wp + du Wr in one TMEM tile (+ the gradient that reaches the layer input along another path)
+        dz = gemm(g, False, wpc, True, m, h, h, a2=duc, b2=wrc, k2=ho, residual=_c(extra_dz))
+    dwp = gemm(g, True, z, True, h, h, m, out_dtype=torch.float32) if need[1] else None
+    dwl = gemm(duc, True, agg, True, ho, h, m, out_dtype=torch.float32) if need[3] else None
+    dwr = gemm(duc, True, z, True, ho, h, m, out_dtype=torch.float32) if need[5] else None
+    return dz, dwp, (dbp if need[2] else None), dwl, dbl, dwr
+
+
 class SageLayer(torch.autograd.Function):
     """u = lin_l(mean_{j -> i} relu(lin(z))_j) + lin_r(z): gnn.SAGEConv(H, H, project=True, aggr='mean') as ONE autograd
     node (models/graph.py:42).  Forward: ReLU-epilogue GEMM -> band / band+star / CSR mean -> dual-operand GEMM.
@@ -625,43 +687,29 @@ class SageLayer(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, wp, bp, wl, bl, wr, gs):
-        z = _c(z)
-        cd = z.dtype
-        m, h = z.shape
-        ho = wl.shape[0]
-        wpc, wlc, wrc = weight_cache.get(wp, cd), weight_cache.get(wl, cd), weight_cache.get(wr, cd)
-        xs = gemm(z, False, wpc, False, m, h, h, bias=bp, act=ACT_RELU)
-        agg = _aggregate(xs, gs, backward=False)
-        # the statistics of the graph-mode LayerNorm that follows (models/graph.py:43) ride on this GEMM's epilogue
-        u = gemm(agg, False, wlc, False, m, ho, h, a2=z, b2=wrc, k2=h, bias=bl, rowstats=True)
-        ctx.save_for_backward(z, xs, agg, wp, wl, wr)
-        ctx.gs, ctx.has_bl = gs, bl is not None
-        return u
+        return _sage_forward(ctx, _c(z), wp, bp, wl, bl, wr, gs)
 
     @staticmethod
     def backward(ctx, du):
-        z, xs, agg, wp, wl, wr = ctx.saved_tensors
-        cd = z.dtype
-        m, h = z.shape
-        ho = wl.shape[0]
-        du = _c(du)
-        dbl = None
-        if ctx.has_bl and ctx.needs_input_grad[4]:
-            dbl = _take_colsum(du)                                        # by-product of the graph-LN backward upstream
-            if dbl is None:
-                dbl = colsum(du)
-        duc = cast(du, cd)
-        wpc, wlc, wrc = weight_cache.get(wp, cd), weight_cache.get(wl, cd), weight_cache.get(wr, cd)
-        dagg = gemm(duc, False, wlc, True, m, h, ho)                      # through lin_l
-        dxs = _aggregate(dagg, ctx.gs, backward=True)                     # transposed mean aggregation
-        g, dbp = act_bwd_colsum(dxs, xs, ACT_RELU, 0.0)                   # through the projection's ReLU (+ its bias grad)
-        dz = None
-        if ctx.needs_input_grad[0]:
-            dz = gemm(g, False, wpc, True, m, h, h, a2=duc, b2=wrc, k2=ho)    # g Wp + du Wr in one TMEM tile
-        dwp = gemm(g, True, z, True, h, h, m, out_dtype=torch.float32) if ctx.needs_input_grad[1] else None
-        dwl = gemm(duc, True, agg, True, ho, h, m, out_dtype=torch.float32) if ctx.needs_input_grad[3] else None
-        dwr = gemm(duc, True, z, True, ho, h, m, out_dtype=torch.float32) if ctx.needs_input_grad[5] else None
-        return dz, dwp, dbp if ctx.needs_input_grad[2] else None, dwl, dbl, dwr, None
+        return (*_sage_backward(ctx, du, ctx.needs_input_grad[:6]), None)
+
+
+class SageLayerPE(torch.autograd.Function):
+    """The FIRST layer of ``Graph``'s stack together with what surrounds it in models/graph.py:63,
+    ``x + net(x + PE(pos))``: takes x, adds the positional encoding itself, and hands x back as a second output for the
+    outer residual.  The residual's gradient therefore arrives HERE, and is folded into the layer's dgrad GEMM epilogue
+    (``dx = g Wp + du Wr + d_residual``) -- the [N, H] add of the two paths into x never runs as a separate kernel."""
+
+    @staticmethod
+    def forward(ctx, x, wp, bp, wl, bl, wr, gs, pos, freq):
+        x = _c(x)
+        z = _posenc_add(x, pos, freq)
+        u = _sage_forward(ctx, z, wp, bp, wl, bl, wr, gs)
+        return u, x                                                   # x comes back as an alias carrying this node's grad_fn
+
+    @staticmethod
+    def backward(ctx, du, dres):
+        return (*_sage_backward(ctx, du, ctx.needs_input_grad[:6], extra_dz=dres), None, None, None)
 
 
 class LinearCat(torch.autograd.Function):
@@ -859,13 +907,7 @@ class PosEncAdd(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, pos, freq):
-        x = _c(x)
-        n, c = x.shape
-        out = torch.empty_like(x)
-        with _Traced("posenc_add", 2.0 * n * c * x.element_size(), "B"):
-            L.call("egp_posenc_add", L.ptr(x), L.ptr(_i64(pos.view(-1), "pos")), L.ptr(_c(freq)), L.ptr(out), n, c, _code(x),
-                   L.stream())
-        return out
+        return _posenc_add(_c(x), pos, freq)
 
     @staticmethod
     def backward(ctx, g):

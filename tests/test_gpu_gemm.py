@@ -169,7 +169,7 @@ def test_linear_autograd_matches_torch():
 
 
 @pytest.mark.parametrize("dtype", [BF, F32])
-@pytest.mark.parametrize("m,n,k,k2", [(4728, 1024, 320, 192), (256, 128, 64, 0), (1000, 64, 512, 0), (32768, 1024, 1024, 1024)])
+@pytest.mark.parametrize("m,n,k,k2", [(19000, 1024, 320, 192), (32768, 1024, 1024, 1024), (20001, 256, 128, 0)])
 def test_gemm_epilogue_row_statistics(dtype, m, n, k, k2):
     """egp_gemm_rowstats: the {sum, sum of squares} pairs left by the epilogue add up to the statistics of the stored
     tensor (rows past M excluded, CTA-pair tiles, dual operands, bf16 and fp32-on-tensor-cores outputs)."""
@@ -182,6 +182,8 @@ def test_gemm_epilogue_row_statistics(dtype, m, n, k, k2):
     out = ops.gemm(A, False, B, False, m, n, k, a2=A2, b2=B2, k2=k2, bias=bias, rowstats=True)
     stats = ops._take_rowstats(out)
     assert stats is not None and stats.dtype == torch.float64
+    small = ops.gemm(A[:300], False, B, False, 300, n, k, rowstats=True)  # too small for the pair kernel: plain GEMM, no tag
+    assert ops._take_rowstats(small) is None
     plain = ops.gemm(A, False, B, False, m, n, k, a2=A2, b2=B2, k2=k2, bias=bias)
     assert torch.equal(out, plain)                                     # the statistics do not change the result
     pairs = stats.view(-1, 2).sum(0)
