@@ -232,6 +232,8 @@ __device__ __forceinline__ uint32_t dropout_keep_bits_keyed(uint64_t vec, uint32
   // vectors beyond 2^30 fold their high bits into the key (a tensor that large is > 8.6e9 elements)
   const uint32_t k = key ^ pcg_hash((uint32_t)(vec >> 30));
   const uint32_t base = k + ((uint32_t)vec << 2);
+  // p = 0.5 (the configured dropout, experiments/mtl.yaml): one fair bit per element, so ONE hash serves the vector
+  if (thr16 == 0x8000u) return pcg_hash(base) >> 24;
   uint32_t bits = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

@@ -885,7 +885,8 @@ static int tc_launch_major(int a_trans, int b_trans, const CUtensorMap* maps, co
   return EGP_ERR_INVALID;
 }
 
-int64_t tc_gemm_rowstats_slots(int64_t N) { return ceil_div(N, 64); }
+// one slot per 256-wide n tile: the statistics epilogue only exists in the CTA-pair kernel (BN = 256)
+int64_t tc_gemm_rowstats_slots(int64_t N) { return ceil_div(N, 256); }
 
 int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, const void* A2,
                    int64_t lda2, const void* B2, int64_t ldb2, int64_t K2, const float* bias, const void* residual,

@@ -107,26 +107,38 @@ gln_stats_kernel(const T* __restrict__ x, GlnSegs segs, int64_t channels, double
 // Statistics of a segment from the {sum, sum of squares} pairs that the producing GEMM's epilogue left per (128-row
 // block, TMEM quarter, n tile) (egp_gemm_rowstats): one block per segment, fixed summation order (deterministic).
 // Replaces gln_stats_kernel -- a full read of the tensor -- when the input of the LayerNorm comes straight out of a GEMM.
-__global__ void __launch_bounds__(kNormThreads)
+constexpr int kRowstatThreads = 1024;
+__global__ void __launch_bounds__(kRowstatThreads)
 gln_stats_from_rowstats_kernel(const double* __restrict__ rowstats, int pairs_per_rowblock, GlnSegs segs, int64_t channels,
                                double* __restrict__ stats) {
   pdl_enter();
   __shared__ double red[32];
   const int seg = blockIdx.x;
   const int64_t rb0 = segs.row[seg] / 128, rb1 = (segs.row[seg + 1] + 127) / 128;
-  const int64_t first = rb0 * pairs_per_rowblock, count = (rb1 - rb0) * pairs_per_rowblock;
-  double s = 0.0, q = 0.0;
-  for (int64_t i = threadIdx.x; i < count; i += blockDim.x) {
-    s += rowstats[2 * (first + i)];
-    q += rowstats[2 * (first + i) + 1];
+  const double2* pr = reinterpret_cast<const double2*>(rowstats) + rb0 * pairs_per_rowblock;
+  const int64_t count = (rb1 - rb0) * pairs_per_rowblock;
+  double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
+  int64_t i = threadIdx.x;
+  for (; i + 3 * kRowstatThreads < count; i += 4 * kRowstatThreads) {   // four independent 16-byte loads in flight
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double2 v = pr[i + u * kRowstatThreads];
+      s[u] += v.x;
+      q[u] += v.y;
+    }
   }
-  s = block_sum(s, red);
-  q = block_sum(q, red);
+  for (; i < count; i += kRowstatThreads) {
+    const double2 v = pr[i];
+    s[0] += v.x;
+    q[0] += v.y;
+  }
+  double ts = block_sum((s[0] + s[1]) + (s[2] + s[3]), red);
+  double tq = block_sum((q[0] + q[1]) + (q[2] + q[3]), red);
   if (threadIdx.x == 0) {
     const int64_t rows = segs.row[seg + 1] - segs.row[seg];
     const double inv_count = rows > 0 ? 1.0 / ((double)rows * (double)channels) : 0.0;
-    const double mu = s * inv_count;
-    double var = q * inv_count - mu * mu;
+    const double mu = ts * inv_count;
+    double var = tq * inv_count - mu * mu;
     var = var > 0.0 ? var : 0.0;
     stats[2 * seg] = mu;
     stats[2 * seg + 1] = sqrt(var);
@@ -879,8 +891,8 @@ int egp_graph_layernorm_seg_fwd_rowstats(const void* x, const float* weight, con
     EGP_REQUIRE(sg.row[i] % 128 == 0, "graph_layernorm_fwd_rowstats: inner segment boundaries must be multiples of 128 rows");
   if (n == 0) return EGP_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  const int pairs = 4 * (int)ceil_div(channels, 64);
-  (void)launch_kernel(gln_stats_from_rowstats_kernel, nseg, kNormThreads, 0, s, rowstats, pairs, sg, channels, stats);
+  const int pairs = 4 * (int)ceil_div(channels, 256);   // (quarter, n tile) pairs per 128-row block: egp_gemm_rowstats layout
+  (void)launch_kernel(gln_stats_from_rowstats_kernel, nseg, kRowstatThreads, 0, s, rowstats, pairs, sg, channels, stats);
   EGP_LAUNCH_CHECK();
   EGP_DISPATCH_DTYPE(dtype, T, {
     const int64_t nvec = gln_max_seg_rows(sg) * channels / Vec<T>::N;

@@ -267,11 +267,12 @@ int egp_adam_step(float* p, float* m, float* v, void* shadow, const int64_t* seg
                   int num_tensors, int64_t* step, const float* lr, float beta1, float beta2, float eps,
                   float weight_decay, void* stream);
 
-/* egp_gemm (bf16 operands, tensor-core path only) that ALSO leaves, per (128-row block, 32-row quarter, 64-column slot),
+/* egp_gemm (bf16 operands, tensor-core path only) that ALSO leaves, per (128-row block, 32-row quarter, 256-column tile),
  * the {sum, sum of squares} of the values it stores -- computed in the epilogue from the fp32 accumulators, so a
  * whole-tensor statistic of C (graph-mode LayerNorm right after SAGEConv, models/graph.py:42-43) needs no extra pass.
- * rowstats: double [ceil(M/128)][4][ceil(N/64)][2] (egp_gemm_rowstats_bytes), zeroed by the call; requires N % 64 == 0
- * and a 16-byte aligned, 16-byte pitched C; EGP_ERR_UNSUPPORTED otherwise (callers fall back to egp_gemm + a stats pass). */
+ * rowstats: double [ceil(M/128)][4][ceil(N/256)][2] (egp_gemm_rowstats_bytes), zeroed by the call.  Served by the CTA-pair
+ * kernel only: K-major operands, N % 64 == 0, enough rows for 256-wide tiles, 16-byte aligned and pitched C;
+ * EGP_ERR_UNSUPPORTED otherwise (callers fall back to egp_gemm + a statistics pass). */
 size_t egp_gemm_rowstats_bytes(int64_t M, int64_t N);
 int egp_gemm_rowstats(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans,
                       const void* A2, int64_t lda2, const void* B2, int64_t ldb2, int64_t K2,

@@ -434,3 +434,26 @@ def test_graph_layernorm_from_gemm_epilogue_statistics(dtype, tol):
     finally:
         ops.ROWSTATS = True
         egopack_b200.set_precision("bf16")
+
+
+@pytest.mark.parametrize("p", [0.5, 0.3])
+def test_fused_dropout_mask_statistics(p):
+    """The fused dropout draws its bits from a keyed multiply-xorshift hash (one hash per vector at p = 0.5, four
+    otherwise): keep rate, per-column and per-row rates, and independence between neighbouring elements, neighbouring rows
+    and successive calls."""
+    n, c = 4096, 1024
+    x = torch.rand(n, c, device=DEV) + 1.0                     # LN(x) * 0 + 1 > 0 everywhere: every zero is a drop
+    w, b = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    torch.manual_seed(7)
+    k1 = (ops.RowLayerNorm.apply(x, w, b, 1e-5, ACT_RELU, p) != 0).float()
+    k2 = (ops.RowLayerNorm.apply(x, w, b, 1e-5, ACT_RELU, p) != 0).float()
+    q = 1.0 - p
+    sd = (p * q) ** 0.5
+    assert abs(float(k1.mean()) - q) < 5 * sd / (n * c) ** 0.5
+    assert float((k1.mean(0) - q).abs().max()) < 5.5 * sd / n ** 0.5          # per column (4096 draws each)
+    assert float((k1.mean(1) - q).abs().max()) < 5.5 * sd / c ** 0.5          # per row (1024 draws each)
+    corr = lambda a, b_: float(((a - q) * (b_ - q)).mean()) / (p * q)
+    assert abs(corr(k1[:, 1:], k1[:, :-1])) < 5e-3                            # neighbours inside a row (same hash word)
+    assert abs(corr(k1[:, 8:], k1[:, :-8])) < 5e-3                            # neighbouring 16-byte vectors
+    assert abs(corr(k1[1:], k1[:-1])) < 5e-3                                  # neighbouring rows
+    assert abs(corr(k1, k2)) < 5e-3                                           # successive calls
