@@ -503,8 +503,8 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
     shapes = {}
     for name, work, unit, a, b, detail in trace:
         ms = a.elapsed_time(b)
-        if name.startswith("sage_mean") and detail:            # the aggregation kernels differ by radius: keep them apart
-            name = f"{name} {detail}"
+        if (name.startswith("sage_mean") or name == "colsum") and detail:   # aggregation kernels differ by radius, column
+            name = f"{name} {detail}"                                         # sums by width (heads: a few hundred columns)
             detail = ""
         r = agg.setdefault(name, {"work": 0.0, "ms": 0.0, "n": 0, "unit": unit})
         r["work"] += work
@@ -537,7 +537,8 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
         ach = a["work"] / (a["ms"] / 1e3) / 1e9
         roof_hbm.append({"bound": "hbm", "kernel": nme, "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
                          "frac": round(ach / pk["hbm"], 4), "traffic": traffic_of(nme)[0], "traffic_note": traffic_of(nme)[1],
-                         "launches_per_step": a["n"] // 2, "ms_per_step": round(a["ms"] / 2, 3), "peak_source": pk["source"]})
+                         "launches_per_step": a["n"] // 2, "ms_per_step": round(a["ms"] / 2, 3),
+                         "mb_per_launch": round(a["work"] / a["n"] / 1e6, 2), "peak_source": pk["source"]})
     roof_hbm.sort(key=lambda r: -r["ms_per_step"])
     if args.trace_out and rank == 0 and full:
         os.makedirs(os.path.dirname(os.path.abspath(args.trace_out)), exist_ok=True)

@@ -375,7 +375,7 @@ def colsum(x: Tensor) -> Tensor:
     out = torch.empty(cols, dtype=torch.float32, device=x.device)
     nb = L.size("egp_colsum_workspace", rows, cols)
     ws = L.workspace(nb, x.device)
-    with _Traced("colsum", 1.0 * rows * cols * x.element_size(), "B"):
+    with _Traced("colsum", 1.0 * rows * cols * x.element_size(), "B", f"c={cols}"):
         L.call("egp_colsum", L.ptr(x), L.ptr(out), rows, cols, x.stride(0), _code(x), L.ptr(ws), nb, L.stream())
     return out
 

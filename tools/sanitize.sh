@@ -20,4 +20,4 @@ timeout 600 compute-sanitizer --tool racecheck --error-exitcode 7 --print-limit 
     python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "graph_layernorm_leaky or row_layernorm or cross_entropy or band_star or colsum" \
     > gpurun_out/r2_sanitizer_racecheck.log 2>&1
 echo "racecheck rc=$?" | tee -a gpurun_out/r2_sanitizer_racecheck.log
-tail -6 gpurun_out/r2_sanitizer_memcheck.log gpurun_out/r2_sanitizer_memcheck_gemm.log gpurun_out/r2_sanitizer_racecheck.log
+for f in memcheck memcheck_gemm racecheck; do tail -n 4 gpurun_out/r2_sanitizer_$f.log; done
