@@ -88,3 +88,76 @@ def test_knn_sampled_rows_at_full_size():
     clear = (srt[:, k] - srt[:, k - 1]) > 1e-6
     same = (idx[rows].sort(1).values == order[:, :k].sort(1).values).all(1)
     assert bool(same[clear].all()) and bool((idx[rows, 0] == order[:, 0])[(srt[:, 1] - srt[:, 0]) > 1e-6].all())
+
+
+def test_band_star_equals_csr_at_the_stacked_c2_size():
+    """Round 2: the stacked c2 step aggregates 98 304 nodes (AR | LTA | PNR, 768 graphs) through ONE band+star structure.
+    Against the generic CSR kernel on the reference's edge list (egp_lta_edge_* / egp_band_edge_*, bit-exact vs the
+    reference's own transform in test_gpu_edges.py): forward and backward, plus the adjointness property."""
+    v, n, c = 256, 128, 1024
+    g = torch.Generator(device=DEV).manual_seed(5)
+    batch = torch.arange(v, device=DEV).repeat_interleave(n)
+    ptr = torch.arange(v + 1, device=DEV) * n
+    pos = torch.arange(n, device=DEV).repeat(v)
+    y = torch.randint(0, 100, (v * n, 2), device=DEV, generator=g)          # verb 0 appears: the `> 0` quirk
+    y.view(v, n, 2)[:, :2] = -1
+    star = ops.lta_star_counts(y, ptr, 1.5)
+    parts = [(batch, ptr, None), (batch, ptr, star), (batch, ptr, None)]
+    gs = ops.band_structure_many(parts, 1)
+    e_band = ops.band_edge_index(pos, batch, ptr, 1.5)
+    e_lta = ops.lta_edge_index(pos, y, batch, ptr, 1.5)
+    edges = torch.cat([e_band, e_lta + v * n, e_band + 2 * v * n], 1)
+    gc = ops.csr_structure(edges, 3 * v * n)
+    assert torch.equal(gs.inv_deg, gc.inv_deg)
+    x = torch.randn(3 * v * n, c, device=DEV, generator=g).bfloat16()
+    w = torch.randn(3 * v * n, c, device=DEV, generator=g).bfloat16()
+    outs = []
+    for s in (gs, gc):
+        xr = x.clone().requires_grad_(True)
+        o = ops.SageMean.apply(xr, s)
+        o.backward(w)
+        outs.append((o.detach(), xr.grad))
+    assert rel_max(outs[0][0], outs[1][0]) < 1e-2 and rel_max(outs[0][1], outs[1][1]) < 1e-2
+    a = (outs[0][0].double() * w.double()).sum()
+    b = (x.double() * outs[0][1].double()).sum()
+    assert abs(float(a - b)) / abs(float(a)) < 2e-2
+
+
+def test_fused_heads_loss_and_adam_at_full_size():
+    """32 768 nodes x (115 verbs, 478 nouns): the fused heads + cross entropy against torch on the same bf16 operands, and
+    one FlatAdam step over the ~27 M parameters of the MTL model against torch.optim.Adam."""
+    from egopack_b200.models.tasks import RecognitionTask
+    from egopack_b200.optim import FlatAdam
+    import egopack_b200
+    egopack_b200.set_precision("bf16")
+    n, H = 32768, 1024
+    g = torch.Generator(device=DEV).manual_seed(6)
+    torch.manual_seed(6)
+    task = RecognitionTask(H, H, (115, 478)).to(DEV)
+    f = torch.randn(n, H, device=DEV, generator=g).bfloat16().requires_grad_(True)
+    y = torch.stack([torch.randint(0, 115, (n,), device=DEV, generator=g), torch.randint(0, 478, (n,), device=DEV, generator=g)], 1)
+    y[torch.rand(n, device=DEV, generator=g) < 0.5] = -1
+    loss = task.loss_from_features(f, y)
+    loss.mean().backward()
+    fr = f.detach().float().requires_grad_(True)
+    want = 0
+    for h, c in enumerate(task.classifiers):
+        lg = torch.nn.functional.linear(fr, c[1].weight.bfloat16().float(), c[1].bias)
+        want = want + torch.nn.functional.cross_entropy(lg, y[:, h], ignore_index=-1, reduction="none")
+    want.mean().backward()
+    assert rel_max(loss, want) < 1e-3 and rel_max(f.grad, fr.grad) < 2e-2
+    # optimiser: 27 M parameters in one kernel
+    shapes = [(1024, 4608)] + [(1024, 1024)] * 21 + [(1024,)] * 30 + [(478, 1024), (115, 1024), (478,), (115,), (1,)]
+    ours = [torch.nn.Parameter(torch.randn(*s, device=DEV, generator=g) * 0.02) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    opt, ropt = FlatAdam(ours, lr=1e-3, weight_decay=1e-5), torch.optim.Adam(ref, lr=1e-3, weight_decay=1e-5)
+    for _ in range(2):
+        for p, q in zip(ours, ref):
+            gr = torch.randn(p.shape, device=DEV, generator=g)
+            p.grad, q.grad = gr, gr.clone()
+        opt.step()
+        ropt.step()
+    assert sum(p.numel() for p in ours) > 26_000_000
+    for p, q in zip(ours, ref):
+        assert rel_max(p, q) < 2e-6
+        assert torch.equal(ops.weight_cache.get(p, torch.bfloat16), p.detach().bfloat16())
