@@ -244,7 +244,7 @@ struct TcCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
 };
 
-struct TcParams {
+struct TcParams {   // exactly 128 bytes (static_assert below): see the note at cand_thr
   int64_t M, N;
   int kb1, kb2;        // k-blocks of the first / second operand pair
   int splits;          // split-K factor (atomic fp32 accumulation when > 1)
@@ -262,11 +262,15 @@ struct TcParams {
   int32_t* cand;       // TOPK kernels: [M, TOPK] column indices of the largest entries of each row (unordered)
   float* cand_thr;     // TOPK kernels (optional): [M, kTopkGroups] smallest score each group KEPT -- every column of the
                        // group that is not a candidate scored at most this (the k-NN miss detector's threshold)
-  double* rowstats;    // optional: per (128-row block, TMEM quarter, n tile) {sum, sum of squares} of the values stored
-  int stat_slots;      // n-tile slots per (row block, quarter) in rowstats
+                       // STATS kernels reuse the two TOPK fields (the variants are exclusive, and the struct must stay at
+                       // 128 bytes: with 144 the 896-byte kernel parameter block grows and ptxas stops keeping the
+                       // parameters in uniform registers -- every instantiation got ~25 % more instructions and the
+                       // forward GEMMs lost 5-19 %): cand_thr = double* rowstats, per (128-row block, TMEM quarter, n tile)
+                       // {sum, sum of squares} of the values stored; topk = n-tile slots per (row block, quarter)
   int debug;           // EGP_TC_DEBUG (timing experiments) bit 0: skip the stores, bit 1: skip the TMEM loads too, bit 2: all CTAs load tile (0,0), bit 3: skip the B loads of odd k-blocks
   uint32_t idesc;
 };
+static_assert(sizeof(TcParams) == 128, "TcParams must stay at 128 bytes (kernel parameter block of 896 bytes)");
 
 // CG = 2 (launched as clusters of two CTAs): the pair owns a 256 x BN tile.  CTA `rank` stages rows
 // [rank*128, rank*128+128) of A and columns [rank*BN/2, (rank+1)*BN/2) of B; the leader (rank 0) issues
@@ -637,7 +641,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             ds = warp_sum(ds);
             dq = warp_sum(dq);
             if (lane == 0) {
-              double* sp = p.rowstats + (((int64_t)m_blk * 4 + quarter) * p.stat_slots + n_blk) * 2;
+              double* sp = reinterpret_cast<double*>(p.cand_thr) + (((int64_t)m_blk * 4 + quarter) * p.topk + n_blk) * 2;
               sp[0] = ds;
               sp[1] = dq;
             }
@@ -918,7 +922,8 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.C = C; p.ldc = ldc;
   p.act = act; p.slope = slope; p.accumulate = accumulate;
   p.topk = 0; p.cand = nullptr; p.cand_thr = nullptr;
-  p.rowstats = rowstats; p.stat_slots = (int)tc_gemm_rowstats_slots(N);
+  const int stat_slots = (int)tc_gemm_rowstats_slots(N);
+  if (rowstats) { p.cand_thr = reinterpret_cast<float*>(rowstats); p.topk = stat_slots; }
   static const int tc_debug = [] { const char* e = getenv("EGP_TC_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = tc_debug;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_trans ? 1 : 0) << 15) |
@@ -966,7 +971,7 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
       set_error("tc_gemm: row statistics need K-major operands, 256-wide CTA-pair tiles, N %% 64 == 0, no split-K");
       return EGP_ERR_UNSUPPORTED;
     }
-    EGP_CUDA(cudaMemsetAsync(rowstats, 0, sizeof(double) * 2 * (size_t)m_tiles * 4 * (size_t)p.stat_slots, stream));
+    EGP_CUDA(cudaMemsetAsync(rowstats, 0, sizeof(double) * 2 * (size_t)m_tiles * 4 * (size_t)stat_slots, stream));
   }
   maps[4] = maps[0];
   maps[5] = maps[0];
