@@ -134,3 +134,39 @@ def test_weight_cache_keys_on_param_generation():
     g0 = ops.param_generation()
     ops.bump_param_generation()
     assert ops.param_generation() == g0 + 1
+
+
+def test_device_feeder_prefetch_thread_and_host_hints():
+    """The helper thread only drives the HOST loader (one item ahead); order, structure, early exit and loader errors
+    behave as in the single-thread mode, and the band test is answered on the host copy (pos_unit_spaced)."""
+    from egopack_b200 import Batch, Data
+    from egopack_b200.feed import DeviceFeeder, unit_spaced_host
+    mk = lambda i, pos: Batch.from_data_list([Data(x=torch.full((4, 2), float(i)), pos=pos)])
+    items = [(mk(i, torch.arange(4)), mk(10 + i, torch.tensor([0, 2, 4, 6])), None) for i in range(5)]
+    out = list(DeviceFeeder(items, "cpu", prefetch_thread=True))
+    assert [float(o[0].x[0, 0]) for o in out] == [0.0, 1.0, 2.0, 3.0, 4.0] and all(o[2] is None for o in out)
+    assert all(o[0].pos_unit_spaced is True and o[1].pos_unit_spaced is False for o in out)
+    assert unit_spaced_host(torch.tensor([0, 1, 2, 0, 1]), torch.tensor([0, 0, 0, 1, 1]))
+    assert not unit_spaced_host(torch.tensor([0, 1, 3]), torch.tensor([0, 0, 0]))
+    for i, _ in enumerate(DeviceFeeder(items, "cpu", prefetch_thread=True)):      # early exit stops the helper thread
+        if i == 1:
+            break
+
+    def broken():
+        yield items[0]
+        raise ValueError("loader failed")
+    with pytest.raises(ValueError, match="loader failed"):
+        list(DeviceFeeder(broken(), "cpu", prefetch_thread=True))
+
+
+def test_lazy_attributes_of_the_data_stand_in():
+    from egopack_b200 import Data
+    calls = []
+    d = Data(x=torch.zeros(3, 1), pos=torch.arange(3))
+    d.set_lazy("edge_index", lambda dd: (calls.append(1), torch.tensor([[0, 1], [1, 0]]))[1])
+    assert "edge_index" in d and "edge_index" in d.keys() and not d.is_materialized("edge_index") and not calls
+    assert d.edge_index.shape == (2, 2) and calls == [1] and d.is_materialized("edge_index")
+    assert d.edge_index.shape == (2, 2) and calls == [1]                       # built once
+    d.set_lazy("edge_index", lambda dd: torch.zeros((2, 0), dtype=torch.long))
+    d.edge_index = None                                                         # assignment drops the producer
+    assert d.edge_index is None and "edge_index" not in d
