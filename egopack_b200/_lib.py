@@ -22,6 +22,8 @@ SIGNATURES: Dict[str, tuple] = {
     "egp_version": (I, []),
     "egp_last_error": (I, [C.c_char_p, SZ]),
     "egp_device_info": (I, [P, P, P]),
+    "egp_set_deterministic": (I, [I]),
+    "egp_get_deterministic": (I, []),
     "egp_band_edge_count": (I, [P, P, P, I64, F, I, I, P, P]),
     "egp_band_edge_fill": (I, [P, P, P, I64, F, I, I, P, I64, P, P]),
     "egp_exclusive_scan_i32": (I, [P, I64, P, P]),

@@ -52,3 +52,20 @@ def precision(mode: str):
         yield
     finally:
         set_precision(old)
+
+
+_DETERMINISTIC = False
+
+
+def set_deterministic(on: bool) -> None:
+    """Bit-reproducible weight gradients: split-K GEMMs write per-split slabs and sum them in a fixed order instead of
+    reduce-adding into the output (``egp_set_deterministic``).  Everything else on the training path is deterministic
+    already.  Costs one extra pass over ``splits x [M, N]`` fp32 per split-K weight gradient."""
+    global _DETERMINISTIC
+    from . import _lib
+    _lib.call("egp_set_deterministic", int(bool(on)))
+    _DETERMINISTIC = bool(on)
+
+
+def is_deterministic() -> bool:
+    return _DETERMINISTIC

@@ -13,8 +13,11 @@ int sgemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64_t
 int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, const void* A2,
                    int64_t lda2, const void* B2, int64_t ldb2, int64_t K2, const float* bias, const void* residual,
                    int64_t ldr, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int act, float slope,
-                   int out_dtype, int accumulate, cudaStream_t stream, double* rowstats);
+                   int out_dtype, int accumulate, cudaStream_t stream, double* rowstats, void* workspace, size_t ws_bytes);
 int64_t tc_gemm_rowstats_slots(int64_t N);
+void tc_set_deterministic(int on);
+int tc_get_deterministic();
+size_t tc_gemm_workspace_bytes();
 bool tc_gemm_supported(const void* A, int64_t lda, const void* B, int64_t ldb, const void* A2, int64_t lda2,
                        const void* B2, int64_t ldb2);
 }  // namespace egp
@@ -25,14 +28,21 @@ extern "C" {
 
 size_t egp_gemm_workspace(int64_t M, int64_t N, int64_t K) {
   (void)M; (void)N; (void)K;
-  return 0;  // split-K accumulates with fp32 atomics straight into C
+  // default: split-K reduce-adds straight into C, no workspace.  Deterministic mode: slabs for an ordered reduction.
+  return tc_gemm_workspace_bytes();
 }
+
+int egp_set_deterministic(int on) {
+  tc_set_deterministic(on);
+  return EGP_OK;
+}
+
+int egp_get_deterministic(void) { return tc_get_deterministic(); }
 
 int egp_gemm(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, const void* A2,
              int64_t lda2, const void* B2, int64_t ldb2, int64_t K2, const float* bias, const void* residual,
              int64_t ldr, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int act, float slope, int in_dtype,
              int out_dtype, int accumulate, void* workspace, size_t ws_bytes, void* stream) {
-  (void)workspace; (void)ws_bytes;
   EGP_REQUIRE(A && B && C, "gemm: null operand");
   EGP_REQUIRE(M >= 0 && N >= 0 && K >= 0 && K2 >= 0, "gemm: negative size");
   EGP_REQUIRE((A2 == nullptr) == (B2 == nullptr), "gemm: A2 and B2 must be given together");
@@ -46,7 +56,7 @@ int egp_gemm(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb
   static const bool force_simt = [] { const char* e = getenv("EGP_FORCE_SIMT"); return e && e[0] == '1'; }();
   if (!force_simt && in_dtype == EGP_BF16 && tc_gemm_supported(A, lda, B, ldb, A2, lda2, B2, ldb2) && K > 0)
     return tc_gemm_launch(A, lda, a_trans, B, ldb, b_trans, A2, lda2, B2, ldb2, K2, bias, residual, ldr, C, ldc, M, N,
-                          K, act, slope, out_dtype, accumulate, s, nullptr);
+                          K, act, slope, out_dtype, accumulate, s, nullptr, workspace, ws_bytes);
   return sgemm_launch(A, lda, a_trans, B, ldb, b_trans, A2, lda2, B2, ldb2, K2, bias, residual, ldr, C, ldc, M, N, K,
                       act, slope, in_dtype, out_dtype, accumulate, s);
 }
@@ -70,7 +80,7 @@ int egp_gemm_rowstats(const void* A, int64_t lda, int a_trans, const void* B, in
     return EGP_ERR_UNSUPPORTED;
   }
   return tc_gemm_launch(A, lda, a_trans, B, ldb, b_trans, A2, lda2, B2, ldb2, K2, bias, residual, ldr, C, ldc, M, N, K, act,
-                        slope, out_dtype, 0, (cudaStream_t)stream, rowstats);
+                        slope, out_dtype, 0, (cudaStream_t)stream, rowstats, nullptr, 0);
 }
 
 }  // extern "C"

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 
@@ -249,6 +250,9 @@ struct TcParams {   // exactly 128 bytes (static_assert below): see the note at 
   int kb1, kb2;        // k-blocks of the first / second operand pair
   int splits;          // split-K factor (atomic fp32 accumulation when > 1)
   int m_tiles, n_tiles;
+  int slab_rows;       // deterministic split-K: split s writes rows [s*slab_rows, ...) of a [splits*slab_rows, N] workspace
+                       // with plain stores (summed afterwards in a fixed order); 0 = reduce-add straight into C.
+                       // (sits in what was alignment padding: the struct stays at 128 bytes)
   const float* bias;
   const void* residual;
   int64_t ldr;
@@ -523,7 +527,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         continue;
       }
-      const bool atomic = p.splits > 1 || p.accumulate;
+      const bool atomic = (p.splits > 1 && p.slab_rows == 0) || p.accumulate;
+      const int64_t slab_off = (int64_t)split * p.slab_rows;   // 0 unless deterministic split-K
       const bool has_k = kb_e > kb_b;
       constexpr int CHT = 128 / (int)sizeof(OutT);  // columns per 128-byte staged row: 64 (bf16) / 32 (fp32)
       if constexpr (BN >= CHT) {
@@ -630,7 +635,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&mapC, stage_w, (int)nb, (int)(m0 + quarter * 32), atomic);
+              tma_store_2d(&mapC, stage_w, (int)nb, (int)(slab_off + m0 + quarter * 32), atomic);
               bulk_commit();
             }
           }
@@ -674,7 +679,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < CH; ++j) v[j] = apply_act(v[j], p.act, p.slope);
           }
-          OutT* crow = C + m * p.ldc + nb;
+          OutT* crow = C + (slab_off + m) * p.ldc + nb;
           if (atomic) {
             if constexpr (sizeof(OutT) == 4) {
 #pragma unroll
@@ -889,13 +894,37 @@ static int tc_launch_major(int a_trans, int b_trans, const CUtensorMap* maps, co
   return EGP_ERR_INVALID;
 }
 
+// Deterministic split-K (egp_set_deterministic): the splits write their partial tiles into slabs of a workspace and this
+// kernel sums the slabs in split order -- bit-reproducible weight gradients, at the price of one extra pass over
+// splits x [M,N] fp32 (the default reduce-adds the splits into C with TMA, whose arrival order varies run to run).
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t slab_stride, float* __restrict__ C, int64_t ldc,
+                     int64_t M, int64_t N, int accumulate) {
+  pdl_enter();
+  const int64_t total = M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / N, n = i - m * N;
+    float acc = accumulate ? C[m * ldc + n] : 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[(int64_t)s * slab_stride + i];
+    C[m * ldc + n] = acc;
+  }
+}
+
+static std::atomic<int> g_deterministic{0};
+void tc_set_deterministic(int on) { g_deterministic.store(on ? 1 : 0); }
+int tc_get_deterministic() { return g_deterministic.load(); }
+// upper bound of the split-K workspace: at most one tile per concurrently running CTA (pair) is in flight per wave
+size_t tc_gemm_workspace_bytes() {
+  return g_deterministic.load() ? sizeof(float) * (size_t)sm_count() * 128 * 256 + 256 : 0;
+}
+
 // one slot per 256-wide n tile: the statistics epilogue only exists in the CTA-pair kernel (BN = 256)
 int64_t tc_gemm_rowstats_slots(int64_t N) { return ceil_div(N, 256); }
 
 int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, const void* A2,
                    int64_t lda2, const void* B2, int64_t ldb2, int64_t K2, const float* bias, const void* residual,
                    int64_t ldr, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int act, float slope,
-                   int out_dtype, int accumulate, cudaStream_t stream, double* rowstats) {
+                   int out_dtype, int accumulate, cudaStream_t stream, double* rowstats, void* workspace, size_t ws_bytes) {
   if (M == 0 || N == 0) return EGP_OK;
   const int sms = sm_count();
   const int m_tiles = (int)ceil_div(M, TBM);
@@ -940,11 +969,30 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
     splits = (kb_all + per - 1) / per;  // no empty split
   }
   p.splits = splits;
+  p.slab_rows = 0;
   if (accumulate && out_dtype != EGP_F32) {
     set_error("tc_gemm: accumulate needs an fp32 output");
     return EGP_ERR_INVALID;
   }
-  if (splits > 1 && !accumulate) {  // atomics need a zeroed destination
+  // deterministic split-K: slabs in the caller's workspace + an ordered reduction (N contiguous in the slabs)
+  void* const c_user = C;
+  const int64_t ldc_user = ldc;
+  const int acc_user = accumulate;
+  const int64_t slab_rows = (int64_t)m_tiles * TBM;
+  const bool slab = splits > 1 && g_deterministic.load() != 0;
+  if (slab) {
+    const size_t need = sizeof(float) * (size_t)splits * (size_t)slab_rows * (size_t)N;
+    if (!workspace || ws_bytes < need + 128) {
+      set_error("tc_gemm: deterministic split-K needs a workspace of %zu bytes (egp_gemm_workspace)", need + 128);
+      return EGP_ERR_WORKSPACE;
+    }
+    C = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(workspace) + 127) & ~(uintptr_t)127);
+    ldc = N;
+    accumulate = 0;
+    p.C = C; p.ldc = ldc; p.accumulate = 0;
+    p.slab_rows = (int)slab_rows;
+  }
+  if (splits > 1 && !accumulate && !slab) {  // atomics need a zeroed destination
     if (ldc == N) EGP_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * (size_t)N, stream));
     else EGP_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, (size_t)M, stream));
   }
@@ -976,30 +1024,42 @@ int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64
   maps[4] = maps[0];
   maps[5] = maps[0];
   if (p.tma_store) {
-    if ((rc = make_map(C, N, M, ldc, 128 / esz, 32, esz, &maps[4])) != EGP_OK) return rc;
+    if ((rc = make_map(C, N, slab ? (int64_t)splits * slab_rows : M, ldc, 128 / esz, 32, esz, &maps[4])) != EGP_OK) return rc;
     if (residual && (rc = make_map(residual, N, M, ldr, 128 / esz, 32, esz, &maps[5])) != EGP_OK) return rc;
   }
   const int total = tiles * splits;
-  if (rowstats)
-    return out_dtype == EGP_F32 ? tc_launch_inst<256, false, false, float, 2, true>(maps, p, total, stream)
-                                : tc_launch_inst<256, false, false, __nv_bfloat16, 2, true>(maps, p, total, stream);
-  if (cg == 2)
-    return out_dtype == EGP_F32 ? tc_launch_major<256, float, 2>(a_trans, b_trans, maps, p, total, stream)
-                                : tc_launch_major<256, __nv_bfloat16, 2>(a_trans, b_trans, maps, p, total, stream);
+  auto launch = [&]() -> int {
+    if (rowstats)
+      return out_dtype == EGP_F32 ? tc_launch_inst<256, false, false, float, 2, true>(maps, p, total, stream)
+                                  : tc_launch_inst<256, false, false, __nv_bfloat16, 2, true>(maps, p, total, stream);
+    if (cg == 2)
+      return out_dtype == EGP_F32 ? tc_launch_major<256, float, 2>(a_trans, b_trans, maps, p, total, stream)
+                                  : tc_launch_major<256, __nv_bfloat16, 2>(a_trans, b_trans, maps, p, total, stream);
 #define EGP_TC_BN(BNV)                                                                                          \
   case BNV:                                                                                                     \
     return out_dtype == EGP_F32 ? tc_launch_major<BNV, float, 1>(a_trans, b_trans, maps, p, total, stream)      \
                                 : tc_launch_major<BNV, __nv_bfloat16, 1>(a_trans, b_trans, maps, p, total, stream);
-  switch (bn) {
-    EGP_TC_BN(256)
-    EGP_TC_BN(128)
-    EGP_TC_BN(64)
-    EGP_TC_BN(32)
-    EGP_TC_BN(16)
-  }
+    switch (bn) {
+      EGP_TC_BN(256)
+      EGP_TC_BN(128)
+      EGP_TC_BN(64)
+      EGP_TC_BN(32)
+      EGP_TC_BN(16)
+    }
 #undef EGP_TC_BN
-  set_error("tc_gemm: no kernel for tile N %d", bn);
-  return EGP_ERR_INVALID;
+    set_error("tc_gemm: no kernel for tile N %d", bn);
+    return EGP_ERR_INVALID;
+  };
+  rc = launch();
+  if (rc != EGP_OK || !slab) return rc;
+  const int64_t elems = M * N;
+  int64_t grid = ceil_div(elems, 256 * 4);
+  const int64_t cap = (int64_t)sms * 8;
+  grid = grid > cap ? cap : (grid < 1 ? 1 : grid);
+  (void)launch_kernel(splitk_reduce_kernel, (unsigned)grid, 256, 0, stream, (const float*)C, splits, slab_rows * N,
+                      reinterpret_cast<float*>(c_user), ldc_user, M, N, acc_user);
+  EGP_LAUNCH_CHECK();
+  return EGP_OK;
 }
 
 // Fused similarity + top-k: S = A[M,K] B[N,K]^T on the tensor cores, the `keep` (8 or 16) largest entries of every row

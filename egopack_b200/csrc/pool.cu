@@ -9,41 +9,67 @@ constexpr int kPoolThreads = 128;
 
 // out[g,c] = max_{i in graph g} x[i,c]; empty graph -> 0 (scatter 'amax' into zeros, include_self=False);
 // ties keep the first row (torch_scatter CUDA arg-max semantics used for the gradient).
+// blockDim = (kPoolThreads, kPoolRowGroups): row group `ty` scans rows r0 + ty, r0 + ty + G, ... of the graph (eight
+// 16-byte loads in flight per thread), then the groups are combined through shared memory -- one CTA per graph alone is
+// latency bound (256 graphs x 128 threads cannot keep 6.5 TB/s of loads in flight).
+constexpr int kPoolRowGroups = 4;
 template <typename T>
-__global__ void __launch_bounds__(kPoolThreads)
+__global__ void __launch_bounds__(kPoolThreads * kPoolRowGroups)
 segment_max_fwd_kernel(const T* __restrict__ x, const int64_t* __restrict__ ptr, T* __restrict__ out,
                        int32_t* __restrict__ arg, int64_t channels) {
   pdl_enter();
   constexpr int VN = Vec<T>::N;
+  constexpr int G = kPoolRowGroups;
+  __shared__ float s_best[G - 1][kPoolThreads][VN];
+  __shared__ int32_t s_arg[G - 1][kPoolThreads][VN];
   const int64_t g = blockIdx.x;
-  const int64_t col = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * VN;
-  if (col >= channels) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t col = ((int64_t)blockIdx.y * kPoolThreads + tx) * VN;
+  const bool live = col < channels;
   const int64_t r0 = ptr[g], r1 = ptr[g + 1];
   float best[VN];
   int32_t bi[VN];
 #pragma unroll
   for (int c = 0; c < VN; ++c) { best[c] = -FLT_MAX; bi[c] = -1; }
-  auto take = [&](const Vec<T>& a, int64_t i) {
+  auto take = [&](const Vec<T>& a, int64_t i) {   // rows arrive in ascending order inside a group: strict > keeps the first
 #pragma unroll
     for (int c = 0; c < VN; ++c)
       if (a.v[c] > best[c] || bi[c] < 0) { best[c] = a.v[c]; bi[c] = (int32_t)i; }
   };
-  int64_t i = r0;
-  for (; i + 8 <= r1; i += 8) {  // eight independent 16-byte loads in flight per thread (one CTA per graph: latency bound)
-    Raw<T> a[8];
+  if (live) {
+    int64_t i = r0 + ty;
+    for (; i + 7 * G < r1; i += 8 * G) {
+      Raw<T> a[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) a[u] = Raw<T>::load(x + (i + u) * channels + col);
+      for (int u = 0; u < 8; ++u) a[u] = Raw<T>::load(x + (i + u * G) * channels + col);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) take(a[u].unpack(), i + u);
+      for (int u = 0; u < 8; ++u) take(a[u].unpack(), i + u * G);
+    }
+    for (; i < r1; i += G) take(Vec<T>::load(x + i * channels + col), i);
   }
-  for (; i < r1; ++i) take(Vec<T>::load(x + i * channels + col), i);
-  Vec<T> o;
+  if (ty > 0) {
 #pragma unroll
-  for (int c = 0; c < VN; ++c) {
-    o.v[c] = bi[c] >= 0 ? best[c] : 0.f;
-    arg[g * channels + col + c] = bi[c];
+    for (int c = 0; c < VN; ++c) { s_best[ty - 1][tx][c] = best[c]; s_arg[ty - 1][tx][c] = bi[c]; }
   }
-  o.store(out + g * channels + col);
+  __syncthreads();
+  if (ty == 0 && live) {
+#pragma unroll
+    for (int q = 0; q < G - 1; ++q)
+#pragma unroll
+      for (int c = 0; c < VN; ++c) {
+        const float ob = s_best[q][tx][c];
+        const int32_t oi = s_arg[q][tx][c];
+        // ties keep the FIRST row (torch_scatter's arg-max): larger value wins, equal values -> lower row index
+        if (oi >= 0 && (bi[c] < 0 || ob > best[c] || (ob == best[c] && oi < bi[c]))) { best[c] = ob; bi[c] = oi; }
+      }
+    Vec<T> o;
+#pragma unroll
+    for (int c = 0; c < VN; ++c) {
+      o.v[c] = bi[c] >= 0 ? best[c] : 0.f;
+      arg[g * channels + col + c] = bi[c];
+    }
+    o.store(out + g * channels + col);
+  }
 }
 
 template <typename T>
@@ -214,7 +240,7 @@ int egp_segment_max_pool_fwd(const void* x, const int64_t* ptr, void* out, int32
   if (num_graphs == 0 || channels == 0) return EGP_OK;
   EGP_DISPATCH_DTYPE(dtype, T, {
     const unsigned gy = (unsigned)ceil_div(channels, (int64_t)kPoolThreads * Vec<T>::N);
-    (void)launch_kernel(segment_max_fwd_kernel<T>, dim3((unsigned)num_graphs, gy), kPoolThreads, 0, (cudaStream_t)stream, 
+    (void)launch_kernel(segment_max_fwd_kernel<T>, dim3((unsigned)num_graphs, gy), dim3(kPoolThreads, kPoolRowGroups), 0, (cudaStream_t)stream, 
         (const T*)x, ptr, (T*)out, arg, channels);
     EGP_LAUNCH_CHECK();
   });

@@ -22,7 +22,7 @@ int sgemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64_t
 int tc_gemm_launch(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, const void* A2,
                    int64_t lda2, const void* B2, int64_t ldb2, int64_t K2, const float* bias, const void* residual,
                    int64_t ldr, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int act, float slope,
-                   int out_dtype, int accumulate, cudaStream_t stream, double* rowstats);
+                   int out_dtype, int accumulate, cudaStream_t stream, double* rowstats, void* workspace, size_t ws_bytes);
 int tc_gemm_topk_launch(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K, int keep,
                         int32_t* cand, float* cand_thr, cudaStream_t stream);
 int tc_topk_groups();
@@ -268,7 +268,7 @@ int egp_cos_topk(const float* fn, const float* pn, const void* fn16, const void*
     } else if (tensor) {
       const __nv_bfloat16* a = (const __nv_bfloat16*)fn16 + r0 * channels;
       rc = tc_gemm_launch(a, channels, 0, pn16, channels, 0, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, 0, S,
-                          num_protos, rows, num_protos, channels, EGP_ACT_NONE, 0.f, EGP_F32, 0, s, nullptr);
+                          num_protos, rows, num_protos, channels, EGP_ACT_NONE, 0.f, EGP_F32, 0, s, nullptr, nullptr, 0);
       if (rc != EGP_OK) return rc;
       if (kk == 16) {
         (void)launch_kernel(row_topk_kernel<16, false, int32_t>, grid, kTopkThreads, 0, s, S, rows, num_protos, 16, cand);

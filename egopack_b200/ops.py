@@ -299,6 +299,15 @@ def _take_rowstats(x: Tensor) -> Optional[Tensor]:
     return None
 
 
+def _gemm_ws(device):
+    """(pointer, bytes) of the split-K slab workspace in the deterministic mode, (None, 0) otherwise."""
+    from . import config
+    if not config.is_deterministic():
+        return None, 0
+    nb = L.size("egp_gemm_workspace", 0, 0, 0)
+    return L.ptr(L.workspace(nb, device, "gemm")), nb
+
+
 def _tc_call(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate, stats):
     """bf16 operands -> egp_gemm, or egp_gemm_rowstats when the epilogue statistics are wanted."""
     if stats is not None:
@@ -307,11 +316,12 @@ def _tc_call(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, a
                L.ptr(_c(bias)), L.ptr(residual), residual.stride(0) if residual is not None else 0,
                L.ptr(out), out.stride(0), m, n, k, int(act), float(slope), L.DTYPE_CODE[out.dtype], L.ptr(stats), L.stream())
         return
+    wsp, wsb = _gemm_ws(a.device)
     L.call("egp_gemm", L.ptr(a), a.stride(0), int(a_trans), L.ptr(b), b.stride(0), int(b_trans),
            L.ptr(a2), a2.stride(0) if a2 is not None else 0, L.ptr(b2), b2.stride(0) if b2 is not None else 0, int(k2),
            L.ptr(_c(bias)), L.ptr(residual), residual.stride(0) if residual is not None else 0,
            L.ptr(out), out.stride(0), m, n, k, int(act), float(slope), BF16, L.DTYPE_CODE[out.dtype],
-           int(accumulate), None, 0, L.stream())
+           int(accumulate), wsp, wsb, L.stream())
 
 
 def _gemm_launch(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate, stats=None):
@@ -323,11 +333,12 @@ def _gemm_launch(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, 
                                      accumulate, stats)
     elif stats is not None:
         return _tc_call(a, a_trans, b, b_trans, a2, b2, k2, bias, residual, out, m, n, k, act, slope, accumulate, stats)
+    wsp, wsb = _gemm_ws(a.device)
     L.call("egp_gemm", L.ptr(a), a.stride(0), int(a_trans), L.ptr(b), b.stride(0), int(b_trans),
            L.ptr(a2), a2.stride(0) if a2 is not None else 0, L.ptr(b2), b2.stride(0) if b2 is not None else 0, int(k2),
            L.ptr(_c(bias)), L.ptr(residual), residual.stride(0) if residual is not None else 0,
            L.ptr(out), out.stride(0), m, n, k, int(act), float(slope), _code(a), L.DTYPE_CODE[out.dtype],
-           int(accumulate), None, 0, L.stream())
+           int(accumulate), wsp, wsb, L.stream())
 
 
 # term products (A term, B term) of the split GEMM, smallest first so the fp32 accumulator adds them in increasing

@@ -220,6 +220,12 @@ int egp_mask_scale(const void* x, const uint8_t* mask, void* out, int64_t n, flo
  * in_dtype EGP_F32  -> fp32 FFMA kernel (parity mode).  out_dtype may differ from in_dtype.
  * accumulate != 0: C += (fp32 C only; used by split-K wgrad).  bias/residual/A2/B2 may be NULL.            */
 size_t egp_gemm_workspace(int64_t M, int64_t N, int64_t K);
+/* Determinism switch.  Default (0): split-K weight gradients reduce-add their splits into C with TMA, whose arrival order
+ * varies from run to run (last-bit differences).  1: the splits write slabs of `workspace` (egp_gemm_workspace bytes) and
+ * are summed in split order by a second kernel -- bit-reproducible.  Everything else on the training path (aggregation,
+ * normalisation statistics, column sums, hub sums, losses) is deterministic in both modes. */
+int egp_set_deterministic(int on);
+int egp_get_deterministic(void);
 int egp_gemm(const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans,
              const void* A2, int64_t lda2, const void* B2, int64_t ldb2, int64_t K2,
              const float* bias, const void* residual, int64_t ldr, void* C, int64_t ldc,

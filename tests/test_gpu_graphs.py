@@ -117,3 +117,39 @@ def test_eager_eval_between_replays_sees_updated_weights():
         runner(_batches(5))
     b = eager_eval()
     assert float((a - b).abs().max()) > 1e-3
+
+
+def test_fused_dropout_draws_fresh_masks_on_every_graph_replay():
+    """VERDICT r1 (weak 3): kernel arguments are frozen at capture time, so the fused dropout reads its per-step counter
+    from device memory (ops.RNG_STATE): every replay must draw a new, statistically sound mask."""
+    from egopack_b200 import ops
+    from egopack_b200.ops import ACT_RELU
+    n, c, p = 2048, 1024, 0.5
+    x = torch.rand(n, c, device=DEV) + 1.0
+    w, b = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    rng = torch.tensor([1234, 0], dtype=torch.int64, device=DEV)
+    ops.RNG_STATE = rng
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ops.RowLayerNorm.apply(x, w, b, 1e-5, ACT_RELU, p)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            y = ops.RowLayerNorm.apply(x, w, b, 1e-5, ACT_RELU, p)
+            rng[1] += 1
+    finally:
+        ops.RNG_STATE = None
+    masks = []
+    for _ in range(3):
+        graph.replay()
+        torch.cuda.synchronize()
+        masks.append((y != 0).float().clone())
+    for m in masks:
+        assert abs(float(m.mean()) - 0.5) < 5 * 0.5 / (n * c) ** 0.5
+    for i in range(3):
+        for j in range(i + 1, 3):
+            corr = float(((masks[i] - 0.5) * (masks[j] - 0.5)).mean()) / 0.25
+            assert abs(corr) < 5e-3, (i, j, corr)
