@@ -217,7 +217,7 @@ def test_deterministic_split_k_is_bit_reproducible():
             base = torch.randn(m, n, generator=g).to(DEV)
             acc = base.clone()
             ops.gemm(A, True, B, True, m, n, k, out_dtype=F32, out=acc, accumulate=True)
-            assert rel_max(acc, ref + base.double().cpu()) < 2e-5
+            assert rel_max(acc, ref + base.double()) < 2e-5
     finally:
         config.set_deterministic(False)
     assert not config.is_deterministic()
