@@ -70,6 +70,35 @@ def install_stubs():
     sys.modules.update({"hydra": hydra, "hydra.utils": hutils})
 
 
+def cross_check_real_pyg():
+    """If a REAL torch_geometric is importable (it is not in this image), hold the restated third-party layer to it before
+    any fixture is written: the fixtures pin the reference's first-party code ON TOP of oracle/pyg_restated.py, so a wrong
+    restatement (SURVEY 8c assumptions A1-A9) must fail loudly here rather than be baked into the golden files."""
+    try:
+        import torch_geometric                     # noqa: F401 -- only succeeds before install_stubs() replaces it
+        from torch_geometric import nn as gnn
+        from torch_geometric.nn import radius_graph
+    except Exception:
+        return "torch_geometric not importable: third-party layer unpinned (restated from the published algorithms)"
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(40, 16, generator=g)
+    pos = torch.arange(40)
+    batch = torch.arange(4).repeat_interleave(10)
+    ei = radius_graph(pos.view(-1, 1).float(), 2.5, batch)
+    mine = pyg.radius_graph(pos, 2.5, batch)
+    canon = lambda e: sorted(zip(e[1].tolist(), e[0].tolist()))
+    assert canon(ei) == canon(mine), "radius_graph restatement disagrees with torch_cluster (A7)"
+    for kw in (dict(project=True), dict(aggr="max", bias=False)):
+        real, ours = gnn.SAGEConv(16, 16, **kw), pyg.SAGEConv(16, 16, **kw)
+        ours.load_state_dict(real.state_dict())
+        assert torch.allclose(real(x, ei), ours(x, ei), atol=1e-6), f"SAGEConv{kw} restatement disagrees (A1/A2)"
+    real, ours = gnn.LayerNorm(16), pyg.LayerNorm(16)
+    assert torch.allclose(real(x), ours(x), atol=1e-6), "graph-mode LayerNorm restatement disagrees (A3)"
+    real, ours = gnn.PositionalEncoding(16), pyg.PositionalEncoding(16)
+    assert torch.allclose(real(pos), ours(pos), atol=1e-6), "PositionalEncoding restatement disagrees (A4)"
+    return f"restated layer checked against torch_geometric {torch_geometric.__version__}"
+
+
 def synth_graphs(gen, sizes, feat, segs, n_verb, n_noun, unlabeled=0.3, pos_shift=0):
     out = []
     for n in sizes:
@@ -87,6 +116,11 @@ def grads_of(module):
 
 
 def main():
+    third_party = cross_check_real_pyg()
+    import json
+    json.dump({"torch": torch.__version__, "third_party_layer": third_party,
+               "reference": REF, "note": "fixtures = outputs of the reference's own models/*.py on top of oracle/pyg_restated.py"},
+              open(os.path.join(OUT, "VERSIONS.json"), "w"), indent=1)
     install_stubs()
     sys.path.insert(0, REF)
     from models.graph import Graph                                       # reference code, unmodified
