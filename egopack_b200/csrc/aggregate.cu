@@ -15,6 +15,8 @@
 //                 at 524 288 nodes against 0.56 ms) and one thread per output vector with L1 re-reads.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace egp {
@@ -182,108 +184,208 @@ sage_hub_fixup_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t chan
 
 // Large radii (K > 4): running window sum held in REGISTERS.  A thread owns one 16-byte column of a strip of rows.
 // For every output row it needs three rows: the one entering the window (first touch -> HBM), the one leaving it
-// and the row itself (both touched <= 2K+1 rows ago by the same CTA -> L1/L2 hits), so DRAM traffic stays at one
-// read + one write of the tensor while no shared-memory ring limits occupancy.  The 3*U loads of U consecutive
-// output rows are issued together.  At a graph boundary (or strip start) the sum restarts from scratch, so no
-// cancellation residue survives a graph.
-// Software-pipelined: the 3*U loads of the NEXT group of U rows are in flight while the current group is summed
-// and stored, so a thread keeps loads outstanding all the time and a few CTAs per SM saturate HBM.  That matters
-// because the combined windows of all RESIDENT threads ((2k+1) rows x 16 B each) must stay in L2 for the leaving / own
-// rows to be re-read from there instead of DRAM: strips are strided over a grid of kBandRunCtasPerSm CTAs per SM
-// (148 x 3 x 128 threads x 33 rows x 16 B = 30 MB at radius 16; with every strip resident it was 78 MB, L2 hit rate 2 %,
-// every row read from DRAM three times).
+// and the row itself (both touched <= 2K+1 rows ago by the same CTA -> L2 hits), so DRAM traffic stays at one read + one
+// write of the tensor while no shared-memory ring limits occupancy.  At a graph boundary (or strip start) the sum restarts
+// from scratch, so no cancellation residue survives a graph.
+//   * A group of U rows whose windows all slide by exactly one row on both ends (every interior row of a graph) takes a
+//     branch-free path: 3*U unclamped 16-byte loads, issued one group ahead into a ping-pong pair of register buffers
+//     (no copies between groups), the window bounds of the group checked with two 16-byte loads, the arithmetic in
+//     packed fp32x2 instructions (FFMA2 / FADD2 / FMUL2 halve the FP32 instruction count), scale vectors only in the
+//     instantiations that have them (SI: backward, SO: forward).
+//   * Every other row (strip start, the k rows either side of a graph boundary, array ends) goes through one small
+//     rolled slow path that loads what it needs directly.
+// The combined windows of all RESIDENT threads ((2k+1) rows x 16 B each) must stay in L2 for the leaving / own rows to be
+// re-read from there instead of DRAM: strips are strided over a grid of kBandRunCtasPerSm CTAs per SM (148 x 3 x 128
+// threads x 33 rows x 16 B = 30 MB at radius 16; with every strip resident it was 78 MB, L2 hit rate 2 %, every row read
+// from DRAM three times).
+// History (profiles/README.md): the first version of this kernel spent ~165 instructions per output vector on clamps,
+// per-row window branches and scalar FP32 (ncu: 56 % issue slots, 3869 GB/s at radius 16); this one ~82 (39 % issue,
+// 5066 GB/s, 1.03x algorithmic DRAM traffic) and is bound by load latency at 12 resident warps per SM.  A TMA bulk
+// prefetch of the entering rows into L2 (cp.async.bulk.prefetch.L2, 0..16 groups ahead) measured 5-50 % SLOWER and was
+// removed.
 constexpr int kBandRunCtasPerSm = 3;
-template <typename T, int U>
+template <typename T>
+struct Pairs;  // a 16-byte vector as fp32 pairs
+template <>
+struct Pairs<float> {
+  static constexpr int NP = 2;
+  float2 p[2];
+  __device__ __forceinline__ static Pairs from(const Raw<float>& r) {
+    Pairs q;
+    q.p[0] = make_float2(__uint_as_float(r.u.x), __uint_as_float(r.u.y));
+    q.p[1] = make_float2(__uint_as_float(r.u.z), __uint_as_float(r.u.w));
+    return q;
+  }
+  __device__ __forceinline__ uint4 pack() const {
+    return make_uint4(__float_as_uint(p[0].x), __float_as_uint(p[0].y), __float_as_uint(p[1].x), __float_as_uint(p[1].y));
+  }
+};
+template <>
+struct Pairs<__nv_bfloat16> {
+  static constexpr int NP = 4;
+  float2 p[4];
+  __device__ __forceinline__ static Pairs from(const Raw<__nv_bfloat16>& r) {
+    Pairs q;
+    const uint32_t w[4] = {r.u.x, r.u.y, r.u.z, r.u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q.p[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+    return q;
+  }
+  __device__ __forceinline__ uint4 pack() const {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(p[i].x, p[i].y);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+template <typename T, int U, bool SI, bool SO>
 __global__ void __launch_bounds__(kAggThreads, kBandRunCtasPerSm)
 sage_mean_band_run_kernel(const T* __restrict__ x, T* __restrict__ out, int n, int64_t channels, int64_t ldx,
-                          int64_t ldo, int rows_per_cta, int k, const int32_t* __restrict__ win_lo,
-                          const int32_t* __restrict__ win_hi, const float* __restrict__ scale_out,
-                          const float* __restrict__ scale_in) {
+                           int64_t ldo, int rows_per_cta, int k, const int32_t* __restrict__ win_lo,
+                           const int32_t* __restrict__ win_hi, const float* __restrict__ scale_out,
+                           const float* __restrict__ scale_in, bool win_vec) {
+  static_assert(U == 4, "the window bounds of a group are fetched as one int4");
   pdl_enter();
   constexpr int VN = Vec<T>::N;
+  constexpr int NP = Pairs<T>::NP;
   const int64_t col = ((int64_t)blockIdx.y * kAggThreads + threadIdx.x) * VN;
   if (col >= channels) return;
   const T* xc = x + col;
-  struct Group {  // speculative loads for U rows: entering (i+k), leaving (i-k-1), self (i); clamped, applied under masks
+  T* oc = out + col;
+  struct Group {      // prefetched rows of one group: entering (i+k), leaving (i-k-1), self (i)
     Raw<T> en[U], lv[U], sf[U];
-    int lo[U], hi[U];
+    float s_en[SI ? U : 1], s_lv[SI ? U : 1], s_sf[SI ? U : 1], s_out[SO ? U : 1];
+    int4 lo, hi;
+    bool ok;          // false: nothing was loaded (group touches an array end or starts a strip)
   };
+  // g must be a multiple of U.  Loads are unclamped: only issued when every address is inside the arrays.
   auto load_group = [&](Group& q, int g, int r1) {
+    q.ok = g + U <= r1 && g - k - 1 >= 0 && g + U - 1 + k < n;
+    if (q.ok) {
+      if (win_vec) {   // 16-byte aligned window arrays (always, for tensors the host side allocates)
+        q.lo = *reinterpret_cast<const int4*>(win_lo + g);
+        q.hi = *reinterpret_cast<const int4*>(win_hi + g);
+      } else {
+        q.lo = make_int4(win_lo[g], win_lo[g + 1], win_lo[g + 2], win_lo[g + 3]);
+        q.hi = make_int4(win_hi[g], win_hi[g + 1], win_hi[g + 2], win_hi[g + 3]);
+      }
+      const T* pe = xc + (int64_t)(g + k) * ldx;
+      const T* pl = xc + (int64_t)(g - k - 1) * ldx;
+      const T* ps = xc + (int64_t)g * ldx;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = min(g + u, r1 - 1);
-      q.lo[u] = win_lo[i];
-      q.hi[u] = win_hi[i];
-      q.en[u] = Raw<T>::load(xc + (int64_t)min(i + k, n - 1) * ldx);
-      q.lv[u] = Raw<T>::load(xc + (int64_t)max(i - k - 1, 0) * ldx);
-      q.sf[u] = Raw<T>::load(xc + (int64_t)i * ldx);
+      for (int u = 0; u < U; ++u) {
+        q.en[u] = Raw<T>::load(pe + (int64_t)u * ldx);
+        q.lv[u] = Raw<T>::load(pl + (int64_t)u * ldx);
+        q.sf[u] = Raw<T>::load(ps + (int64_t)u * ldx);
+        if constexpr (SI) {
+          q.s_en[u] = scale_in[g + k + u];
+          q.s_lv[u] = -scale_in[g - k - 1 + u];
+          q.s_sf[u] = -scale_in[g + u];
+        }
+        if constexpr (SO) q.s_out[u] = scale_out[g + u];
+      }
     }
   };
-  float acc[VN];
-  auto add_row = [&](int j, float sign) {
-    const Vec<T> v = Vec<T>::load(xc + (int64_t)j * ldx);
-    const float s = sign * (scale_in ? scale_in[j] : 1.f);
+  float2 acc[NP];
+  auto clear = [&]() {
 #pragma unroll
-    for (int c = 0; c < VN; ++c) acc[c] += s * v.v[c];
+    for (int c = 0; c < NP; ++c) acc[c] = make_float2(0.f, 0.f);
   };
+  auto add_row = [&](int j, float sign) {   // slow path: acc += sign * s_in(j) * x[j]
+    const Pairs<T> v = Pairs<T>::from(Raw<T>::load(xc + (int64_t)j * ldx));
+    const float s = SI ? sign * scale_in[j] : sign;
+    const float2 s2 = make_float2(s, s);
+#pragma unroll
+    for (int c = 0; c < NP; ++c) acc[c] = __ffma2_rn(v.p[c], s2, acc[c]);
+  };
+  const float2 neg1 = make_float2(-1.f, -1.f);
   const int stride = (int)gridDim.x * rows_per_cta;
   int r0 = (int)blockIdx.x * rows_per_cta;
-  if (r0 >= n) return;
-  Group cur, nxt;
-  load_group(cur, r0, min(r0 + rows_per_cta, n));
+  int plo = 0, phi = -1;  // window currently summed in acc: [plo, phi] (empty)
+  // one group of U rows: `cur` holds its prefetched rows, the next group's are fetched into `nxt` first
+  auto step = [&](int g, int r1, Group& cur, Group& nxt) {
+    if (g + U < r1) load_group(nxt, g + U, r1);
+    else nxt.ok = false;
+    bool steady = cur.ok && plo == g - k - 1 && phi == g + k - 1;
+    if (steady) {
+      const int a = g - k, b = g + k;
+      steady = cur.lo.x == a && cur.lo.y == a + 1 && cur.lo.z == a + 2 && cur.lo.w == a + 3 &&
+               cur.hi.x == b && cur.hi.y == b + 1 && cur.hi.z == b + 2 && cur.hi.w == b + 3;
+    }
+    if (steady) {
+      T* po = oc + (int64_t)g * ldo;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const Pairs<T> e = Pairs<T>::from(cur.en[u]), l = Pairs<T>::from(cur.lv[u]), s = Pairs<T>::from(cur.sf[u]);
+        Pairs<T> res;
+        if constexpr (SI) {
+          const float2 se = make_float2(cur.s_en[u], cur.s_en[u]), sl = make_float2(cur.s_lv[u], cur.s_lv[u]);
+          const float2 ss = make_float2(cur.s_sf[u], cur.s_sf[u]);
+#pragma unroll
+          for (int c = 0; c < NP; ++c) {
+            acc[c] = __ffma2_rn(e.p[c], se, acc[c]);
+            acc[c] = __ffma2_rn(l.p[c], sl, acc[c]);
+            res.p[c] = __ffma2_rn(s.p[c], ss, acc[c]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < NP; ++c) {
+            acc[c] = __fadd2_rn(acc[c], e.p[c]);
+            acc[c] = __ffma2_rn(l.p[c], neg1, acc[c]);
+            res.p[c] = __ffma2_rn(s.p[c], neg1, acc[c]);
+          }
+        }
+        if constexpr (SO) {
+          const float2 so = make_float2(cur.s_out[u], cur.s_out[u]);
+#pragma unroll
+          for (int c = 0; c < NP; ++c) res.p[c] = __fmul2_rn(res.p[c], so);
+        }
+        // streaming store: the output must not push the window rows out of L2
+        __stcs(reinterpret_cast<uint4*>(po + (int64_t)u * ldo), res.pack());
+      }
+      plo += U;
+      phi += U;
+    } else {
+      const int ge = min(g + U, r1);
+#pragma unroll 1
+      for (int i = g; i < ge; ++i) {
+        const int lo = win_lo[i], hi = win_hi[i];
+        if (lo > phi || phi < plo) {  // new graph / strip start: rebuild the window sum
+          clear();
+          for (int j = lo; j <= hi; ++j) add_row(j, 1.f);
+        } else {
+          for (int j = phi + 1; j <= hi; ++j) add_row(j, 1.f);
+          for (int j = plo; j < lo; ++j) add_row(j, -1.f);
+        }
+        plo = lo;
+        phi = hi;
+        const Pairs<T> s = Pairs<T>::from(Raw<T>::load(xc + (int64_t)i * ldx));
+        const float nss = SI ? -scale_in[i] : -1.f;
+        const float so = SO ? scale_out[i] : 1.f;
+        const float2 nss2 = make_float2(nss, nss), so2 = make_float2(so, so);
+        Pairs<T> res;
+#pragma unroll
+        for (int c = 0; c < NP; ++c) res.p[c] = __fmul2_rn(__ffma2_rn(s.p[c], nss2, acc[c]), so2);
+        __stcs(reinterpret_cast<uint4*>(oc + (int64_t)i * ldo), res.pack());
+      }
+    }
+  };
+  Group ga, gb;   // ping-pong: no register copies between groups
 #pragma unroll 1
   for (; r0 < n; r0 += stride) {
     const int r1 = min(r0 + rows_per_cta, n);
-#pragma unroll
-    for (int c = 0; c < VN; ++c) acc[c] = 0.f;
-    int plo = 0, phi = -1;  // window currently summed in acc: [plo, phi] (empty)
+    clear();
+    plo = 0;
+    phi = -1;
+    ga.ok = false;          // a strip starts with a rebuild
 #pragma unroll 1
-    for (int g = r0; g < r1; g += U) {
-      // next group: the following rows of this strip, or the first rows of this CTA's next strip
-      if (g + U < r1) load_group(nxt, g + U, r1);
-      else if (r0 + stride < n) load_group(nxt, r0 + stride, min(r0 + stride + rows_per_cta, n));
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = g + u;
-        if (i < r1) {
-          const int lo = cur.lo[u], hi = cur.hi[u];
-          if (lo > phi || phi < plo) {  // new graph / strip start: rebuild the window sum
-#pragma unroll
-            for (int c = 0; c < VN; ++c) acc[c] = 0.f;
-            for (int j = lo; j <= hi; ++j) add_row(j, 1.f);
-          } else {
-            if (hi == phi + 1 && hi == i + k) {  // the common case: one row enters ...
-              const Vec<T> v = cur.en[u].unpack();
-              const float s = scale_in ? scale_in[hi] : 1.f;
-#pragma unroll
-              for (int c = 0; c < VN; ++c) acc[c] += s * v.v[c];
-            } else {
-              for (int j = phi + 1; j <= hi; ++j) add_row(j, 1.f);
-            }
-            if (lo == plo + 1 && plo == i - k - 1) {  // ... and one row leaves
-              const Vec<T> v = cur.lv[u].unpack();
-              const float s = scale_in ? scale_in[plo] : 1.f;
-#pragma unroll
-              for (int c = 0; c < VN; ++c) acc[c] -= s * v.v[c];
-            } else {
-              for (int j = plo; j < lo; ++j) add_row(j, -1.f);
-            }
-          }
-          plo = lo;
-          phi = hi;
-          const Vec<T> self = cur.sf[u].unpack();
-          const float ss = scale_in ? scale_in[i] : 1.f;
-          const float so = scale_out ? scale_out[i] : 1.f;
-          Vec<T> res;
-#pragma unroll
-          for (int c = 0; c < VN; ++c) res.v[c] = (acc[c] - ss * self.v[c]) * so;
-          // streaming store: the output must not push the window rows out of L2 either
-          T tmp[VN];
-          res.store(tmp);
-          __stcs(reinterpret_cast<uint4*>(out + (int64_t)i * ldo + col), *reinterpret_cast<const uint4*>(tmp));
-        }
-      }
-      cur = nxt;
+    for (int g = r0; g < r1; g += 2 * U) {
+      step(g, r1, ga, gb);
+      if (g + U < r1) step(g + U, r1, gb, ga);
     }
   }
 }
@@ -394,8 +496,17 @@ static int launch_band_run(const void* x, void* out, int64_t n, int64_t channels
   rows = (rows + U - 1) / U * U;
   const int64_t strips = ceil_div(n, rows);
   dim3 grid((unsigned)(strips < cap ? strips : cap), gy);
-  (void)launch_kernel(sage_mean_band_run_kernel<T, U>, grid, kAggThreads, 0, stream, (const T*)x, (T*)out, (int)n, channels, ldx, ldo,
-                                                                    (int)rows, k, win_lo, win_hi, scale_out, scale_in);
+  auto run2 = [&](auto si, auto so) {
+    (void)launch_kernel(sage_mean_band_run_kernel<T, U, decltype(si)::value, decltype(so)::value>, grid, kAggThreads, 0, stream,
+                        (const T*)x, (T*)out, (int)n, channels, ldx, ldo, (int)rows, k, win_lo, win_hi, scale_out, scale_in,
+                        aligned16(win_lo) && aligned16(win_hi));
+  };
+  using Yes = std::true_type;
+  using No = std::false_type;
+  if (scale_in && scale_out) run2(Yes{}, Yes{});
+  else if (scale_in) run2(Yes{}, No{});
+  else if (scale_out) run2(No{}, Yes{});
+  else run2(No{}, No{});
   EGP_LAUNCH_CHECK();
   return EGP_OK;
 }

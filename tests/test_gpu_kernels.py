@@ -45,6 +45,46 @@ def test_sage_mean_band_and_csr_forward_backward(dtype, tol, k):
         assert rel_max(y, want) < 2e-7
 
 
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+@pytest.mark.parametrize("k", [5, 9, 16, 32])
+def test_wide_band_matches_csr_over_many_strips(dtype, tol, k):
+    """The running-window kernel (radius > 4) against the CSR kernel on ragged graphs, enough rows that every CTA walks
+    several strips, graphs shorter than the window, a row count that is not a multiple of the group size, both scaling
+    directions (forward: s_out; backward: s_in)."""
+    g = torch.Generator().manual_seed(100 + k)
+    sizes = torch.randint(1, 700, (400,), generator=g).tolist() + [3, 1, 2 * k + 1, 2 * k + 2, 4096, 7]
+    if sum(sizes) % 4 == 0:
+        sizes.append(1)
+    batch, ptr = graph_sizes_to_index(sizes)
+    n, c = batch.numel(), 64
+    idx = torch.arange(n)
+    start = ptr[batch]
+    end = ptr[batch + 1] - 1
+    src, dst = [], []
+    for d in range(1, k + 1):
+        ok = idx + d <= end
+        src += [idx[ok] + d, idx[ok]]
+        dst += [idx[ok], idx[ok] + d]
+    ei = torch.stack([torch.cat(src), torch.cat(dst)]).to(DEV)
+    band = ops.band_structure(batch.to(DEV), ptr.to(DEV), k)
+    csr = ops.csr_structure(ei, n)
+    x = torch.randn(n, c, generator=g).to(dtype).to(DEV)
+    w = torch.randn(n, c, generator=g).to(dtype).to(DEV)
+    outs = []
+    for gs in (band, csr):
+        xd = x.clone().requires_grad_(True)
+        y = ops.SageMean.apply(xd, gs)
+        y.backward(w)
+        outs.append((y, xd.grad))
+    assert rel_max(outs[0][0], outs[1][0]) < tol and rel_max(outs[0][1], outs[1][1]) < tol
+    # window arrays that are not 16-byte aligned take the scalar window loads: same bits
+    lo = torch.empty(n + 1, dtype=torch.int32, device=DEV)[1:].copy_(band.win_lo)
+    hi = torch.empty(n + 1, dtype=torch.int32, device=DEV)[1:].copy_(band.win_hi)
+    import dataclasses
+    odd = dataclasses.replace(band, win_lo=lo, win_hi=hi)
+    assert torch.equal(ops.SageMean.apply(x, odd), outs[0][0].detach())
+
+
 def _lta_batch(gen, num_graphs, k, sizes=None):
     """Random LTA-shaped graphs: n_in inputs (verb -1) then forecasts whose verb may be 0 (the `> 0` quirk) and, for
     some graphs, trailing unlabeled-but-not-input nodes; also graphs without inputs / without forecasts."""

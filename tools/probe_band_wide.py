@@ -17,16 +17,20 @@ ptr = torch.arange(v + 1, device="cuda") * per
 gs = ops.band_structure(batch, ptr, k)
 x = torch.randn(N, H, device="cuda").bfloat16()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for _ in range(2):
-    ops._aggregate(x, gs, False)
-ts = []
-for _ in range(5):
-    flush.zero_()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    ops._aggregate(x, gs, False)
-    e1.record()
-    torch.cuda.synchronize()
-    ts.append(e0.elapsed_time(e1))
-ms = sorted(ts)[2]
-print(f"radius {k}, {N} nodes: {ms:.3f} ms, {2 * N * H * 2 / ms / 1e6:.0f} GB/s algorithmic")
+import hashlib  # noqa: E402
+
+for transpose in (False, True):
+    for _ in range(2):
+        y = ops._aggregate(x, gs, transpose)
+    ts = []
+    for _ in range(5):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops._aggregate(x, gs, transpose)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[2]
+    digest = hashlib.sha1(y.view(torch.int16).cpu().numpy().tobytes()).hexdigest()[:12]
+    print(f"radius {k}, {N} nodes, transpose={transpose}: {ms:.3f} ms, {2 * N * H * 2 / ms / 1e6:.0f} GB/s algorithmic, sha1 {digest}")
