@@ -204,44 +204,6 @@ sage_hub_fixup_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t chan
 // prefetch of the entering rows into L2 (cp.async.bulk.prefetch.L2, 0..16 groups ahead) measured 5-50 % SLOWER and was
 // removed.
 constexpr int kBandRunCtasPerSm = 3;
-template <typename T>
-struct Pairs;  // a 16-byte vector as fp32 pairs
-template <>
-struct Pairs<float> {
-  static constexpr int NP = 2;
-  float2 p[2];
-  __device__ __forceinline__ static Pairs from(const Raw<float>& r) {
-    Pairs q;
-    q.p[0] = make_float2(__uint_as_float(r.u.x), __uint_as_float(r.u.y));
-    q.p[1] = make_float2(__uint_as_float(r.u.z), __uint_as_float(r.u.w));
-    return q;
-  }
-  __device__ __forceinline__ uint4 pack() const {
-    return make_uint4(__float_as_uint(p[0].x), __float_as_uint(p[0].y), __float_as_uint(p[1].x), __float_as_uint(p[1].y));
-  }
-};
-template <>
-struct Pairs<__nv_bfloat16> {
-  static constexpr int NP = 4;
-  float2 p[4];
-  __device__ __forceinline__ static Pairs from(const Raw<__nv_bfloat16>& r) {
-    Pairs q;
-    const uint32_t w[4] = {r.u.x, r.u.y, r.u.z, r.u.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) q.p[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
-    return q;
-  }
-  __device__ __forceinline__ uint4 pack() const {
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const __nv_bfloat162 h = __floats2bfloat162_rn(p[i].x, p[i].y);
-      w[i] = *reinterpret_cast<const uint32_t*>(&h);
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
-  }
-};
-
 template <typename T, int U, bool SI, bool SO>
 __global__ void __launch_bounds__(kAggThreads, kBandRunCtasPerSm)
 sage_mean_band_run_kernel(const T* __restrict__ x, T* __restrict__ out, int n, int64_t channels, int64_t ldx,

@@ -147,6 +147,48 @@ __device__ __forceinline__ Vec<__nv_bfloat16> Raw<__nv_bfloat16>::unpack() const
   return r;
 }
 
+// A 16-byte vector as fp32 PAIRS, for the packed fp32x2 instructions of sm_100 (FADD2 / FMUL2 / FFMA2: one issue slot
+// per two lanes of arithmetic -- what the instruction-issue-bound streaming kernels need).
+template <typename T>
+struct Pairs;
+template <>
+struct Pairs<float> {
+  static constexpr int NP = 2;
+  float2 p[2];
+  __device__ __forceinline__ static Pairs from(const Raw<float>& r) {
+    Pairs q;
+    q.p[0] = make_float2(__uint_as_float(r.u.x), __uint_as_float(r.u.y));
+    q.p[1] = make_float2(__uint_as_float(r.u.z), __uint_as_float(r.u.w));
+    return q;
+  }
+  __device__ __forceinline__ uint4 pack() const {
+    return make_uint4(__float_as_uint(p[0].x), __float_as_uint(p[0].y), __float_as_uint(p[1].x), __float_as_uint(p[1].y));
+  }
+};
+template <>
+struct Pairs<__nv_bfloat16> {
+  static constexpr int NP = 4;
+  float2 p[4];
+  __device__ __forceinline__ static Pairs from(const Raw<__nv_bfloat16>& r) {
+    Pairs q;
+    const uint32_t w[4] = {r.u.x, r.u.y, r.u.z, r.u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q.p[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+    return q;
+  }
+  __device__ __forceinline__ uint4 pack() const {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(p[i].x, p[i].y);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+__device__ __forceinline__ float2 splat2(float s) { return make_float2(s, s); }
+
 template <typename T>
 __device__ __forceinline__ float to_float(T x);
 template <>
@@ -242,6 +284,33 @@ __device__ __forceinline__ uint32_t dropout_keep_bits_keyed(uint64_t vec, uint32
     bits |= ((w >> 16) >= thr16 ? 1u : 0u) << (2 * i + 1);
   }
   return bits;
+}
+
+// Zero the dropped elements of a PACKED 16-byte output vector: the keep bits are spread so that each lands in the top
+// bit of its own byte (one multiply per four bits), and PRMT's sign-replicate mode turns those into byte masks --
+// 1.5 integer instructions per bf16 element instead of a bit test + select each.
+__device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+  return d;
+}
+template <typename T>
+__device__ __forceinline__ void dropout_mask_packed(uint4& v, uint32_t keep);
+template <>
+__device__ __forceinline__ void dropout_mask_packed<__nv_bfloat16>(uint4& v, uint32_t keep) {   // 8 bits, 2 per word
+  const uint32_t r0 = (keep & 0xFu) * 0x10204080u, r1 = ((keep >> 4) & 0xFu) * 0x10204080u;
+  v.x &= prmt_sx(r0, 0x9988u);
+  v.y &= prmt_sx(r0, 0xBBAAu);
+  v.z &= prmt_sx(r1, 0x9988u);
+  v.w &= prmt_sx(r1, 0xBBAAu);
+}
+template <>
+__device__ __forceinline__ void dropout_mask_packed<float>(uint4& v, uint32_t keep) {            // 4 bits, 1 per word
+  const uint32_t r0 = (keep & 0xFu) * 0x10204080u;
+  v.x &= prmt_sx(r0, 0x8888u);
+  v.y &= prmt_sx(r0, 0x9999u);
+  v.z &= prmt_sx(r0, 0xAAAAu);
+  v.w &= prmt_sx(r0, 0xBBBBu);
 }
 
 __device__ __forceinline__ uint32_t dropout_keep_bits(uint64_t vec, uint64_t seed, uint64_t offset, uint32_t thr16) {

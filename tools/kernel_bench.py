@@ -22,7 +22,7 @@ from egopack_b200.ops import ACT_LEAKY, ACT_RELU  # noqa: E402
 
 DEV = "cuda"
 BF = torch.bfloat16
-N, H, K0 = 32768, 1024, 4608
+N, H, K0 = int(os.environ.get("EGP_KB_N", 32768)), 1024, 4608   # EGP_KB_N: rows (default = one task batch of c2)
 
 
 def peaks():
