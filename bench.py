@@ -149,7 +149,7 @@ class ClockSampler:
     the samples whose timestamps fall inside the timed region (padded by one sampling period)."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    PERIOD_MS = 20
+    PERIOD_MS = 50          # NVML queries take driver locks; 20 ms polling was seen next to a 127 ms launch stall
 
     def __init__(self, index: int):
         self.rows, self.proc, self.index = [], None, index
@@ -349,6 +349,10 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
     for k_ in ops.KNN_STATS:
         ops.KNN_STATS[k_] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # no cyclic-GC pass inside a timed region (a generation-2 sweep over the module / autograd heap stalls the launching
+    # thread for tens of ms -- longer than the launch queue can hide); reference counting still frees every tensor
+    gc.collect()
+    gc.disable()
     t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
@@ -356,6 +360,7 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
     e1.record()
     barrier()
     t_end = time.time()
+    gc.enable()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clock_info = clocks.stop(t_begin, t_end)
     launches = _lib.kernel_launches()
@@ -423,12 +428,15 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
         del probe_dst
         feeder = DeviceFeeder(host_loader(args.steps), dev, feed_tf)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gc.collect()
+        gc.disable()
         e0.record()
         for b in feeder:
             loss = step(b)
             last = float(loss.item())                          # D2H of the loss every step
         e1.record()
         barrier()
+        gc.enable()
         e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
         assert feeder.h2d_bytes == h2d_bytes * args.steps, (feeder.h2d_bytes, h2d_bytes)
         e2e = {"value": round(world * n_nodes / (e2e_ms / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
