@@ -13,7 +13,11 @@ if want bench; then
   head -c 1500 gpurun_out/r2_bench_n1.json; echo; tail -2 gpurun_out/r2_bench_n1.err
   python bench.py --impl reference --steps 3 --warmup 1 --cpu-sweep > gpurun_out/r2_bench_reference.json 2>/dev/null; head -c 600 gpurun_out/r2_bench_reference.json; echo
 fi
-if want kbench; then python tools/kernel_bench.py > gpurun_out/r2_kernel_bench.txt 2>&1; tail -70 gpurun_out/r2_kernel_bench.txt; fi
+if want kbench; then
+  python tools/kernel_bench.py > gpurun_out/r2_kernel_bench.txt 2>&1; tail -70 gpurun_out/r2_kernel_bench.txt
+  # the memory-bound kernels again at the row count of the stacked c2 pass (the default table is one task batch)
+  EGP_KB_N=98304 python tools/kernel_bench.py 2>&1 | grep -v "gemm\|cublas\|cos_topk" > gpurun_out/r2_kernel_bench_n98304.txt; cat gpurun_out/r2_kernel_bench_n98304.txt
+fi
 if want launches; then
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launch_list_ncu.csv \
       python bench.py --steps 1 --warmup 1 --quick --no-cpu-baseline > gpurun_out/r2_launch_bench.log 2>&1
@@ -31,7 +35,7 @@ if want ncu; then
   cap sage_mean_band_star_bwd 'sage_mean_band_reg_kernel<[^>]*8, \(int\)2>' $B
   cap sage_hub_fixup 'sage_hub_fixup' $B
   cap rln_bwd_block 'rln_bwd_block_kernel' $B
-  cap rln_fwd 'rln_fwd_kernel' $B
+  cap rln_fwd 'rln_fwd_full_kernel' $B
   cap gln_bwd_reduce 'gln_bwd_reduce_kernel' $B
   cap gln_bwd_apply 'gln_bwd_apply_kernel' $B
   cap gln_stats 'gln_stats_kernel' $B
