@@ -149,12 +149,14 @@ class ClockSampler:
     the samples whose timestamps fall inside the timed region (padded by one sampling period)."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    PERIOD_MS = 50          # NVML queries take driver locks; 20 ms polling was seen next to a 127 ms launch stall
+    PERIOD_MS = int(os.environ.get("EGP_BENCH_SAMPLER_MS", "50"))   # NVML queries take driver locks: see profiles/README.md
 
     def __init__(self, index: int):
         self.rows, self.proc, self.index = [], None, index
 
     def start(self):
+        if self.PERIOD_MS <= 0:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", str(self.PERIOD_MS)],
@@ -227,6 +229,7 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
     import egopack_b200
     from egopack_b200 import _lib, ops, steps
     from egopack_b200 import synthetic as syn
+    from egopack_b200.data import replicated_base
     from egopack_b200.dp import GradientAllReduce
     from egopack_b200.feed import DeviceFeeder, bind_host_memory_to_gpu
     from egopack_b200.models.graph import Graph
@@ -304,9 +307,16 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
             resident[t] = feed_tf[t](d)
         h2d_bytes = 0
     else:
-        host = {t: syn.make_batch(t, videos, nodes, gen, band_k=k_radius, pin=True, feature_dtype=feat_dtype)
+        # compact: PNR features are one vector per node repeated over the segments (the reference's dataset,
+        # data/ego4d_oscc.py:291); the loader hands them over as a stride-0 view, so the base alone crosses PCIe
+        host = {t: syn.make_batch(t, videos, nodes, gen, band_k=k_radius, pin=True, feature_dtype=feat_dtype,
+                                   compact=os.environ.get("EGP_BENCH_COMPACT", "1") != "0")
                 for t in task_names}
-        h2d_bytes = sum(v.numel() * v.element_size() for b in host.values() for v in (b.x, b.pos, b.y, b.batch, b.ptr))
+
+        def wire(x):                                          # the tensor that actually crosses the bus
+            base = replicated_base(x)
+            return x if base is None else base
+        h2d_bytes = sum(v.numel() * v.element_size() for b in host.values() for v in (wire(b.x), b.pos, b.y, b.batch, b.ptr))
 
     def host_loader(n):
         for _ in range(n):
@@ -349,18 +359,27 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
     for k_ in ops.KNN_STATS:
         ops.KNN_STATS[k_] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # no cyclic-GC pass inside a timed region (a generation-2 sweep over the module / autograd heap stalls the launching
-    # thread for tens of ms -- longer than the launch queue can hide); reference counting still frees every tensor
+    # keep full cyclic-GC sweeps cheap inside a timed region: everything alive now (modules, parameters, the loaders'
+    # batches) moves to the permanent generation, so a generation-2 pass only walks what the steps themselves create.
+    # (Switching the collector OFF is not an option: a step leaves reference cycles that hold its activations, and
+    # without the collector the allocator grows by a step's worth of memory per step -- measured 11.8 -> 15.4 ms/step.)
     gc.collect()
-    gc.disable()
+    gc.freeze()
+    marks, host_t = [], []                                   # one event per step: where a slow run lost its time
     t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         loss = step(resident)
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append(ev)
+        host_t.append(time.time())
     e1.record()
     barrier()
     t_end = time.time()
-    gc.enable()
+    gc.unfreeze()
+    step_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+    host_ms = [(b - a) * 1e3 for a, b in zip([t_begin] + host_t[:-1], host_t)]
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clock_info = clocks.stop(t_begin, t_end)
     launches = _lib.kernel_launches()
@@ -413,36 +432,43 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
         barrier()
         # what the platform gives this rank for the feature copies ALONE (all ranks copying at once, GPU otherwise idle):
         # the ceiling of any feed, reported next to the e2e rate
-        probe_dst = {t: torch.empty(hb.x.shape, dtype=hb.x.dtype, device=dev) for t, hb in host.items()}
+        probe_dst = {t: torch.empty(wire(hb.x).shape, dtype=hb.x.dtype, device=dev) for t, hb in host.items()}
         pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for rep in range(4):
             if rep == 1:
                 barrier()
                 pe0.record()
             for t, hb in host.items():
-                probe_dst[t].copy_(hb.x, non_blocking=True)
+                probe_dst[t].copy_(wire(hb.x), non_blocking=True)
         pe1.record()
         barrier()
         probe_ms = max_over_ranks(pe0.elapsed_time(pe1)) / 3
-        h2d_alone = sum(hb.x.numel() * hb.x.element_size() for hb in host.values()) / (probe_ms / 1e3) / 1e9
+        h2d_alone = sum(wire(hb.x).numel() * hb.x.element_size() for hb in host.values()) / (probe_ms / 1e3) / 1e9
         del probe_dst
         feeder = DeviceFeeder(host_loader(args.steps), dev, feed_tf)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         gc.collect()
-        gc.disable()
+        gc.freeze()
+        e2e_marks = []
         e0.record()
         for b in feeder:
             loss = step(b)
             last = float(loss.item())                          # D2H of the loss every step
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            e2e_marks.append(ev)
         e1.record()
         barrier()
-        gc.enable()
+        gc.unfreeze()
+        e2e_step_ms = [a.elapsed_time(b) for a, b in zip([e0] + e2e_marks[:-1], e2e_marks)]
         e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
         assert feeder.h2d_bytes == h2d_bytes * args.steps, (feeder.h2d_bytes, h2d_bytes)
         e2e = {"value": round(world * n_nodes / (e2e_ms / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3),
                "h2d_gbps_per_gpu": round(h2d_bytes / (e2e_ms / 1e3) / 1e9, 1),
                "h2d_alone_gbps_per_gpu": round(h2d_alone, 1),
+               "step_ms": {"median": round(statistics.median(e2e_step_ms), 3), "min": round(min(e2e_step_ms), 3),
+                           "max": round(max(e2e_step_ms), 3)},
                "note": "egopack_b200.feed.DeviceFeeder: pinned host -> device copy of every step's inputs on a copy stream "
                        "(enqueued before the previous step is handed out), device-side graph transforms (band_k / star hints, "
                        "lazy edge_index), loss.item() per step"}
@@ -561,9 +587,13 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
               "graphs_per_task_per_gpu": videos, "nodes_per_graph": nodes,
               "nodes_per_step_per_gpu": n_nodes,
               "features": f"[N,3,1536] {feat_name} N(0,1)" + (" (stored by the loader as bf16: Batch.to_feature_dtype; bit-identical "
-                                                             "to fp32 features in the bf16 compute mode)" if feat_name == "bf16" else ""),
+                                                             "to fp32 features in the bf16 compute mode)" if feat_name == "bf16" else "")
+                          + ("; PNR rows are one 1536-vector per node repeated over the 3 segments, as the reference's dataset builds "
+                             "them (data/ego4d_oscc.py:291) -- the feed ships the vector once and repeats it on the device"
+                             if "pnr" in task_names else ""),
               "parallelism": f"dp{world}", "optimizer": "FlatAdam (egp_adam_step)" if args.optimizer == "flat" else "torch fused Adam",
-              "l2": (f"inputs larger than L2 ({h2d_bytes / 2**20:.0f} MiB of features per step)" if not on_device else
+              "l2": (f"inputs larger than L2 ({n_nodes * 4608 * (2 if feat_name == 'bf16' else 4) / 2**20:.0f} MiB of features per step, "
+                     f"{h2d_bytes / 2**20:.0f} MiB of them over PCIe)" if not on_device else
                      f"inputs larger than L2 ({n_nodes * 4608 * 2 / 2**20:.0f} MiB of features per step, drawn on the device)"),
               "final_loss": round(last, 4)}
     if numa is not None:
@@ -576,6 +606,10 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": config, "clocks": clock_info,
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+        # per-step spread of the timed region (one CUDA event after every step; `value` stays total time / K as the contract
+        # says): a host-side stall longer than the launch queue hides shows up as ONE slow step with a matching host gap
+        "step_ms": {"median": round(statistics.median(step_ms), 3), "min": round(min(step_ms), 3),
+                    "max": round(max(step_ms), 3), "host_max": round(max(host_ms), 3)},
     }
     if roof_hbm:
         out["roofline_hbm"] = roof_hbm

@@ -12,6 +12,29 @@ from typing import Any, Dict, List, Sequence
 import torch
 
 
+def replicated_base(x):
+    """``[N, D]`` base of a feature tensor ``[N, R, D]`` whose R segments are the SAME memory (a stride-0 view, what
+    ``base.unsqueeze(1).expand(-1, R, -1)`` gives), else None.
+
+    The reference's PNR dataset hands over one 1536-vector per node repeated over the three segments
+    (``x=...unsqueeze(1).repeat(1, 3, 1)``, data/ego4d_oscc.py:291).  A loader that writes ``expand`` instead of ``repeat``
+    keeps the same values without the copies; collation, pinning, the feature-dtype conversion and the host -> device
+    feed below preserve that form, so only the base crosses PCIe and the repeat happens on the device."""
+    if not torch.is_tensor(x) or x.dim() != 3 or x.shape[1] < 2 or x.stride(1) != 0:
+        return None
+    return x[:, 0, :]
+
+
+def expand_base(base, repeats: int):
+    return base.unsqueeze(1).expand(-1, repeats, -1)
+
+
+def _map_features(x, fn):
+    """``fn`` applied to the feature tensor, or to its base when the segments are replicated (form preserved)."""
+    base = replicated_base(x)
+    return fn(x) if base is None else expand_base(fn(base.contiguous()), x.shape[1])
+
+
 class Data:
     def __init__(self, x=None, edge_index=None, edge_attr=None, y=None, pos=None, **kwargs):
         object.__setattr__(self, "_fields", {})
@@ -70,7 +93,11 @@ class Data:
     def to(self, device, non_blocking: bool = False) -> "Data":
         for k, v in list(self._fields.items()):
             if torch.is_tensor(v):
-                self._fields[k] = v.to(device, non_blocking=non_blocking)
+                if k == "x" and replicated_base(v) is not None:     # ship the base, repeat on the destination
+                    v = _map_features(v, lambda t: t.to(device, non_blocking=non_blocking)).contiguous()
+                else:
+                    v = v.to(device, non_blocking=non_blocking)
+                self._fields[k] = v
         self._fields.pop("_egp_structure", None)            # device-specific cache
         return self
 
@@ -81,14 +108,13 @@ class Data:
         x = self._fields.get("x")
         if x is not None and x.dtype != dtype:
             pinned = x.device.type == "cpu" and x.is_pinned()
-            x = x.to(dtype)
-            self._fields["x"] = x.pin_memory() if pinned else x
+            self._fields["x"] = _map_features(x, lambda t: t.to(dtype).pin_memory() if pinned else t.to(dtype))
         return self
 
     def pin_memory(self) -> "Data":
         for k, v in list(self._fields.items()):
             if torch.is_tensor(v):
-                self._fields[k] = v.pin_memory()
+                self._fields[k] = _map_features(v, lambda t: t.pin_memory()) if k == "x" else v.pin_memory()
         return self
 
     def __repr__(self) -> str:
@@ -123,6 +149,10 @@ class Batch(Data):
                 band = ks.pop() if len(ks) == 1 else None
             elif k == "edge_index":
                 out.edge_index = torch.cat(columns[k], dim=-1)
+            elif k == "x" and all(replicated_base(v) is not None for v in columns[k]) \
+                    and len({v.shape[1] for v in columns[k]}) == 1:
+                # every sample's segments are replicated: concatenate the bases, keep the form
+                setattr(out, k, expand_base(torch.cat([replicated_base(v) for v in columns[k]], dim=0), columns[k][0].shape[1]))
             elif torch.is_tensor(columns[k][0]):
                 setattr(out, k, torch.cat(columns[k], dim=0))
             else:

@@ -21,7 +21,7 @@ import threading
 
 import torch
 
-from .data import Batch, Data
+from .data import Batch, Data, _map_features, expand_base, replicated_base
 
 __all__ = ["multiloader", "DeviceFeeder", "bind_host_memory_to_gpu", "unit_spaced_host"]
 
@@ -131,6 +131,9 @@ class DeviceFeeder:
       ``pin_memory=True`` (utils/dataloading.py:64) to skip that.
     * ``feature_dtype``: convert ``x`` on the host before the copy (a loader that stores bf16 features should do this
       once per sample instead: ``Batch.to_feature_dtype``).
+    * replicated segments: an ``x`` whose segments are one memory (``data.replicated_base``: what a PNR loader that writes
+      ``expand`` for the reference's ``repeat`` hands over, data/ego4d_oscc.py:291) crosses PCIe as its ``[N, D]`` base and is
+      repeated on the device; collation, pinning and ``feature_dtype`` keep that form.
     * ``fuse_features``: the ``x`` tensors of the task batches of one step land in ONE device allocation, back to back
       (each batch still sees its own rows), so ``Graph.forward_many`` can feed them to the first Linear as a single
       GEMM operand.
@@ -160,7 +163,7 @@ class DeviceFeeder:
         if b is None or not isinstance(b, Data):
             return b
         if self.feature_dtype is not None and b.x is not None and b.x.dtype != self.feature_dtype and b.x.device.type == "cpu":
-            b.x = b.x.to(self.feature_dtype)
+            b.x = _map_features(b.x, lambda t: t.to(self.feature_dtype))
         if b.pos is not None and b.pos.device.type == "cpu" and getattr(b, "pos_unit_spaced", None) is None \
                 and not b.pos.is_floating_point():
             b.pos_unit_spaced = unit_spaced_host(b.pos, b.batch)
@@ -168,7 +171,7 @@ class DeviceFeeder:
             for k in list(b._fields):
                 v = b._fields[k]
                 if torch.is_tensor(v) and v.device.type == "cpu" and not v.is_pinned():
-                    b._fields[k] = v.pin_memory()
+                    b._fields[k] = _map_features(v, lambda t: t.pin_memory()) if k == "x" else v.pin_memory()
         return b
 
     def _prepare_item(self, item):
@@ -188,12 +191,23 @@ class DeviceFeeder:
             if k.startswith("_"):
                 continue
             if torch.is_tensor(v):
-                self.h2d_bytes += v.numel() * v.element_size() if v.device != self.device else 0
-                if k == "x" and x_slot is not None:
-                    x_slot.copy_(v, non_blocking=True)
+                base = replicated_base(v) if k == "x" and v.device.type == "cpu" else None
+                if base is not None:
+                    # replicated segments (the PNR loader, data/ego4d_oscc.py:291): only the base crosses the bus, the
+                    # repeat is a device-side copy on this stream -- the consumer sees the same [N, R, D] tensor
+                    self.h2d_bytes += base.numel() * base.element_size()
+                    dev_base = base.to(self.device, non_blocking=True)
+                    if x_slot is None:
+                        x_slot = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                    x_slot.copy_(expand_base(dev_base, v.shape[1]))
                     v = x_slot
                 else:
-                    v = v.to(self.device, non_blocking=True)
+                    self.h2d_bytes += v.numel() * v.element_size() if v.device != self.device else 0
+                    if k == "x" and x_slot is not None:
+                        x_slot.copy_(v, non_blocking=True)
+                        v = x_slot
+                    else:
+                        v = v.to(self.device, non_blocking=True)
             setattr(out, k, v)
         return out
 

@@ -10,7 +10,7 @@ from typing import Dict, Optional
 
 import torch
 
-from .data import Batch
+from .data import Batch, expand_base
 
 N_VERBS, N_NOUNS = 115, 478
 FEATURE_DIM, NUM_SEGMENTS = 1536, 3
@@ -23,12 +23,20 @@ def generator(seed: int, config_id: int = 0, rank: int = 0) -> torch.Generator:
 def make_batch(task: str, num_graphs: int, nodes_per_graph: int, gen: torch.Generator, *, feature_dim: int = FEATURE_DIM,
                num_segments: int = NUM_SEGMENTS, band_k: Optional[int] = 1, unlabeled: float = 0.0,
                n_verbs: int = N_VERBS, n_nouns: int = N_NOUNS, lta_inputs: int = 2, pin: bool = False,
-               feature_dtype: Optional[torch.dtype] = None) -> Batch:
+               feature_dtype: Optional[torch.dtype] = None, compact: bool = False) -> Batch:
     """One collated task batch WITHOUT ``edge_index`` (the transform adds it; ``band_k`` is the structural hint
-    our RadiusGraph would record).  task in {'ar','lta','oscc','pnr'}."""
+    our RadiusGraph would record).  task in {'ar','lta','oscc','pnr'}.
+
+    PNR features are ONE vector per node repeated over the segments, as the reference's dataset builds them
+    (``x=features.unsqueeze(1).repeat(1, 3, 1)``, data/ego4d_oscc.py:291): materialised like there by default, or with
+    ``compact=True`` as the stride-0 view a loader that defers the repeat hands over (``data.replicated_base``)."""
     n = num_graphs * nodes_per_graph
     b = Batch()
-    b.x = torch.randn(n, num_segments, feature_dim, generator=gen)
+    if task == "pnr" and num_segments > 1:
+        base = torch.randn(n, feature_dim, generator=gen)
+        b.x = expand_base(base, num_segments) if compact else base.unsqueeze(1).repeat(1, num_segments, 1)
+    else:
+        b.x = torch.randn(n, num_segments, feature_dim, generator=gen)
     b.pos = torch.arange(nodes_per_graph, dtype=torch.long).repeat(num_graphs)
     b.batch = torch.arange(num_graphs, dtype=torch.long).repeat_interleave(nodes_per_graph)
     b.ptr = torch.arange(num_graphs + 1, dtype=torch.long) * nodes_per_graph

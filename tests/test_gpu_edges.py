@@ -168,3 +168,39 @@ def test_transforms_are_lazy_and_sync_free_on_device_batches():
     odd = Batch.from_data_list([Data(x=torch.zeros(4, 1), pos=torch.tensor([0, 2, 4, 6]))]).to(DEV)
     odd = RadiusGraph(r=2.5)(odd)
     assert odd.band_k is None and odd.is_materialized("edge_index")
+
+
+def test_device_feeder_ships_replicated_segments_once():
+    """PNR features are one vector per node repeated over the segments (data/ego4d_oscc.py:291).  A loader that hands them
+    over as a stride-0 view keeps that form through collation, the feature-dtype conversion and pinning; the feeder copies
+    the base only and repeats it on the device: the consumer sees the same [N, R, D] tensor, in the fused allocation."""
+    from egopack_b200 import Batch, Data, synthetic as syn
+    from egopack_b200.data import replicated_base
+    from egopack_b200.feed import DeviceFeeder
+    from egopack_b200.models.transforms import RadiusGraph
+    D, S = 16, 3
+    full = syn.make_batch("pnr", 3, 8, torch.Generator().manual_seed(9), feature_dim=D, num_segments=S)
+    comp = syn.make_batch("pnr", 3, 8, torch.Generator().manual_seed(9), feature_dim=D, num_segments=S, compact=True)
+    assert full.x.is_contiguous() and replicated_base(full.x) is None and replicated_base(comp.x) is not None
+    assert torch.equal(full.x, comp.x) and torch.equal(full.x[:, 0], full.x[:, 2])
+    ar = syn.make_batch("ar", 2, 8, torch.Generator().manual_seed(10), feature_dim=D, num_segments=S, n_verbs=5, n_nouns=7)
+    for dtype in (None, torch.bfloat16):
+        feeder = DeviceFeeder([{"ar": ar, "pnr": comp}], DEV, RadiusGraph(r=1.5), feature_dtype=dtype)
+        (out,) = list(feeder)
+        want = full.x if dtype is None else full.x.to(dtype)
+        assert out["pnr"].x.is_contiguous() and out["pnr"].x.shape == full.x.shape and torch.equal(out["pnr"].x.cpu(), want)
+        item = 4 if dtype is None else 2
+        per_batch = lambda b, nx: nx * item + sum(v.numel() * v.element_size() for v in (b.pos, b.y, b.batch, b.ptr))
+        assert feeder.h2d_bytes == per_batch(ar, ar.x.numel()) + per_batch(comp, comp.x.numel() // S)
+        # one allocation for the step's features: the PNR rows sit right behind the AR rows
+        assert out["pnr"].x.data_ptr() == out["ar"].x.data_ptr() + ar.x.numel() * item
+        assert replicated_base(comp.x) is not None                       # the host batch is left alone
+    # per-sample Data objects collate without materialising the repeat; .to(device) repeats on the device
+    samples = [Data(x=torch.randn(5, D).unsqueeze(1).expand(-1, S, -1), pos=torch.arange(5)) for _ in range(3)]
+    b = Batch.from_data_list(samples)
+    assert replicated_base(b.x) is not None and b.x.shape == (15, S, D)
+    want = torch.cat([d.x for d in samples])
+    b.to_feature_dtype(torch.bfloat16)
+    assert replicated_base(b.x) is not None
+    d = b.to(DEV)
+    assert d.x.is_contiguous() and torch.equal(d.x.cpu(), want.to(torch.bfloat16))

@@ -170,3 +170,22 @@ def test_lazy_attributes_of_the_data_stand_in():
     d.set_lazy("edge_index", lambda dd: torch.zeros((2, 0), dtype=torch.long))
     d.edge_index = None                                                         # assignment drops the producer
     assert d.edge_index is None and "edge_index" not in d
+
+
+def test_replicated_segment_features_keep_their_form_on_the_host():
+    """data.replicated_base / Batch.from_data_list / to_feature_dtype: the PNR loader's repeat (data/ego4d_oscc.py:291)
+    carried as a stride-0 view, values identical to the materialised form."""
+    from egopack_b200 import Batch, Data, synthetic as syn
+    from egopack_b200.data import expand_base, replicated_base
+    full = syn.make_batch("pnr", 2, 6, torch.Generator().manual_seed(3), feature_dim=8, num_segments=3)
+    comp = syn.make_batch("pnr", 2, 6, torch.Generator().manual_seed(3), feature_dim=8, num_segments=3, compact=True,
+                          feature_dtype=torch.bfloat16)
+    assert replicated_base(full.x) is None and torch.equal(full.x[:, 0], full.x[:, 1])
+    base = replicated_base(comp.x)
+    assert base is not None and base.shape == (12, 8) and base.dtype == torch.bfloat16
+    assert torch.equal(comp.x, full.x.to(torch.bfloat16)) and torch.equal(full.y, comp.y)
+    assert replicated_base(torch.randn(4, 3, 8)) is None and replicated_base(torch.randn(4, 8)) is None
+    assert replicated_base(expand_base(torch.randn(4, 8), 1)) is None          # one segment: nothing to save
+    mixed = [Data(x=expand_base(torch.randn(3, 8), 3), pos=torch.arange(3)), Data(x=torch.randn(2, 3, 8), pos=torch.arange(2))]
+    b = Batch.from_data_list(mixed)                                           # not all replicated: plain concatenation
+    assert replicated_base(b.x) is None and b.x.shape == (5, 3, 8) and torch.equal(b.x[:3], mixed[0].x)
