@@ -366,6 +366,8 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
     gc.collect()
     gc.freeze()
     marks, host_t = [], []                                   # one event per step: where a slow run lost its time
+    dbg_steps = [] if os.environ.get("EGP_BENCH_DEBUG_STEPS") == "1" else None
+    mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
@@ -374,12 +376,19 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
         ev.record()
         marks.append(ev)
         host_t.append(time.time())
+        if dbg_steps is not None:
+            st = torch.cuda.memory_stats(dev)
+            dbg_steps.append((st.get("num_device_alloc", 0), st.get("reserved_bytes.all.current", 0), gc.get_count()))
     e1.record()
     barrier()
     t_end = time.time()
     gc.unfreeze()
+    mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0
     step_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
     host_ms = [(b - a) * 1e3 for a, b in zip([t_begin] + host_t[:-1], host_t)]
+    if dbg_steps is not None:
+        for i, (h, g_, d_) in enumerate(zip(host_ms, step_ms, dbg_steps)):
+            print(f"[steps] {i} host {h:.2f} ms gpu {g_:.2f} ms mallocs {d_[0]} reserved {d_[1] >> 20} MiB gc {d_[2]}", file=sys.stderr)
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clock_info = clocks.stop(t_begin, t_end)
     launches = _lib.kernel_launches()
@@ -427,7 +436,7 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
     # out step i, so they overlap the step; nothing in the hand-over waits on the GPU
     e2e = None
     if full:
-        for b in DeviceFeeder(host_loader(2), dev, feed_tf):
+        for b in DeviceFeeder(host_loader(max(4, args.warmup)), dev, feed_tf):   # the feed's staging buffers reach steady state
             float(step(b).item())
         barrier()
         # what the platform gives this rank for the feature copies ALONE (all ranks copying at once, GPU otherwise idle):
@@ -450,6 +459,7 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
         gc.collect()
         gc.freeze()
         e2e_marks = []
+        e2e_mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
         e0.record()
         for b in feeder:
             loss = step(b)
@@ -460,6 +470,7 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
         e1.record()
         barrier()
         gc.unfreeze()
+        e2e_mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - e2e_mallocs0
         e2e_step_ms = [a.elapsed_time(b) for a, b in zip([e0] + e2e_marks[:-1], e2e_marks)]
         e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
         assert feeder.h2d_bytes == h2d_bytes * args.steps, (feeder.h2d_bytes, h2d_bytes)
@@ -468,7 +479,8 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
                "h2d_gbps_per_gpu": round(h2d_bytes / (e2e_ms / 1e3) / 1e9, 1),
                "h2d_alone_gbps_per_gpu": round(h2d_alone, 1),
                "step_ms": {"median": round(statistics.median(e2e_step_ms), 3), "min": round(min(e2e_step_ms), 3),
-                           "max": round(max(e2e_step_ms), 3)},
+                           "max": round(max(e2e_step_ms), 3), "argmax": int(e2e_step_ms.index(max(e2e_step_ms))),
+                           "cuda_mallocs": int(e2e_mallocs)},
                "note": "egopack_b200.feed.DeviceFeeder: pinned host -> device copy of every step's inputs on a copy stream "
                        "(enqueued before the previous step is handed out), device-side graph transforms (band_k / star hints, "
                        "lazy edge_index), loss.item() per step"}
@@ -609,7 +621,7 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
         # per-step spread of the timed region (one CUDA event after every step; `value` stays total time / K as the contract
         # says): a host-side stall longer than the launch queue hides shows up as ONE slow step with a matching host gap
         "step_ms": {"median": round(statistics.median(step_ms), 3), "min": round(min(step_ms), 3),
-                    "max": round(max(step_ms), 3), "host_max": round(max(host_ms), 3)},
+                    "max": round(max(step_ms), 3), "host_max": round(max(host_ms), 3), "cuda_mallocs": int(mallocs)},
     }
     if roof_hbm:
         out["roofline_hbm"] = roof_hbm

@@ -114,6 +114,20 @@ def unit_spaced_host(pos: torch.Tensor, batch: Optional[torch.Tensor]) -> bool:
     return bool(ok.all())
 
 
+_COPY_STREAMS: dict = {}
+
+
+def _copy_stream(device: torch.device) -> "torch.cuda.Stream":
+    """ONE copy stream per device for every feeder of the process.  torch's caching allocator keeps its free blocks per
+    stream: a feeder with a stream of its own (say, one feeder per epoch) finds none of the staging buffers its predecessor
+    returned and sends every allocation of its first steps to cudaMalloc (8 calls, and a first step of 50-330 ms instead of
+    26, in bench.py's end-to-end loop) while the old stream's blocks stay cached for nobody."""
+    key = (device.type, device.index)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device)
+    return _COPY_STREAMS[key]
+
+
 class DeviceFeeder:
     """Iterates a host loader and yields the same structure with every batch resident on ``device`` and its graph
     structure described there.
@@ -146,7 +160,7 @@ class DeviceFeeder:
         self._cuda = self.device.type == "cuda"
         if self._cuda and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        self._stream = torch.cuda.Stream(self.device) if self._cuda else None
+        self._stream = _copy_stream(self.device) if self._cuda else None
         self.h2d_bytes = 0                                      # bytes copied so far (what bench.py reports)
 
     # -- structure helpers ---------------------------------------------------------------------------------
