@@ -16,7 +16,8 @@ namespace egp {
 
 constexpr int kAdamThreads = 256;
 constexpr int kAdamMaxTensors = 160;   // gradient pointers passed by value per launch (1.25 KB of kernel parameters)
-constexpr int kAdamChunk = 4096;       // elements per work item; a chunk never crosses a tensor boundary
+// work items are chunks of <= 4096 elements that never cross a tensor boundary; the CALLER builds the chunk table
+// (egopack_b200/optim.py)
 
 struct AdamGrads {
   const float* g[kAdamMaxTensors];
