@@ -22,6 +22,10 @@ configurations (c3 EgoPack backpack, c4 long video) measured device-resident in 
 Features: the loader stores the Omnivore features as bf16 (``Batch.to_feature_dtype``; ``--feature-dtype fp32`` keeps
 the reference's fp32 storage).  In the bf16 compute mode that is bit-identical to feeding fp32 features (the first
 GEMM's operand is the same round-to-nearest-even either way, tests/test_gpu_models.py) and halves the PCIe bytes.
+PNR features are one vector per node repeated over the three segments, as the reference's dataset builds them
+(data/ego4d_oscc.py:291) -- for every arm, the CPU one included; the e2e feed ships that vector once and repeats it on the
+device (``egopack_b200.data.replicated_base``; ``EGP_BENCH_COMPACT=0`` ships the materialised tensor instead).
+``step_ms`` = per-step spread of the timed regions (median / min / max, cudaMalloc calls inside them).
 """
 from __future__ import annotations
 
@@ -484,9 +488,13 @@ def native_run(args, rank: int, world: int, local_rank: int, workload: str = "c2
                "step_ms": {"median": round(statistics.median(e2e_step_ms), 3), "min": round(min(e2e_step_ms), 3),
                            "max": round(max(e2e_step_ms), 3), "argmax": int(e2e_step_ms.index(max(e2e_step_ms))),
                            "cuda_mallocs": int(e2e_mallocs)},
+               "h2d_bytes_per_step_if_pnr_were_materialised": int(sum(
+                   v.numel() * v.element_size() for b in host.values() for v in (b.x, b.pos, b.y, b.batch, b.ptr))),
                "note": "egopack_b200.feed.DeviceFeeder: pinned host -> device copy of every step's inputs on a copy stream "
                        "(enqueued before the previous step is handed out), device-side graph transforms (band_k / star hints, "
-                       "lazy edge_index), loss.item() per step"}
+                       "lazy edge_index), loss.item() per step; PNR features (one vector per node repeated over the segments, "
+                       "data/ego4d_oscc.py:291) cross the bus once and are repeated on the device (EGP_BENCH_COMPACT=0 ships "
+                       "them materialised)"}
         b = None
 
     # ---- launch-bound regime: the reference's own batch size (16 graphs/task), eager vs one CUDA graph per step ------
