@@ -204,3 +204,26 @@ def test_device_feeder_ships_replicated_segments_once():
     assert replicated_base(b.x) is not None
     d = b.to(DEV)
     assert d.x.is_contiguous() and torch.equal(d.x.cpu(), want.to(torch.bfloat16))
+
+
+def test_feeders_share_one_copy_stream_and_the_allocator_cache():
+    """torch's caching allocator keeps free blocks per stream: a second feeder (next epoch) must find the staging buffers
+    the first one returned, i.e. run without a single cudaMalloc."""
+    from egopack_b200 import synthetic as syn
+    from egopack_b200.feed import DeviceFeeder
+    from egopack_b200.models.transforms import RadiusGraph
+    gen = torch.Generator().manual_seed(11)
+    items = [{"ar": syn.make_batch("ar", 4, 64, gen, feature_dim=256, num_segments=3, n_verbs=5, n_nouns=7, pin=True),
+              "pnr": syn.make_batch("pnr", 4, 64, gen, feature_dim=256, num_segments=3, pin=True, compact=True)}
+             for _ in range(4)]
+    first = DeviceFeeder(items, DEV, RadiusGraph(r=1.5))
+    for out in first:
+        out["ar"].x.sum().item()
+    torch.cuda.synchronize()
+    before = torch.cuda.memory_stats(DEV)["num_device_alloc"]
+    second = DeviceFeeder(items, DEV, RadiusGraph(r=1.5))
+    assert second._stream is first._stream
+    for out in second:
+        out["ar"].x.sum().item()
+    torch.cuda.synchronize()
+    assert torch.cuda.memory_stats(DEV)["num_device_alloc"] == before
